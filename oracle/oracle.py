@@ -1,0 +1,222 @@
+"""ctypes loader for the CPU oracle (oracle/brg_oracle.c) and the reference-native cross-check
+(oracle/_ref/libsi_ref.so, compiled from the reference's vendored superintervals.hpp).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ABSENT = 0xFFFFFFFF
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force=False):
+    """Compile liboracle.so (and _ref when /root/reference is present).  Building the checker is not using it."""
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "brg_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_oracle())
+        L.brgo_build.restype = C.c_void_p
+        L.brgo_build.argtypes = [C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint32]
+        L.brgo_index_destroy.argtypes = [C.c_void_p]
+        for f in (L.brgo_count_overlaps, L.brgo_coverage):
+            f.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_int, _i64p, C.c_int]
+        L.brgo_nearest_k1.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_int, C.c_int,
+                                      _u32p, _u8p, C.c_void_p, C.c_int]
+        L.brgo_nearest_k.restype = C.c_uint64
+        L.brgo_nearest_k.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                     _u32p, _u8p, _u32p, C.c_void_p]
+        L.brgo_overlap_pairs.restype = C.c_uint64
+        L.brgo_overlap_pairs.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.brgo_overlap_counts.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, _u64p, C.c_int]
+        L.brgo_merge_intervals.restype = C.c_uint64
+        L.brgo_merge_intervals.argtypes = [_i32p, _i32p, C.c_uint64, _i32p, _i32p]
+        L.brgo_free.argtypes = [C.c_void_p]
+        L.brgo_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _keyptr(key):
+    if key is None:
+        return None, None
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    return k, k.ctypes.data
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class OracleIndex:
+    """Build-once / probe-many CPU index over (key_id, start, end) rows -- the reference's per-contig
+    CountOverlapIndex / merged COITree / NearestIntervalIndex / join COITree all at once."""
+
+    def __init__(self, key, start, end, n_keys=None):
+        start, end = _i32(start), _i32(end)
+        self._k, kp = _keyptr(key)
+        if n_keys is None:
+            n_keys = 1 if key is None else (int(self._k[self._k != ABSENT].max()) + 1 if len(self._k) and (self._k != ABSENT).any() else 0)
+        self.n_keys = n_keys
+        self.n = len(start)
+        self._h = lib().brgo_build(kp, start, end, len(start), n_keys)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().brgo_index_destroy(self._h)
+            self._h = None
+
+    def count_overlaps(self, key, start, end, strict=False, threads=1):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        out = np.empty(len(start), np.int64)
+        lib().brgo_count_overlaps(self._h, kp, start, end, len(start), int(strict), out, threads)
+        return out
+
+    def coverage(self, key, start, end, strict=False, threads=1):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        out = np.empty(len(start), np.int64)
+        lib().brgo_coverage(self._h, kp, start, end, len(start), int(strict), out, threads)
+        return out
+
+    def nearest_k1(self, key, start, end, include_overlaps=True, strict=False, compute_distance=True, threads=1):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        n = len(start)
+        left = np.empty(n, np.uint32)
+        valid = np.empty(n, np.uint8)
+        dist = np.empty(n, np.int64) if compute_distance else None
+        lib().brgo_nearest_k1(self._h, kp, start, end, n, int(include_overlaps), int(strict), left, valid,
+                              dist.ctypes.data if dist is not None else None, threads)
+        return left, valid.astype(bool), dist
+
+    def nearest_k(self, key, start, end, k, include_overlaps=True, strict=False, compute_distance=True):
+        start, end = _i32(start), _i32(end)
+        kk, kp = _keyptr(key)
+        n = len(start)
+        cap = max(1, n * max(k, 1))
+        left = np.empty(cap, np.uint32)
+        valid = np.empty(cap, np.uint8)
+        right = np.empty(cap, np.uint32)
+        dist = np.empty(cap, np.int64) if compute_distance else None
+        w = lib().brgo_nearest_k(self._h, kp, start, end, n, k, int(include_overlaps), int(strict), left, valid, right,
+                                 dist.ctypes.data if dist is not None else None)
+        return left[:w].copy(), valid[:w].astype(bool), right[:w].copy(), (dist[:w].copy() if dist is not None else None)
+
+    def overlap_pairs(self, key, start, end):
+        """(build_idx, probe_idx) uint32 arrays, probe-major, match order within a probe unspecified."""
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        b, p = C.c_void_p(), C.c_void_p()
+        m = lib().brgo_overlap_pairs(self._h, kp, start, end, len(start), C.byref(b), C.byref(p))
+        bi = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint32)), shape=(m,)).copy() if m else np.empty(0, np.uint32)
+        pi = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(m,)).copy() if m else np.empty(0, np.uint32)
+        lib().brgo_free(b)
+        lib().brgo_free(p)
+        return bi, pi
+
+    def overlap_counts(self, key, start, end, threads=1):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        out = np.empty(len(start), np.uint64)
+        lib().brgo_overlap_counts(self._h, kp, start, end, len(start), out, threads)
+        return out
+
+
+def merge_intervals(first, last):
+    first, last = _i32(first), _i32(last)
+    of, ol = np.empty(max(1, len(first)), np.int32), np.empty(max(1, len(first)), np.int32)
+    m = lib().brgo_merge_intervals(first, last, len(first), of, ol)
+    return of[:m].copy(), ol[:m].copy()
+
+
+def max_threads():
+    return lib().brgo_max_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-native cross-check: the reference's vendored superintervals.hpp (oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+def ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libsi_ref.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libsi_ref.so"))
+        R.si_ref_build.restype = C.c_void_p
+        R.si_ref_build.argtypes = [C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint32]
+        R.si_ref_destroy.argtypes = [C.c_void_p]
+        R.si_ref_counts.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, _u64p, C.c_int]
+        R.si_ref_pairs.restype = C.c_uint64
+        R.si_ref_pairs.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        R.si_ref_pairs_count_mt.restype = C.c_uint64
+        R.si_ref_pairs_count_mt.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_int]
+        R.si_ref_free.argtypes = [C.c_void_p]
+        _ref = R
+    return _ref
+
+
+class SuperIntervalsRef:
+    def __init__(self, key, start, end, n_keys):
+        start, end = _i32(start), _i32(end)
+        self._k, kp = _keyptr(key)
+        self._h = ref().si_ref_build(kp, start, end, len(start), n_keys)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref().si_ref_destroy(self._h)
+            self._h = None
+
+    def counts(self, key, start, end, threads=1):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        out = np.empty(len(start), np.uint64)
+        ref().si_ref_counts(self._h, kp, start, end, len(start), out, threads)
+        return out
+
+    def pairs(self, key, start, end):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        b, p = C.c_void_p(), C.c_void_p()
+        m = ref().si_ref_pairs(self._h, kp, start, end, len(start), C.byref(b), C.byref(p))
+        bi = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint32)), shape=(m,)).copy() if m else np.empty(0, np.uint32)
+        pi = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(m,)).copy() if m else np.empty(0, np.uint32)
+        ref().si_ref_free(b)
+        ref().si_ref_free(p)
+        return bi, pi
+
+    def pairs_count_mt(self, key, start, end, threads):
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        return ref().si_ref_pairs_count_mt(self._h, kp, start, end, len(start), threads)
+
+
+def canonical_pairs(build_idx, probe_idx):
+    """Canonical sort for set comparison of pairs (match order within a probe is unspecified, SURVEY a'12)."""
+    o = np.lexsort((build_idx, probe_idx))
+    return np.asarray(build_idx)[o], np.asarray(probe_idx)[o]
