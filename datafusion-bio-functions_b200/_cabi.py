@@ -1,0 +1,119 @@
+"""ctypes binding of include/bioranges.h (libbioranges.so).  This is the only way Python reaches the engine:
+every call goes through the C ABI a Rust/DataFusion host would bind.  There is NO fallback: if the shared
+library is missing or no sm_100 device is usable, the calls raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbioranges.so")
+KEY_ABSENT = 0xFFFFFFFF
+
+WANT_COUNT, WANT_COVERAGE, WANT_NEAREST, WANT_PAIRS, WANT_ALL = 1, 2, 4, 8, 15
+PAIRS_INNER, PAIRS_SEMI, PAIRS_ANTI = 0, 1, 2
+
+# every symbol include/bioranges.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "brg_last_error", "brg_version", "brg_ctx_create", "brg_ctx_destroy", "brg_ctx_device", "brg_ctx_sm_count",
+    "brg_pinned_alloc", "brg_pinned_free", "brg_build", "brg_build_dev", "brg_index_destroy", "brg_index_rows",
+    "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_count_overlaps",
+    "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
+    "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_rows_len", "brg_rows_build_idx",
+    "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
+]
+
+
+class BioRangesError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libbioranges status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Loads libbioranges.so (built in-tree by `make -C datafusion-bio-functions_b200` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension must be built (python -c 'import __graft_entry__ as g; g.build()')."
+            " There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.brg_last_error.restype = C.c_char_p
+    L.brg_version.restype = i32
+    L.brg_kernel_launches.restype = u64
+    L.brg_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.brg_ctx_destroy.argtypes = [vp]
+    L.brg_ctx_destroy.restype = None
+    L.brg_ctx_device.argtypes = [vp]
+    L.brg_ctx_sm_count.argtypes = [vp]
+    L.brg_pinned_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.brg_pinned_free.argtypes = [vp]
+    L.brg_pinned_free.restype = None
+    L.brg_build.argtypes = [vp, vp, vp, vp, u64, u32, u32, C.POINTER(vp)]
+    L.brg_build_dev.argtypes = [vp, vp, vp, vp, u64, u32, u32, vp, C.POINTER(vp)]
+    L.brg_index_destroy.argtypes = [vp]
+    L.brg_index_destroy.restype = None
+    for f in (L.brg_index_rows, L.brg_index_merged_rows, L.brg_index_device_bytes):
+        f.argtypes = [vp]
+        f.restype = u64
+    L.brg_index_export.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+    L.brg_index_import.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.brg_count_overlaps.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
+    L.brg_coverage.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
+    L.brg_count_overlaps_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
+    L.brg_coverage_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
+    L.brg_nearest_k1.argtypes = [vp, vp, vp, vp, vp, u64, i32, i32, vp, vp, vp]
+    L.brg_nearest_k1_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, i32, vp, vp, vp, vp]
+    L.brg_nearest.argtypes = [vp, vp, vp, vp, vp, u64, u32, i32, i32, i32, C.POINTER(vp)]
+    L.brg_overlap_pairs.argtypes = [vp, vp, vp, vp, vp, u64, i32, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.brg_pairs_count_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
+    L.brg_pairs_emit_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
+    L.brg_rows_len.argtypes = [vp]
+    L.brg_rows_len.restype = u64
+    for f in (L.brg_rows_build_idx, L.brg_rows_probe_idx, L.brg_rows_valid_bits, L.brg_rows_distance):
+        f.argtypes = [vp]
+        f.restype = vp
+    L.brg_rows_release.argtypes = [vp]
+    L.brg_rows_release.restype = None
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != 0:
+        raise BioRangesError(status, lib().brg_last_error().decode("utf-8", "replace"))
+
+
+def np_ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def as_i32(a):
+    a = np.asarray(a)
+    if a.dtype != np.int32:
+        raise TypeError(f"coordinate column must be int32 at the C ABI (got {a.dtype}); resolve it on the host first")
+    return np.ascontiguousarray(a)
+
+
+def as_key(a):
+    if a is None:
+        return None
+    return np.ascontiguousarray(np.asarray(a), dtype=np.uint32)
+
+
+def copy_from(ptr, n, dtype):
+    """copy n elements of dtype out of library-owned memory"""
+    if n == 0 or not ptr:
+        return np.empty(0, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+def unpack_bits(bits_u8, n):
+    return np.unpackbits(bits_u8, bitorder="little")[:n].astype(bool)

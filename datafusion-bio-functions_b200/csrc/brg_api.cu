@@ -1,0 +1,895 @@
+// brg_api.cu -- the C ABI of libbioranges.so (see include/bioranges.h) and the host-side orchestration:
+// context / stream lanes, index build pipeline (K1 sort -> K2 scans -> rank directories -> one HBM slab),
+// chunked host<->device pipelines for the probe entry points, variable-length results in pooled pinned memory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/bioranges.h"
+#include "brg_internal.cuh"
+
+namespace brg {
+
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+std::atomic<uint64_t> g_launches{0};
+
+// ---------------------------------------------------------------------------------------------------
+// small RAII helpers (host code only)
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    uint64_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int ensure(uint64_t b) {
+        if (b <= bytes) return 0;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        if (b == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaMalloc(") + std::to_string(b) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+        bytes = b;
+        return 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBlock { void* p; uint64_t bytes; };
+
+struct Lane {
+    cudaStream_t h2d = nullptr, k = nullptr, d2h = nullptr;
+    static constexpr int NBUF = 2;
+    DevBuf in_key[NBUF], in_s[NBUF], in_e[NBUF], out0[NBUF], out1[NBUF], out2[NBUF];
+    cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
+    DevBuf scratch_a, scratch_b, scratch_c, scratch_d;  // counts / offsets / scan scratch / flags
+    bool busy = false;
+};
+
+}  // namespace brg
+
+using namespace brg;
+
+struct brg_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t build_stream = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Lane*> lanes;
+    std::vector<PinnedBlock> pinned_free;
+    uint64_t chunk_rows = 8ull << 20;
+};
+
+// serialisable description of the slab
+struct DirDesc { uint64_t off_kd, off_D; uint32_t shift, entries; };
+struct IndexHeader {
+    uint32_t magic, version;
+    uint32_t n_keys, n, n_merged, flags;
+    uint64_t slab_bytes;
+    uint64_t off_s_start, off_s_end, off_s_pos, off_pme, off_e_end, off_e_start, off_e_pos, off_m_first, off_m_last,
+        off_m_pre;
+    DirDesc dir[5];  // 0 s_start, 1 e_end, 2 pme, 3 m_first, 4 m_last
+};
+static const uint32_t kMagic = 0x31475242u;  // "BRG1"
+static const uint64_t kNone = ~0ull;
+
+struct brg_index {
+    brg_ctx* ctx = nullptr;
+    IndexHeader h{};
+    void* slab = nullptr;
+    IndexView view{};
+};
+
+static IndexView make_view(const IndexHeader& h, void* slab) {
+    char* b = reinterpret_cast<char*>(slab);
+    auto P = [&](uint64_t off) -> void* { return off == kNone ? nullptr : (void*)(b + off); };
+    IndexView v{};
+    v.n_keys = h.n_keys; v.n = h.n; v.n_merged = h.n_merged; v.flags = h.flags;
+    v.s_start = (const int32_t*)P(h.off_s_start); v.s_end = (const int32_t*)P(h.off_s_end);
+    v.s_pos = (const uint32_t*)P(h.off_s_pos); v.pme = (const int32_t*)P(h.off_pme);
+    v.e_end = (const int32_t*)P(h.off_e_end); v.e_start = (const int32_t*)P(h.off_e_start);
+    v.e_pos = (const uint32_t*)P(h.off_e_pos);
+    v.m_first = (const int32_t*)P(h.off_m_first); v.m_last = (const int32_t*)P(h.off_m_last);
+    v.m_pre = (const int32_t*)P(h.off_m_pre);
+    const int32_t* arrs[5] = {v.s_start, v.e_end, v.pme, v.m_first, v.m_last};
+    DirView* dv[5] = {&v.d_sstart, &v.d_eend, &v.d_pme, &v.d_mfirst, &v.d_mlast};
+    for (int i = 0; i < 5; i++) {
+        dv[i]->kd = (const KeyDir*)P(h.dir[i].off_kd);
+        dv[i]->D = (const uint32_t*)P(h.dir[i].off_D);
+        dv[i]->A = arrs[i];
+        dv[i]->shift = h.dir[i].shift;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small kernels used only by the orchestration
+// ---------------------------------------------------------------------------------------------------
+namespace brg {
+__global__ void init_rows_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ s,
+                                 const int32_t* __restrict__ e, uint64_t n, uint32_t* k_out, uint32_t* s_out,
+                                 uint32_t* e_out, uint32_t* pos_out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    k_out[i] = key ? key[i] : 0u;
+    s_out[i] = (uint32_t)s[i];
+    e_out[i] = (uint32_t)e[i];
+    pos_out[i] = (uint32_t)i;
+}
+__global__ void pack_bits_kernel(const uint32_t* __restrict__ v, uint64_t n, uint32_t* __restrict__ bits) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n_round = (n + 31) & ~31ull;
+    if (i >= n_round) return;
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, i < n && v[i] != 0);
+    if ((threadIdx.x & 31) == 0) bits[i >> 5] = b;
+}
+// largest m in [1, n] with offsets[m] <= max_rows (at least one probe row is always consumed)
+__global__ void find_cut_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t max_rows, uint64_t* out) {
+    uint64_t lo = 1, hi = n;  // answer in [lo, hi]
+    while (lo < hi) {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= max_rows) lo = mid; else hi = mid - 1;
+    }
+    out[0] = lo;
+    out[1] = offsets[lo];
+}
+}  // namespace brg
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" BRG_API const char* brg_last_error(void) { return t_error.c_str(); }
+extern "C" BRG_API int brg_version(void) { return 100; }
+extern "C" BRG_API uint64_t brg_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" BRG_API int brg_ctx_create(int device_id, brg_ctx** out) {
+    if (!out) { set_error("brg_ctx_create: out is NULL"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libbioranges has no CPU fallback)");
+        cudaGetLastError();
+        return BRG_ERR_CUDA;
+    }
+    if (device_id < 0 || device_id >= n_dev) { set_error("brg_ctx_create: bad device id"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    BRG_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10) {
+        set_error(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                  "; libbioranges is built for sm_100a only");
+        return BRG_ERR_CUDA;
+    }
+    brg_ctx* c = new brg_ctx();
+    c->device = device_id;
+    c->sms = prop.multiProcessorCount;
+    BRG_CUDA(cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking));
+    if (const char* env = getenv("BRG_CHUNK_ROWS")) {
+        uint64_t v = strtoull(env, nullptr, 10);
+        if (v >= 1024) c->chunk_rows = v;
+    }
+    *out = c;
+    return BRG_OK;
+}
+
+static void lane_free(Lane* l) {
+    for (int b = 0; b < Lane::NBUF; b++) {
+        if (l->ev_in[b]) cudaEventDestroy(l->ev_in[b]);
+        if (l->ev_k[b]) cudaEventDestroy(l->ev_k[b]);
+        if (l->ev_out[b]) cudaEventDestroy(l->ev_out[b]);
+    }
+    if (l->h2d) cudaStreamDestroy(l->h2d);
+    if (l->k) cudaStreamDestroy(l->k);
+    if (l->d2h) cudaStreamDestroy(l->d2h);
+    delete l;
+}
+
+extern "C" BRG_API void brg_ctx_destroy(brg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (Lane* l : c->lanes) lane_free(l);
+    for (auto& b : c->pinned_free) cudaFreeHost(b.p);
+    if (c->build_stream) cudaStreamDestroy(c->build_stream);
+    delete c;
+}
+extern "C" BRG_API int brg_ctx_device(const brg_ctx* c) { return c ? c->device : -1; }
+extern "C" BRG_API int brg_ctx_sm_count(const brg_ctx* c) { return c ? c->sms : 0; }
+
+extern "C" BRG_API int brg_pinned_alloc(uint64_t bytes, void** out) {
+    if (!out) return BRG_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error(std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); cudaGetLastError(); *out = nullptr; return BRG_ERR_OOM; }
+    return BRG_OK;
+}
+extern "C" BRG_API void brg_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int lane_acquire(brg_ctx* c, Lane** out) {
+    std::unique_lock<std::mutex> lk(c->mu);
+    for (;;) {
+        for (Lane* l : c->lanes)
+            if (!l->busy) { l->busy = true; *out = l; return 0; }
+        if (c->lanes.size() < 4) {
+            Lane* l = new Lane();
+            cudaError_t e = cudaStreamCreateWithFlags(&l->h2d, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->k, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->d2h, cudaStreamNonBlocking);
+            for (int b = 0; b < Lane::NBUF && e == cudaSuccess; b++) {
+                e = cudaEventCreateWithFlags(&l->ev_in[b], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_k[b], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->ev_out[b], cudaEventDisableTiming);
+            }
+            if (e != cudaSuccess) { set_error(std::string("lane create: ") + cudaGetErrorString(e)); lane_free(l); return BRG_ERR_CUDA; }
+            l->busy = true;
+            c->lanes.push_back(l);
+            *out = l;
+            return 0;
+        }
+        c->cv.wait(lk);
+    }
+}
+static void lane_release(brg_ctx* c, Lane* l) {
+    { std::lock_guard<std::mutex> lk(c->mu); l->busy = false; }
+    c->cv.notify_one();
+}
+struct LaneGuard {
+    brg_ctx* c; Lane* l = nullptr;
+    explicit LaneGuard(brg_ctx* c_) : c(c_) {}
+    int acquire() { return lane_acquire(c, &l); }
+    ~LaneGuard() { if (l) lane_release(c, l); }
+};
+
+static int pinned_get(brg_ctx* c, uint64_t bytes, PinnedBlock* out) {
+    if (bytes == 0) bytes = 1;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int best = -1;
+        for (int i = 0; i < (int)c->pinned_free.size(); i++)
+            if (c->pinned_free[i].bytes >= bytes && (best < 0 || c->pinned_free[i].bytes < c->pinned_free[best].bytes)) best = i;
+        if (best >= 0 && c->pinned_free[best].bytes <= 4 * bytes + (1u << 20)) {
+            *out = c->pinned_free[best];
+            c->pinned_free.erase(c->pinned_free.begin() + best);
+            return 0;
+        }
+    }
+    uint64_t cap = (bytes + (1u << 20) - 1) & ~((1ull << 20) - 1);
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, cap, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error(std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+    out->p = p; out->bytes = cap;
+    return 0;
+}
+static void pinned_put(brg_ctx* c, PinnedBlock b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->pinned_free.size() >= 16) { cudaFreeHost(b.p); return; }
+    c->pinned_free.push_back(b);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------------
+static inline uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
+
+struct DirBuild {
+    DevBuf kd;         // KeyDir[n_keys]
+    uint32_t shift = 0;
+    uint32_t entries = 0;
+};
+
+static const uint32_t kTargetPerBin = 4;
+
+// phase 1 of a directory: key ranges + choice of the bin width
+static int dir_plan(const int32_t* A, const uint32_t* off, uint32_t n_keys, uint64_t n_elems, DirBuild* db,
+                    unsigned long long* d_bins, uint32_t* d_total, cudaStream_t st) {
+    int rc = db->kd.ensure((uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+    if (rc) return rc;
+    rc = dir_key_ranges(A, off, n_keys, db->kd.as<KeyDir>(), d_bins, st);
+    if (rc) return rc;
+    unsigned long long bins[32];
+    BRG_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof(bins), cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
+    uint64_t budget = std::max<uint64_t>(n_elems / kTargetPerBin, 2ull * n_keys);
+    budget = std::max<uint64_t>(budget, 64);
+    uint32_t shift = 31;
+    for (uint32_t s = 0; s < 32; s++)
+        if (bins[s] <= budget) { shift = s; break; }
+    db->shift = shift;
+    rc = dir_assign_bases(db->kd.as<KeyDir>(), n_keys, shift, d_total, st);
+    if (rc) return rc;
+    uint32_t total = 0;
+    BRG_CUDA(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
+    db->entries = total;
+    return 0;
+}
+
+extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const int32_t* d_start, const int32_t* d_end,
+                             uint64_t n, uint32_t n_keys, uint32_t want, void* stream, brg_index** out) {
+    if (!ctx || !out) { set_error("brg_build: NULL ctx/out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (n > 0 && (!d_start || !d_end)) { set_error("brg_build: NULL column"); return BRG_ERR_INVALID; }
+    if ((want & BRG_WANT_ALL) == 0) { set_error("brg_build: empty want mask"); return BRG_ERR_INVALID; }
+    if (n >= 0xFFFFFFFFull) {  // nearest.rs:357-361 / interval_join.rs:1624: row ids are UInt32
+        set_error("left row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity");
+        return BRG_ERR_OVERFLOW;
+    }
+    if (n_keys == BRG_KEY_ABSENT) { set_error("brg_build: n_keys too large"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->build_stream;
+    want &= BRG_WANT_ALL;
+    const bool full = (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0;
+    const bool need_e = (want & (BRG_WANT_COUNT | BRG_WANT_NEAREST)) != 0;
+    const bool need_pme = (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS | BRG_WANT_COVERAGE)) != 0;
+    const bool need_cov = (want & BRG_WANT_COVERAGE) != 0;
+
+    // ---- temporaries: two ping-pong row sets (key,start,end,pos) + scan/histogram scratch -----------
+    const uint64_t nn = std::max<uint64_t>(n, 1);
+    DevBuf setA[4], setB[4], hist, scan, small;
+    int rc;
+    for (int i = 0; i < 4; i++) {
+        if ((rc = setA[i].ensure(nn * 4))) return rc;
+        if ((rc = setB[i].ensure(nn * 4))) return rc;
+    }
+    if ((rc = hist.ensure(radix_hist_words(nn) * 4))) return rc;
+    if ((rc = scan.ensure((scan_scratch_words(std::max<uint64_t>(radix_hist_words(nn), nn)) + 16) * 4))) return rc;
+    if ((rc = small.ensure(4096))) return rc;
+    unsigned long long* d_bins = small.as<unsigned long long>();           // 32 x u64
+    uint32_t* d_scalar = reinterpret_cast<uint32_t*>(small.as<char>() + 512);  // misc u32 results
+
+    uint32_t* a[4] = {setA[0].as<uint32_t>(), setA[1].as<uint32_t>(), setA[2].as<uint32_t>(), setA[3].as<uint32_t>()};
+    uint32_t* b[4] = {setB[0].as<uint32_t>(), setB[1].as<uint32_t>(), setB[2].as<uint32_t>(), setB[3].as<uint32_t>()};
+    if (n) {
+        init_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_key, d_start, d_end, n, a[0], a[1], a[2], a[3]);
+        BRG_LAUNCH_CHECK();
+    }
+    // number of 8-bit passes that cover key ids 0..n_keys (n_keys itself = "invalid key" bucket)
+    int key_passes = 0;
+    for (uint64_t v = n_keys; v > 0; v >>= 8) key_passes++;
+
+    // ---- S-order: (key, start, end, pos) -----------------------------------------------------------------
+    std::vector<SortPass> passes;
+    if (full) for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
+    for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
+    for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
+    int res = 0;
+    rc = radix_sort_rows(a, b, 4, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4,
+                         scan.as<uint32_t>(), st, &res);
+    if (rc) return rc;
+    uint32_t** S = res == 0 ? a : b;   // sorted rows
+    uint32_t** T = res == 0 ? b : a;   // free set
+
+    // segment offsets per key; rows with key >= n_keys form the ignored tail
+    DevBuf off, m_off;
+    if ((rc = off.ensure(((uint64_t)n_keys + 2) * 4))) return rc;
+    if ((rc = segment_offsets(S[0], n, n_keys, off.as<uint32_t>(), st))) return rc;
+    uint32_t n_valid = 0;
+    BRG_CUDA(cudaMemcpyAsync(&n_valid, off.as<uint32_t>() + n_keys, 4, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
+
+    // prefix_max_end over the S-order (per key)
+    DevBuf pme;
+    if (need_pme) {
+        if ((rc = pme.ensure(nn * 4))) return rc;
+        if ((rc = segmented_running_max(S[0], (const int32_t*)S[2], pme.as<int32_t>(), n_valid, scan.as<int32_t>(), st))) return rc;
+    }
+
+    // merged intervals (coverage)
+    DevBuf m_first, m_last, m_key, m_pre;
+    uint32_t n_merged = 0;
+    if (need_cov) {
+        if ((rc = m_first.ensure(nn * 4)) || (rc = m_last.ensure(nn * 4)) || (rc = m_key.ensure(nn * 4)) ||
+            (rc = m_pre.ensure((nn + 1) * 4)) || (rc = m_off.ensure(((uint64_t)n_keys + 2) * 4)))
+            return rc;
+        // T[1], T[2] are free: flags / merged index
+        rc = merge_sorted_intervals(S[0], (const int32_t*)S[1], pme.as<int32_t>(), n_valid, T[1], T[2], scan.as<uint32_t>(),
+                                    m_first.as<int32_t>(), m_last.as<int32_t>(), m_key.as<uint32_t>(), d_scalar, st);
+        if (rc) return rc;
+        BRG_CUDA(cudaMemcpyAsync(&n_merged, d_scalar, 4, cudaMemcpyDeviceToHost, st));
+        BRG_CUDA(cudaStreamSynchronize(st));
+        if ((rc = segment_offsets(m_key.as<uint32_t>(), n_merged, n_keys, m_off.as<uint32_t>(), st))) return rc;
+        if ((rc = merged_width_prefix(m_first.as<int32_t>(), m_last.as<int32_t>(), n_merged, T[1], m_pre.as<int32_t>(),
+                                      scan.as<uint32_t>(), st)))
+            return rc;
+    }
+
+    // keep the S-order columns: they are consumed by the E-order sort below
+    DevBuf s_start, s_end, s_pos;
+    if ((rc = s_start.ensure(nn * 4))) return rc;
+    BRG_CUDA(cudaMemcpyAsync(s_start.p, S[1], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
+    if (full) {
+        if ((rc = s_end.ensure(nn * 4)) || (rc = s_pos.ensure(nn * 4))) return rc;
+        BRG_CUDA(cudaMemcpyAsync(s_end.p, S[2], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
+        BRG_CUDA(cudaMemcpyAsync(s_pos.p, S[3], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- E-order: (key, end, start, pos): stable sort of the S-order rows by end, then key -----------------
+    uint32_t** E = nullptr;
+    if (need_e) {
+        passes.clear();
+        for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
+        for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
+        int res2 = 0;
+        rc = radix_sort_rows(S, T, 4, n_valid, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4,
+                             scan.as<uint32_t>(), st, &res2);
+        if (rc) return rc;
+        E = res2 == 0 ? S : T;
+    }
+
+    // ---- rank directories ----------------------------------------------------------------------------------
+    DirBuild db[5];
+    const bool need_dir[5] = {(want & (BRG_WANT_COUNT | BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0, need_e,
+                              (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0, need_cov, need_cov};
+    const int32_t* dirA[5] = {s_start.as<int32_t>(), E ? (const int32_t*)E[2] : nullptr, pme.as<int32_t>(),
+                              m_first.as<int32_t>(), m_last.as<int32_t>()};
+    const uint32_t* dirOff[5] = {off.as<uint32_t>(), off.as<uint32_t>(), off.as<uint32_t>(), m_off.as<uint32_t>(),
+                                 m_off.as<uint32_t>()};
+    const uint64_t dirN[5] = {n_valid, n_valid, n_valid, n_merged, n_merged};
+    for (int i = 0; i < 5; i++) {
+        if (!need_dir[i]) continue;
+        if ((rc = dir_plan(dirA[i], dirOff[i], n_keys, dirN[i], &db[i], d_bins, d_scalar, st))) return rc;
+    }
+
+    // ---- lay out and fill the slab -------------------------------------------------------------------------
+    IndexHeader h{};
+    h.magic = kMagic; h.version = 1;
+    h.n_keys = n_keys; h.n = n_valid; h.n_merged = n_merged; h.flags = want;
+    uint64_t cur = 0;
+    auto place = [&](bool on, uint64_t bytes) -> uint64_t {
+        if (!on) return kNone;
+        uint64_t o = cur;
+        cur = align256(cur + std::max<uint64_t>(bytes, 4));
+        return o;
+    };
+    const uint64_t nv4 = (uint64_t)n_valid * 4;
+    h.off_s_start = place(need_dir[0], nv4);
+    h.off_s_end = place(full, nv4);
+    h.off_s_pos = place(full, nv4);
+    h.off_pme = place(need_dir[2], nv4);
+    h.off_e_end = place(need_e, nv4);
+    h.off_e_start = place(need_e && full, nv4);
+    h.off_e_pos = place(need_e && full, nv4);
+    h.off_m_first = place(need_cov, (uint64_t)n_merged * 4);
+    h.off_m_last = place(need_cov, (uint64_t)n_merged * 4);
+    h.off_m_pre = place(need_cov, ((uint64_t)n_merged + 1) * 4);
+    for (int i = 0; i < 5; i++) {
+        h.dir[i].off_kd = place(need_dir[i], (uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+        h.dir[i].off_D = place(need_dir[i], ((uint64_t)db[i].entries + 1) * 4);
+        h.dir[i].shift = db[i].shift;
+        h.dir[i].entries = db[i].entries;
+    }
+    h.slab_bytes = std::max<uint64_t>(cur, 256);
+
+    void* slab = nullptr;
+    {
+        cudaError_t e = cudaMalloc(&slab, h.slab_bytes);
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc(index slab ") + std::to_string(h.slab_bytes) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+    }
+    char* base = reinterpret_cast<char*>(slab);
+    auto copy_in = [&](uint64_t off_, const void* src, uint64_t bytes) -> cudaError_t {
+        if (off_ == kNone || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(base + off_, src, bytes, cudaMemcpyDeviceToDevice, st);
+    };
+    cudaError_t ce = cudaSuccess;
+    auto chk = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
+    chk(copy_in(h.off_s_start, s_start.p, nv4));
+    chk(copy_in(h.off_s_end, s_end.p, nv4));
+    chk(copy_in(h.off_s_pos, s_pos.p, nv4));
+    chk(copy_in(h.off_pme, pme.p, nv4));
+    if (E) {
+        chk(copy_in(h.off_e_end, E[2], nv4));
+        chk(copy_in(h.off_e_start, E[1], nv4));
+        chk(copy_in(h.off_e_pos, E[3], nv4));
+    }
+    chk(copy_in(h.off_m_first, m_first.p, (uint64_t)n_merged * 4));
+    chk(copy_in(h.off_m_last, m_last.p, (uint64_t)n_merged * 4));
+    chk(copy_in(h.off_m_pre, m_pre.p, ((uint64_t)n_merged + 1) * 4));
+    for (int i = 0; i < 5; i++)
+        if (need_dir[i]) chk(copy_in(h.dir[i].off_kd, db[i].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
+    if (ce != cudaSuccess) { cudaFree(slab); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
+    for (int i = 0; i < 5; i++) {
+        if (!need_dir[i]) continue;
+        rc = dir_fill(dirA[i], db[i].kd.as<KeyDir>(), n_keys, db[i].shift, (uint32_t*)(base + h.dir[i].off_D), db[i].entries, st);
+        if (rc) { cudaFree(slab); return rc; }
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(slab); set_error(std::string("build sync: ") + cudaGetErrorString(e)); return BRG_ERR_CUDA; }
+    }
+    brg_index* ix = new brg_index();
+    ix->ctx = ctx; ix->h = h; ix->slab = slab; ix->view = make_view(h, slab);
+    *out = ix;
+    return BRG_OK;
+}
+
+extern "C" BRG_API int brg_build(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                         uint32_t n_keys, uint32_t want, brg_index** out) {
+    if (!ctx || !out) { set_error("brg_build: NULL ctx/out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (n > 0 && (!start || !end)) { set_error("brg_build: NULL column"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    DevBuf dk, ds, de;
+    int rc;
+    const uint64_t bytes = std::max<uint64_t>(n, 1) * 4;
+    if ((rc = ds.ensure(bytes)) || (rc = de.ensure(bytes))) return rc;
+    if (key && (rc = dk.ensure(bytes))) return rc;
+    cudaStream_t st = ctx->build_stream;
+    if (n) {
+        if (key) BRG_CUDA(cudaMemcpyAsync(dk.p, key, n * 4, cudaMemcpyHostToDevice, st));
+        BRG_CUDA(cudaMemcpyAsync(ds.p, start, n * 4, cudaMemcpyHostToDevice, st));
+        BRG_CUDA(cudaMemcpyAsync(de.p, end, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    rc = brg_build_dev(ctx, key ? dk.as<uint32_t>() : nullptr, ds.as<int32_t>(), de.as<int32_t>(), n, n_keys, want, st, out);
+    cudaStreamSynchronize(st);
+    return rc;
+}
+
+extern "C" BRG_API void brg_index_destroy(brg_index* ix) {
+    if (!ix) return;
+    if (ix->ctx) cudaSetDevice(ix->ctx->device);
+    if (ix->slab) cudaFree(ix->slab);
+    delete ix;
+}
+extern "C" BRG_API uint64_t brg_index_rows(const brg_index* ix) { return ix ? ix->h.n : 0; }
+extern "C" BRG_API uint64_t brg_index_merged_rows(const brg_index* ix) { return ix ? ix->h.n_merged : 0; }
+extern "C" BRG_API uint64_t brg_index_device_bytes(const brg_index* ix) { return ix ? ix->h.slab_bytes : 0; }
+
+extern "C" BRG_API int brg_index_export(const brg_index* ix, void* header_buf, uint64_t cap, uint64_t* header_len, void** d_slab,
+                                uint64_t* slab_bytes) {
+    if (!ix) { set_error("brg_index_export: NULL index"); return BRG_ERR_INVALID; }
+    if (header_len) *header_len = sizeof(IndexHeader);
+    if (d_slab) *d_slab = ix->slab;
+    if (slab_bytes) *slab_bytes = ix->h.slab_bytes;
+    if (header_buf) {
+        if (cap < sizeof(IndexHeader)) { set_error("brg_index_export: header buffer too small"); return BRG_ERR_INVALID; }
+        memcpy(header_buf, &ix->h, sizeof(IndexHeader));
+    }
+    return BRG_OK;
+}
+extern "C" BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64_t header_len, brg_index** out, void** d_slab,
+                                uint64_t* slab_bytes) {
+    if (!ctx || !header || !out) { set_error("brg_index_import: NULL argument"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (header_len != sizeof(IndexHeader)) { set_error("brg_index_import: header size mismatch"); return BRG_ERR_INVALID; }
+    IndexHeader h;
+    memcpy(&h, header, sizeof(h));
+    if (h.magic != kMagic || h.version != 1) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    void* slab = nullptr;
+    cudaError_t e = cudaMalloc(&slab, h.slab_bytes);
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(index slab): ") + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+    brg_index* ix = new brg_index();
+    ix->ctx = ctx; ix->h = h; ix->slab = slab; ix->view = make_view(h, slab);
+    *out = ix;
+    if (d_slab) *d_slab = slab;
+    if (slab_bytes) *slab_bytes = h.slab_bytes;
+    return BRG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-buffer probes
+// ---------------------------------------------------------------------------------------------------
+static int check_probe(const brg_ctx* ctx, const brg_index* ix, uint32_t need, const char* what) {
+    if (!ctx || !ix) { set_error(std::string(what) + ": NULL ctx/index"); return BRG_ERR_INVALID; }
+    if ((ix->h.flags & need) == 0) { set_error(std::string(what) + ": index was built without the required structures"); return BRG_ERR_INVALID; }
+    return 0;
+}
+
+extern "C" BRG_API int brg_count_overlaps_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
+                                      const int32_t* e, uint64_t n, int strict, int64_t* out, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COUNT | BRG_WANT_NEAREST, "brg_count_overlaps");
+    if (rc) return rc;
+    return launch_count(ix->view, k, s, e, n, strict, out, (cudaStream_t)stream);
+}
+extern "C" BRG_API int brg_coverage_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s, const int32_t* e,
+                                uint64_t n, int strict, int64_t* out, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COVERAGE, "brg_coverage");
+    if (rc) return rc;
+    return launch_coverage(ix->view, k, s, e, n, strict, out, (cudaStream_t)stream);
+}
+extern "C" BRG_API int brg_nearest_k1_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
+                                  const int32_t* e, uint64_t n, int include_overlaps, int strict, uint32_t* left_idx,
+                                  uint32_t* valid_bits, int64_t* dist, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_NEAREST, "brg_nearest_k1");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("right row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    return launch_nearest_k1(ix->view, k, s, e, n, include_overlaps, strict, left_idx, valid_bits, dist, (cudaStream_t)stream);
+}
+
+static int pairs_scratch(Lane* l, uint64_t n) {
+    int rc;
+    if ((rc = l->scratch_a.ensure(std::max<uint64_t>(n, 1) * 4))) return rc;          // counts (u32)
+    if ((rc = l->scratch_c.ensure((scan_scratch_words(std::max<uint64_t>(n, 1)) + 16) * 4))) return rc;
+    return 0;
+}
+
+extern "C" BRG_API int brg_pairs_count_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
+                                   const int32_t* e, uint64_t n, uint64_t* d_offsets, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_pairs_count");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    LaneGuard g(ctx);
+    if ((rc = g.acquire())) return rc;
+    if ((rc = pairs_scratch(g.l, n))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_pairs_count(ix->view, k, s, e, n, g.l->scratch_a.as<uint32_t>(), st))) return rc;
+    rc = exclusive_scan_u32_to_u64(g.l->scratch_a.as<uint32_t>(), d_offsets, n, g.l->scratch_c.as<uint64_t>(), st);
+    if (rc) return rc;
+    // the lane's scratch is reused by the next call on this lane: make sure this one is done with it
+    BRG_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+extern "C" BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
+                                  const int32_t* e, uint64_t n, const uint64_t* d_offsets, uint32_t* d_build_idx,
+                                  uint32_t* d_probe_idx, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_pairs_emit");
+    if (rc) return rc;
+    return launch_pairs_emit(ix->view, k, s, e, n, d_offsets, d_build_idx, d_probe_idx, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer probes with fixed-size outputs: chunked, double-buffered H2D / kernel / D2H pipeline
+// ---------------------------------------------------------------------------------------------------
+enum FixedOp { OP_COUNT, OP_COVERAGE, OP_NEAREST1 };
+
+static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32_t* key, const int32_t* start,
+                     const int32_t* end, uint64_t n, int include_overlaps, int strict, int64_t* out_i64,
+                     uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist) {
+    if (n == 0) return BRG_OK;
+    if (!start || !end) { set_error("probe: NULL column"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    LaneGuard g(ctx);
+    int rc;
+    if ((rc = g.acquire())) return rc;
+    Lane* l = g.l;
+    // chunk rows are a multiple of 32 so that validity bitmap words never straddle chunks
+    const uint64_t C = std::min<uint64_t>((ctx->chunk_rows + 31) & ~31ull, (n + 31) & ~31ull);
+    for (int b = 0; b < Lane::NBUF; b++) {
+        if (key && (rc = l->in_key[b].ensure(C * 4))) return rc;
+        if ((rc = l->in_s[b].ensure(C * 4)) || (rc = l->in_e[b].ensure(C * 4))) return rc;
+        if (op == OP_NEAREST1) {
+            if ((rc = l->out0[b].ensure(C * 4)) || (rc = l->out1[b].ensure(C / 8 + 4))) return rc;
+            if (out_dist && (rc = l->out2[b].ensure(C * 8))) return rc;
+        } else {
+            if ((rc = l->out0[b].ensure(C * 8))) return rc;
+        }
+    }
+    uint64_t done = 0;
+    for (uint64_t j = 0; done < n; j++, done += C) {
+        const int b = (int)(j % Lane::NBUF);
+        const uint64_t m = std::min<uint64_t>(C, n - done);
+        // inputs of buffer b may be overwritten once the kernel that read them has finished
+        BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
+        if (key) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
+        BRG_CUDA(cudaMemcpyAsync(l->in_s[b].p, start + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
+        BRG_CUDA(cudaMemcpyAsync(l->in_e[b].p, end + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
+        BRG_CUDA(cudaEventRecord(l->ev_in[b], l->h2d));
+        // kernel: after its inputs landed and after the previous results of buffer b left the device
+        BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_in[b], 0));
+        BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_out[b], 0));
+        const uint32_t* dk = key ? l->in_key[b].as<uint32_t>() : nullptr;
+        if (op == OP_COUNT)
+            rc = launch_count(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
+        else if (op == OP_COVERAGE)
+            rc = launch_coverage(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
+        else
+            rc = launch_nearest_k1(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, include_overlaps, strict,
+                                   l->out0[b].as<uint32_t>(), l->out1[b].as<uint32_t>(), out_dist ? l->out2[b].as<int64_t>() : nullptr, l->k);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        BRG_CUDA(cudaEventRecord(l->ev_k[b], l->k));
+        BRG_CUDA(cudaStreamWaitEvent(l->d2h, l->ev_k[b], 0));
+        if (op == OP_NEAREST1) {
+            BRG_CUDA(cudaMemcpyAsync(out_left + done, l->out0[b].p, m * 4, cudaMemcpyDeviceToHost, l->d2h));
+            BRG_CUDA(cudaMemcpyAsync(out_bits + done / 8, l->out1[b].p, ((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, l->d2h));
+            if (out_dist) BRG_CUDA(cudaMemcpyAsync(out_dist + done, l->out2[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+        } else {
+            BRG_CUDA(cudaMemcpyAsync(out_i64 + done, l->out0[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+        }
+        BRG_CUDA(cudaEventRecord(l->ev_out[b], l->d2h));
+    }
+    BRG_CUDA(cudaStreamSynchronize(l->d2h));
+    BRG_CUDA(cudaStreamSynchronize(l->k));
+    BRG_CUDA(cudaStreamSynchronize(l->h2d));
+    return BRG_OK;
+}
+
+extern "C" BRG_API int brg_count_overlaps(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
+                                  const int32_t* end, uint64_t n, int strict, int64_t* out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COUNT | BRG_WANT_NEAREST, "brg_count_overlaps");
+    if (rc) return rc;
+    if (n && !out) { set_error("brg_count_overlaps: NULL output"); return BRG_ERR_INVALID; }
+    return run_fixed(ctx, ix, OP_COUNT, key, start, end, n, 0, strict, out, nullptr, nullptr, nullptr);
+}
+extern "C" BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
+                            const int32_t* end, uint64_t n, int strict, int64_t* out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COVERAGE, "brg_coverage");
+    if (rc) return rc;
+    if (n && !out) { set_error("brg_coverage: NULL output"); return BRG_ERR_INVALID; }
+    return run_fixed(ctx, ix, OP_COVERAGE, key, start, end, n, 0, strict, out, nullptr, nullptr, nullptr);
+}
+extern "C" BRG_API int brg_nearest_k1(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
+                              const int32_t* end, uint64_t n, int include_overlaps, int strict, uint32_t* out_left,
+                              uint8_t* out_bits, int64_t* out_dist) {
+    int rc = check_probe(ctx, ix, BRG_WANT_NEAREST, "brg_nearest_k1");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("right row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!out_left || !out_bits)) { set_error("brg_nearest_k1: NULL output"); return BRG_ERR_INVALID; }
+    return run_fixed(ctx, ix, OP_NEAREST1, key, start, end, n, include_overlaps, strict, nullptr, out_left, out_bits, out_dist);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variable-length results
+// ---------------------------------------------------------------------------------------------------
+struct brg_rows {
+    brg_ctx* ctx = nullptr;
+    uint64_t len = 0;
+    PinnedBlock blk_build{}, blk_probe{}, blk_bits{}, blk_dist{};
+};
+extern "C" BRG_API uint64_t brg_rows_len(const brg_rows* r) { return r ? r->len : 0; }
+extern "C" BRG_API const uint32_t* brg_rows_build_idx(const brg_rows* r) { return r ? (const uint32_t*)r->blk_build.p : nullptr; }
+extern "C" BRG_API const uint32_t* brg_rows_probe_idx(const brg_rows* r) { return r ? (const uint32_t*)r->blk_probe.p : nullptr; }
+extern "C" BRG_API const uint8_t* brg_rows_valid_bits(const brg_rows* r) { return r ? (const uint8_t*)r->blk_bits.p : nullptr; }
+extern "C" BRG_API const int64_t* brg_rows_distance(const brg_rows* r) { return r ? (const int64_t*)r->blk_dist.p : nullptr; }
+extern "C" BRG_API void brg_rows_release(brg_rows* r) {
+    if (!r) return;
+    pinned_put(r->ctx, r->blk_build); pinned_put(r->ctx, r->blk_probe);
+    pinned_put(r->ctx, r->blk_bits); pinned_put(r->ctx, r->blk_dist);
+    delete r;
+}
+
+// copies the probe columns of rows [0,n) to the lane's input buffers (set 0) on the lane's kernel stream
+static int upload_probe(Lane* l, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n) {
+    int rc;
+    const uint64_t b = std::max<uint64_t>(n, 1) * 4;
+    if (key && (rc = l->in_key[0].ensure(b))) return rc;
+    if ((rc = l->in_s[0].ensure(b)) || (rc = l->in_e[0].ensure(b))) return rc;
+    if (n) {
+        if (key) BRG_CUDA(cudaMemcpyAsync(l->in_key[0].p, key, n * 4, cudaMemcpyHostToDevice, l->k));
+        BRG_CUDA(cudaMemcpyAsync(l->in_s[0].p, start, n * 4, cudaMemcpyHostToDevice, l->k));
+        BRG_CUDA(cudaMemcpyAsync(l->in_e[0].p, end, n * 4, cudaMemcpyHostToDevice, l->k));
+    }
+    return 0;
+}
+
+extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
+                                 const int32_t* end, uint64_t n, int mode, uint64_t max_rows, brg_rows** out,
+                                 uint64_t* consumed) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_overlap_pairs");
+    if (rc) return rc;
+    if (!out) { set_error("brg_overlap_pairs: NULL out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (mode < BRG_PAIRS_INNER || mode > BRG_PAIRS_ANTI) { set_error("brg_overlap_pairs: bad mode"); return BRG_ERR_INVALID; }
+    if (n > 0xFFFFFFFFull) { set_error("probe row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!start || !end)) { set_error("brg_overlap_pairs: NULL column"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    brg_rows* r = new brg_rows();
+    r->ctx = ctx;
+    if (consumed) *consumed = n;
+    if (n == 0) { *out = r; return BRG_OK; }
+    LaneGuard g(ctx);
+    if ((rc = g.acquire())) { delete r; return rc; }
+    Lane* l = g.l;
+    cudaStream_t st = l->k;
+    auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };
+    if ((rc = upload_probe(l, key, start, end, n))) return fail(rc);
+    if ((rc = pairs_scratch(l, n))) return fail(rc);
+    if ((rc = l->scratch_b.ensure((n + 1) * 8))) return fail(rc);  // offsets u64
+    const uint32_t* dk = key ? l->in_key[0].as<uint32_t>() : nullptr;
+    const int32_t* ds = l->in_s[0].as<int32_t>();
+    const int32_t* de = l->in_e[0].as<int32_t>();
+    uint32_t* counts = l->scratch_a.as<uint32_t>();
+    uint64_t* offsets = l->scratch_b.as<uint64_t>();
+    if ((rc = launch_pairs_count(ix->view, dk, ds, de, n, counts, st))) return fail(rc);
+    if (mode != BRG_PAIRS_INNER) {
+        if ((rc = l->scratch_d.ensure(n * 4))) return fail(rc);
+        if ((rc = launch_semi_anti_flags(counts, n, mode == BRG_PAIRS_ANTI, l->scratch_d.as<uint32_t>(), st))) return fail(rc);
+        counts = l->scratch_d.as<uint32_t>();
+    }
+    if ((rc = exclusive_scan_u32_to_u64(counts, offsets, n, l->scratch_c.as<uint64_t>(), st))) return fail(rc);
+    uint64_t n_use = n, total = 0;
+    {
+        cudaError_t e = cudaMemcpyAsync(&total, offsets + n, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("pairs total: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    if (max_rows > 0 && total > max_rows) {
+        uint64_t* d_cut = reinterpret_cast<uint64_t*>(l->scratch_c.p);
+        find_cut_kernel<<<1, 1, 0, st>>>(offsets, n, max_rows, d_cut);
+        g_launches.fetch_add(1);
+        uint64_t cut[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(cut, d_cut, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("pairs cut: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+        n_use = cut[0];
+        total = cut[1];
+    }
+    if (consumed) *consumed = n_use;
+    r->len = total;
+    // device outputs: reuse the lane's output buffers
+    if ((rc = l->out0[0].ensure(std::max<uint64_t>(total, 1) * 4))) return fail(rc);
+    if (mode == BRG_PAIRS_INNER && (rc = l->out1[0].ensure(std::max<uint64_t>(total, 1) * 4))) return fail(rc);
+    if ((rc = pinned_get(ctx, total * 4, &r->blk_probe))) return fail(rc);
+    if (mode == BRG_PAIRS_INNER && (rc = pinned_get(ctx, total * 4, &r->blk_build))) return fail(rc);
+    if (total) {
+        if (mode == BRG_PAIRS_INNER) {
+            rc = launch_pairs_emit(ix->view, dk, ds, de, n_use, offsets, l->out1[0].as<uint32_t>(), l->out0[0].as<uint32_t>(), st);
+        } else {
+            rc = launch_compact_rows(counts, offsets, n_use, l->out0[0].as<uint32_t>(), st);
+        }
+        if (rc) return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(r->blk_probe.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && mode == BRG_PAIRS_INNER)
+            e = cudaMemcpyAsync(r->blk_build.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("pairs D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    *out = r;
+    return BRG_OK;
+}
+
+extern "C" BRG_API int brg_nearest(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
+                           const int32_t* end, uint64_t n, uint32_t k, int include_overlaps, int compute_distance,
+                           int strict, brg_rows** out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_NEAREST, "brg_nearest");
+    if (rc) return rc;
+    if (!out) { set_error("brg_nearest: NULL out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (k == 0) { set_error("nearest: k must be >= 1"); return BRG_ERR_INVALID; }  // table_function.rs:191-214
+    if (n > 0xFFFFFFFFull) { set_error("right row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!start || !end)) { set_error("brg_nearest: NULL column"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    brg_rows* r = new brg_rows();
+    r->ctx = ctx;
+    if (n == 0) { *out = r; return BRG_OK; }
+    LaneGuard g(ctx);
+    if ((rc = g.acquire())) { delete r; return rc; }
+    Lane* l = g.l;
+    cudaStream_t st = l->k;
+    auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };
+    if ((rc = upload_probe(l, key, start, end, n))) return fail(rc);
+    if ((rc = pairs_scratch(l, n))) return fail(rc);
+    if ((rc = l->scratch_b.ensure((n + 1) * 8))) return fail(rc);
+    const uint32_t* dk = key ? l->in_key[0].as<uint32_t>() : nullptr;
+    const int32_t* ds = l->in_s[0].as<int32_t>();
+    const int32_t* de = l->in_e[0].as<int32_t>();
+    uint32_t* counts = l->scratch_a.as<uint32_t>();
+    uint64_t* offsets = l->scratch_b.as<uint64_t>();
+    if ((rc = launch_nearest_k_count(ix->view, dk, ds, de, n, k, include_overlaps, strict, counts, st))) return fail(rc);
+    if ((rc = exclusive_scan_u32_to_u64(counts, offsets, n, l->scratch_c.as<uint64_t>(), st))) return fail(rc);
+    uint64_t total = 0;
+    {
+        cudaError_t e = cudaMemcpyAsync(&total, offsets + n, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("nearest total: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    r->len = total;
+    const uint64_t bit_words = (total + 31) / 32;
+    if ((rc = l->out0[0].ensure(total * 4)) || (rc = l->out1[0].ensure(total * 4)) || (rc = l->scratch_d.ensure(total * 4)) ||
+        (rc = l->out0[1].ensure(bit_words * 4 + 4)))
+        return fail(rc);
+    if (compute_distance && (rc = l->out2[0].ensure(total * 8))) return fail(rc);
+    if ((rc = pinned_get(ctx, total * 4, &r->blk_build)) || (rc = pinned_get(ctx, total * 4, &r->blk_probe)) ||
+        (rc = pinned_get(ctx, bit_words * 4 + 4, &r->blk_bits)))
+        return fail(rc);
+    if (compute_distance && (rc = pinned_get(ctx, total * 8, &r->blk_dist))) return fail(rc);
+    int64_t* d_dist = compute_distance ? l->out2[0].as<int64_t>() : nullptr;
+    rc = launch_nearest_k_emit(ix->view, dk, ds, de, n, k, include_overlaps, strict, offsets, l->out0[0].as<uint32_t>(),
+                               l->scratch_d.as<uint32_t>(), l->out1[0].as<uint32_t>(), d_dist, st);
+    if (rc) return fail(rc);
+    pack_bits_kernel<<<(unsigned)((((total + 31) & ~31ull) + 255) / 256), 256, 0, st>>>(l->scratch_d.as<uint32_t>(), total,
+                                                                                         l->out0[1].as<uint32_t>());
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaMemcpyAsync(r->blk_build.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_probe.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_bits.p, l->out0[1].p, bit_words * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && compute_distance) e = cudaMemcpyAsync(r->blk_dist.p, d_dist, total * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(std::string("nearest D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    *out = r;
+    return BRG_OK;
+}

@@ -1,0 +1,184 @@
+// brg_internal.cuh -- shared declarations of the sm_100a interval engine (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+namespace brg {
+
+constexpr int kSMs = 148;  // B200: 148 SMs (2 dies x 74); grids are sized in multiples of this
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the ABI; the message is thread-local
+// ------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define BRG_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            brg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+            return 2; /* BRG_ERR_CUDA */                                                            \
+        }                                                                                           \
+    } while (0)
+
+#define BRG_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        brg::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) {                                                                    \
+            brg::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));                \
+            return 2;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Rank directory: one level of direct addressing in front of a per-key sorted i32 array A.
+// For key c the value range [lo, hi] is cut into nb bins of width 2^shift; D[base + j] is the global
+// index of the first element of the key's segment whose bin is >= j, D[base + nb] = seg_end.
+// rank_le(q) therefore needs one KeyDir sector, two adjacent D words and a search over one bin.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) KeyDir {
+    int32_t lo;         // smallest value of the segment
+    uint32_t nb;        // number of bins (0 when the segment is empty)
+    uint32_t base;      // first D entry of this key
+    uint32_t seg_begin; // segment [seg_begin, seg_end) in A
+    uint32_t seg_end;
+    uint32_t pad[3];    // 32 B = one L2 sector
+};
+
+struct DirView {
+    const KeyDir* kd;
+    const uint32_t* D;
+    const int32_t* A;
+    uint32_t shift;
+};
+
+// Device view of an index (pointers into the single HBM slab)
+struct IndexView {
+    uint32_t n_keys;
+    uint32_t n;        // build rows with a valid key
+    uint32_t n_merged; // merged (coverage) intervals
+    uint32_t flags;    // BRG_WANT_* actually built
+    // S-order: rows sorted by (key, start, end, pos)
+    const int32_t* s_start;
+    const int32_t* s_end;
+    const uint32_t* s_pos;
+    const int32_t* pme; // per-key inclusive running max of s_end  (nearest_index.rs:58-63)
+    // E-order: rows sorted by (key, end, start, pos)
+    const int32_t* e_end;
+    const int32_t* e_start;
+    const uint32_t* e_pos;
+    // merged intervals per key (interval_tree.rs:52-73) + exclusive prefix of widths max(1,last-first)
+    const int32_t* m_first;
+    const int32_t* m_last;
+    const int32_t* m_pre;
+    DirView d_sstart, d_eend, d_pme, d_mfirst, d_mlast;
+};
+
+// ------------------------------------------------------------------------------------------------
+// launchers (each returns a brg_status; all work is enqueued on `st`)
+// ------------------------------------------------------------------------------------------------
+// K1 radix sort of rows (SoA of up to 4 u32 words per row)
+struct SortPass {
+    int src;          // which word array supplies the digit
+    int shift;        // bit offset of the 8-bit digit
+    int flip_sign;    // 1: value is i32, order as signed (flip the sign bit)
+    uint32_t clamp;   // values above clamp are treated as clamp (invalid keys sort last); 0xFFFFFFFF = off
+};
+// sorts n rows; in/out are ping-pong sets of `n_arr` u32 arrays; returns which set holds the result in *res
+int radix_sort_rows(uint32_t* const* a, uint32_t* const* b, int n_arr, uint64_t n, const SortPass* passes,
+                    int n_passes, uint32_t* d_hist_scratch, uint64_t hist_scratch_words, uint32_t* d_scan_scratch,
+                    cudaStream_t st, int* res);
+uint64_t radix_hist_words(uint64_t n);
+
+// K2 scans
+uint64_t scan_scratch_words(uint64_t n);
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);
+int exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* scratch,
+                              cudaStream_t st);
+int segmented_running_max(const uint32_t* key, const int32_t* val, int32_t* out, uint64_t n, int32_t* scratch,
+                          cudaStream_t st);
+// merge_intervals on the S-order arrays: writes m_first/m_last/(m_key) and *d_n_merged
+int merge_sorted_intervals(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme, uint64_t n,
+                           uint32_t* d_flags /*n*/, uint32_t* d_midx /*n*/, uint32_t* scan_scratch, int32_t* m_first,
+                           int32_t* m_last, uint32_t* m_key, uint32_t* d_n_merged, cudaStream_t st);
+int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t n_merged, uint32_t* widths_tmp,
+                        int32_t* m_pre /*n_merged+1*/, uint32_t* scan_scratch, cudaStream_t st);
+// segment offsets off[0..n_keys] from a sorted key array (keys >= n_keys are the invalid tail)
+int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uint32_t* off, cudaStream_t st);
+// rank directory
+int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
+                   cudaStream_t st);
+int dir_assign_bases(KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* d_total_entries, cudaStream_t st);
+int dir_fill(const int32_t* A, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* D, uint32_t total_entries,
+             cudaStream_t st);
+
+// K3 probes
+int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
+                 int64_t* out, cudaStream_t st);
+int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                    int strict, int64_t* out, cudaStream_t st);
+int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                      int include_overlaps, int strict, uint32_t* left_idx, uint32_t* valid_bits, int64_t* dist,
+                      cudaStream_t st);
+int launch_nearest_k_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                           uint32_t k, int include_overlaps, int strict, uint32_t* counts, cudaStream_t st);
+int launch_nearest_k_emit(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                          uint32_t k, int include_overlaps, int strict, const uint64_t* offsets, uint32_t* build_idx,
+                          uint32_t* valid_bytes, uint32_t* probe_idx, int64_t* dist, cudaStream_t st);
+// K4 pairs
+int launch_pairs_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                       uint32_t* counts, cudaStream_t st);
+int launch_pairs_emit(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                      const uint64_t* offsets, uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
+int launch_semi_anti_flags(const uint32_t* counts, uint64_t n, int anti, uint32_t* flags, cudaStream_t st);
+int launch_compact_rows(const uint32_t* flags, const uint64_t* offsets, uint64_t n, uint32_t* probe_idx,
+                        cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ KeyDir load_keydir(const KeyDir* kd, uint32_t c) {
+    const int4* p = reinterpret_cast<const int4*>(kd + c);
+    int4 a = __ldg(p);
+    int4 b = __ldg(p + 1);
+    KeyDir k;
+    k.lo = a.x; k.nb = (uint32_t)a.y; k.base = (uint32_t)a.z; k.seg_begin = (uint32_t)a.w; k.seg_end = (uint32_t)b.x;
+    return k;
+}
+
+// global index of the first element of key c's segment that is > q  (== seg_begin + #(A <= q))
+__device__ __forceinline__ uint32_t rank_le_kd(const DirView& d, const KeyDir& k, int32_t q) {
+    if (k.nb == 0 || q < k.lo) return k.seg_begin;
+    uint32_t b = ((uint32_t)q - (uint32_t)k.lo) >> d.shift;
+    if (b >= k.nb) return k.seg_end;
+    uint32_t lo = __ldg(d.D + k.base + b), hi = __ldg(d.D + k.base + b + 1);
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(d.A + mid) <= q) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// global index of the first element that is >= q (== seg_begin + #(A < q))
+__device__ __forceinline__ uint32_t rank_lt_kd(const DirView& d, const KeyDir& k, int32_t q) {
+    if (q == INT32_MIN) return k.seg_begin;
+    return rank_le_kd(d, k, q - 1);
+}
+
+__device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+
+// streaming (touch-once) loads/stores: keep the probe stream out of L1 and first in line for L2 eviction so the
+// index stays resident in the 126 MB L2
+__device__ __forceinline__ int32_t ld_stream(const int32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(int64_t* p, int64_t v) { __stcs(reinterpret_cast<long long*>(p), (long long)v); }
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
+#endif
+
+}  // namespace brg

@@ -1,0 +1,331 @@
+// brg_probe.cu -- K3: probe kernels (count_overlaps, coverage, nearest) for sm_100a.
+//
+// Every probe row is independent given the read-only index.  The kernels stream the probe columns once
+// (touch-once loads, evict-first), answer each row with rank queries through the rank directories (one 32 B
+// KeyDir sector + two adjacent directory words + a search confined to one small bin of the sorted array, all
+// L2/L1 resident), and stream the result columns once.  Nothing is a contraction: no tensor cores.
+//
+//   count_overlaps : #(starts <= qe) - #(ends < qs)                       interval_tree.rs:41-49
+//   coverage       : clipped boundary terms + prefix-sum of interior merged widths
+//                                                                         interval_tree.rs:145-152
+//   nearest (k=1)  : first overlap by (start,end,pos) via prefix_max_end, else nearest left/right neighbour
+//                                                                         nearest_index.rs:91-101,192-266
+//   nearest (k>1)  : overlaps in (start,end,pos) order, then a two-pointer walk outwards
+//                                                                         nearest_index.rs:103-190
+#include "brg_internal.cuh"
+
+namespace brg {
+
+constexpr int PB_THREADS = 256;
+
+__device__ __forceinline__ uint32_t load_key(const uint32_t* key, uint64_t i) { return key ? ld_stream(key + i) : 0u; }
+
+// ---------------------------------------------------------------------------------------------------
+// count_overlaps
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PB_THREADS) count_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                           const int32_t* __restrict__ start,
+                                                           const int32_t* __restrict__ end, uint64_t n, int strict,
+                                                           int64_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
+        uint32_t c = load_key(key, i);
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }  // interval_tree.rs:253-256
+        int64_t cnt = 0;
+        if (c < ix.n_keys && !(qe < qs)) {                    // unknown contig -> 0 (:265); guard (:42-44)
+            KeyDir ks = load_keydir(ix.d_sstart.kd, c);
+            KeyDir ke = load_keydir(ix.d_eend.kd, c);
+            uint32_t started = rank_le_kd(ix.d_sstart, ks, qe);       // seg_begin + #(starts <= qe)
+            uint32_t ended_before = rank_lt_kd(ix.d_eend, ke, qs);    // seg_begin + #(ends < qs)
+            cnt = (int64_t)started - (int64_t)ended_before;
+        }
+        st_stream(out + i, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// coverage
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t cov_term(int32_t qs, int32_t qe, int32_t first, int32_t last) {
+    int32_t hi = min(wadd(qe, 1), last);   // min(end + 1, node.last)
+    int32_t lo = max(wsub(qs, 1), first);  // max(start - 1, node.first)
+    int32_t ov = wsub(hi, lo);
+    return ov < 1 ? 1 : ov;                // max(1, ...)
+}
+
+__global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                              const int32_t* __restrict__ start,
+                                                              const int32_t* __restrict__ end, uint64_t n, int strict,
+                                                              int64_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
+        uint32_t c = load_key(key, i);
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
+        int32_t acc = 0;
+        if (c < ix.n_keys) {
+            KeyDir kl = load_keydir(ix.d_mlast.kd, c);
+            KeyDir kf = load_keydir(ix.d_mfirst.kd, c);
+            // merged intervals are disjoint and ascending in both first and last: the ones overlapping [qs,qe]
+            // (first <= qe && last >= qs, the coitrees predicate) are exactly the index range [lo, hi)
+            uint32_t lo = rank_lt_kd(ix.d_mlast, kl, qs);   // first j with last_j >= qs
+            uint32_t hi = rank_le_kd(ix.d_mfirst, kf, qe);  // first j with first_j > qe
+            if (lo < hi && (qs == INT32_MIN || qe == INT32_MAX)) {
+                // `start - 1` / `end + 1` wrap in the reference's release arithmetic: keep the literal per-interval sum
+                for (uint32_t j = lo; j < hi; j++)
+                    acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + j), __ldg(ix.m_last + j)));
+            } else if (lo < hi) {
+                acc = cov_term(qs, qe, __ldg(ix.m_first + lo), __ldg(ix.m_last + lo));
+                if (hi - lo > 1) {
+                    acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + hi - 1), __ldg(ix.m_last + hi - 1)));
+                    // interior intervals lie strictly inside (qs-1, qe+1): their term is max(1, last-first)
+                    acc = wadd(acc, wsub(__ldg(ix.m_pre + hi - 1), __ldg(ix.m_pre + lo + 1)));
+                }
+            }
+        }
+        st_stream(out + i, (int64_t)acc);  // interval_tree.rs:207
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// nearest
+// ---------------------------------------------------------------------------------------------------
+struct Cand {
+    int32_t s, e;
+    uint32_t pos;
+};
+// nearest_index.rs:252-260
+__device__ __forceinline__ int64_t cand_distance(int32_t qs, int32_t qe, int32_t is, int32_t ie) {
+    if (qe < is) return (int64_t)is - (int64_t)qe;
+    if (ie < qs) return (int64_t)qs - (int64_t)ie;
+    return 0;
+}
+// cmp_candidate(a,b) <= 0  (nearest_index.rs:262-266): (distance, start, end, position)
+__device__ __forceinline__ bool cand_le(int32_t qs, int32_t qe, const Cand& a, const Cand& b) {
+    int64_t ad = cand_distance(qs, qe, a.s, a.e), bd = cand_distance(qs, qe, b.s, b.e);
+    if (ad != bd) return ad < bd;
+    if (a.s != b.s) return a.s < b.s;
+    if (a.e != b.e) return a.e < b.e;
+    return a.pos <= b.pos;
+}
+__device__ __forceinline__ Cand load_s(const IndexView& ix, uint32_t i) {
+    return Cand{__ldg(ix.s_start + i), __ldg(ix.s_end + i), __ldg(ix.s_pos + i)};
+}
+__device__ __forceinline__ Cand load_e(const IndexView& ix, uint32_t i) {
+    return Cand{__ldg(ix.e_start + i), __ldg(ix.e_end + i), __ldg(ix.e_pos + i)};
+}
+
+// one probe: returns true and fills `best` when an interval is found
+__device__ __forceinline__ bool nearest_one(const IndexView& ix, uint32_t c, int32_t qs, int32_t qe,
+                                            int include_overlaps, Cand* best) {
+    KeyDir ks = load_keydir(ix.d_sstart.kd, c);
+    if (ks.seg_begin == ks.seg_end) return false;                       // is_empty (nearest_index.rs:92-94)
+    const uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);              // partition_point(first <= end)
+    if (include_overlaps && !(qe < qs) && n_le > ks.seg_begin && __ldg(ix.pme + n_le - 1) >= qs) {
+        KeyDir kp = load_keydir(ix.d_pme.kd, c);                        // first_overlap_by_start (:222-234)
+        uint32_t idx = rank_lt_kd(ix.d_pme, kp, qs);                    // first i with prefix_max_end[i] >= qs
+        *best = load_s(ix, idx);
+        return true;
+    }
+    KeyDir ke = load_keydir(ix.d_eend.kd, c);                           // nearest_non_overlap_one (:192-220)
+    const uint32_t left_idx = rank_lt_kd(ix.d_eend, ke, qs);            // partition_point(last < start)
+    const bool has_left = left_idx > ke.seg_begin, has_right = n_le < ks.seg_end;
+    if (!has_left && !has_right) return false;
+    Cand l, r;
+    if (has_left) l = load_e(ix, left_idx - 1);
+    if (has_right) r = load_s(ix, n_le);
+    if (has_left && has_right) *best = cand_le(qs, qe, l, r) ? l : r;
+    else *best = has_left ? l : r;
+    return true;
+}
+
+__global__ void __launch_bounds__(PB_THREADS) nearest_k1_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                                const int32_t* __restrict__ start,
+                                                                const int32_t* __restrict__ end, uint64_t n,
+                                                                int include_overlaps, int strict,
+                                                                uint32_t* __restrict__ left_idx,
+                                                                uint32_t* __restrict__ valid_bits,
+                                                                int64_t* __restrict__ dist) {
+    // whole warps stay converged so that the ballot below packs 32 validity bits per store
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool found = false;
+        Cand b{0, 0, 0};
+        int32_t rs = 0, re = 0;
+        if (i < n) {
+            rs = ld_stream(start + i); re = ld_stream(end + i);
+            uint32_t c = load_key(key, i);
+            int32_t qs = rs, qe = re;
+            if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }  // nearest.rs:341-344
+            if (c < ix.n_keys) found = nearest_one(ix, c, qs, qe, include_overlaps, &b);
+        }
+        uint32_t bits = __ballot_sync(0xFFFFFFFFu, found);
+        if ((threadIdx.x & 31) == 0) valid_bits[i >> 5] = bits;  // Arrow validity bitmap, LSB first
+        if (i < n) {
+            st_stream(left_idx + i, found ? b.pos : 0u);
+            // distance from RAW probe coordinates (nearest.rs:367-375)
+            if (dist) st_stream(dist + i, found ? cand_distance(rs, re, b.s, b.e) : (int64_t)0);
+        }
+    }
+}
+
+// k > 1: shared walker for the count and emit passes
+template <bool EMIT>
+__device__ __forceinline__ uint32_t nearest_k_walk(const IndexView& ix, uint32_t c, int32_t qs, int32_t qe, int32_t rs,
+                                                   int32_t re, uint32_t k, int include_overlaps, uint32_t probe_row,
+                                                   uint64_t out_base, uint32_t* build_idx, uint32_t* valid,
+                                                   uint32_t* probe_idx, int64_t* dist) {
+    uint32_t n_out = 0;
+    auto emit = [&](const Cand& x) {
+        if (EMIT) {
+            uint64_t o = out_base + n_out;
+            build_idx[o] = x.pos;
+            valid[o] = 1u;
+            probe_idx[o] = probe_row;
+            if (dist) dist[o] = cand_distance(rs, re, x.s, x.e);
+        }
+        n_out++;
+    };
+    KeyDir ks = load_keydir(ix.d_sstart.kd, c);
+    if (ks.seg_begin == ks.seg_end || k == 0) return 0;
+    const uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);
+    if (include_overlaps && n_le > ks.seg_begin) {
+        // tree.query + sort by (start,end,position) (nearest_index.rs:124-139): S-order already is that order;
+        // rows before the first prefix_max_end >= qs cannot reach qs
+        KeyDir kp = load_keydir(ix.d_pme.kd, c);
+        uint32_t i0 = rank_lt_kd(ix.d_pme, kp, qs);
+        for (uint32_t i = i0; i < n_le && n_out < k; i++) {
+            int32_t e = __ldg(ix.s_end + i);
+            if (e >= qs) emit(Cand{__ldg(ix.s_start + i), e, __ldg(ix.s_pos + i)});
+        }
+    }
+    if (n_out == k) return n_out;
+    KeyDir ke = load_keydir(ix.d_eend.kd, c);
+    uint32_t left_idx = rank_lt_kd(ix.d_eend, ke, qs);
+    uint32_t right_idx = n_le;
+    // An interval can sit in BOTH lists (end < qs and start > qe) only for a degenerate probe (qe < qs) or an
+    // inverted build interval; the reference de-duplicates with a hash set (`seen`, nearest_index.rs:121,186).
+    // Here membership is decided by order: the left list is consumed downwards in (end,start,position) order and
+    // the right list upwards in (start,end,position) order.
+    while (n_out < k) {
+        const bool has_left = left_idx > ke.seg_begin, has_right = right_idx < ks.seg_end;
+        if (!has_left && !has_right) break;
+        Cand l, r, next;
+        if (has_left) l = load_e(ix, left_idx - 1);
+        if (has_right) r = load_s(ix, right_idx);
+        bool take_left = has_left && (!has_right || cand_le(qs, qe, l, r));
+        bool dup = false;
+        if (take_left) {
+            left_idx--;
+            next = l;
+            // `seen` (nearest_index.rs:186): already emitted from the right list iff it starts after qe and sorts
+            // before the current right head in (start,end,position) order
+            if (l.s > qe) {
+                if (!has_right) dup = true;
+                else dup = (l.s != r.s) ? l.s < r.s : (l.e != r.e) ? l.e < r.e : l.pos < r.pos;
+            }
+        } else {
+            right_idx++;
+            next = r;
+            if (r.e < qs) {
+                // already emitted from the left list iff it sorts after the current left head in (end,start,position)
+                if (!has_left) dup = true;
+                else dup = (r.e != l.e) ? r.e > l.e : (r.s != l.s) ? r.s > l.s : r.pos > l.pos;
+            }
+        }
+        if (!include_overlaps && cand_distance(qs, qe, next.s, next.e) == 0) continue;  // nearest_index.rs:182-184
+        if (!dup) emit(next);
+    }
+    return n_out;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(PB_THREADS) nearest_k_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                               const int32_t* __restrict__ start,
+                                                               const int32_t* __restrict__ end, uint64_t n, uint32_t k,
+                                                               int include_overlaps, int strict,
+                                                               uint32_t* __restrict__ counts,
+                                                               const uint64_t* __restrict__ offsets,
+                                                               uint32_t* __restrict__ build_idx,
+                                                               uint32_t* __restrict__ valid,
+                                                               uint32_t* __restrict__ probe_idx,
+                                                               int64_t* __restrict__ dist) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t rs = ld_stream(start + i), re = ld_stream(end + i);
+        uint32_t c = load_key(key, i);
+        int32_t qs = rs, qe = re;
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
+        uint64_t base = EMIT ? offsets[i] : 0;
+        uint32_t m = 0;
+        if (c < ix.n_keys)
+            m = nearest_k_walk<EMIT>(ix, c, qs, qe, rs, re, k, include_overlaps, (uint32_t)i, base, build_idx, valid,
+                                     probe_idx, dist);
+        if (EMIT) {
+            if (m == 0) {  // nearest.rs:433-439: one NULL row
+                build_idx[base] = 0u;
+                valid[base] = 0u;
+                probe_idx[base] = (uint32_t)i;
+                if (dist) dist[base] = 0;
+            }
+        } else {
+            counts[i] = m ? m : 1u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+static inline unsigned probe_grid(uint64_t n, int per_sm) {
+    // persistent-style grid: a multiple of the SM count, grid-stride over rows
+    uint64_t want = (n + PB_THREADS - 1) / PB_THREADS;
+    uint64_t cap = (uint64_t)kSMs * per_sm;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
+                 int64_t* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    count_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, out);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                    int strict, int64_t* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    coverage_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, out);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                      int include_overlaps, int strict, uint32_t* left_idx, uint32_t* valid_bits, int64_t* dist,
+                      cudaStream_t st) {
+    if (n == 0) return 0;
+    nearest_k1_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, include_overlaps, strict, left_idx,
+                                                               valid_bits, dist);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_nearest_k_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                           uint32_t k, int include_overlaps, int strict, uint32_t* counts, cudaStream_t st) {
+    if (n == 0) return 0;
+    nearest_k_kernel<false><<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, k, include_overlaps, strict,
+                                                                     counts, nullptr, nullptr, nullptr, nullptr, nullptr);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int launch_nearest_k_emit(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                          uint32_t k, int include_overlaps, int strict, const uint64_t* offsets, uint32_t* build_idx,
+                          uint32_t* valid, uint32_t* probe_idx, int64_t* dist, cudaStream_t st) {
+    if (n == 0) return 0;
+    nearest_k_kernel<true><<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, k, include_overlaps, strict,
+                                                                    nullptr, offsets, build_idx, valid, probe_idx, dist);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace brg

@@ -1,0 +1,400 @@
+// brg_scan.cu -- K2: device-wide scans and the build-side post-processing that runs on them (sm_100a).
+//
+//  * exclusive prefix sums (radix-sort histogram table, merged-interval indices, width prefix, pair offsets)
+//  * per-key segmented running max of `end` over the start-sorted rows  == prefix_max_end
+//    (nearest_index.rs:58-63) and the accumulator of merge_intervals (interval_tree.rs:52-73)
+//  * merge_intervals itself as flag -> scan -> compact, and the width prefix used by coverage
+//  * segment offsets per key and the rank directories (see brg_internal.cuh)
+//
+// Scans are reduce-then-scan with warp-shuffle block scans: tile reduce -> one-CTA scan of the tile
+// aggregates -> tile scan with carry-in.  All of it is HBM-bound streaming (2 reads + 1 write per element).
+#include "brg_internal.cuh"
+
+namespace brg {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;  // 2048
+
+// ---------------------------------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------------------------------
+struct SegMaxT {
+    int32_t v;
+    uint32_t f;  // 1 when a segment head lies inside the span this value summarises
+};
+template <typename T>
+struct SumOp {
+    __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+    __device__ __forceinline__ static T identity() { return T(0); }
+};
+struct SegMaxOp {
+    __device__ __forceinline__ SegMaxT operator()(SegMaxT a, SegMaxT b) const {
+        SegMaxT r;
+        r.v = b.f ? b.v : max(a.v, b.v);
+        r.f = a.f | b.f;
+        return r;
+    }
+    __device__ __forceinline__ static SegMaxT identity() { return SegMaxT{INT32_MIN, 0u}; }
+};
+
+__device__ __forceinline__ uint32_t shfl_up_t(uint32_t v, int o) { return __shfl_up_sync(0xFFFFFFFFu, v, o); }
+__device__ __forceinline__ uint64_t shfl_up_t(uint64_t v, int o) { return __shfl_up_sync(0xFFFFFFFFu, v, o); }
+__device__ __forceinline__ SegMaxT shfl_up_t(SegMaxT v, int o) {
+    SegMaxT r;
+    r.v = __shfl_up_sync(0xFFFFFFFFu, v.v, o);
+    r.f = __shfl_up_sync(0xFFFFFFFFu, v.f, o);
+    return r;
+}
+
+// inclusive scan of one value per thread across the CTA; returns the inclusive value, *block_total = aggregate
+template <typename T, typename Op, int THREADS>
+__device__ __forceinline__ T block_inclusive_scan(T x, Op op, T* smem /*THREADS/32*/, T* block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T y = shfl_up_t(x, o);
+        if (lane >= o) x = op(y, x);
+    }
+    if (lane == 31) smem[w] = x;
+    __syncthreads();
+    T carry = Op::identity();
+    T tot = Op::identity();
+#pragma unroll
+    for (int ww = 0; ww < THREADS / 32; ww++) {
+        T s = smem[ww];
+        if (ww < w) carry = op(carry, s);
+        tot = op(tot, s);
+    }
+    __syncthreads();
+    *block_total = tot;
+    return op(carry, x);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// loaders / storers
+// ---------------------------------------------------------------------------------------------------
+struct LoadU32 {
+    const uint32_t* in;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return in[i]; }
+};
+struct LoadU32as64 {
+    const uint32_t* in;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)in[i]; }
+};
+struct LoadSegMax {
+    const uint32_t* key;
+    const int32_t* val;
+    __device__ __forceinline__ SegMaxT operator()(uint64_t i) const {
+        SegMaxT r;
+        r.v = val[i];
+        r.f = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+        return r;
+    }
+};
+struct StoreU32 {
+    uint32_t* out;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t v) const { out[i] = v; }
+};
+struct StoreU64 {
+    uint64_t* out;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t v) const { out[i] = v; }
+};
+struct StoreSegMax {
+    int32_t* out;
+    __device__ __forceinline__ void operator()(uint64_t i, SegMaxT v) const { out[i] = v.v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename T, typename Op, typename Load>
+__global__ void __launch_bounds__(SC_THREADS) tile_reduce_kernel(Load ld, uint64_t n, T* __restrict__ partials) {
+    __shared__ T sm[SC_THREADS / 32];
+    Op op;
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    T acc = Op::identity();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++)
+        if (base + j < n) acc = op(acc, ld(base + j));
+    T tot;
+    block_inclusive_scan<T, Op, SC_THREADS>(acc, op, sm, &tot);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+// one CTA: in-place exclusive scan of the tile aggregates; optional grand total
+template <typename T, typename Op>
+__global__ void __launch_bounds__(1024) partials_scan_kernel(T* __restrict__ partials, uint64_t nb, T* total_out) {
+    __shared__ T sm[32];
+    __shared__ T inc_sm[1024];
+    Op op;
+    T carry = Op::identity();
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        uint64_t i = base + threadIdx.x;
+        T x = i < nb ? partials[i] : Op::identity();
+        T tot;
+        T inc = block_inclusive_scan<T, Op, 1024>(x, op, sm, &tot);
+        inc_sm[threadIdx.x] = inc;
+        __syncthreads();
+        T ex = threadIdx.x == 0 ? Op::identity() : inc_sm[threadIdx.x - 1];
+        if (i < nb) partials[i] = op(carry, ex);
+        carry = op(carry, tot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <typename T, typename Op, typename Load, typename Store, bool INCLUSIVE>
+__global__ void __launch_bounds__(SC_THREADS) tile_scan_kernel(Load ld, Store stf, uint64_t n,
+                                                               const T* __restrict__ partials) {
+    __shared__ T sm[SC_THREADS / 32];
+    Op op;
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    T x[SC_ITEMS];
+    T acc = Op::identity();
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        x[j] = (base + j < n) ? ld(base + j) : Op::identity();
+        acc = op(acc, x[j]);
+    }
+    T tot;
+    T inc = block_inclusive_scan<T, Op, SC_THREADS>(acc, op, sm, &tot);
+    // exclusive prefix of this thread = carry-in (+) inclusive of the previous thread
+    __shared__ T prev_inc[SC_THREADS];
+    prev_inc[threadIdx.x] = inc;
+    __syncthreads();
+    T run = partials[blockIdx.x];
+    if (threadIdx.x > 0) run = op(run, prev_inc[threadIdx.x - 1]);
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; j++) {
+        if (INCLUSIVE) {
+            run = op(run, x[j]);
+            if (base + j < n) stf(base + j, run);
+        } else {
+            if (base + j < n) stf(base + j, run);
+            run = op(run, x[j]);
+        }
+    }
+}
+
+template <typename T, typename Op, typename Load, typename Store, bool INCLUSIVE>
+static int run_scan(Load ld, Store stf, uint64_t n, T* scratch, T* total_out, cudaStream_t st) {
+    if (n == 0) {
+        if (total_out) {
+            BRG_CUDA(cudaMemsetAsync(total_out, 0, sizeof(T), st));
+        }
+        return 0;
+    }
+    const uint64_t nb = (n + SC_TILE - 1) / SC_TILE;
+    tile_reduce_kernel<T, Op, Load><<<(unsigned)nb, SC_THREADS, 0, st>>>(ld, n, scratch);
+    BRG_LAUNCH_CHECK();
+    partials_scan_kernel<T, Op><<<1, 1024, 0, st>>>(scratch, nb, total_out);
+    BRG_LAUNCH_CHECK();
+    tile_scan_kernel<T, Op, Load, Store, INCLUSIVE><<<(unsigned)nb, SC_THREADS, 0, st>>>(ld, stf, n, scratch);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+uint64_t scan_scratch_words(uint64_t n) {
+    // in 32-bit words; sized for the widest element (SegMaxT / u64 = 2 words), +2 for totals
+    return 2 * ((n + SC_TILE - 1) / SC_TILE + 2);
+}
+
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st) {
+    return run_scan<uint32_t, SumOp<uint32_t>, LoadU32, StoreU32, false>(LoadU32{in}, StoreU32{out}, n, scratch, nullptr,
+                                                                       st);
+}
+static int exclusive_scan_u32_total(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch,
+                                    uint32_t* total_out, cudaStream_t st) {
+    return run_scan<uint32_t, SumOp<uint32_t>, LoadU32, StoreU32, false>(LoadU32{in}, StoreU32{out}, n, scratch,
+                                                                       total_out, st);
+}
+int exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, cudaStream_t st) {
+    // out[n] receives the grand total
+    return run_scan<uint64_t, SumOp<uint64_t>, LoadU32as64, StoreU64, false>(LoadU32as64{in}, StoreU64{out}, n, scratch,
+                                                                           out + n, st);
+}
+int segmented_running_max(const uint32_t* key, const int32_t* val, int32_t* out, uint64_t n, int32_t* scratch,
+                          cudaStream_t st) {
+    return run_scan<SegMaxT, SegMaxOp, LoadSegMax, StoreSegMax, true>(LoadSegMax{key, val}, StoreSegMax{out}, n,
+                                                                    reinterpret_cast<SegMaxT*>(scratch), nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge_intervals (interval_tree.rs:52-73) on start-sorted rows: a row opens a new merged interval iff it is
+// the first of its key or its start is > the running max end of everything before it in the key
+// (`interval.first <= current.last` merges, so touching intervals merge and [1,5],[6,10] do not).
+// ---------------------------------------------------------------------------------------------------
+__global__ void merge_flags_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ s_start,
+                                   const int32_t* __restrict__ pme, uint64_t n, uint32_t* __restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || key[i] != key[i - 1] || s_start[i] > pme[i - 1]) ? 1u : 0u;
+}
+__global__ void merge_write_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ s_start,
+                                   const int32_t* __restrict__ pme, const uint32_t* __restrict__ flags,
+                                   const uint32_t* __restrict__ midx, uint64_t n, int32_t* __restrict__ m_first,
+                                   int32_t* __restrict__ m_last, uint32_t* __restrict__ m_key) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = flags[i];
+    uint32_t mi = midx[i] + h - 1;  // merged interval this row belongs to
+    if (h) {
+        m_first[mi] = s_start[i];
+        m_key[mi] = key[i];
+    }
+    if (i + 1 == n || flags[i + 1]) m_last[mi] = pme[i];
+}
+__global__ void merged_width_kernel(const int32_t* __restrict__ m_first, const int32_t* __restrict__ m_last,
+                                    uint64_t m, uint32_t* __restrict__ w) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int32_t d = wsub(m_last[i], m_first[i]);  // interior term of get_coverage: max(1, last - first) (interval_tree.rs:148)
+    w[i] = (uint32_t)(d < 1 ? 1 : d);
+}
+
+int merge_sorted_intervals(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme, uint64_t n,
+                           uint32_t* d_flags, uint32_t* d_midx, uint32_t* scan_scratch, int32_t* m_first,
+                           int32_t* m_last, uint32_t* m_key, uint32_t* d_n_merged, cudaStream_t st) {
+    if (n == 0) {
+        BRG_CUDA(cudaMemsetAsync(d_n_merged, 0, 4, st));
+        return 0;
+    }
+    unsigned g = (unsigned)((n + 255) / 256);
+    merge_flags_kernel<<<g, 256, 0, st>>>(s_key, s_start, pme, n, d_flags);
+    BRG_LAUNCH_CHECK();
+    int rc = exclusive_scan_u32_total(d_flags, d_midx, n, scan_scratch, d_n_merged, st);
+    if (rc) return rc;
+    merge_write_kernel<<<g, 256, 0, st>>>(s_key, s_start, pme, d_flags, d_midx, n, m_first, m_last, m_key);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t m, uint32_t* widths_tmp, int32_t* m_pre,
+                        uint32_t* scan_scratch, cudaStream_t st) {
+    if (m == 0) {
+        BRG_CUDA(cudaMemsetAsync(m_pre, 0, 4, st));
+        return 0;
+    }
+    merged_width_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m_first, m_last, m, widths_tmp);
+    BRG_LAUNCH_CHECK();
+    // wrapping u32 sums == the reference's wrapping i32 accumulator (interval_tree.rs:146-151)
+    return exclusive_scan_u32_total(widths_tmp, reinterpret_cast<uint32_t*>(m_pre), m, scan_scratch,
+                                    reinterpret_cast<uint32_t*>(m_pre) + m, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// segment offsets: off[c] = first row whose key is >= c, for c = 0..n_keys  (keys >= n_keys: invalid tail)
+// ---------------------------------------------------------------------------------------------------
+__global__ void segment_offsets_kernel(const uint32_t* __restrict__ key, uint64_t n, uint32_t n_keys,
+                                       uint32_t* __restrict__ off) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t kprev = (i == 0) ? -1 : (int64_t)min(key[i - 1], n_keys);
+    int64_t kcur = (i == n) ? (int64_t)n_keys : (int64_t)min(key[i], n_keys);
+    for (int64_t c = kprev + 1; c <= kcur; c++) off[c] = (uint32_t)i;
+}
+int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uint32_t* off, cudaStream_t st) {
+    segment_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(sorted_key, n, n_keys, off);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rank directory construction
+// ---------------------------------------------------------------------------------------------------
+__global__ void dir_key_ranges_kernel(const int32_t* __restrict__ A, const uint32_t* __restrict__ off, uint32_t n_keys,
+                                      KeyDir* __restrict__ kd, unsigned long long* __restrict__ bins_by_shift) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_keys) return;
+    uint32_t b = off[c], e = off[c + 1];
+    KeyDir k;
+    k.seg_begin = b; k.seg_end = e; k.base = 0; k.pad[0] = k.pad[1] = k.pad[2] = 0;
+    if (b == e) {
+        k.lo = 0; k.nb = 0;
+    } else {
+        int32_t lo = A[b], hi = A[e - 1];
+        uint32_t range = (uint32_t)hi - (uint32_t)lo;
+        k.lo = lo;
+        k.nb = range;  // provisional: the range; dir_assign_bases turns it into a bin count
+        for (int s = 0; s < 32; s++) atomicAdd(&bins_by_shift[s], (unsigned long long)(range >> s) + 1ull);
+    }
+    kd[c] = k;
+}
+int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins,
+                   cudaStream_t st) {
+    BRG_CUDA(cudaMemsetAsync(d_bins, 0, 32 * sizeof(unsigned long long), st));
+    if (n_keys == 0) return 0;
+    dir_key_ranges_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(A, off, n_keys, kd, d_bins);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// one CTA: nb = (range >> shift) + 1 for non-empty keys; base = exclusive prefix of (nb + 1)
+__global__ void __launch_bounds__(1024) dir_assign_bases_kernel(KeyDir* __restrict__ kd, uint32_t n_keys, uint32_t shift,
+                                                                uint32_t* __restrict__ total) {
+    __shared__ uint32_t sm[32];
+    SumOp<uint32_t> op;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_keys; base += 1024) {
+        uint32_t c = base + threadIdx.x;
+        uint32_t cnt = 0, nb = 0;
+        bool live = c < n_keys && kd[c].seg_begin != kd[c].seg_end;
+        if (live) {
+            nb = (kd[c].nb >> shift) + 1;
+            cnt = nb + 1;
+        }
+        uint32_t tot;
+        uint32_t inc = block_inclusive_scan<uint32_t, SumOp<uint32_t>, 1024>(cnt, op, sm, &tot);
+        if (c < n_keys) {
+            kd[c].nb = nb;
+            kd[c].base = carry + inc - cnt;
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+int dir_assign_bases(KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* d_total, cudaStream_t st) {
+    dir_assign_bases_kernel<<<1, 1024, 0, st>>>(kd, n_keys, shift, d_total);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// one thread per directory entry: binary-search its bin boundary inside the key's segment
+__global__ void dir_fill_kernel(const int32_t* __restrict__ A, const KeyDir* __restrict__ kd, uint32_t n_keys,
+                                uint32_t shift, uint32_t* __restrict__ D, uint32_t total) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    // last key with base <= g that owns entries
+    uint32_t lo = 0, hi = n_keys;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (kd[mid].base <= g) lo = mid; else hi = mid;
+    }
+    // keys with no entries share the base of their successor: walk back to the owner
+    uint32_t c = lo;
+    while (kd[c].nb == 0 || g - kd[c].base > kd[c].nb) {
+        if (c == 0) return;
+        c--;
+    }
+    KeyDir k = kd[c];
+    uint32_t j = g - k.base;
+    if (j == k.nb) { D[g] = k.seg_end; return; }
+    int64_t thr = (int64_t)k.lo + ((int64_t)j << shift);  // first value of bin j
+    uint32_t a = k.seg_begin, b = k.seg_end;
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if ((int64_t)A[mid] < thr) a = mid + 1; else b = mid;
+    }
+    D[g] = a;
+}
+int dir_fill(const int32_t* A, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* D, uint32_t total,
+             cudaStream_t st) {
+    if (total == 0 || n_keys == 0) return 0;
+    dir_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(A, kd, n_keys, shift, D, total);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace brg

@@ -1,0 +1,235 @@
+"""Object wrappers over the C ABI.  Host-buffer methods take numpy arrays (the caller-owned Arrow value buffers of
+the reference's RecordBatches) and include the transfers; `*_dev` methods take torch CUDA tensors and enqueue on
+torch's current stream (PyTorch is used for device memory and streams only)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as A
+
+
+class Context:
+    """One per GPU (one process per GPU): streams, staging buffers, scratch.  brg_ctx_create / brg_ctx_destroy."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        A.check(A.lib().brg_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def sm_count(self):
+        return A.lib().brg_ctx_sm_count(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            A.lib().brg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- build ------------------------------------------------------------------------------------------
+    def build(self, key, start, end, n_keys, want=A.WANT_ALL):
+        key = A.as_key(key)
+        start, end = A.as_i32(start), A.as_i32(end)
+        if len(start) != len(end) or (key is not None and len(key) != len(start)):
+            raise ValueError("build columns differ in length")
+        h = C.c_void_p()
+        A.check(A.lib().brg_build(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys),
+                                  int(want), C.byref(h)))
+        return Index(self, h)
+
+    def build_dev(self, key, start, end, n_keys, want=A.WANT_ALL):
+        import torch
+
+        n = start.numel()
+        h = C.c_void_p()
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_build_dev(self._h, _tptr(key), _tptr(start), _tptr(end), n, int(n_keys), int(want), st,
+                                      C.byref(h)))
+        return Index(self, h)
+
+    def import_index(self, header_bytes):
+        """Allocates an empty replica slab for an index exported on another rank; returns (Index, slab_tensor)."""
+        import torch
+
+        h, slab, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        buf = (C.c_char * len(header_bytes)).from_buffer_copy(header_bytes)
+        A.check(A.lib().brg_index_import(self._h, buf, len(header_bytes), C.byref(h), C.byref(slab), C.byref(nbytes)))
+        ix = Index(self, h)
+        return ix, _wrap_device(slab.value, nbytes.value, self.device)
+
+
+def _tptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def _wrap_device(ptr, nbytes, device):
+    """torch uint8 view of library-owned device memory (for torch.distributed.broadcast of the index slab)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    holder = _Holder()
+    holder.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(holder, device=f"cuda:{device}")
+
+
+class Index:
+    """Immutable build-side index resident in HBM (brg_index)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            A.lib().brg_index_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rows(self):
+        return A.lib().brg_index_rows(self._h)
+
+    @property
+    def merged_rows(self):
+        return A.lib().brg_index_merged_rows(self._h)
+
+    @property
+    def device_bytes(self):
+        return A.lib().brg_index_device_bytes(self._h)
+
+    def export(self):
+        """(header bytes, slab tensor) for replication to other GPUs."""
+        n = C.c_uint64()
+        slab, nbytes = C.c_void_p(), C.c_uint64()
+        A.check(A.lib().brg_index_export(self._h, None, 0, C.byref(n), C.byref(slab), C.byref(nbytes)))
+        buf = (C.c_char * n.value)()
+        A.check(A.lib().brg_index_export(self._h, buf, n.value, C.byref(n), C.byref(slab), C.byref(nbytes)))
+        return bytes(buf), _wrap_device(slab.value, nbytes.value, self.ctx.device)
+
+    # ---- host-buffer probes (the drop-in calls) ---------------------------------------------------------------
+    def _cols(self, key, start, end):
+        key = A.as_key(key)
+        start, end = A.as_i32(start), A.as_i32(end)
+        if len(start) != len(end) or (key is not None and len(key) != len(start)):
+            raise ValueError("probe columns differ in length")
+        return key, start, end
+
+    def count_overlaps(self, key, start, end, strict=False, out=None):
+        key, start, end = self._cols(key, start, end)
+        out = np.empty(len(start), np.int64) if out is None else out
+        A.check(A.lib().brg_count_overlaps(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start),
+                                           int(strict), A.np_ptr(out)))
+        return out
+
+    def coverage(self, key, start, end, strict=False, out=None):
+        key, start, end = self._cols(key, start, end)
+        out = np.empty(len(start), np.int64) if out is None else out
+        A.check(A.lib().brg_coverage(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start),
+                                     int(strict), A.np_ptr(out)))
+        return out
+
+    def nearest_k1(self, key, start, end, include_overlaps=True, strict=False, compute_distance=True):
+        key, start, end = self._cols(key, start, end)
+        n = len(start)
+        left = np.empty(n, np.uint32)
+        bits = np.zeros(((n + 31) // 32) * 4, np.uint8)
+        dist = np.empty(n, np.int64) if compute_distance else None
+        A.check(A.lib().brg_nearest_k1(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), n,
+                                       int(include_overlaps), int(strict), A.np_ptr(left), A.np_ptr(bits), A.np_ptr(dist)))
+        return left, A.unpack_bits(bits, n), dist
+
+    def nearest_k(self, key, start, end, k, include_overlaps=True, strict=False, compute_distance=True):
+        key, start, end = self._cols(key, start, end)
+        r = C.c_void_p()
+        A.check(A.lib().brg_nearest(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(k),
+                                    int(include_overlaps), int(compute_distance), int(strict), C.byref(r)))
+        try:
+            L = A.lib()
+            m = L.brg_rows_len(r)
+            left = A.copy_from(L.brg_rows_build_idx(r), m, np.uint32)
+            right = A.copy_from(L.brg_rows_probe_idx(r), m, np.uint32)
+            bits = A.copy_from(L.brg_rows_valid_bits(r), ((m + 31) // 32) * 4, np.uint8)
+            dist = A.copy_from(L.brg_rows_distance(r), m, np.int64) if compute_distance else None
+        finally:
+            A.lib().brg_rows_release(r)
+        return left, A.unpack_bits(bits, m), right, dist
+
+    def overlap_pairs(self, key, start, end, mode=A.PAIRS_INNER, max_rows=0, return_consumed=False):
+        key, start, end = self._cols(key, start, end)
+        r, consumed = C.c_void_p(), C.c_uint64()
+        A.check(A.lib().brg_overlap_pairs(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start),
+                                          int(mode), int(max_rows), C.byref(r), C.byref(consumed)))
+        try:
+            L = A.lib()
+            m = L.brg_rows_len(r)
+            b = A.copy_from(L.brg_rows_build_idx(r), m, np.uint32) if mode == A.PAIRS_INNER else None
+            p = A.copy_from(L.brg_rows_probe_idx(r), m, np.uint32)
+        finally:
+            A.lib().brg_rows_release(r)
+        if mode != A.PAIRS_INNER:
+            return (p, consumed.value) if return_consumed else p
+        return (b, p, consumed.value) if return_consumed else (b, p)
+
+    # ---- device-buffer probes (inputs resident in HBM; enqueue on torch's current stream) ----------------------
+    def count_overlaps_dev(self, key, start, end, out, strict=False):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_count_overlaps_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                               int(strict), _tptr(out), st))
+        return out
+
+    def coverage_dev(self, key, start, end, out, strict=False):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_coverage_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                         int(strict), _tptr(out), st))
+        return out
+
+    def nearest_k1_dev(self, key, start, end, left_idx, valid_bits, dist, include_overlaps=True, strict=False):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_nearest_k1_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                           int(include_overlaps), int(strict), _tptr(left_idx), _tptr(valid_bits),
+                                           _tptr(dist), st))
+
+    def pairs_count_dev(self, key, start, end, offsets):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_pairs_count_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                            _tptr(offsets), st))
+
+    def pairs_emit_dev(self, key, start, end, offsets, build_idx, probe_idx):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_pairs_emit_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                           _tptr(offsets), _tptr(build_idx), _tptr(probe_idx), st))
+
+
+_default = {}
+
+
+def default_context(device=0):
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

@@ -1,0 +1,168 @@
+/*
+ * bioranges.h -- C ABI of the B200-native interval-overlap engine (libbioranges.so).
+ *
+ * This is the drop-in boundary for the interval-overlap hot path of datafusion-bio-function-ranges.
+ * The reference has no FFI seam today; each entry point below replaces the internal Rust seam cited
+ * next to it (paths relative to /root/reference/datafusion/bio-function-ranges/src).  The Rust host
+ * code (IntervalJoinExec / CountOverlapsExec / NearestExec) keeps its DataFusion trait surface and calls
+ * these functions through `extern "C"` (binding shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.  All functions return 0 (BRG_OK) or a brg_status;
+ *    the message of the last failure on the calling thread is brg_last_error().  Nothing throws or aborts.
+ *  - coordinates are i32, closed [start,end] (the reference resolves every position column to &[i32],
+ *    array_utils.rs:73-131).  `key_id` is the host-side dense dictionary id (0..n_keys-1) of the contig /
+ *    join-key tuple; BRG_KEY_ABSENT on the probe side means "key not present in the build side"
+ *    (HashMap::get -> None: interval_tree.rs:265, nearest.rs:354, interval_join.rs:857).  key_id may be
+ *    NULL when there is a single key (all rows key 0).
+ *  - "host" entry points take caller-owned host buffers (Arrow value buffers; pinned or pageable) and
+ *    include the host<->device copies; "_dev" entry points take device pointers, enqueue on the given
+ *    cudaStream_t (passed as void*) and do not synchronise.
+ *  - brg_index is immutable after build and may be probed concurrently from many threads
+ *    (the reference shares it as Arc across partitions: joins/utils.rs:73-107).
+ *  - There is no CPU fallback: every entry point fails with BRG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BIORANGES_H
+#define BIORANGES_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BRG_API __attribute__((visibility("default")))
+#else
+#define BRG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRG_KEY_ABSENT 0xFFFFFFFFu
+
+typedef enum {
+    BRG_OK = 0,
+    BRG_ERR_INVALID = 1,     /* bad argument */
+    BRG_ERR_CUDA = 2,        /* CUDA runtime failure / no device */
+    BRG_ERR_OOM = 3,         /* host or device allocation failed */
+    BRG_ERR_OVERFLOW = 4,    /* row count exceeds UInt32 index capacity (nearest.rs:357-361) */
+    BRG_ERR_UNSUPPORTED = 5
+} brg_status;
+
+/* which structures brg_build materialises (bitmask) */
+enum {
+    BRG_WANT_COUNT = 1,    /* sorted starts / sorted ends            (interval_tree.rs:20-38)   */
+    BRG_WANT_COVERAGE = 2, /* merged intervals + width prefix sums   (interval_tree.rs:52-111)  */
+    BRG_WANT_NEAREST = 4,  /* by_start, prefix_max_end, by_end       (nearest_index.rs:45-85)   */
+    BRG_WANT_PAIRS = 8,    /* start-sorted rows + prefix_max_end     (interval_join.rs:748-763) */
+    BRG_WANT_ALL = 15
+};
+
+/* probe-side modes of brg_overlap_pairs (interval_join.rs:1014-1048, 1433-1463, 1614-1653) */
+enum {
+    BRG_PAIRS_INNER = 0, /* every (build_row, probe_row) pair, probe-major                      */
+    BRG_PAIRS_SEMI = 1,  /* probe rows with >= 1 match (RightSemi); build_idx is not produced   */
+    BRG_PAIRS_ANTI = 2   /* probe rows with no match   (RightAnti); build_idx is not produced   */
+};
+
+typedef struct brg_ctx brg_ctx;     /* one per GPU: streams, staging buffers, scratch */
+typedef struct brg_index brg_index; /* immutable build-side index resident in HBM      */
+typedef struct brg_rows brg_rows;   /* variable-length result in library-owned pinned host memory */
+
+BRG_API const char* brg_last_error(void);
+BRG_API int brg_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+BRG_API int brg_ctx_create(int device_id, brg_ctx** out);
+BRG_API void brg_ctx_destroy(brg_ctx* ctx);
+BRG_API int brg_ctx_device(const brg_ctx* ctx);
+BRG_API int brg_ctx_sm_count(const brg_ctx* ctx);
+
+/* pinned host memory for callers that want zero-staging transfers (Arrow buffers can be allocated here) */
+BRG_API int brg_pinned_alloc(uint64_t bytes, void** out);
+BRG_API void brg_pinned_free(void* p);
+
+/* ---- build (replaces collect_left_input + IntervalJoinAlgorithm::new, interval_join.rs:584-668,746-772;
+ *             build_count_index_from_batches / build_coitree_from_batches, interval_tree.rs:75-143;
+ *             build_nearest_indexes + NearestIntervalIndex::from_records, nearest.rs:498-547,
+ *             nearest_index.rs:45-85).  Row i of the input is build row id i (`position`). -------------- */
+BRG_API int brg_build(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n_rows,
+              uint32_t n_keys, uint32_t want, brg_index** out);
+BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key_id, const int32_t* d_start, const int32_t* d_end,
+                  uint64_t n_rows, uint32_t n_keys, uint32_t want, void* stream, brg_index** out);
+BRG_API void brg_index_destroy(brg_index* idx);
+BRG_API uint64_t brg_index_rows(const brg_index* idx);        /* build rows with a valid key */
+BRG_API uint64_t brg_index_merged_rows(const brg_index* idx); /* merged (coverage) intervals  */
+BRG_API uint64_t brg_index_device_bytes(const brg_index* idx);
+
+/* Replication across GPUs (one process per GPU): the index is one device slab plus a small POD header.
+ * Rank 0 exports, every other rank imports the header, receives the slab with ncclBroadcast
+ * (torch.distributed.broadcast on a tensor wrapping the slab) -- mirrors PartitionMode::CollectLeft,
+ * interval_join.rs:396-399,466-480. */
+BRG_API int brg_index_export(const brg_index* idx, void* header_buf, uint64_t header_cap, uint64_t* header_len,
+                     void** d_slab, uint64_t* slab_bytes);
+BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64_t header_len, brg_index** out, void** d_slab,
+                     uint64_t* slab_bytes);
+
+/* ---- count_overlaps (replaces CountOverlapIndex::query_count + get_count_stream's row loop,
+ *      interval_tree.rs:41-49, 224-280).  strict => probe start+1 / end-1 (interval_tree.rs:253-256). ---- */
+BRG_API int brg_count_overlaps(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
+                       const int32_t* end, uint64_t n, int strict, int64_t* out_count);
+BRG_API int brg_count_overlaps_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                           const int32_t* d_end, uint64_t n, int strict, int64_t* d_out_count, void* stream);
+
+/* ---- coverage (replaces get_coverage + get_stream's row loop, interval_tree.rs:145-152, 155-221) ------ */
+BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
+                 const int32_t* end, uint64_t n, int strict, int64_t* out_coverage);
+BRG_API int brg_coverage_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                     const int32_t* d_end, uint64_t n, int strict, int64_t* d_out_coverage, void* stream);
+
+/* ---- nearest, k = 1 (replaces NearestIntervalIndex::nearest_one + the k==1 row loop, nearest_index.rs:91-101,
+ *      192-234; nearest.rs:331-385; also the CoitreesNearest join arm, interval_join.rs:864-870, 1627-1636).
+ *      One output row per probe row.  out_left_idx[i] = build row (0 when there is no match);
+ *      out_valid_bits = Arrow validity bitmap (LSB-first, ceil(n/8) bytes, padded to 4 bytes) shared by the
+ *      left columns and the distance column; out_distance (may be NULL) from RAW probe coordinates
+ *      (nearest.rs:367-375), 0 where invalid. */
+BRG_API int brg_nearest_k1(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
+                   const int32_t* end, uint64_t n, int include_overlaps, int strict, uint32_t* out_left_idx,
+                   uint8_t* out_valid_bits, int64_t* out_distance);
+BRG_API int brg_nearest_k1_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                       const int32_t* d_end, uint64_t n, int include_overlaps, int strict, uint32_t* d_out_left_idx,
+                       uint32_t* d_out_valid_bits, int64_t* d_out_distance, void* stream);
+
+/* ---- nearest, any k >= 1 (replaces nearest_k + the k>1 row loop, nearest_index.rs:103-190, nearest.rs:386-456).
+ *      Up to k rows per probe row, one NULL row when there is none.  Result columns: build_idx, valid bitmap,
+ *      probe_idx, distance (when compute_distance). */
+BRG_API int brg_nearest(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start, const int32_t* end,
+                uint64_t n, uint32_t k, int include_overlaps, int compute_distance, int strict, brg_rows** out);
+
+/* ---- overlap pairs (replaces IntervalJoinAlgorithm::get (Coitrees arm) + RLE expansion,
+ *      interval_join.rs:849-863, 1614-1653; RightSemi/RightAnti 1433-1463).  start/end are the columns the
+ *      host evaluated (for `<`/`>` predicates the host has already applied `end - 1`, intervals.rs:63-124).
+ *      max_rows > 0 caps the output like the low-memory mode (interval_join.rs:1466-1573): the call consumes
+ *      the longest prefix of probe rows whose pairs fit (at least one row) and reports it in
+ *      *probe_rows_consumed; probe_idx values are relative to the start of this call's probe arrays. */
+BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
+                      const int32_t* end, uint64_t n, int mode, uint64_t max_rows, brg_rows** out,
+                      uint64_t* probe_rows_consumed);
+/* device two-pass form: count -> exclusive scan (d_offsets[n+1], u64) ; then emit into caller buffers */
+BRG_API int brg_pairs_count_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                        const int32_t* d_end, uint64_t n, uint64_t* d_offsets, void* stream);
+BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                       const int32_t* d_end, uint64_t n, const uint64_t* d_offsets, uint32_t* d_build_idx,
+                       uint32_t* d_probe_idx, void* stream);
+
+/* ---- variable-length results ------------------------------------------------------------------------ */
+BRG_API uint64_t brg_rows_len(const brg_rows* r);
+BRG_API const uint32_t* brg_rows_build_idx(const brg_rows* r); /* NULL for SEMI/ANTI                   */
+BRG_API const uint32_t* brg_rows_probe_idx(const brg_rows* r);
+BRG_API const uint8_t* brg_rows_valid_bits(const brg_rows* r); /* NULL when every row is valid (pairs) */
+BRG_API const int64_t* brg_rows_distance(const brg_rows* r);   /* NULL unless nearest with distance    */
+BRG_API void brg_rows_release(brg_rows* r);
+
+/* ---- instrumentation: kernels launched by this library on the calling process (bench `gpu_launches`) -- */
+BRG_API uint64_t brg_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIORANGES_H */

@@ -1,0 +1,229 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI (host-buffer entry points, as the
+Rust host would call them) and is compared bit-exactly with the CPU oracle and with the reference's golden vectors."""
+import numpy as np
+import pytest
+
+import reference_cases as rc
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import bio_ranges_b200 as brg
+
+    c = brg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def make_index(ctx):
+    def _mk(key, start, end, n_keys):
+        return ctx.build(key, np.asarray(start, np.int32), np.asarray(end, np.int32), n_keys)
+
+    return _mk
+
+
+@pytest.mark.parametrize("case", rc.ALL_CASES, ids=lambda c: c.__name__)
+def test_gpu_reference_case(case, make_index):
+    """the reference's own unit literals / CSV tables / golden parquet, on the CUDA path"""
+    case(make_index)
+
+
+def _rand(rng, n, n_keys, lo, hi, maxlen, absent_frac=0.0):
+    k = rng.integers(0, n_keys, n).astype(np.uint32)
+    s = rng.integers(lo, hi, n).astype(np.int64)
+    e = s + rng.integers(0, maxlen, n)
+    if absent_frac:
+        k[rng.random(n) < absent_frac] = O.ABSENT
+    return k, s.astype(np.int32), np.clip(e, -2**31, 2**31 - 1).astype(np.int32)
+
+
+def _compare_all(ctx, bk, bs, be, pk, ps, pe, nk, ks=(2, 5)):
+    gi = ctx.build(bk, bs, be, nk)
+    oi = O.OracleIndex(bk, bs, be, nk)
+    for strict in (False, True):
+        assert (gi.count_overlaps(pk, ps, pe, strict=strict) == oi.count_overlaps(pk, ps, pe, strict=strict)).all()
+        assert (gi.coverage(pk, ps, pe, strict=strict) == oi.coverage(pk, ps, pe, strict=strict)).all()
+        for inc in (True, False):
+            gl, gv, gd = gi.nearest_k1(pk, ps, pe, include_overlaps=inc, strict=strict)
+            ol, ov, od = oi.nearest_k1(pk, ps, pe, include_overlaps=inc, strict=strict)
+            assert (gv == ov).all()
+            assert (gl == ol).all() and (gd == od).all()
+            for k in ks:
+                g = gi.nearest_k(pk, ps, pe, k, include_overlaps=inc, strict=strict)
+                o = oi.nearest_k(pk, ps, pe, k, include_overlaps=inc, strict=strict)
+                assert len(g[0]) == len(o[0])
+                for a, b in zip(g, o):
+                    assert (a == b).all()  # same rows in the same order (probe-major, reference emission order)
+    gb, gp = O.canonical_pairs(*gi.overlap_pairs(pk, ps, pe))
+    ob, op = O.canonical_pairs(*oi.overlap_pairs(pk, ps, pe))
+    assert len(gb) == len(ob) and (gb == ob).all() and (gp == op).all()
+    cnt = oi.overlap_counts(pk, ps, pe)
+    import bio_ranges_b200 as brg
+
+    semi = gi.overlap_pairs(pk, ps, pe, mode=brg.PAIRS_SEMI)
+    anti = gi.overlap_pairs(pk, ps, pe, mode=brg.PAIRS_ANTI)
+    assert (semi == np.nonzero(cnt > 0)[0]).all() and (anti == np.nonzero(cnt == 0)[0]).all()
+    gi.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_gpu_vs_oracle_random(ctx, seed):
+    rng = np.random.default_rng(seed)
+    nk = int(rng.choice([1, 3, 24, 300]))
+    nb = int(rng.choice([1, 50, 5000, 60000]))
+    maxlen = int(rng.choice([1, 40, 5000, 200000]))
+    span = int(rng.choice([1000, 10**6, 2 * 10**9]))
+    bk, bs, be = _rand(rng, nb, nk, -span if seed % 2 else 0, span, maxlen)
+    pk, ps, pe = _rand(rng, 20000, nk, -span if seed % 2 else 0, span, int(rng.choice([1, 200, 3000])), absent_frac=0.05)
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, nk)
+
+
+def test_gpu_edge_cases(ctx):
+    rng = np.random.default_rng(77)
+    # empty build side, keys without rows, empty probe side
+    z32, zu = np.zeros(0, np.int32), np.zeros(0, np.uint32)
+    pk, ps, pe = _rand(rng, 1000, 4, 0, 5000, 50, absent_frac=0.2)
+    _compare_all(ctx, zu, z32, z32, pk, ps, pe, 4)
+    bk, bs, be = _rand(rng, 3000, 2, 0, 5000, 80)
+    bk[:] = 3  # only key 3 of 6 has rows
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, 6)
+    gi = ctx.build(bk, bs, be, 6)
+    assert gi.count_overlaps(zu, z32, z32).shape == (0,)
+    assert gi.overlap_pairs(zu, z32, z32)[0].shape == (0,)
+    # duplicates, point intervals, many identical rows
+    bs = np.repeat(np.array([10, 10, 10, 500, 500, 7], np.int32), 50)
+    be = np.repeat(np.array([10, 20, 10, 900, 500, 7], np.int32), 50)
+    bk = np.zeros(len(bs), np.uint32)
+    pk = np.zeros(400, np.uint32)
+    ps = rng.integers(0, 1000, 400).astype(np.int32)
+    pe = (ps + rng.integers(0, 30, 400)).astype(np.int32)
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, 1, ks=(3, 60, 400))
+    # degenerate probes after the strict adjustment (length 0/1 probes): count is pinned to 0 by the guard, nearest
+    # falls to the neighbour search; coverage/pairs use the unguarded closed predicate (declared unpinned)
+    bk, bs, be = _rand(rng, 2000, 1, 0, 3000, 100)
+    pk = np.zeros(1500, np.uint32)
+    ps = rng.integers(0, 3000, 1500).astype(np.int32)
+    pe = (ps + rng.integers(-3, 2, 1500)).astype(np.int32)
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, 1)
+    # extreme coordinates (wrapping i32 arithmetic must match the reference's release-mode behaviour)
+    ext = np.array([-2**31, -2**31 + 1, -5, 0, 5, 2**31 - 2, 2**31 - 1], np.int64)
+    bs = rng.choice(ext, 300)
+    be = np.maximum(bs, rng.choice(ext, 300))
+    ps = rng.choice(ext, 300)
+    pe = np.maximum(ps, rng.choice(ext, 300))
+    _compare_all(ctx, np.zeros(300, np.uint32), bs.astype(np.int32), be.astype(np.int32), np.zeros(300, np.uint32),
+                 ps.astype(np.int32), pe.astype(np.int32), 1)
+
+
+def test_gpu_nested_long_intervals(ctx):
+    """one chromosome-long interval + many short ones: pair enumeration must stay exact (over-scan case)"""
+    rng = np.random.default_rng(5)
+    bk, bs, be = _rand(rng, 4000, 1, 0, 10**6, 300)
+    bs[0], be[0] = 0, 10**6 + 500
+    pk, ps, pe = _rand(rng, 3000, 1, 0, 10**6, 200)
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, 1, ks=(2,))
+
+
+def test_gpu_config1_count_overlaps_1m_x_100k(ctx):
+    """BASELINE configs[0]: count_overlaps 1M reads x 100k targets, 1 contig -- full size, bit-exact vs the oracle"""
+    rng = np.random.default_rng(42)
+    bs = rng.integers(0, 2**28, 100_000).astype(np.int32)
+    be = (bs + rng.integers(100, 10_000, 100_000)).astype(np.int32)
+    ps = rng.integers(0, 2**28, 1_000_000).astype(np.int32)
+    pe = (ps + 150).astype(np.int32)
+    gi = ctx.build(None, bs, be, 1)
+    oi = O.OracleIndex(None, bs, be, 1)
+    for order in ("unsorted", "sorted"):
+        if order == "sorted":
+            o = np.argsort(ps, kind="stable")
+            ps, pe = ps[o], pe[o]
+        got = gi.count_overlaps(None, ps, pe)
+        want = oi.count_overlaps(None, ps, pe, threads=O.max_threads())
+        assert (got == want).all(), order
+        assert (gi.coverage(None, ps, pe) == oi.coverage(None, ps, pe, threads=O.max_threads())).all()
+        gl, gv, gd = gi.nearest_k1(None, ps, pe)
+        ol, ov, od = oi.nearest_k1(None, ps, pe, threads=O.max_threads())
+        assert (gl == ol).all() and (gv == ov).all() and (gd == od).all()
+
+
+def test_gpu_pairs_chunking_max_rows(ctx):
+    """low-memory style chunking (IJ:1466-1573): concatenating capped calls reproduces the uncapped result"""
+    rng = np.random.default_rng(9)
+    bk, bs, be = _rand(rng, 20000, 3, 0, 200000, 400)
+    pk, ps, pe = _rand(rng, 5000, 3, 0, 200000, 300)
+    gi = ctx.build(bk, bs, be, 3)
+    fb, fp = gi.overlap_pairs(pk, ps, pe)
+    done, bb, pp = 0, [], []
+    while done < len(ps):
+        b, p, used = gi.overlap_pairs(pk[done:], ps[done:], pe[done:], max_rows=1000, return_consumed=True)
+        assert used >= 1 and (len(b) <= 1000 or used == 1)
+        bb.append(b)
+        pp.append(p + done)
+        done += used
+    assert (np.concatenate(bb) == fb).all() and (np.concatenate(pp) == fp).all()
+
+
+def test_gpu_large_scale_properties(ctx):
+    """size-independent properties at a size the oracle would not finish quickly (16M probes x 2M build, 24 contigs)"""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(43)
+    nb, npb, nk = 2_000_000, 16_000_000, 24
+    bk = torch.randint(0, nk, (nb,), device="cuda", generator=g, dtype=torch.int32)
+    bs = torch.randint(0, 2**27, (nb,), device="cuda", generator=g, dtype=torch.int32)
+    be = bs + torch.randint(1, 2000, (nb,), device="cuda", generator=g, dtype=torch.int32)
+    pk = torch.randint(0, nk, (npb,), device="cuda", generator=g, dtype=torch.int32)
+    ps = torch.randint(0, 2**27, (npb,), device="cuda", generator=g, dtype=torch.int32)
+    pe = ps + 150
+    ix = ctx.build_dev(bk, bs, be, nk)
+    out = torch.empty(npb, dtype=torch.int64, device="cuda")
+    ix.count_overlaps_dev(pk, ps, pe, out)
+    torch.cuda.synchronize()
+    # (1) checksum of checksums: sum of counts == number of pairs found by the independent pair pipeline
+    offsets = torch.empty(npb + 1, dtype=torch.int64, device="cuda")
+    ix.pairs_count_dev(pk, ps, pe, offsets)
+    torch.cuda.synchronize()
+    total_pairs = int(offsets[-1].item())
+    assert int(out.sum().item()) == total_pairs
+    # (2) order independence: a permutation of the probes permutes the counts
+    perm = torch.randperm(npb, device="cuda", generator=g)
+    out2 = torch.empty_like(out)
+    ix.count_overlaps_dev(pk[perm].contiguous(), ps[perm].contiguous(), pe[perm].contiguous(), out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out[perm])
+    # (3) a sample of rows against the oracle
+    oi = O.OracleIndex(bk.cpu().numpy().astype(np.uint32), bs.cpu().numpy(), be.cpu().numpy(), nk)
+    sel = torch.arange(0, npb, 64, device="cuda")
+    want = oi.count_overlaps(pk[sel].cpu().numpy().astype(np.uint32), ps[sel].cpu().numpy(), pe[sel].cpu().numpy(),
+                             threads=O.max_threads())
+    assert (out[sel].cpu().numpy() == want).all()
+    # (4) emitted pairs satisfy the predicate and are exactly `total_pairs` many
+    bi = torch.empty(total_pairs, dtype=torch.int32, device="cuda")
+    pi = torch.empty(total_pairs, dtype=torch.int32, device="cuda")
+    ix.pairs_emit_dev(pk, ps, pe, offsets, bi, pi)
+    torch.cuda.synchronize()
+    b64, p64 = bi.long(), pi.long()
+    assert bool(((bk[b64] == pk[p64]) & (bs[b64] <= pe[p64]) & (be[b64] >= ps[p64])).all())
+    assert bool((p64[1:] >= p64[:-1]).all())  # probe-major
+
+
+def test_gpu_index_export_import_roundtrip(ctx):
+    """replication path used for multi-GPU: export header + slab, import into a fresh index, same answers"""
+    import torch
+
+    rng = np.random.default_rng(3)
+    bk, bs, be = _rand(rng, 50000, 5, 0, 10**6, 500)
+    pk, ps, pe = _rand(rng, 20000, 5, 0, 10**6, 200)
+    ix = ctx.build(bk, bs, be, 5)
+    header, slab = ix.export()
+    ix2, slab2 = ctx.import_index(header)
+    slab2.copy_(slab)
+    torch.cuda.synchronize()
+    assert (ix.count_overlaps(pk, ps, pe) == ix2.count_overlaps(pk, ps, pe)).all()
+    assert (ix.coverage(pk, ps, pe) == ix2.coverage(pk, ps, pe)).all()
+    a, b = ix.nearest_k1(pk, ps, pe), ix2.nearest_k1(pk, ps, pe)
+    assert all((x == y).all() for x, y in zip(a, b))
