@@ -12,7 +12,10 @@
 //                                                                         nearest_index.rs:91-101,192-266
 //   nearest (k>1)  : overlaps in (start,end,pos) order, then a two-pointer walk outwards
 //                                                                         nearest_index.rs:103-190
+#include <algorithm>
+
 #include "brg_internal.cuh"
+#include "brg_tile.cuh"
 
 namespace brg {
 
@@ -41,6 +44,64 @@ __global__ void __launch_bounds__(PB_THREADS) count_kernel(IndexView ix, const u
             cnt = (int64_t)started - (int64_t)ended_before;
         }
         st_stream(out + i, cnt);
+    }
+}
+
+// Tiled variant (the hot path): TMA-staged probe tiles + warp-window rank search, see brg_tile.cuh.
+__device__ __forceinline__ void store8_i64(int64_t* out, const long long (&v)[PV]) {
+    longlong2* o = reinterpret_cast<longlong2*>(out);
+#pragma unroll
+    for (int j = 0; j < PV / 2; j++) __stcs(o + j, make_longlong2(v[2 * j], v[2 * j + 1]));
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                    const int32_t* __restrict__ start,
+                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                    int strict, int64_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
+    int32_t* win0 = ring->w[threadIdx.x >> 5].win[0];
+    int32_t* win1 = ring->w[threadIdx.x >> 5].win[1];
+    ProbePipe pipe(ring, key, start, end, n_rows);
+    ProbeTile t;
+    WarpCursor cs, ce;
+    cs.reset();
+    ce.reset();
+    KeyDir ks, ke;
+    uint32_t kd_key = 0xFFFFFFFFu;
+    while (pipe.next(t)) {
+        if (strict) {  // interval_tree.rs:253-256
+#pragma unroll
+            for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
+        }
+        long long cnt[PV];
+        uint32_t kuni;
+        if (warp_uniform_key(t.key, t.active, ix.n_keys, &kuni)) {
+            if (kuni != kd_key) {
+                kd_key = kuni;
+                ks = load_keydir(ix.d_sstart.kd, kuni);
+                ke = load_keydir(ix.d_eend.kd, kuni);
+            }
+            uint32_t started[PV], ended[PV];
+            warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, started, win0);  // seg_begin + #(starts <= qe)
+            warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, ended, win1);       // seg_begin + #(ends < qs)
+#pragma unroll
+            for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
+                cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
+        } else {
+            // mixed keys inside the warp (contig boundary) or keys absent from the build side: per-row directory search
+#pragma unroll
+            for (int j = 0; j < PV; j++) {
+                long long r = 0;
+                if (t.active && t.key[j] < ix.n_keys && !(t.qe[j] < t.qs[j])) {   // unknown contig -> 0 (:265)
+                    const KeyDir a = load_keydir(ix.d_sstart.kd, t.key[j]);
+                    const KeyDir b = load_keydir(ix.d_eend.kd, t.key[j]);
+                    r = (long long)rank_le_kd(ix.d_sstart, a, t.qe[j]) - (long long)rank_lt_kd(ix.d_eend, b, t.qs[j]);
+                }
+                cnt[j] = r;
+            }
+        }
+        if (t.active) store8_i64(out + t.row0, cnt);
     }
 }
 
@@ -279,6 +340,18 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k_kernel(IndexView ix, con
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
+// persistent grid for the tiled kernels: 3 CTAs per SM (shared-memory bound), never more CTAs than tiles
+static inline unsigned tiled_grid(uint64_t rows) {
+    uint64_t tiles = (rows + TP_TILE - 1) / TP_TILE;
+    uint64_t cap = (uint64_t)kSMs * 3;
+    return (unsigned)std::max<uint64_t>(1, std::min(tiles, cap));
+}
+static int tiled_config(const void* fn) {
+    // opt in to > 48 KB dynamic shared memory (once per kernel per process; cheap to repeat)
+    BRG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
+    return 0;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned probe_grid(uint64_t n, int per_sm) {
     // persistent-style grid: a multiple of the SM count, grid-stride over rows
     uint64_t want = (n + PB_THREADS - 1) / PB_THREADS;
@@ -290,8 +363,19 @@ static inline unsigned probe_grid(uint64_t n, int per_sm) {
 int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
                  int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
-    count_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, out);
-    BRG_LAUNCH_CHECK();
+    uint64_t done = 0;
+    if (aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+        done = (n / PV) * PV;
+        int rc = tiled_config((const void*)count_kernel_tiled);
+        if (rc) return rc;
+        count_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out);
+        BRG_LAUNCH_CHECK();
+    }
+    if (done < n) {  // unaligned buffers or the last n % PV rows
+        count_kernel<<<probe_grid(n - done, 32), PB_THREADS, 0, st>>>(ix, key ? key + done : nullptr, s + done, e + done,
+                                                                      n - done, strict, out + done);
+        BRG_LAUNCH_CHECK();
+    }
     return 0;
 }
 int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
