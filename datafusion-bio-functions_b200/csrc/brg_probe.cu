@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
                                                                     int strict, int64_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
-    int32_t* win0 = ring->w[threadIdx.x >> 5].win[0];
-    int32_t* win1 = ring->w[threadIdx.x >> 5].win[1];
+    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
     ProbePipe pipe(ring, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cs, ce;
@@ -70,9 +70,16 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
     KeyDir ks, ke;
     uint32_t kd_key = 0xFFFFFFFFu;
     while (pipe.next(t)) {
-        if (strict) {  // interval_tree.rs:253-256
+        if (strict) {  // interval_tree.rs:253-256; keep the shared copy of the columns in step with the registers
 #pragma unroll
             for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
+            if (t.active) {
+                int4* ps = reinterpret_cast<int4*>(t.s_qs + (threadIdx.x & 31) * PV);
+                int4* pe = reinterpret_cast<int4*>(t.s_qe + (threadIdx.x & 31) * PV);
+                ps[0] = make_int4(t.qs[0], t.qs[1], t.qs[2], t.qs[3]); ps[1] = make_int4(t.qs[4], t.qs[5], t.qs[6], t.qs[7]);
+                pe[0] = make_int4(t.qe[0], t.qe[1], t.qe[2], t.qe[3]); pe[1] = make_int4(t.qe[4], t.qe[5], t.qe[6], t.qe[7]);
+            }
+            __syncwarp();
         }
         long long cnt[PV];
         uint32_t kuni;
@@ -83,8 +90,9 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             uint32_t started[PV], ended[PV];
-            warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, started, win0);  // seg_begin + #(starts <= qe)
-            warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, ended, win1);       // seg_begin + #(ends < qs)
+            // seg_begin + #(starts <= qe)  and  seg_begin + #(ends < qs)
+            warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, started);
+            warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux1, ended);
 #pragma unroll
             for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
                 cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
@@ -102,6 +110,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
             }
         }
         if (t.active) store8_i64(out + t.row0, cnt);
+        pipe.release();
     }
 }
 

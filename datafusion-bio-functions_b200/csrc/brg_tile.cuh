@@ -5,16 +5,18 @@
 // independently of what the warps are doing.  (The first version of the kernels issued per-thread 4-byte loads and
 // was latency-bound: 29 % DRAM throughput with every warp stalled on its probe loads, profiles/r1_count_v0_ncu.txt.)
 //
-// Search: every thread owns PV consecutive probe rows, a warp owns 32*PV consecutive rows, a CTA walks a CONTIGUOUS
-// range of tiles.  Genomic probe tables are coordinate-sorted (the reference relies on that locality too,
-// nearest.rs:320-322), so the ranks of one warp's rows fall into a short window of the sorted build array, and the
-// window of the warp's next tile starts where the previous one ended.  Per sorted array the warp keeps a cursor
-// (WarpCursor); a tile costs one coalesced load of the next few dozen build values (which ARE the window), a ballot
-// to find the window end, and then every lane merges its PV rows against the window in shared memory: binary search
-// for its first row, short forward walks for the following rows.  No dependent global loads, no directory lookups on
-// the hot path.  Anything that breaks the pattern -- key change inside the warp, queries going backwards, a window
-// wider than the shared buffer (unsorted input) -- falls back to the rank directory (brg_internal.cuh), per warp or
-// per row, so results are exact for any input order.
+// Search: every thread owns PV consecutive probe rows, a warp owns a contiguous range of 256-row chunks.  Genomic
+// probe tables are coordinate-sorted (the reference relies on that locality too, nearest.rs:320-322), so the ranks of
+// one chunk fall into a short window of the sorted build array and the window of the next chunk starts where the
+// previous one ended.  Per sorted array the warp keeps a cursor (WarpCursor).  A chunk then costs
+//   * one coalesced load of the next few dozen build values (they ARE the window) + a ballot to find its end,
+//   * an INVERSE search: each of the (few) window elements binary-searches the (many) probe values of the chunk in
+//     shared memory, drops a 1 into a 256-bin shared histogram at its insertion point, and an inclusive prefix sum
+//     of the histogram (8 serial adds per lane + one warp scan) yields the rank of all 256 rows at once.
+// That is ~100 instructions per lane for 8 rows instead of 8 independent searches.  It needs the chunk's query values
+// to be non-decreasing (checked with one vote).  Anything that breaks the pattern -- unsorted rows, a key change
+// inside the chunk, a partial chunk, a window wider than the shared buffer -- falls back to a per-row search over a
+// shared-memory copy of the window or to the rank directory (brg_internal.cuh), so results are exact for any input.
 #pragma once
 #include "brg_internal.cuh"
 
@@ -74,7 +76,7 @@ struct __align__(128) WarpRing {
     int32_t start[TP_STAGES][TP_WTILE];
     int32_t end[TP_STAGES][TP_WTILE];
     uint32_t key[TP_STAGES][TP_WTILE];
-    int32_t win[TP_NWIN][TP_WCAP];
+    uint32_t aux[TP_NWIN][TP_WCAP];  // per array: histogram of the inverse search / window copy of the fallback
     uint64_t full[TP_STAGES];
     uint64_t pad_[14];
 };
@@ -87,6 +89,9 @@ struct ProbeTile {
     uint32_t key[PV];
     uint64_t row0;   // global row of this thread's first probe
     bool active;     // thread owns rows in this chunk
+    bool full;       // all 32 lanes own rows (256-row chunk)
+    int32_t* s_qs;   // the chunk's start / end columns in shared memory (valid until release())
+    int32_t* s_qe;
 };
 
 // Usage:  ProbePipe pipe(...); while (pipe.next(tile)) { ...the warp stays converged... }
@@ -166,10 +171,16 @@ struct ProbePipe {
 #pragma unroll
             for (int j = 0; j < PV; j++) { tile.qs[j] = 0; tile.qe[j] = 0; tile.key[j] = 0xFFFFFFFFu; }
         }
-        __syncwarp();  // every lane holds its rows in registers: the stage can be refilled
+        tile.full = rows == (uint32_t)TP_WTILE;
+        tile.s_qs = ring->start[s];
+        tile.s_qe = ring->end[s];
+        return true;
+    }
+    // the chunk's shared-memory columns are no longer needed: refill the stage with the chunk after next
+    __device__ __forceinline__ void release() {
+        __syncwarp();
         if ((threadIdx.x & 31) == 0) issue(it + TP_STAGES);
         it++;
-        return true;
     }
 };
 
@@ -200,99 +211,123 @@ struct WarpCursor {
 
 // r[j] = global index of the first element of key k's segment that is  > q[j] (LT = false)  or  >= q[j] (LT = true).
 // Must be called by all 32 lanes; `k`/`kid` warp-uniform.  Lanes with active == false contribute nothing and get
-// unspecified ranks.  `win` is this warp's shared window buffer (TP_WCAP entries).
+// unspecified ranks.  Q = the chunk's 256 query values in shared memory (same values as q, row-major), only read
+// when `full`.  aux = this warp's 256-word scratch for this array.
 template <bool LT>
 __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
-                                                  const int32_t (&q)[PV], bool active, uint32_t (&r)[PV], int32_t* win) {
+                                                  const int32_t (&q)[PV], bool active, bool full, const int32_t* Q,
+                                                  uint32_t* aux, uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
-    int32_t mn = INT32_MAX, mx = INT32_MIN;
-    if (active) {
+    // ---- are the chunk's queries non-decreasing? -------------------------------------------------------------------
+    bool mono = full;
+    if (full) {
+        bool up = true;
 #pragma unroll
-        for (int j = 0; j < PV; j++) { mn = min(mn, q[j]); mx = max(mx, q[j]); }
+        for (int j = 1; j < PV; j++) up &= q[j] >= q[j - 1];
+        const int32_t prev_last = __shfl_up_sync(0xFFFFFFFFu, q[PV - 1], 1);
+        up &= (lane == 0) | (q[0] >= prev_last);
+        mono = __all_sync(0xFFFFFFFFu, up);
     }
-    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if (mn > mx) return;  // no active lane in this warp
+    int32_t mn, mx;
+    if (mono) {
+        mn = __shfl_sync(0xFFFFFFFFu, q[0], 0);
+        mx = __shfl_sync(0xFFFFFFFFu, q[PV - 1], 31);
+    } else {
+        mn = INT32_MAX; mx = INT32_MIN;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < PV; j++) { mn = min(mn, q[j]); mx = max(mx, q[j]); }
+        }
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if (mn > mx) return;  // no active lane in this warp
+    }
     // ---- window start: the cursor when the queries moved forward, else a directory lookup ------------------------
     uint32_t lo;
     if (cur.valid && cur.key == kid && mn >= cur.bound) lo = cur.pos;
     else lo = LT ? rank_lt_kd(d, k, mn) : rank_le_kd(d, k, mn);
-    // ---- window = the next build values up to the largest query: coalesced chunk loads + ballots ----------------
-    uint32_t wn = 0;
-    bool open = true;  // the window may extend beyond what has been loaded so far
-    constexpr int CH = 2;
+
+    if (mono) {
+        // ---- inverse search ---------------------------------------------------------------------------------------
+        uint4* a4 = reinterpret_cast<uint4*>(aux) + 2 * lane;
+        a4[0] = make_uint4(0, 0, 0, 0);
+        a4[1] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t wn = 0;
+        bool open = true;
 #pragma unroll 1
-    for (uint32_t base = 0; open && base + 32 * CH <= (uint32_t)TP_WCAP; base += 32 * CH) {
-        int32_t v[CH];
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const uint32_t idx = lo + base + 32 * c + lane;
-            v[c] = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
-        }
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const uint32_t idx = lo + base + 32 * c + lane;
-            const bool in = idx < k.seg_end && (LT ? v[c] < mx : v[c] <= mx);
+        for (uint32_t base = 0; open && base < (uint32_t)TP_WCAP; base += 32) {
+            const uint32_t idx = lo + base + lane;
+            const int32_t v = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
+            const bool in = idx < k.seg_end && (LT ? v < mx : v <= mx);
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
-            win[base + 32 * c + lane] = in ? v[c] : INT32_MAX;
-            if (open) {
-                wn += __popc(m);
-                open = (m == 0xFFFFFFFFu);
-            }
-        }
-    }
-    __syncwarp();
-    if (!open) {
-        cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
-        // wn < TP_WCAP and win[wn] is a +inf pad: merge every lane's rows against the window
-        uint32_t p = 0;
-        {   // first row: binary search over [0, wn)
-            uint32_t a = 0, b = wn;
-            const int32_t q0 = q[0];
-            while (a < b) {
-                const uint32_t mid = (a + b) >> 1;
-                const int32_t v = win[mid];
-                if (LT ? v < q0 : v <= q0) a = mid + 1; else b = mid;
-            }
-            p = a;
-        }
-        r[0] = lo + p;
+            wn += __popc(m);
+            open = (m == 0xFFFFFFFFu);
+            if (m) {
+                // insertion point of v among the 256 sorted queries:  LE: #(Q < v)   LT: #(Q <= v)
+                uint32_t pos = 0;
 #pragma unroll
-        for (int j = 1; j < PV; j++) {
-            const int32_t qj = q[j];
-            if (qj >= q[j - 1]) {
-                // rows are sorted: walk forward (a handful of steps), then finish by binary search if still short
-                int guard = 0;
-                while (p < wn && (LT ? win[p] < qj : win[p] <= qj)) {
-                    p++;
-                    if (++guard == 8) {
-                        uint32_t a = p, b = wn;
-                        while (a < b) {
-                            const uint32_t mid = (a + b) >> 1;
-                            const int32_t v = win[mid];
-                            if (LT ? v < qj : v <= qj) a = mid + 1; else b = mid;
-                        }
-                        p = a;
-                        break;
-                    }
+                for (uint32_t step = 128; step; step >>= 1) {
+                    const int32_t qv = Q[pos + step - 1];
+                    pos += (LT ? (qv <= v) : (qv < v)) ? step : 0u;
                 }
-            } else {
-                uint32_t a = 0, b = p;
-                while (a < b) {
-                    const uint32_t mid = (a + b) >> 1;
-                    const int32_t v = win[mid];
-                    if (LT ? v < qj : v <= qj) a = mid + 1; else b = mid;
-                }
-                p = a;
+                // (the 8 steps cover Q[0..254]; an in-window element never lies above Q[255] = mx, so pos <= 255 is exact)
+                if (in) atomicAdd(&aux[pos], 1u);
             }
-            r[j] = lo + p;
         }
         __syncwarp();
-        return;
+        if (!open) {
+            cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
+            const uint4 h0 = a4[0], h1 = a4[1];
+            uint32_t c[PV] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int j = 1; j < PV; j++) c[j] += c[j - 1];
+            uint32_t incl = c[PV - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const uint32_t before = lo + incl - c[PV - 1];
+#pragma unroll
+            for (int j = 0; j < PV; j++) r[j] = before + c[j];
+            __syncwarp();
+            return;
+        }
+        cur.valid = false;
+        __syncwarp();
+    } else {
+        // ---- per-row search over a shared copy of the window ------------------------------------------------------
+        const uint32_t hi = LT ? rank_lt_kd(d, k, mx) : rank_le_kd(d, k, mx);
+        const uint32_t wn = hi - lo;
+        cur.pos = hi; cur.bound = mx; cur.key = kid; cur.valid = true;
+        if (wn == 0) {
+#pragma unroll
+            for (int j = 0; j < PV; j++) r[j] = lo;
+            return;
+        }
+        if (wn < (uint32_t)TP_WCAP / 2) {
+            int32_t* win = reinterpret_cast<int32_t*>(aux);
+            const uint32_t top = 1u << (31 - __clz(wn));  // padded with +inf up to 2*top-1 entries: no bound checks
+            for (uint32_t t = lane; t < 2 * top - 1; t += 32) win[t] = (t < wn) ? __ldg(d.A + lo + t) : INT32_MAX;
+            __syncwarp();
+            uint32_t pos[PV];
+#pragma unroll
+            for (int j = 0; j < PV; j++) pos[j] = 0;
+            for (uint32_t step = top; step; step >>= 1) {
+#pragma unroll
+                for (int j = 0; j < PV; j++) {
+                    const int32_t v = win[pos[j] + step - 1];
+                    pos[j] += (LT ? (v < q[j]) : (v <= q[j])) ? step : 0u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PV; j++) r[j] = lo + min(pos[j], wn);  // q == INT32_MAX can count the padding
+            __syncwarp();
+            return;
+        }
     }
-    // window wider than the shared buffer (unsorted probes): per-row directory search
-    cur.valid = false;
-    __syncwarp();
+    // ---- window wider than the shared buffer (unsorted probes): per-row directory search ----------------------------
 #pragma unroll
     for (int j = 0; j < PV; j++) r[j] = active ? (LT ? rank_lt_kd(d, k, q[j]) : rank_le_kd(d, k, q[j])) : k.seg_begin;
 }
