@@ -169,6 +169,12 @@ extern "C" BRG_API int brg_ctx_create(int device_id, brg_ctx** out) {
     c->device = device_id;
     c->sms = prop.multiProcessorCount;
     BRG_CUDA(cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking));
+    {   // stream-ordered scratch (cudaMallocAsync) must not go back to the OS between calls
+        cudaMemPool_t pool;
+        BRG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_id));
+        uint64_t keep = ~0ull;
+        BRG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     if (const char* env = getenv("BRG_CHUNK_ROWS")) {
         uint64_t v = strtoull(env, nullptr, 10);
         if (v >= 1024) c->chunk_rows = v;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void store8_i64(int64_t* out, const long long (&v)[PV
 __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
                                                                     const int32_t* __restrict__ start,
                                                                     const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                    int strict, int64_t* __restrict__ out) {
+                                                                    int strict, int64_t* __restrict__ out, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
@@ -81,36 +81,55 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
             }
             __syncwarp();
         }
-        long long cnt[PV];
         uint32_t kuni;
-        if (warp_uniform_key(t.key, t.active, ix.n_keys, &kuni)) {
+        bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
+        uint32_t started[PV], ended[PV];
+        if (ok) {
             if (kuni != kd_key) {
                 kd_key = kuni;
                 ks = load_keydir(ix.d_sstart.kd, kuni);
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
-            uint32_t started[PV], ended[PV];
             // seg_begin + #(starts <= qe)  and  seg_begin + #(ends < qs)
-            warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, started);
-            warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux1, ended);
+            ok = warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, started);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux1, ended);
+        }
+        if (ok) {
+            long long cnt[PV];
 #pragma unroll
             for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
                 cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
+            if (t.active) store8_i64(out + t.row0, cnt);
         } else {
-            // mixed keys inside the warp (contig boundary) or keys absent from the build side: per-row directory search
-#pragma unroll
-            for (int j = 0; j < PV; j++) {
-                long long r = 0;
-                if (t.active && t.key[j] < ix.n_keys && !(t.qe[j] < t.qs[j])) {   // unknown contig -> 0 (:265)
-                    const KeyDir a = load_keydir(ix.d_sstart.kd, t.key[j]);
-                    const KeyDir b = load_keydir(ix.d_eend.kd, t.key[j]);
-                    r = (long long)rank_le_kd(ix.d_sstart, a, t.qe[j]) - (long long)rank_lt_kd(ix.d_eend, b, t.qs[j]);
-                }
-                cnt[j] = r;
-            }
+            // mixed keys (contig boundary, unsorted input), keys absent from the build side, or a window wider than the
+            // shared buffer: hand the chunk to the per-row kernel
+            cs.valid = false;
+            ce.valid = false;
+            todo_push(todo, t.chunk);
         }
-        if (t.active) store8_i64(out + t.row0, cnt);
         pipe.release();
+    }
+}
+
+// deferred chunks: one row per thread, rank directory, full occupancy (memory-level parallelism for random probes)
+__global__ void __launch_bounds__(TP_WTILE) count_kernel_todo(IndexView ix, const uint32_t* __restrict__ key,
+                                                              const int32_t* __restrict__ start,
+                                                              const int32_t* __restrict__ end, uint64_t n_rows, int strict,
+                                                              int64_t* __restrict__ out, TodoList todo) {
+    const uint32_t n_todo = *todo.count;
+    for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {
+        const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
+        if (i >= n_rows) continue;
+        int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
+        const uint32_t k = load_key(key, i);
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
+        int64_t cnt = 0;
+        if (k < ix.n_keys && !(qe < qs)) {
+            const KeyDir ks = load_keydir(ix.d_sstart.kd, k);
+            const KeyDir ke = load_keydir(ix.d_eend.kd, k);
+            cnt = (int64_t)rank_le_kd(ix.d_sstart, ks, qe) - (int64_t)rank_lt_kd(ix.d_eend, ke, qs);
+        }
+        st_stream(out + i, cnt);
     }
 }
 
@@ -355,6 +374,24 @@ static inline unsigned tiled_grid(uint64_t rows) {
     uint64_t cap = (uint64_t)kSMs * 3;
     return (unsigned)std::max<uint64_t>(1, std::min(tiles, cap));
 }
+// to-do list of deferred chunks: stream-ordered allocation, so concurrent calls on different streams never share it
+static int todo_alloc(uint64_t rows, TodoList* td, cudaStream_t st) {
+    const uint64_t chunks = (rows + TP_WTILE - 1) / TP_WTILE;
+    void* p = nullptr;
+    BRG_CUDA(cudaMallocAsync(&p, (chunks + 1) * sizeof(uint32_t), st));
+    td->count = reinterpret_cast<uint32_t*>(p);
+    td->chunks = td->count + 1;
+    BRG_CUDA(cudaMemsetAsync(td->count, 0, sizeof(uint32_t), st));
+    return 0;
+}
+static int todo_free(const TodoList& td, cudaStream_t st) {
+    BRG_CUDA(cudaFreeAsync(td.count, st));
+    return 0;
+}
+static inline unsigned todo_grid(uint64_t rows) {
+    uint64_t chunks = (rows + TP_WTILE - 1) / TP_WTILE;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(chunks, (uint64_t)kSMs * 8));
+}
 static int tiled_config(const void* fn) {
     // opt in to > 48 KB dynamic shared memory (once per kernel per process; cheap to repeat)
     BRG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
@@ -377,8 +414,13 @@ int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, con
         done = (n / PV) * PV;
         int rc = tiled_config((const void*)count_kernel_tiled);
         if (rc) return rc;
-        count_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out);
+        TodoList todo;
+        if ((rc = todo_alloc(done, &todo, st))) return rc;
+        count_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out, todo);
         BRG_LAUNCH_CHECK();
+        count_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
+        BRG_LAUNCH_CHECK();
+        if ((rc = todo_free(todo, st))) return rc;
     }
     if (done < n) {  // unaligned buffers or the last n % PV rows
         count_kernel<<<probe_grid(n - done, 32), PB_THREADS, 0, st>>>(ix, key ? key + done : nullptr, s + done, e + done,

@@ -88,6 +88,7 @@ struct ProbeTile {
     int32_t qs[PV], qe[PV];
     uint32_t key[PV];
     uint64_t row0;   // global row of this thread's first probe
+    uint64_t chunk;  // index of this 256-row chunk
     bool active;     // thread owns rows in this chunk
     bool full;       // all 32 lanes own rows (256-row chunk)
     int32_t* s_qs;   // the chunk's start / end columns in shared memory (valid until release())
@@ -150,6 +151,7 @@ struct ProbePipe {
         const uint32_t my = (threadIdx.x & 31) * PV;
         tile.active = my < rows;
         tile.row0 = row + my;
+        tile.chunk = c;
         if (tile.active) {
             const int4* ps = reinterpret_cast<const int4*>(&ring->start[s][my]);
             const int4* pe = reinterpret_cast<const int4*>(&ring->end[s][my]);
@@ -206,15 +208,17 @@ struct WarpCursor {
     int32_t bound;
     uint32_t key;
     bool valid;
-    __device__ __forceinline__ void reset() { valid = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; }
+    int32_t pre;  // prefetched A[pos + lane] (or +inf past the segment): the first 32 window candidates of the next chunk
+    __device__ __forceinline__ void reset() { valid = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; pre = INT32_MAX; }
 };
 
 // r[j] = global index of the first element of key k's segment that is  > q[j] (LT = false)  or  >= q[j] (LT = true).
 // Must be called by all 32 lanes; `k`/`kid` warp-uniform.  Lanes with active == false contribute nothing and get
-// unspecified ranks.  Q = the chunk's 256 query values in shared memory (same values as q, row-major), only read
+// unspecified ranks.  Returns false when the chunk's window does not fit the shared buffer (the caller defers the chunk
+// to the per-row kernel).  Q = the chunk's 256 query values in shared memory (same values as q, row-major), only read
 // when `full`.  aux = this warp's 256-word scratch for this array.
 template <bool LT>
-__device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+__device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
                                                   const int32_t (&q)[PV], bool active, bool full, const int32_t* Q,
                                                   uint32_t* aux, uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
@@ -240,11 +244,12 @@ __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView
         }
         mn = __reduce_min_sync(0xFFFFFFFFu, mn);
         mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-        if (mn > mx) return;  // no active lane in this warp
+        if (mn > mx) return true;  // no active lane in this warp
     }
     // ---- window start: the cursor when the queries moved forward, else a directory lookup ------------------------
     uint32_t lo;
-    if (cur.valid && cur.key == kid && mn >= cur.bound) lo = cur.pos;
+    const bool reuse = cur.valid && cur.key == kid && mn >= cur.bound;
+    if (reuse) lo = cur.pos;
     else lo = LT ? rank_lt_kd(d, k, mn) : rank_le_kd(d, k, mn);
 
     if (mono) {
@@ -258,7 +263,9 @@ __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView
 #pragma unroll 1
         for (uint32_t base = 0; open && base < (uint32_t)TP_WCAP; base += 32) {
             const uint32_t idx = lo + base + lane;
-            const int32_t v = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
+            int32_t v;
+            if (reuse && base == 0) v = cur.pre;  // loaded while the previous chunk was being finished
+            else v = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
             const bool in = idx < k.seg_end && (LT ? v < mx : v <= mx);
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
             wn += __popc(m);
@@ -278,6 +285,7 @@ __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView
         __syncwarp();
         if (!open) {
             cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
+            cur.pre = (cur.pos + lane < k.seg_end) ? __ldg(d.A + cur.pos + lane) : INT32_MAX;
             const uint4 h0 = a4[0], h1 = a4[1];
             uint32_t c[PV] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
@@ -292,19 +300,19 @@ __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView
 #pragma unroll
             for (int j = 0; j < PV; j++) r[j] = before + c[j];
             __syncwarp();
-            return;
+            return true;
         }
-        cur.valid = false;
         __syncwarp();
     } else {
         // ---- per-row search over a shared copy of the window ------------------------------------------------------
         const uint32_t hi = LT ? rank_lt_kd(d, k, mx) : rank_le_kd(d, k, mx);
         const uint32_t wn = hi - lo;
         cur.pos = hi; cur.bound = mx; cur.key = kid; cur.valid = true;
+        cur.pre = (hi + lane < k.seg_end) ? __ldg(d.A + hi + lane) : INT32_MAX;
         if (wn == 0) {
 #pragma unroll
             for (int j = 0; j < PV; j++) r[j] = lo;
-            return;
+            return true;
         }
         if (wn < (uint32_t)TP_WCAP / 2) {
             int32_t* win = reinterpret_cast<int32_t*>(aux);
@@ -324,12 +332,22 @@ __device__ __forceinline__ void warp_window_ranks(WarpCursor& cur, const DirView
 #pragma unroll
             for (int j = 0; j < PV; j++) r[j] = lo + min(pos[j], wn);  // q == INT32_MAX can count the padding
             __syncwarp();
-            return;
+            return true;
         }
     }
-    // ---- window wider than the shared buffer (unsorted probes): per-row directory search ----------------------------
-#pragma unroll
-    for (int j = 0; j < PV; j++) r[j] = active ? (LT ? rank_lt_kd(d, k, q[j]) : rank_le_kd(d, k, q[j])) : k.seg_begin;
+    // ---- window wider than the shared buffer (unsorted probes): the caller defers the chunk to the per-row kernel ---
+    cur.valid = false;
+    return false;
+}
+
+// Chunks the tiled kernels cannot serve from a window (mixed keys, unsorted rows) are appended to a to-do list and
+// answered afterwards by a one-row-per-thread kernel that searches the rank directory at full occupancy.
+struct TodoList {
+    uint32_t* count;
+    uint32_t* chunks;
+};
+__device__ __forceinline__ void todo_push(const TodoList& td, uint64_t chunk) {
+    if ((threadIdx.x & 31) == 0) td.chunks[atomicAdd(td.count, 1u)] = (uint32_t)chunk;
 }
 #endif
 
