@@ -13,6 +13,8 @@
 //   nearest (k>1)  : overlaps in (start,end,pos) order, then a two-pointer walk outwards
 //                                                                         nearest_index.rs:103-190
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "brg_internal.cuh"
 #include "brg_tile.cuh"
@@ -70,17 +72,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
     KeyDir ks, ke;
     uint32_t kd_key = 0xFFFFFFFFu;
     while (pipe.next(t)) {
-        if (strict) {  // interval_tree.rs:253-256; keep the shared copy of the columns in step with the registers
-#pragma unroll
-            for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
-            if (t.active) {
-                int4* ps = reinterpret_cast<int4*>(t.s_qs + (threadIdx.x & 31) * PV);
-                int4* pe = reinterpret_cast<int4*>(t.s_qe + (threadIdx.x & 31) * PV);
-                ps[0] = make_int4(t.qs[0], t.qs[1], t.qs[2], t.qs[3]); ps[1] = make_int4(t.qs[4], t.qs[5], t.qs[6], t.qs[7]);
-                pe[0] = make_int4(t.qe[0], t.qe[1], t.qe[2], t.qe[3]); pe[1] = make_int4(t.qe[4], t.qe[5], t.qe[6], t.qe[7]);
-            }
-            __syncwarp();
-        }
+        if (strict) strict_adjust(t);
         uint32_t kuni;
         bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
         uint32_t started[PV], ended[PV];
@@ -177,6 +169,88 @@ __global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, cons
     }
 }
 
+// one row given the index range [lo, hi) of merged intervals that overlap it (interval_tree.rs:145-152)
+__device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint32_t lo, uint32_t hi, int32_t qs, int32_t qe) {
+    int32_t acc = 0;
+    if (lo < hi && (qs == INT32_MIN || qe == INT32_MAX)) {
+        // `start - 1` / `end + 1` wrap in the reference's release arithmetic: keep the literal per-interval sum
+        for (uint32_t j = lo; j < hi; j++) acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + j), __ldg(ix.m_last + j)));
+    } else if (lo < hi) {
+        acc = cov_term(qs, qe, __ldg(ix.m_first + lo), __ldg(ix.m_last + lo));
+        if (hi - lo > 1) {
+            acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + hi - 1), __ldg(ix.m_last + hi - 1)));
+            // interior intervals lie strictly inside (qs-1, qe+1): their term is max(1, last-first)
+            acc = wadd(acc, wsub(__ldg(ix.m_pre + hi - 1), __ldg(ix.m_pre + lo + 1)));
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                       const int32_t* __restrict__ start,
+                                                                       const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                       int strict, int64_t* __restrict__ out, TodoList todo) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
+    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    ProbePipe pipe(ring, key, start, end, n_rows);
+    ProbeTile t;
+    WarpCursor cl, cf;
+    cl.reset();
+    cf.reset();
+    KeyDir kl, kf;
+    uint32_t kd_key = 0xFFFFFFFFu;
+    while (pipe.next(t)) {
+        if (strict) strict_adjust(t);
+        uint32_t kuni;
+        bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
+        uint32_t lo[PV], hi[PV];
+        if (ok) {
+            if (kuni != kd_key) {
+                kd_key = kuni;
+                kl = load_keydir(ix.d_mlast.kd, kuni);
+                kf = load_keydir(ix.d_mfirst.kd, kuni);
+            }
+            // merged intervals overlapping [qs,qe] are exactly [first j with last_j >= qs, first j with first_j > qe)
+            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, t.full, t.s_qs, aux0, lo);
+            ok = ok && warp_window_ranks<false>(cf, ix.d_mfirst, kf, kuni, t.qe, t.active, t.full, t.s_qe, aux1, hi);
+        }
+        if (ok) {
+            long long cov[PV];
+#pragma unroll
+            for (int j = 0; j < PV; j++) cov[j] = t.active ? (long long)coverage_from_range(ix, lo[j], hi[j], t.qs[j], t.qe[j]) : 0ll;
+            if (t.active) store8_i64(out + t.row0, cov);
+        } else {
+            cl.valid = false;
+            cf.valid = false;
+            todo_push(todo, t.chunk);
+        }
+        pipe.release();
+    }
+}
+
+__global__ void __launch_bounds__(TP_WTILE) coverage_kernel_todo(IndexView ix, const uint32_t* __restrict__ key,
+                                                                 const int32_t* __restrict__ start,
+                                                                 const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                 int strict, int64_t* __restrict__ out, TodoList todo) {
+    const uint32_t n_todo = *todo.count;
+    for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {
+        const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
+        if (i >= n_rows) continue;
+        int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
+        const uint32_t k = load_key(key, i);
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
+        int32_t acc = 0;
+        if (k < ix.n_keys) {
+            const KeyDir kl = load_keydir(ix.d_mlast.kd, k);
+            const KeyDir kf = load_keydir(ix.d_mfirst.kd, k);
+            acc = coverage_from_range(ix, rank_lt_kd(ix.d_mlast, kl, qs), rank_le_kd(ix.d_mfirst, kf, qe), qs, qe);
+        }
+        st_stream(out + i, (int64_t)acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // nearest
 // ---------------------------------------------------------------------------------------------------
@@ -257,6 +331,115 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k1_kernel(IndexView ix, co
             // distance from RAW probe coordinates (nearest.rs:367-375)
             if (dist) st_stream(dist + i, found ? cand_distance(rs, re, b.s, b.e) : (int64_t)0);
         }
+    }
+}
+
+// nearest_one with the three ranks already known:
+//   n_le = seg_begin + #(starts <= qe), i_pme = first i with prefix_max_end[i] >= qs, left_idx = seg_begin + #(ends < qs)
+__device__ __forceinline__ bool nearest_from_ranks(const IndexView& ix, uint32_t seg_begin, uint32_t seg_end, uint32_t n_le,
+                                                   uint32_t i_pme, uint32_t left_idx, int32_t qs, int32_t qe,
+                                                   int include_overlaps, Cand* best) {
+    if (seg_begin == seg_end) return false;
+    if (include_overlaps && !(qe < qs) && n_le > seg_begin && __ldg(ix.pme + n_le - 1) >= qs) {
+        *best = load_s(ix, i_pme);
+        return true;
+    }
+    const bool has_left = left_idx > seg_begin, has_right = n_le < seg_end;
+    if (!has_left && !has_right) return false;
+    Cand l, r;
+    if (has_left) l = load_e(ix, left_idx - 1);
+    if (has_right) r = load_s(ix, n_le);
+    if (has_left && has_right) *best = cand_le(qs, qe, l, r) ? l : r;
+    else *best = has_left ? l : r;
+    return true;
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                         const int32_t* __restrict__ start,
+                                                                         const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                         int include_overlaps, int strict,
+                                                                         uint32_t* __restrict__ left_idx,
+                                                                         uint8_t* __restrict__ valid_bytes,
+                                                                         int64_t* __restrict__ dist, TodoList todo) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
+    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
+    ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256 here: every chunk is full
+    ProbeTile t;
+    WarpCursor cs, cp, ce;
+    cs.reset();
+    cp.reset();
+    ce.reset();
+    KeyDir ks, kp, ke;
+    uint32_t kd_key = 0xFFFFFFFFu;
+    while (pipe.next(t)) {
+        if (strict) strict_adjust(t);
+        uint32_t kuni;
+        bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
+        uint32_t n_le[PV], i_pme[PV], l_idx[PV];
+        if (ok) {
+            if (kuni != kd_key) {
+                kd_key = kuni;
+                ks = load_keydir(ix.d_sstart.kd, kuni);
+                kp = load_keydir(ix.d_pme.kd, kuni);
+                ke = load_keydir(ix.d_eend.kd, kuni);
+            }
+            ok = warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, n_le);
+            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, t.full, t.s_qs, aux1, i_pme);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux2, l_idx);
+        }
+        if (ok) {
+            uint32_t pos[PV];
+            long long dd[PV];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < PV; j++) {
+                Cand b{0, 0, 0};
+                const bool found = nearest_from_ranks(ix, ks.seg_begin, ks.seg_end, n_le[j], i_pme[j], l_idx[j], t.qs[j], t.qe[j],
+                                                      include_overlaps, &b);
+                bits |= found ? (1u << j) : 0u;
+                pos[j] = found ? b.pos : 0u;
+                // distance from RAW probe coordinates (nearest.rs:367-375): undo the strict adjustment
+                const int32_t rs = strict ? wsub(t.qs[j], 1) : t.qs[j], re = strict ? wadd(t.qe[j], 1) : t.qe[j];
+                dd[j] = found ? cand_distance(rs, re, b.s, b.e) : 0ll;
+            }
+            uint4* lp = reinterpret_cast<uint4*>(left_idx + t.row0);
+            __stcs(lp, make_uint4(pos[0], pos[1], pos[2], pos[3]));
+            __stcs(lp + 1, make_uint4(pos[4], pos[5], pos[6], pos[7]));
+            valid_bytes[t.row0 >> 3] = (uint8_t)bits;  // Arrow validity bitmap, LSB first: byte r/8 holds rows r..r+7
+            if (dist) store8_i64(dist + t.row0, dd);
+        } else {
+            cs.valid = false;
+            cp.valid = false;
+            ce.valid = false;
+            todo_push(todo, t.chunk);
+        }
+        pipe.release();
+    }
+}
+
+__global__ void __launch_bounds__(TP_WTILE) nearest_k1_kernel_todo(IndexView ix, const uint32_t* __restrict__ key,
+                                                                   const int32_t* __restrict__ start,
+                                                                   const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                   int include_overlaps, int strict,
+                                                                   uint32_t* __restrict__ left_idx,
+                                                                   uint32_t* __restrict__ valid_bits,
+                                                                   int64_t* __restrict__ dist, TodoList todo) {
+    const uint32_t n_todo = *todo.count;
+    for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {  // whole 256-row chunks: warps stay converged
+        const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
+        const int32_t rs = ld_stream(start + i), re = ld_stream(end + i);
+        const uint32_t k = load_key(key, i);
+        int32_t qs = rs, qe = re;
+        if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
+        Cand b{0, 0, 0};
+        const bool found = k < ix.n_keys && nearest_one(ix, k, qs, qe, include_overlaps, &b);
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, found);
+        if ((threadIdx.x & 31) == 0) valid_bits[i >> 5] = bits;
+        st_stream(left_idx + i, found ? b.pos : 0u);
+        if (dist) st_stream(dist + i, found ? cand_distance(rs, re, b.s, b.e) : (int64_t)0);
     }
 }
 
@@ -369,9 +552,9 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k_kernel(IndexView ix, con
 // launchers
 // ---------------------------------------------------------------------------------------------------
 // persistent grid for the tiled kernels: 3 CTAs per SM (shared-memory bound), never more CTAs than tiles
-static inline unsigned tiled_grid(uint64_t rows) {
+static inline unsigned tiled_grid(uint64_t rows, int per_sm = 3) {
     uint64_t tiles = (rows + TP_TILE - 1) / TP_TILE;
-    uint64_t cap = (uint64_t)kSMs * 3;
+    uint64_t cap = (uint64_t)kSMs * per_sm;
     return (unsigned)std::max<uint64_t>(1, std::min(tiles, cap));
 }
 // to-do list of deferred chunks: stream-ordered allocation, so concurrent calls on different streams never share it
@@ -397,6 +580,15 @@ static int tiled_config(const void* fn) {
     BRG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
     return 0;
 }
+// Which probe kernels use the TMA-tiled path.  Measured on B200 (profiles/r1_notes.md): count_overlaps 0.64 ms tiled vs
+// 1.07 ms per-row; coverage 0.73 vs 0.69 and nearest 0.93 vs 0.80 -- their per-row epilogues (dependent loads of the
+// merged / candidate rows) do not yet overlap across the 8 rows a lane owns, so the per-row kernels stay the default for
+// those two until the epilogues are staged through shared memory as well.  BRG_TILED=count,coverage,nearest overrides.
+static bool tiled_enabled(const char* what, bool dflt) {
+    static const char* env = getenv("BRG_TILED");
+    if (!env) return dflt;
+    return strstr(env, what) != nullptr;
+}
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned probe_grid(uint64_t n, int per_sm) {
     // persistent-style grid: a multiple of the SM count, grid-stride over rows
@@ -410,7 +602,7 @@ int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, con
                  int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t done = 0;
-    if (aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+    if (tiled_enabled("count", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
         int rc = tiled_config((const void*)count_kernel_tiled);
         if (rc) return rc;
@@ -432,17 +624,52 @@ int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, con
 int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
                     int strict, int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
-    coverage_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, out);
-    BRG_LAUNCH_CHECK();
+    uint64_t done = 0;
+    if (tiled_enabled("coverage", false) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+        done = (n / PV) * PV;
+        int rc = tiled_config((const void*)coverage_kernel_tiled);
+        if (rc) return rc;
+        TodoList todo;
+        if ((rc = todo_alloc(done, &todo, st))) return rc;
+        coverage_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out, todo);
+        BRG_LAUNCH_CHECK();
+        coverage_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
+        BRG_LAUNCH_CHECK();
+        if ((rc = todo_free(todo, st))) return rc;
+    }
+    if (done < n) {
+        coverage_kernel<<<probe_grid(n - done, 32), PB_THREADS, 0, st>>>(ix, key ? key + done : nullptr, s + done, e + done,
+                                                                         n - done, strict, out + done);
+        BRG_LAUNCH_CHECK();
+    }
     return 0;
 }
 int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
                       int include_overlaps, int strict, uint32_t* left_idx, uint32_t* valid_bits, int64_t* dist,
                       cudaStream_t st) {
     if (n == 0) return 0;
-    nearest_k1_kernel<<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, include_overlaps, strict, left_idx,
-                                                               valid_bits, dist);
-    BRG_LAUNCH_CHECK();
+    uint64_t done = 0;
+    if (tiled_enabled("nearest", false) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(left_idx) && aligned16(dist) &&
+        n >= TP_WTILE) {
+        done = (n / TP_WTILE) * TP_WTILE;  // whole chunks only: validity words never straddle the two kernels
+        int rc = tiled_config((const void*)nearest_k1_kernel_tiled);
+        if (rc) return rc;
+        TodoList todo;
+        if ((rc = todo_alloc(done, &todo, st))) return rc;
+        nearest_k1_kernel_tiled<<<tiled_grid(done, 2), TP_THREADS, sizeof(ProbeRing), st>>>(
+            ix, key, s, e, done, include_overlaps, strict, left_idx, reinterpret_cast<uint8_t*>(valid_bits), dist, todo);
+        BRG_LAUNCH_CHECK();
+        nearest_k1_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, include_overlaps, strict, left_idx,
+                                                                     valid_bits, dist, todo);
+        BRG_LAUNCH_CHECK();
+        if ((rc = todo_free(todo, st))) return rc;
+    }
+    if (done < n) {
+        nearest_k1_kernel<<<probe_grid(n - done, 32), PB_THREADS, 0, st>>>(
+            ix, key ? key + done : nullptr, s + done, e + done, n - done, include_overlaps, strict, left_idx + done,
+            valid_bits + done / 32, dist ? dist + done : nullptr);
+        BRG_LAUNCH_CHECK();
+    }
     return 0;
 }
 int launch_nearest_k_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,

@@ -29,7 +29,7 @@ constexpr int TP_WTILE = 32 * PV;           // 256 consecutive rows per warp chu
 constexpr int TP_TILE = TP_THREADS * PV;    // rows in flight per CTA step
 constexpr int TP_STAGES = 2;
 constexpr int TP_WCAP = 256;                // window capacity per warp and array (elements)
-constexpr int TP_NWIN = 2;                  // window buffers per warp
+constexpr int TP_NWIN = 3;                  // scratch buffers per warp (one per sorted array searched)
 
 #ifdef __CUDACC__
 // ---- TMA / mbarrier primitives (inline PTX) -----------------------------------------------------------------
@@ -185,6 +185,20 @@ struct ProbePipe {
         it++;
     }
 };
+
+// strict filter: probe start+1 / end-1 (interval_tree.rs:253-256, nearest.rs:341-344); the shared copy of the columns is
+// kept in step with the registers because the inverse search reads the queries from shared memory
+__device__ __forceinline__ void strict_adjust(ProbeTile& t) {
+#pragma unroll
+    for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
+    if (t.active) {
+        int4* ps = reinterpret_cast<int4*>(t.s_qs + (threadIdx.x & 31) * PV);
+        int4* pe = reinterpret_cast<int4*>(t.s_qe + (threadIdx.x & 31) * PV);
+        ps[0] = make_int4(t.qs[0], t.qs[1], t.qs[2], t.qs[3]); ps[1] = make_int4(t.qs[4], t.qs[5], t.qs[6], t.qs[7]);
+        pe[0] = make_int4(t.qe[0], t.qe[1], t.qe[2], t.qe[3]); pe[1] = make_int4(t.qe[4], t.qe[5], t.qe[6], t.qe[7]);
+    }
+    __syncwarp();
+}
 
 // All PV keys of every lane of the warp equal one valid key?  (AND == OR over all 256 keys.)  Inactive lanes pass
 // their own neutral values via `active`.
