@@ -1,0 +1,101 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, `torch.distributed` for the rendezvous.
+
+The path shards with no data-path collective (mirrors PartitionMode::CollectLeft, interval_join.rs:396-399,466-480):
+  * the build-side index is built on rank 0 and REPLICATED: its POD header travels as a byte tensor, its single device
+    slab with one broadcast (NCCL over NVLink on GPUs);
+  * probe rows are split into contiguous row ranges, rank g gets rows [g*n/N, (g+1)*n/N);
+  * every rank produces the results of its own range; concatenating the per-rank results in rank order reproduces the
+    single-GPU row order (pairs: probe_idx is rebased by the shard's first row).
+
+Nothing here touches CUDA directly: the index object only has to offer export() -> (header bytes, slab tensor) and the
+context import_index(header bytes) -> (index, empty slab tensor), so the same code runs over gloo with CPU tensors in
+the world_size-2 tests.
+"""
+import numpy as np
+
+
+def shard_bounds(n_rows, world):
+    """[(lo, hi)] * world: contiguous, ordered, sizes differ by at most one row."""
+    n_rows, world = int(n_rows), int(world)
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    return [(g * n_rows // world, (g + 1) * n_rows // world) for g in range(world)]
+
+
+def shard_range(n_rows, rank, world):
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    return shard_bounds(n_rows, world)[rank]
+
+
+def replicate_index(ctx, index, dist, rank, world, device, src=0):
+    """Every rank returns an index equal to rank `src`'s.  `index` is only read on rank `src`."""
+    import torch
+
+    if world == 1:
+        return index
+    if rank == src:
+        header, slab = index.export()
+        hdr = torch.tensor(list(header), dtype=torch.uint8, device=device)
+        hlen = torch.tensor([hdr.numel()], dtype=torch.int64, device=device)
+    else:
+        hlen = torch.zeros(1, dtype=torch.int64, device=device)
+    dist.broadcast(hlen, src)
+    if rank != src:
+        hdr = torch.empty(int(hlen.item()), dtype=torch.uint8, device=device)
+    dist.broadcast(hdr, src)
+    if rank != src:
+        index, slab = ctx.import_index(bytes(hdr.cpu().numpy().tobytes()))
+    dist.broadcast(slab, src)
+    return index
+
+
+def gather_rows_in_order(local, dist, rank, world, device="cpu"):
+    """Concatenation of every rank's 1-D numpy array in rank order, on every rank (variable lengths)."""
+    import torch
+
+    if world == 1:
+        return local
+    local = np.ascontiguousarray(local)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    raw = np.zeros(cap * local.dtype.itemsize, np.uint8)
+    raw[: local.nbytes] = local.view(np.uint8).reshape(-1)
+    mine = torch.from_numpy(raw).to(device)
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine)
+    parts = [b.cpu().numpy()[: s * local.dtype.itemsize].view(local.dtype) for b, s in zip(bufs, sizes)]
+    return np.concatenate(parts)
+
+
+class ShardedProbe:
+    """Probe-side driver of one rank: slices the probe columns to this rank's row range and rebases row ids."""
+
+    def __init__(self, index, rank, world):
+        self.index, self.rank, self.world = index, int(rank), int(world)
+
+    def _slice(self, key, start, end):
+        lo, hi = shard_range(len(start), self.rank, self.world)
+        return lo, (None if key is None else key[lo:hi]), start[lo:hi], end[lo:hi]
+
+    def count_overlaps(self, key, start, end, strict=False):
+        _, k, s, e = self._slice(key, start, end)
+        return self.index.count_overlaps(k, s, e, strict=strict)
+
+    def coverage(self, key, start, end, strict=False):
+        _, k, s, e = self._slice(key, start, end)
+        return self.index.coverage(k, s, e, strict=strict)
+
+    def nearest_k1(self, key, start, end, include_overlaps=True, strict=False, compute_distance=True):
+        _, k, s, e = self._slice(key, start, end)
+        return self.index.nearest_k1(k, s, e, include_overlaps=include_overlaps, strict=strict,
+                                     compute_distance=compute_distance)
+
+    def overlap_pairs(self, key, start, end):
+        """(build_idx, probe_idx) of this shard with probe_idx in GLOBAL row numbering."""
+        lo, k, s, e = self._slice(key, start, end)
+        b, p = self.index.overlap_pairs(k, s, e)
+        return b, (p.astype(np.uint64) + lo).astype(np.uint32)
