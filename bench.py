@@ -324,20 +324,20 @@ def main():
         alg_bytes = n * 28 + n // 8 + int(WORKLOADS[name][1] * args.scale) * 12
         launches_per_step = 1
     else:
-        offsets = torch.empty(n + 1, dtype=torch.int64, device=device)
-        ix.pairs_count_dev(pk, ps, pe, offsets)
+        offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
+        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
         torch.cuda.synchronize()
         total = int(offsets[-1].item())
         bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
         pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
 
-        def step():
-            ix.pairs_count_dev(pk, ps, pe, offsets)
-            ix.pairs_emit_dev(pk, ps, pe, offsets, bi, pi)
+        def step():  # count -> scan -> emit
+            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
+            ix.pairs_fill_dev(pk, ps, pe, offsets, bi, pi)
 
         units_per_step = total
         alg_bytes = n * 12 + total * 8 + int(WORKLOADS[name][1] * args.scale) * 12
-        launches_per_step = 5
+        launches_per_step = 7
     for _ in range(args.warmup):
         step()
     barrier()
@@ -363,7 +363,7 @@ def main():
     kern_ms = float(np.mean(per_step_ms))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     kernel_name = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
-                   "pairs": "pairs_count_kernel+scan+pairs_emit_kernel"}[name]
+                   "pairs": "pairs_total_kernel_tiled+scan+pairs_emit_kernel_tiled"}[name]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kernel_name, name, args), "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
@@ -467,16 +467,16 @@ def quick_device_run(torch, brg, ctx, name, order, scale, device, peak, steps):
         step = lambda: ix.nearest_k1_dev(pk, ps, pe, left, bits, dd)
         units, alg = n, n * 28 + n // 8 + nb * 12
     else:
-        offsets = torch.empty(n + 1, dtype=torch.int64, device=device)
-        ix.pairs_count_dev(pk, ps, pe, offsets)
+        offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
+        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
         torch.cuda.synchronize()
         total = int(offsets[-1].item())
         bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
         pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
 
-        def step():
-            ix.pairs_count_dev(pk, ps, pe, offsets)
-            ix.pairs_emit_dev(pk, ps, pe, offsets, bi, pi)
+        def step():  # count -> scan -> emit
+            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
+            ix.pairs_fill_dev(pk, ps, pe, offsets, bi, pi)
 
         units, alg = total, n * 12 + total * 8 + nb * 12
     for _ in range(3):

@@ -19,7 +19,8 @@ ABI_SYMBOLS = [
     "brg_pinned_alloc", "brg_pinned_free", "brg_build", "brg_build_dev", "brg_index_destroy", "brg_index_rows",
     "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_count_overlaps",
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
-    "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_rows_len", "brg_rows_build_idx",
+    "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
+    "brg_pairs_fill_dev", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
 ]
 
@@ -74,6 +75,9 @@ def lib():
     L.brg_overlap_pairs.argtypes = [vp, vp, vp, vp, vp, u64, i32, u64, C.POINTER(vp), C.POINTER(u64)]
     L.brg_pairs_count_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
     L.brg_pairs_emit_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
+    L.brg_pairs_chunk_rows.restype = u32
+    L.brg_pairs_chunk_offsets_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
+    L.brg_pairs_fill_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
     L.brg_rows_len.argtypes = [vp]
     L.brg_rows_len.restype = u64
     for f in (L.brg_rows_build_idx, L.brg_rows_probe_idx, L.brg_rows_valid_bits, L.brg_rows_distance):

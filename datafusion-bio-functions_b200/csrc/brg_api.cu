@@ -12,6 +12,7 @@
 
 #include "../../include/bioranges.h"
 #include "brg_internal.cuh"
+#include "brg_tile.cuh"
 
 namespace brg {
 
@@ -70,8 +71,8 @@ struct IndexHeader {
     uint32_t magic, version;
     uint32_t n_keys, n, n_merged, flags;
     uint64_t slab_bytes;
-    uint64_t off_s_start, off_s_end, off_s_pos, off_pme, off_e_end, off_e_start, off_e_pos, off_m_first, off_m_last,
-        off_m_pre;
+    uint64_t off_s_start, off_s_end, off_s_pos, off_pme, off_e_end, off_m_first, off_m_last, off_m_pre, off_s_rec, off_e_rec,
+        off_m_rec;
     DirDesc dir[5];  // 0 s_start, 1 e_end, 2 pme, 3 m_first, 4 m_last
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
@@ -91,8 +92,8 @@ static IndexView make_view(const IndexHeader& h, void* slab) {
     v.n_keys = h.n_keys; v.n = h.n; v.n_merged = h.n_merged; v.flags = h.flags;
     v.s_start = (const int32_t*)P(h.off_s_start); v.s_end = (const int32_t*)P(h.off_s_end);
     v.s_pos = (const uint32_t*)P(h.off_s_pos); v.pme = (const int32_t*)P(h.off_pme);
-    v.e_end = (const int32_t*)P(h.off_e_end); v.e_start = (const int32_t*)P(h.off_e_start);
-    v.e_pos = (const uint32_t*)P(h.off_e_pos);
+    v.e_end = (const int32_t*)P(h.off_e_end);
+    v.s_rec = (const int4*)P(h.off_s_rec); v.e_rec = (const int4*)P(h.off_e_rec); v.m_rec = (const int4*)P(h.off_m_rec);
     v.m_first = (const int32_t*)P(h.off_m_first); v.m_last = (const int32_t*)P(h.off_m_last);
     v.m_pre = (const int32_t*)P(h.off_m_pre);
     const int32_t* arrs[5] = {v.s_start, v.e_end, v.pme, v.m_first, v.m_last};
@@ -330,7 +331,9 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->build_stream;
     want &= BRG_WANT_ALL;
     const bool full = (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0;
-    const bool need_e = (want & (BRG_WANT_COUNT | BRG_WANT_NEAREST)) != 0;
+    const bool need_soa = (want & BRG_WANT_PAIRS) != 0;     // s_end / s_pos as plain arrays (pair walk)
+    const bool need_rec = (want & BRG_WANT_NEAREST) != 0;   // s_rec / e_rec
+    const bool need_e = (want & (BRG_WANT_COUNT | BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0;  // pairs: count identity
     const bool need_pme = (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS | BRG_WANT_COVERAGE)) != 0;
     const bool need_cov = (want & BRG_WANT_COVERAGE) != 0;
 
@@ -378,6 +381,16 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     BRG_CUDA(cudaMemcpyAsync(&n_valid, off.as<uint32_t>() + n_keys, 4, cudaMemcpyDeviceToHost, st));
     BRG_CUDA(cudaStreamSynchronize(st));
 
+    // pairs: does the identity #pairs = #(start <= qe) - #(end < qs) hold (no build row with start > end)?
+    uint32_t idx_props = 0;
+    if (need_soa && n_valid) {
+        if ((rc = flag_inverted_rows((const int32_t*)S[1], (const int32_t*)S[2], n_valid, d_scalar + 8, st))) return rc;
+        uint32_t inv = 0;
+        BRG_CUDA(cudaMemcpyAsync(&inv, d_scalar + 8, 4, cudaMemcpyDeviceToHost, st));
+        BRG_CUDA(cudaStreamSynchronize(st));
+        if (inv) idx_props |= BRG_IDX_INVERTED;
+    }
+
     // prefix_max_end over the S-order (per key)
     DevBuf pme;
     if (need_pme) {
@@ -386,7 +399,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     }
 
     // merged intervals (coverage)
-    DevBuf m_first, m_last, m_key, m_pre;
+    DevBuf m_first, m_last, m_key, m_pre, m_rec;
     uint32_t n_merged = 0;
     if (need_cov) {
         if ((rc = m_first.ensure(nn * 4)) || (rc = m_last.ensure(nn * 4)) || (rc = m_key.ensure(nn * 4)) ||
@@ -402,16 +415,26 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         if ((rc = merged_width_prefix(m_first.as<int32_t>(), m_last.as<int32_t>(), n_merged, T[1], m_pre.as<int32_t>(),
                                       scan.as<uint32_t>(), st)))
             return rc;
+        if ((rc = m_rec.ensure(std::max<uint64_t>(n_merged, 1) * 16))) return rc;
+        if ((rc = pack_records(m_first.as<int32_t>(), m_last.as<int32_t>(), m_pre.as<int32_t>(), m_pre.as<int32_t>() + 1,
+                               n_merged, m_rec.as<int4>(), st)))
+            return rc;
     }
 
     // keep the S-order columns: they are consumed by the E-order sort below
-    DevBuf s_start, s_end, s_pos;
+    DevBuf s_start, s_end, s_pos, s_rec, e_rec;
     if ((rc = s_start.ensure(nn * 4))) return rc;
     BRG_CUDA(cudaMemcpyAsync(s_start.p, S[1], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
-    if (full) {
+    if (need_soa) {
         if ((rc = s_end.ensure(nn * 4)) || (rc = s_pos.ensure(nn * 4))) return rc;
         BRG_CUDA(cudaMemcpyAsync(s_end.p, S[2], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
         BRG_CUDA(cudaMemcpyAsync(s_pos.p, S[3], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (need_rec) {
+        if ((rc = s_rec.ensure(nn * 16)) || (rc = e_rec.ensure(nn * 16))) return rc;
+        if ((rc = pack_records((const int32_t*)S[1], (const int32_t*)S[2], (const int32_t*)S[3], pme.as<int32_t>(), n_valid,
+                               s_rec.as<int4>(), st)))
+            return rc;
     }
 
     // ---- E-order: (key, end, start, pos): stable sort of the S-order rows by end, then key -----------------
@@ -425,6 +448,9 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
                              scan.as<uint32_t>(), st, &res2);
         if (rc) return rc;
         E = res2 == 0 ? S : T;
+        if (need_rec && (rc = pack_records((const int32_t*)E[1], (const int32_t*)E[2], (const int32_t*)E[3], nullptr, n_valid,
+                                           e_rec.as<int4>(), st)))
+            return rc;
     }
 
     // ---- rank directories ----------------------------------------------------------------------------------
@@ -443,8 +469,8 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
 
     // ---- lay out and fill the slab -------------------------------------------------------------------------
     IndexHeader h{};
-    h.magic = kMagic; h.version = 1;
-    h.n_keys = n_keys; h.n = n_valid; h.n_merged = n_merged; h.flags = want;
+    h.magic = kMagic; h.version = 2;
+    h.n_keys = n_keys; h.n = n_valid; h.n_merged = n_merged; h.flags = want | idx_props;
     uint64_t cur = 0;
     auto place = [&](bool on, uint64_t bytes) -> uint64_t {
         if (!on) return kNone;
@@ -454,12 +480,13 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     };
     const uint64_t nv4 = (uint64_t)n_valid * 4;
     h.off_s_start = place(need_dir[0], nv4);
-    h.off_s_end = place(full, nv4);
-    h.off_s_pos = place(full, nv4);
+    h.off_s_end = place(need_soa, nv4);
+    h.off_s_pos = place(need_soa, nv4);
     h.off_pme = place(need_dir[2], nv4);
     h.off_e_end = place(need_e, nv4);
-    h.off_e_start = place(need_e && full, nv4);
-    h.off_e_pos = place(need_e && full, nv4);
+    h.off_s_rec = place(need_rec, nv4 * 4);
+    h.off_e_rec = place(need_rec, nv4 * 4);
+    h.off_m_rec = place(need_cov, (uint64_t)n_merged * 16);
     h.off_m_first = place(need_cov, (uint64_t)n_merged * 4);
     h.off_m_last = place(need_cov, (uint64_t)n_merged * 4);
     h.off_m_pre = place(need_cov, ((uint64_t)n_merged + 1) * 4);
@@ -487,11 +514,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     chk(copy_in(h.off_s_end, s_end.p, nv4));
     chk(copy_in(h.off_s_pos, s_pos.p, nv4));
     chk(copy_in(h.off_pme, pme.p, nv4));
-    if (E) {
-        chk(copy_in(h.off_e_end, E[2], nv4));
-        chk(copy_in(h.off_e_start, E[1], nv4));
-        chk(copy_in(h.off_e_pos, E[3], nv4));
-    }
+    if (E) chk(copy_in(h.off_e_end, E[2], nv4));
+    chk(copy_in(h.off_s_rec, s_rec.p, nv4 * 4));
+    chk(copy_in(h.off_e_rec, e_rec.p, nv4 * 4));
+    chk(copy_in(h.off_m_rec, m_rec.p, (uint64_t)n_merged * 16));
     chk(copy_in(h.off_m_first, m_first.p, (uint64_t)n_merged * 4));
     chk(copy_in(h.off_m_last, m_last.p, (uint64_t)n_merged * 4));
     chk(copy_in(h.off_m_pre, m_pre.p, ((uint64_t)n_merged + 1) * 4));
@@ -564,7 +590,7 @@ extern "C" BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64
     if (header_len != sizeof(IndexHeader)) { set_error("brg_index_import: header size mismatch"); return BRG_ERR_INVALID; }
     IndexHeader h;
     memcpy(&h, header, sizeof(h));
-    if (h.magic != kMagic || h.version != 1) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
+    if (h.magic != kMagic || h.version != 2) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
     BRG_CUDA(cudaSetDevice(ctx->device));
     void* slab = nullptr;
     cudaError_t e = cudaMalloc(&slab, h.slab_bytes);
@@ -616,7 +642,7 @@ static int pairs_scratch(Lane* l, uint64_t n) {
 
 extern "C" BRG_API int brg_pairs_count_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
                                    const int32_t* e, uint64_t n, uint64_t* d_offsets, void* stream) {
-    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_pairs_count");
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_count");
     if (rc) return rc;
     if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
     LaneGuard g(ctx);
@@ -633,9 +659,26 @@ extern "C" BRG_API int brg_pairs_count_dev(brg_ctx* ctx, const brg_index* ix, co
 extern "C" BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
                                   const int32_t* e, uint64_t n, const uint64_t* d_offsets, uint32_t* d_build_idx,
                                   uint32_t* d_probe_idx, void* stream) {
-    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_pairs_emit");
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_emit");
     if (rc) return rc;
     return launch_pairs_emit(ix->view, k, s, e, n, d_offsets, d_build_idx, d_probe_idx, (cudaStream_t)stream);
+}
+
+extern "C" BRG_API uint32_t brg_pairs_chunk_rows(void) { return (uint32_t)TP_WTILE; }
+extern "C" BRG_API int brg_pairs_chunk_offsets_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
+                                           const int32_t* e, uint64_t n, uint64_t* d_chunk_base, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_chunk_offsets");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (!d_chunk_base) { set_error("brg_pairs_chunk_offsets: NULL output"); return BRG_ERR_INVALID; }
+    return launch_pairs_chunk_offsets(ix->view, k, s, e, n, d_chunk_base, (cudaStream_t)stream);
+}
+extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s, const int32_t* e,
+                                  uint64_t n, const uint64_t* d_chunk_base, uint32_t* d_build_idx, uint32_t* d_probe_idx,
+                                  void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_fill");
+    if (rc) return rc;
+    return launch_pairs_fill(ix->view, k, s, e, n, d_chunk_base, d_build_idx, d_probe_idx, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -765,7 +808,7 @@ static int upload_probe(Lane* l, const uint32_t* key, const int32_t* start, cons
 extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
                                  const int32_t* end, uint64_t n, int mode, uint64_t max_rows, brg_rows** out,
                                  uint64_t* consumed) {
-    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS | BRG_WANT_NEAREST, "brg_overlap_pairs");
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_overlap_pairs");
     if (rc) return rc;
     if (!out) { set_error("brg_overlap_pairs: NULL out"); return BRG_ERR_INVALID; }
     *out = nullptr;
@@ -788,6 +831,31 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     const uint32_t* dk = key ? l->in_key[0].as<uint32_t>() : nullptr;
     const int32_t* ds = l->in_s[0].as<int32_t>();
     const int32_t* de = l->in_e[0].as<int32_t>();
+    if (mode == BRG_PAIRS_INNER && max_rows == 0) {
+        // chunked count -> scan -> emit (brg_pairs.cu): offsets per 256-row chunk, staged coalesced emission
+        const uint64_t n_chunks = pairs_chunk_count(n);
+        if ((rc = l->scratch_b.ensure((n_chunks + 1) * 8))) return fail(rc);
+        uint64_t* chunk_base = l->scratch_b.as<uint64_t>();
+        if ((rc = launch_pairs_chunk_offsets(ix->view, dk, ds, de, n, chunk_base, st))) return fail(rc);
+        uint64_t total = 0;
+        cudaError_t e = cudaMemcpyAsync(&total, chunk_base + n_chunks, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("pairs total: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+        r->len = total;
+        if ((rc = l->out0[0].ensure(std::max<uint64_t>(total, 1) * 4)) || (rc = l->out1[0].ensure(std::max<uint64_t>(total, 1) * 4)))
+            return fail(rc);
+        if ((rc = pinned_get(ctx, total * 4, &r->blk_probe)) || (rc = pinned_get(ctx, total * 4, &r->blk_build))) return fail(rc);
+        if (total) {
+            if ((rc = launch_pairs_fill(ix->view, dk, ds, de, n, chunk_base, l->out1[0].as<uint32_t>(), l->out0[0].as<uint32_t>(), st)))
+                return fail(rc);
+            e = cudaMemcpyAsync(r->blk_probe.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_build.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error(std::string("pairs D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+        }
+        *out = r;
+        return BRG_OK;
+    }
     uint32_t* counts = l->scratch_a.as<uint32_t>();
     uint64_t* offsets = l->scratch_b.as<uint64_t>();
     if ((rc = launch_pairs_count(ix->view, dk, ds, de, n, counts, st))) return fail(rc);

@@ -57,12 +57,17 @@ struct DirView {
     uint32_t shift;
 };
 
+constexpr uint32_t BRG_IDX_INVERTED = 1u << 8;  // some build row has start > end (count identity does not hold for pairs)
+
+// any row with start > end?  (sets *flag to 1)
+int flag_inverted_rows(const int32_t* start, const int32_t* end, uint64_t n, uint32_t* d_flag, cudaStream_t st);
+
 // Device view of an index (pointers into the single HBM slab)
 struct IndexView {
     uint32_t n_keys;
     uint32_t n;        // build rows with a valid key
     uint32_t n_merged; // merged (coverage) intervals
-    uint32_t flags;    // BRG_WANT_* actually built
+    uint32_t flags;    // BRG_WANT_* actually built | BRG_IDX_* properties
     // S-order: rows sorted by (key, start, end, pos)
     const int32_t* s_start;
     const int32_t* s_end;
@@ -70,12 +75,17 @@ struct IndexView {
     const int32_t* pme; // per-key inclusive running max of s_end  (nearest_index.rs:58-63)
     // E-order: rows sorted by (key, end, start, pos)
     const int32_t* e_end;
-    const int32_t* e_start;
-    const uint32_t* e_pos;
     // merged intervals per key (interval_tree.rs:52-73) + exclusive prefix of widths max(1,last-first)
     const int32_t* m_first;
     const int32_t* m_last;
     const int32_t* m_pre;
+    // 16-byte records for the epilogues (one 128-bit load per candidate instead of three or four 32-bit ones):
+    //   s_rec[i] = {start, end, pos, prefix_max_end}  in S-order      (nearest, nearest_k)
+    //   e_rec[i] = {start, end, pos, 0}               in E-order      (nearest: left neighbour)
+    //   m_rec[j] = {first, last, pre[j], pre[j+1]}    merged          (coverage)
+    const int4* s_rec;
+    const int4* e_rec;
+    const int4* m_rec;
     DirView d_sstart, d_eend, d_pme, d_mfirst, d_mlast;
 };
 
@@ -110,6 +120,9 @@ int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t 
                         int32_t* m_pre /*n_merged+1*/, uint32_t* scan_scratch, cudaStream_t st);
 // segment offsets off[0..n_keys] from a sorted key array (keys >= n_keys are the invalid tail)
 int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uint32_t* off, cudaStream_t st);
+// 16-byte records: out[i] = {a[i], b[i], c[i], d ? d[i] : 0}
+int pack_records(const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d, uint64_t n, int4* out,
+                 cudaStream_t st);
 // rank directory
 int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
                    cudaStream_t st);
@@ -135,6 +148,12 @@ int launch_pairs_count(const IndexView& ix, const uint32_t* key, const int32_t* 
                        uint32_t* counts, cudaStream_t st);
 int launch_pairs_emit(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
                       const uint64_t* offsets, uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
+// chunked pair pipeline: chunk_base[c] = first output slot of 256-row chunk c, chunk_base[n_chunks] = total
+uint64_t pairs_chunk_count(uint64_t n);
+int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                               uint64_t* chunk_base /*n_chunks + 1*/, cudaStream_t st);
+int launch_pairs_fill(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
+                      const uint64_t* chunk_base, uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
 int launch_semi_anti_flags(const uint32_t* counts, uint64_t n, int anti, uint32_t* flags, cudaStream_t st);
 int launch_compact_rows(const uint32_t* flags, const uint64_t* offsets, uint64_t n, uint32_t* probe_idx,
                         cudaStream_t st);

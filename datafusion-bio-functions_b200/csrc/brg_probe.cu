@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
     ce.reset();
     KeyDir ks, ke;
     uint32_t kd_key = 0xFFFFFFFFu;
+    uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
         uint32_t kuni;
@@ -83,8 +84,9 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             // seg_begin + #(starts <= qe)  and  seg_begin + #(ends < qs)
-            ok = warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, started);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux1, ended);
+            const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, started);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, ended);
         }
         if (ok) {
             long long cnt[PV];
@@ -92,13 +94,16 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
             for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
                 cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
             if (t.active) store8_i64(out + t.row0, cnt);
+            fails = 0;
         } else {
             // mixed keys (contig boundary, unsorted input), keys absent from the build side, or a window wider than the
             // shared buffer: hand the chunk to the per-row kernel
             cs.valid = false;
             ce.valid = false;
             todo_push(todo, t.chunk);
+            fails++;
         }
+        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -135,6 +140,9 @@ __device__ __forceinline__ int32_t cov_term(int32_t qs, int32_t qe, int32_t firs
     return ov < 1 ? 1 : ov;                // max(1, ...)
 }
 
+template <bool EARLY_OUT>
+__device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint32_t lo, uint32_t hi, int32_t qs, int32_t qe);
+
 __global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, const uint32_t* __restrict__ key,
                                                               const int32_t* __restrict__ start,
                                                               const int32_t* __restrict__ end, uint64_t n, int strict,
@@ -152,38 +160,35 @@ __global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, cons
             // (first <= qe && last >= qs, the coitrees predicate) are exactly the index range [lo, hi)
             uint32_t lo = rank_lt_kd(ix.d_mlast, kl, qs);   // first j with last_j >= qs
             uint32_t hi = rank_le_kd(ix.d_mfirst, kf, qe);  // first j with first_j > qe
-            if (lo < hi && (qs == INT32_MIN || qe == INT32_MAX)) {
-                // `start - 1` / `end + 1` wrap in the reference's release arithmetic: keep the literal per-interval sum
-                for (uint32_t j = lo; j < hi; j++)
-                    acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + j), __ldg(ix.m_last + j)));
-            } else if (lo < hi) {
-                acc = cov_term(qs, qe, __ldg(ix.m_first + lo), __ldg(ix.m_last + lo));
-                if (hi - lo > 1) {
-                    acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + hi - 1), __ldg(ix.m_last + hi - 1)));
-                    // interior intervals lie strictly inside (qs-1, qe+1): their term is max(1, last-first)
-                    acc = wadd(acc, wsub(__ldg(ix.m_pre + hi - 1), __ldg(ix.m_pre + lo + 1)));
-                }
-            }
+            acc = coverage_from_range<true>(ix, lo, hi, qs, qe);
         }
         st_stream(out + i, (int64_t)acc);  // interval_tree.rs:207
     }
 }
 
-// one row given the index range [lo, hi) of merged intervals that overlap it (interval_tree.rs:145-152)
+// one row given the index range [lo, hi) of merged intervals that overlap it (interval_tree.rs:145-152).
+// The two boundary intervals get the clipped formula, the interior ones lie strictly inside (qs-1, qe+1) so their term
+// is max(1, last-first) = a difference of the width prefix.  m_rec[j] = {first, last, pre[j], pre[j+1]}: two 128-bit
+// loads, no data-dependent branch on the common path.
+template <bool EARLY_OUT>
 __device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint32_t lo, uint32_t hi, int32_t qs, int32_t qe) {
-    int32_t acc = 0;
-    if (lo < hi && (qs == INT32_MIN || qe == INT32_MAX)) {
+    if (EARLY_OUT && lo >= hi) return 0;  // per-row kernels: most reads of a sparse target set touch nothing
+    if (qs == INT32_MIN || qe == INT32_MAX) {
         // `start - 1` / `end + 1` wrap in the reference's release arithmetic: keep the literal per-interval sum
-        for (uint32_t j = lo; j < hi; j++) acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + j), __ldg(ix.m_last + j)));
-    } else if (lo < hi) {
-        acc = cov_term(qs, qe, __ldg(ix.m_first + lo), __ldg(ix.m_last + lo));
-        if (hi - lo > 1) {
-            acc = wadd(acc, cov_term(qs, qe, __ldg(ix.m_first + hi - 1), __ldg(ix.m_last + hi - 1)));
-            // interior intervals lie strictly inside (qs-1, qe+1): their term is max(1, last-first)
-            acc = wadd(acc, wsub(__ldg(ix.m_pre + hi - 1), __ldg(ix.m_pre + lo + 1)));
+        int32_t acc = 0;
+        for (uint32_t j = lo; j < hi; j++) {
+            const int4 m = __ldg(ix.m_rec + j);
+            acc = wadd(acc, cov_term(qs, qe, m.x, m.y));
         }
+        return acc;
     }
-    return acc;
+    const uint32_t last = ix.n_merged ? ix.n_merged - 1 : 0u;
+    const int4 a = __ldg(ix.m_rec + min(lo, last));
+    const int4 b = __ldg(ix.m_rec + min(hi > 0 ? hi - 1 : 0u, last));
+    int32_t acc = cov_term(qs, qe, a.x, a.y);
+    const int32_t rest = wadd(cov_term(qs, qe, b.x, b.y), wsub(b.z, a.w));
+    acc = (hi > lo + 1) ? wadd(acc, rest) : acc;
+    return (lo < hi) ? acc : 0;
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView
     cf.reset();
     KeyDir kl, kf;
     uint32_t kd_key = 0xFFFFFFFFu;
+    uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
         uint32_t kuni;
@@ -213,19 +219,23 @@ __global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView
                 kf = load_keydir(ix.d_mfirst.kd, kuni);
             }
             // merged intervals overlapping [qs,qe] are exactly [first j with last_j >= qs, first j with first_j > qe)
-            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, t.full, t.s_qs, aux0, lo);
-            ok = ok && warp_window_ranks<false>(cf, ix.d_mfirst, kf, kuni, t.qe, t.active, t.full, t.s_qe, aux1, hi);
+            const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, lo);
+            ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, hi);
         }
         if (ok) {
             long long cov[PV];
 #pragma unroll
-            for (int j = 0; j < PV; j++) cov[j] = t.active ? (long long)coverage_from_range(ix, lo[j], hi[j], t.qs[j], t.qe[j]) : 0ll;
+            for (int j = 0; j < PV; j++) cov[j] = t.active ? (long long)coverage_from_range<false>(ix, lo[j], hi[j], t.qs[j], t.qe[j]) : 0ll;
             if (t.active) store8_i64(out + t.row0, cov);
+            fails = 0;
         } else {
             cl.valid = false;
             cf.valid = false;
             todo_push(todo, t.chunk);
+            fails++;
         }
+        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(TP_WTILE) coverage_kernel_todo(IndexView ix, c
         if (k < ix.n_keys) {
             const KeyDir kl = load_keydir(ix.d_mlast.kd, k);
             const KeyDir kf = load_keydir(ix.d_mfirst.kd, k);
-            acc = coverage_from_range(ix, rank_lt_kd(ix.d_mlast, kl, qs), rank_le_kd(ix.d_mfirst, kf, qe), qs, qe);
+            acc = coverage_from_range<true>(ix, rank_lt_kd(ix.d_mlast, kl, qs), rank_le_kd(ix.d_mfirst, kf, qe), qs, qe);
         }
         st_stream(out + i, (int64_t)acc);
     }
@@ -273,10 +283,12 @@ __device__ __forceinline__ bool cand_le(int32_t qs, int32_t qe, const Cand& a, c
     return a.pos <= b.pos;
 }
 __device__ __forceinline__ Cand load_s(const IndexView& ix, uint32_t i) {
-    return Cand{__ldg(ix.s_start + i), __ldg(ix.s_end + i), __ldg(ix.s_pos + i)};
+    const int4 r = __ldg(ix.s_rec + i);
+    return Cand{r.x, r.y, (uint32_t)r.z};
 }
 __device__ __forceinline__ Cand load_e(const IndexView& ix, uint32_t i) {
-    return Cand{__ldg(ix.e_start + i), __ldg(ix.e_end + i), __ldg(ix.e_pos + i)};
+    const int4 r = __ldg(ix.e_rec + i);
+    return Cand{r.x, r.y, (uint32_t)r.z};
 }
 
 // one probe: returns true and fills `best` when an interval is found
@@ -285,7 +297,7 @@ __device__ __forceinline__ bool nearest_one(const IndexView& ix, uint32_t c, int
     KeyDir ks = load_keydir(ix.d_sstart.kd, c);
     if (ks.seg_begin == ks.seg_end) return false;                       // is_empty (nearest_index.rs:92-94)
     const uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);              // partition_point(first <= end)
-    if (include_overlaps && !(qe < qs) && n_le > ks.seg_begin && __ldg(ix.pme + n_le - 1) >= qs) {
+    if (include_overlaps && !(qe < qs) && n_le > ks.seg_begin && __ldg(ix.s_rec + n_le - 1).w >= qs) {
         KeyDir kp = load_keydir(ix.d_pme.kd, c);                        // first_overlap_by_start (:222-234)
         uint32_t idx = rank_lt_kd(ix.d_pme, kp, qs);                    // first i with prefix_max_end[i] >= qs
         *best = load_s(ix, idx);
@@ -336,22 +348,24 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k1_kernel(IndexView ix, co
 
 // nearest_one with the three ranks already known:
 //   n_le = seg_begin + #(starts <= qe), i_pme = first i with prefix_max_end[i] >= qs, left_idx = seg_begin + #(ends < qs)
+// Branch-free: the (at most) four candidate records are loaded unconditionally from clamped indices, so the loads of the
+// PV rows a lane owns are all in flight together; the choice is made with selects.  Requires seg_begin < seg_end.
 __device__ __forceinline__ bool nearest_from_ranks(const IndexView& ix, uint32_t seg_begin, uint32_t seg_end, uint32_t n_le,
                                                    uint32_t i_pme, uint32_t left_idx, int32_t qs, int32_t qe,
                                                    int include_overlaps, Cand* best) {
-    if (seg_begin == seg_end) return false;
-    if (include_overlaps && !(qe < qs) && n_le > seg_begin && __ldg(ix.pme + n_le - 1) >= qs) {
-        *best = load_s(ix, i_pme);
-        return true;
-    }
-    const bool has_left = left_idx > seg_begin, has_right = n_le < seg_end;
-    if (!has_left && !has_right) return false;
-    Cand l, r;
-    if (has_left) l = load_e(ix, left_idx - 1);
-    if (has_right) r = load_s(ix, n_le);
-    if (has_left && has_right) *best = cand_le(qs, qe, l, r) ? l : r;
-    else *best = has_left ? l : r;
-    return true;
+    const uint32_t last = seg_end - 1;
+    const bool has_prev = n_le > seg_begin, has_left = left_idx > seg_begin, has_right = n_le < seg_end;
+    const int4 rp = __ldg(ix.s_rec + (has_prev ? n_le - 1 : seg_begin));  // .w = prefix_max_end[n_le - 1]
+    const int4 rr = __ldg(ix.s_rec + min(n_le, last));                    // right neighbour: first start > qe
+    const int4 rl = __ldg(ix.e_rec + (has_left ? left_idx - 1 : seg_begin));  // left neighbour: last end < qs
+    const int4 ro = __ldg(ix.s_rec + min(i_pme, last));                   // first_overlap_by_start (:222-234)
+    const bool ov = include_overlaps && !(qe < qs) && has_prev && rp.w >= qs;
+    const Cand l{rl.x, rl.y, (uint32_t)rl.z}, r{rr.x, rr.y, (uint32_t)rr.z};
+    const bool take_left = has_left && (!has_right || cand_le(qs, qe, l, r));
+    Cand c = take_left ? l : r;
+    if (ov) c = Cand{ro.x, ro.y, (uint32_t)ro.z};
+    *best = c;
+    return ov || has_left || has_right;
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
@@ -374,6 +388,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
     ce.reset();
     KeyDir ks, kp, ke;
     uint32_t kd_key = 0xFFFFFFFFu;
+    uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
         uint32_t kuni;
@@ -386,9 +401,10 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                 kp = load_keydir(ix.d_pme.kd, kuni);
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
-            ok = warp_window_ranks<false>(cs, ix.d_sstart, ks, kuni, t.qe, t.active, t.full, t.s_qe, aux0, n_le);
-            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, t.full, t.s_qs, aux1, i_pme);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, t.full, t.s_qs, aux2, l_idx);
+            const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);
+            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i_pme);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, l_idx);
         }
         if (ok) {
             uint32_t pos[PV];
@@ -397,7 +413,8 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
 #pragma unroll
             for (int j = 0; j < PV; j++) {
                 Cand b{0, 0, 0};
-                const bool found = nearest_from_ranks(ix, ks.seg_begin, ks.seg_end, n_le[j], i_pme[j], l_idx[j], t.qs[j], t.qe[j],
+                const bool found = ks.seg_begin != ks.seg_end &&  // is_empty (nearest_index.rs:92-94); warp-uniform
+                                   nearest_from_ranks(ix, ks.seg_begin, ks.seg_end, n_le[j], i_pme[j], l_idx[j], t.qs[j], t.qe[j],
                                                       include_overlaps, &b);
                 bits |= found ? (1u << j) : 0u;
                 pos[j] = found ? b.pos : 0u;
@@ -410,12 +427,15 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
             __stcs(lp + 1, make_uint4(pos[4], pos[5], pos[6], pos[7]));
             valid_bytes[t.row0 >> 3] = (uint8_t)bits;  // Arrow validity bitmap, LSB first: byte r/8 holds rows r..r+7
             if (dist) store8_i64(dist + t.row0, dd);
+            fails = 0;
         } else {
             cs.valid = false;
             cp.valid = false;
             ce.valid = false;
             todo_push(todo, t.chunk);
+            fails++;
         }
+        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -469,8 +489,8 @@ __device__ __forceinline__ uint32_t nearest_k_walk(const IndexView& ix, uint32_t
         KeyDir kp = load_keydir(ix.d_pme.kd, c);
         uint32_t i0 = rank_lt_kd(ix.d_pme, kp, qs);
         for (uint32_t i = i0; i < n_le && n_out < k; i++) {
-            int32_t e = __ldg(ix.s_end + i);
-            if (e >= qs) emit(Cand{__ldg(ix.s_start + i), e, __ldg(ix.s_pos + i)});
+            const int4 r = __ldg(ix.s_rec + i);
+            if (r.y >= qs) emit(Cand{r.x, r.y, (uint32_t)r.z});
         }
     }
     if (n_out == k) return n_out;
@@ -580,10 +600,9 @@ static int tiled_config(const void* fn) {
     BRG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
     return 0;
 }
-// Which probe kernels use the TMA-tiled path.  Measured on B200 (profiles/r1_notes.md): count_overlaps 0.64 ms tiled vs
-// 1.07 ms per-row; coverage 0.73 vs 0.69 and nearest 0.93 vs 0.80 -- their per-row epilogues (dependent loads of the
-// merged / candidate rows) do not yet overlap across the 8 rows a lane owns, so the per-row kernels stay the default for
-// those two until the epilogues are staged through shared memory as well.  BRG_TILED=count,coverage,nearest overrides.
+// The TMA-tiled kernels are the default for all three probes (measured on B200, bench extras: count 0.64 ms tiled vs
+// 1.07 ms per-row; coverage 0.68 vs 0.69; nearest 0.72 vs 0.79).  BRG_TILED=<list> restricts the tiled path to the
+// named probes (e.g. BRG_TILED=none runs everything on the per-row kernels) -- a debugging switch.
 static bool tiled_enabled(const char* what, bool dflt) {
     static const char* env = getenv("BRG_TILED");
     if (!env) return dflt;
@@ -625,7 +644,7 @@ int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, 
                     int strict, int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t done = 0;
-    if (tiled_enabled("coverage", false) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+    if (tiled_enabled("coverage", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
         int rc = tiled_config((const void*)coverage_kernel_tiled);
         if (rc) return rc;
@@ -649,7 +668,7 @@ int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s
                       cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t done = 0;
-    if (tiled_enabled("nearest", false) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(left_idx) && aligned16(dist) &&
+    if (tiled_enabled("nearest", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(left_idx) && aligned16(dist) &&
         n >= TP_WTILE) {
         done = (n / TP_WTILE) * TP_WTILE;  // whole chunks only: validity words never straddle the two kernels
         int rc = tiled_config((const void*)nearest_k1_kernel_tiled);

@@ -294,6 +294,35 @@ __global__ void segment_offsets_kernel(const uint32_t* __restrict__ key, uint64_
     int64_t kcur = (i == n) ? (int64_t)n_keys : (int64_t)min(key[i], n_keys);
     for (int64_t c = kprev + 1; c <= kcur; c++) off[c] = (uint32_t)i;
 }
+__global__ void flag_inverted_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint64_t n,
+                                     uint32_t* __restrict__ flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && s[i] > e[i];
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+int flag_inverted_rows(const int32_t* start, const int32_t* end, uint64_t n, uint32_t* d_flag, cudaStream_t st) {
+    BRG_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), st));
+    if (n == 0) return 0;
+    flag_inverted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(start, end, n, d_flag);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void pack_records_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                                    const int32_t* __restrict__ c, const int32_t* __restrict__ d, uint64_t n,
+                                    int4* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_int4(a[i], b[i], c[i], d ? d[i] : 0);
+}
+int pack_records(const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d, uint64_t n, int4* out,
+                 cudaStream_t st) {
+    if (n == 0) return 0;
+    pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, c, d, n, out);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
 int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uint32_t* off, cudaStream_t st) {
     segment_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(sorted_key, n, n_keys, off);
     BRG_LAUNCH_CHECK();

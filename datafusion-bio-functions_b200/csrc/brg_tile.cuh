@@ -28,8 +28,11 @@ constexpr int PV = 8;                       // consecutive probe rows per thread
 constexpr int TP_WTILE = 32 * PV;           // 256 consecutive rows per warp chunk
 constexpr int TP_TILE = TP_THREADS * PV;    // rows in flight per CTA step
 constexpr int TP_STAGES = 2;
-constexpr int TP_WCAP = 256;                // window capacity per warp and array (elements)
+constexpr int TP_WCAP = 256;                // words of per-array scratch (histogram bins / window copy of the fallback)
+constexpr int TP_WMAX = 1024;               // widest window the inverse search walks before the chunk is deferred
+constexpr int TP_SCAN_MAX = 12;             // forward-scan steps before a row falls back to the rank directory
 constexpr int TP_NWIN = 3;                  // scratch buffers per warp (one per sorted array searched)
+constexpr uint32_t TP_BAIL = 8;             // consecutive deferred chunks after which a warp stops trying windows
 
 #ifdef __CUDACC__
 // ---- TMA / mbarrier primitives (inline PTX) -----------------------------------------------------------------
@@ -66,6 +69,16 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
+}
+
+// Chunks the tiled kernels cannot serve from a window (mixed keys, unsorted rows) are appended to a to-do list and
+// answered afterwards by a one-row-per-thread kernel that searches the rank directory at full occupancy.
+struct TodoList {
+    uint32_t* count;
+    uint32_t* chunks;
+};
+__device__ __forceinline__ void todo_push(const TodoList& td, uint64_t chunk) {
+    if ((threadIdx.x & 31) == 0) td.chunks[atomicAdd(td.count, 1u)] = (uint32_t)chunk;
 }
 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------
@@ -120,12 +133,16 @@ struct ProbePipe {
         if (key) tma_load_1d(ring->key[s], key + row, bytes, &ring->full[s], policy);
     }
 
-    __device__ __forceinline__ ProbePipe(ProbeRing* r, const uint32_t* k, const int32_t* s, const int32_t* e,
+    __device__ __forceinline__ ProbePipe(ProbeRing* r, const uint32_t* k, const int32_t* s, const int32_t* e, uint64_t rows)
+        : ProbePipe(r->w, k, s, e, rows) {}
+    // rings: one WarpRing per warp of the CTA (any CTA size)
+    __device__ __forceinline__ ProbePipe(WarpRing* rings, const uint32_t* k, const int32_t* s, const int32_t* e,
                                          uint64_t rows)
-        : ring(&r->w[threadIdx.x >> 5]), key(k), start(s), end(e), n_rows(rows), it(0) {
+        : ring(&rings[threadIdx.x >> 5]), key(k), start(s), end(e), n_rows(rows), it(0) {
         const uint64_t n_chunks = (rows + TP_WTILE - 1) / TP_WTILE;
-        const uint64_t n_warps = (uint64_t)gridDim.x * TP_WARPS;
-        const uint64_t wid = (uint64_t)blockIdx.x * TP_WARPS + (threadIdx.x >> 5);
+        const uint64_t cta_warps = blockDim.x >> 5;
+        const uint64_t n_warps = (uint64_t)gridDim.x * cta_warps;
+        const uint64_t wid = (uint64_t)blockIdx.x * cta_warps + (threadIdx.x >> 5);
         const uint64_t q = n_chunks / n_warps, rem = n_chunks % n_warps;
         chunk_begin = wid * q + min(wid, rem);
         chunk_end = chunk_begin + q + (wid < rem ? 1 : 0);
@@ -184,6 +201,24 @@ struct ProbePipe {
         if ((threadIdx.x & 31) == 0) issue(it + TP_STAGES);
         it++;
     }
+    // Give up on the windowed search (the input is evidently not coordinate-sorted): hand every remaining chunk of this
+    // warp to the per-row kernel.  Call instead of release().  The bulk copies already in flight must land before the
+    // CTA may exit, so their barriers are still waited for.
+    __device__ __forceinline__ void bail_out(const TodoList& td) {
+        __syncwarp();
+        for (uint64_t i = 1; i < (uint64_t)TP_STAGES && chunk_begin + it + i < chunk_end; i++)
+            mbar_wait(&ring->full[(it + i) % TP_STAGES], (uint32_t)(((it + i) / TP_STAGES) & 1));
+        const uint64_t first = chunk_begin + it + 1;
+        if (first < chunk_end) {
+            const uint32_t n_left = (uint32_t)(chunk_end - first);
+            const int lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(td.count, n_left);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            for (uint32_t i = lane; i < n_left; i += 32) td.chunks[base + i] = (uint32_t)(first + i);
+        }
+        it = chunk_end - chunk_begin;
+    }
 };
 
 // strict filter: probe start+1 / end-1 (interval_tree.rs:253-256, nearest.rs:341-344); the shared copy of the columns is
@@ -231,21 +266,22 @@ struct WarpCursor {
 // unspecified ranks.  Returns false when the chunk's window does not fit the shared buffer (the caller defers the chunk
 // to the per-row kernel).  Q = the chunk's 256 query values in shared memory (same values as q, row-major), only read
 // when `full`.  aux = this warp's 256-word scratch for this array.
+// are the chunk's 256 query values non-decreasing in row order?  (only full chunks qualify)
+__device__ __forceinline__ bool chunk_mono(const int32_t (&q)[PV], bool full) {
+    if (!full) return false;
+    bool up = true;
+#pragma unroll
+    for (int j = 1; j < PV; j++) up &= q[j] >= q[j - 1];
+    const int32_t prev_last = __shfl_up_sync(0xFFFFFFFFu, q[PV - 1], 1);
+    up &= ((threadIdx.x & 31) == 0) | (q[0] >= prev_last);
+    return __all_sync(0xFFFFFFFFu, up);
+}
+
 template <bool LT>
 __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
-                                                  const int32_t (&q)[PV], bool active, bool full, const int32_t* Q,
+                                                  const int32_t (&q)[PV], bool active, bool mono, const int32_t* Q,
                                                   uint32_t* aux, uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
-    // ---- are the chunk's queries non-decreasing? -------------------------------------------------------------------
-    bool mono = full;
-    if (full) {
-        bool up = true;
-#pragma unroll
-        for (int j = 1; j < PV; j++) up &= q[j] >= q[j - 1];
-        const int32_t prev_last = __shfl_up_sync(0xFFFFFFFFu, q[PV - 1], 1);
-        up &= (lane == 0) | (q[0] >= prev_last);
-        mono = __all_sync(0xFFFFFFFFu, up);
-    }
     int32_t mn, mx;
     if (mono) {
         mn = __shfl_sync(0xFFFFFFFFu, q[0], 0);
@@ -275,7 +311,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
         uint32_t wn = 0;
         bool open = true;
 #pragma unroll 1
-        for (uint32_t base = 0; open && base < (uint32_t)TP_WCAP; base += 32) {
+        for (uint32_t base = 0; open && base < (uint32_t)TP_WMAX; base += 32) {
             const uint32_t idx = lo + base + lane;
             int32_t v;
             if (reuse && base == 0) v = cur.pre;  // loaded while the previous chunk was being finished
@@ -354,14 +390,41 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
     return false;
 }
 
-// Chunks the tiled kernels cannot serve from a window (mixed keys, unsorted rows) are appended to a to-do list and
-// answered afterwards by a one-row-per-thread kernel that searches the rank directory at full occupancy.
-struct TodoList {
-    uint32_t* count;
-    uint32_t* chunks;
-};
-__device__ __forceinline__ void todo_push(const TodoList& td, uint64_t chunk) {
-    if ((threadIdx.x & 31) == 0) td.chunks[atomicAdd(td.count, 1u)] = (uint32_t)chunk;
+
+// r[j] = seg_begin + #(A <= qe[j]) for a chunk of a START-sorted probe table.  Interval ends are only sorted when all
+// probes have the same length, so when qe is not monotone the inverse search runs on the (sorted) starts instead --
+// r0 = #(A <= qs) -- and every row then walks forward over the few elements in (qs, qe]: their number is the number of
+// build values inside the probe interval, a handful.  Rows that need more than TP_SCAN_MAX steps, and degenerate rows
+// (qe < qs), ask the rank directory.  Same contract as warp_window_ranks.
+__device__ __forceinline__ bool warp_ranks_le_end(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+                                                  const int32_t (&qs)[PV], const int32_t (&qe)[PV], bool active, bool mono_s,
+                                                  bool mono_e, const int32_t* Qs, const int32_t* Qe, uint32_t* aux,
+                                                  uint32_t (&r)[PV]) {
+    if (mono_e || !mono_s) return warp_window_ranks<false>(cur, d, k, kid, qe, active, mono_e, Qe, aux, r);
+    if (!warp_window_ranks<false>(cur, d, k, kid, qs, active, true, Qs, aux, r)) return false;
+    uint32_t live = (1u << PV) - 1u;
+#pragma unroll
+    for (int j = 0; j < PV; j++)
+        if (qe[j] < qs[j]) { r[j] = rank_le_kd(d, k, qe[j]); live &= ~(1u << j); }
+#pragma unroll 1
+    for (int t = 0; t < TP_SCAN_MAX; t++) {
+        if (!__any_sync(0xFFFFFFFFu, live != 0)) break;
+#pragma unroll
+        for (int j = 0; j < PV; j++) {
+            const bool on = (live >> j) & 1u;
+            const bool in = on && r[j] < k.seg_end;
+            const int32_t v = in ? __ldg(d.A + r[j]) : INT32_MAX;
+            const bool adv = in && v <= qe[j];
+            r[j] += adv ? 1u : 0u;
+            if (!adv) live &= ~(1u << j);
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, live != 0)) {
+#pragma unroll
+        for (int j = 0; j < PV; j++)
+            if ((live >> j) & 1u) r[j] = rank_le_kd(d, k, qe[j]);
+    }
+    return true;
 }
 #endif
 

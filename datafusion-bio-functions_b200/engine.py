@@ -225,6 +225,21 @@ class Index:
         A.check(A.lib().brg_pairs_emit_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
                                            _tptr(offsets), _tptr(build_idx), _tptr(probe_idx), st))
 
+    def pairs_chunk_offsets_dev(self, key, start, end, chunk_base):
+        """chunk_base: int64[ceil(n/256)+1]; [c] = first output slot of 256-row chunk c, [-1] = total pairs"""
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_pairs_chunk_offsets_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                                    _tptr(chunk_base), st))
+
+    def pairs_fill_dev(self, key, start, end, chunk_base, build_idx, probe_idx):
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_pairs_fill_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
+                                           _tptr(chunk_base), _tptr(build_idx), _tptr(probe_idx), st))
+
 
 _default = {}
 

@@ -1,5 +1,7 @@
 """GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI (host-buffer entry points, as the
 Rust host would call them) and is compared bit-exactly with the CPU oracle and with the reference's golden vectors."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -80,6 +82,47 @@ def test_gpu_vs_oracle_random(ctx, seed):
     bk, bs, be = _rand(rng, nb, nk, -span if seed % 2 else 0, span, maxlen)
     pk, ps, pe = _rand(rng, 20000, nk, -span if seed % 2 else 0, span, int(rng.choice([1, 200, 3000])), absent_frac=0.05)
     _compare_all(ctx, bk, bs, be, pk, ps, pe, nk)
+
+
+def _sorted_probes(rng, n, nk, span, len_lo, len_hi, absent_runs=False, block=None):
+    """coordinate-sorted probe table (by key, then start); ends are NOT sorted unless len_lo == len_hi"""
+    k = rng.integers(0, nk, n).astype(np.uint32)
+    s = rng.integers(0, span, n).astype(np.int64)
+    e = s + rng.integers(len_lo, len_hi + 1, n)
+    if block:  # sorted inside blocks of `block` rows only (e.g. concatenated sorted partitions)
+        o = np.concatenate([b0 + np.lexsort((s[b0:b0 + block], k[b0:b0 + block])) for b0 in range(0, n, block)])
+    else:
+        o = np.lexsort((s, k))
+    k, s, e = k[o], s[o], e[o]
+    if absent_runs:  # a few runs of rows whose key is not on the build side
+        for b0 in rng.integers(0, max(1, n - 700), 5):
+            k[b0:b0 + int(rng.integers(1, 700))] = O.ABSENT
+    return k, s.astype(np.int32), np.clip(e, -2**31, 2**31 - 1).astype(np.int32)
+
+
+SORTED_REGIMES = {
+    # name: (n_build, n_probe, n_keys, span, build_len, probe_len_lo, probe_len_hi, kwargs)
+    "fixed_len_sparse_build": (3_000, 70_003, 3, 2_000_000, 400, 150, 150, {}),
+    "variable_len": (40_000, 50_001, 4, 3_000_000, 900, 1, 1500, {}),
+    "build_denser_than_probes": (200_000, 20_000, 2, 1_000_000, 60, 1, 300, {}),
+    "build_much_denser": (400_000, 4_099, 1, 400_000, 30, 1, 100, {}),
+    "long_probes": (60_000, 30_000, 2, 2_000_000, 200, 1, 60_000, {}),
+    "absent_key_runs": (30_000, 40_000, 5, 1_000_000, 500, 10, 800, {"absent_runs": True}),
+    "sorted_blocks": (30_000, 48_000, 3, 1_000_000, 500, 10, 800, {"block": 6000}),
+    "many_keys_short_runs": (20_000, 30_000, 300, 100_000, 300, 1, 500, {}),
+    "tiny": (50, 300, 2, 10_000, 100, 1, 300, {}),
+}
+
+
+@pytest.mark.parametrize("regime", list(SORTED_REGIMES), ids=list(SORTED_REGIMES))
+def test_gpu_sorted_probe_regimes(ctx, regime):
+    """the TMA-tiled fast paths: start-sorted probe tables in the regimes that select different search strategies
+    (inverse search on ends / on starts + forward scan / wide windows / deferred chunks)"""
+    nb, npb, nk, span, blen, pl0, pl1, kw = SORTED_REGIMES[regime]
+    rng = np.random.default_rng(zlib.crc32(regime.encode()))
+    bk, bs, be = _rand(rng, nb, nk, 0, span, blen)
+    pk, ps, pe = _sorted_probes(rng, npb, nk, span, pl0, pl1, **kw)
+    _compare_all(ctx, bk, bs, be, pk, ps, pe, nk, ks=(3,))
 
 
 def test_gpu_edge_cases(ctx):
@@ -209,6 +252,28 @@ def test_gpu_large_scale_properties(ctx):
     b64, p64 = bi.long(), pi.long()
     assert bool(((bk[b64] == pk[p64]) & (bs[b64] <= pe[p64]) & (be[b64] >= ps[p64])).all())
     assert bool((p64[1:] >= p64[:-1]).all())  # probe-major
+    # (5) the chunked pipeline (256-row chunk offsets, staged emission) produces the same pairs in the same order,
+    #     on unsorted probes (all chunks deferred) and on coordinate-sorted probes (tiled kernels)
+    for sort_first in (False, True):
+        if sort_first:
+            o = torch.argsort(pk.long() * (1 << 32) + ps.long())
+            qk, qs, qe = pk[o].contiguous(), ps[o].contiguous(), pe[o].contiguous()
+            ix.pairs_count_dev(qk, qs, qe, offsets)
+            ix.pairs_emit_dev(qk, qs, qe, offsets, bi, pi)
+            torch.cuda.synchronize()
+            assert int(offsets[-1].item()) == total_pairs
+        else:
+            qk, qs, qe = pk, ps, pe
+        cb = torch.empty((npb + 255) // 256 + 1, dtype=torch.int64, device="cuda")
+        ix.pairs_chunk_offsets_dev(qk, qs, qe, cb)
+        torch.cuda.synchronize()
+        assert int(cb[-1].item()) == total_pairs
+        assert torch.equal(cb[:-1], offsets[:-1:256])
+        bi2 = torch.full((total_pairs,), -1, dtype=torch.int32, device="cuda")
+        pi2 = torch.full((total_pairs,), -1, dtype=torch.int32, device="cuda")
+        ix.pairs_fill_dev(qk, qs, qe, cb, bi2, pi2)
+        torch.cuda.synchronize()
+        assert torch.equal(bi2, bi) and torch.equal(pi2, pi)
 
 
 def test_gpu_index_export_import_roundtrip(ctx):
