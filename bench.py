@@ -325,15 +325,16 @@ def main():
         launches_per_step = 1
     else:
         offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
-        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
+        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
+        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
         torch.cuda.synchronize()
         total = int(offsets[-1].item())
         bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
         pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
 
         def step():  # count -> scan -> emit
-            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
-            ix.pairs_fill_dev(pk, ps, pe, offsets, bi, pi)
+            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
+            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
 
         units_per_step = total
         alg_bytes = n * 12 + total * 8 + int(WORKLOADS[name][1] * args.scale) * 12
@@ -363,7 +364,7 @@ def main():
     kern_ms = float(np.mean(per_step_ms))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     kernel_name = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
-                   "pairs": "pairs_total_kernel_tiled+scan+pairs_emit_kernel_tiled"}[name]
+                   "pairs": "pairs_ranges_kernel_tiled+scan+pairs_emit_kernel_flat"}[name]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kernel_name, name, args), "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
@@ -468,15 +469,16 @@ def quick_device_run(torch, brg, ctx, name, order, scale, device, peak, steps):
         units, alg = n, n * 28 + n // 8 + nb * 12
     else:
         offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
-        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
+        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
+        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
         torch.cuda.synchronize()
         total = int(offsets[-1].item())
         bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
         pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
 
         def step():  # count -> scan -> emit
-            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets)
-            ix.pairs_fill_dev(pk, ps, pe, offsets, bi, pi)
+            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
+            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
 
         units, alg = total, n * 12 + total * 8 + nb * 12
     for _ in range(3):

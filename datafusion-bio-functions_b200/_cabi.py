@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbioranges.so")
+LIB_PATH = os.environ.get("BRG_LIB") or os.path.join(_HERE, "libbioranges.so")  # BRG_LIB: developer switch (kernel variants)
 KEY_ABSENT = 0xFFFFFFFF
 
 WANT_COUNT, WANT_COVERAGE, WANT_NEAREST, WANT_PAIRS, WANT_ALL = 1, 2, 4, 8, 15
@@ -76,8 +76,8 @@ def lib():
     L.brg_pairs_count_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
     L.brg_pairs_emit_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
     L.brg_pairs_chunk_rows.restype = u32
-    L.brg_pairs_chunk_offsets_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp]
-    L.brg_pairs_fill_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
+    L.brg_pairs_chunk_offsets_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp]
+    L.brg_pairs_fill_dev.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp]
     L.brg_rows_len.argtypes = [vp]
     L.brg_rows_len.restype = u64
     for f in (L.brg_rows_build_idx, L.brg_rows_probe_idx, L.brg_rows_valid_bits, L.brg_rows_distance):

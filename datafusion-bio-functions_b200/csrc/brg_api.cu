@@ -666,19 +666,20 @@ extern "C" BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* ix, con
 
 extern "C" BRG_API uint32_t brg_pairs_chunk_rows(void) { return (uint32_t)TP_WTILE; }
 extern "C" BRG_API int brg_pairs_chunk_offsets_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
-                                           const int32_t* e, uint64_t n, uint64_t* d_chunk_base, void* stream) {
+                                           const int32_t* e, uint64_t n, uint64_t* d_chunk_base, uint64_t* d_row_ranges,
+                                           void* stream) {
     int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_chunk_offsets");
     if (rc) return rc;
     if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
-    if (!d_chunk_base) { set_error("brg_pairs_chunk_offsets: NULL output"); return BRG_ERR_INVALID; }
-    return launch_pairs_chunk_offsets(ix->view, k, s, e, n, d_chunk_base, (cudaStream_t)stream);
+    if (!d_chunk_base || (n && !d_row_ranges)) { set_error("brg_pairs_chunk_offsets: NULL output"); return BRG_ERR_INVALID; }
+    return launch_pairs_chunk_offsets(ix->view, k, s, e, n, d_chunk_base, d_row_ranges, (cudaStream_t)stream);
 }
-extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s, const int32_t* e,
-                                  uint64_t n, const uint64_t* d_chunk_base, uint32_t* d_build_idx, uint32_t* d_probe_idx,
-                                  void* stream) {
+extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, const int32_t* s, uint64_t n,
+                                  const uint64_t* d_chunk_base, const uint64_t* d_row_ranges, uint32_t* d_build_idx,
+                                  uint32_t* d_probe_idx, void* stream) {
     int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_fill");
     if (rc) return rc;
-    return launch_pairs_fill(ix->view, k, s, e, n, d_chunk_base, d_build_idx, d_probe_idx, (cudaStream_t)stream);
+    return launch_pairs_fill(ix->view, s, n, d_chunk_base, d_row_ranges, d_build_idx, d_probe_idx, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -834,9 +835,10 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     if (mode == BRG_PAIRS_INNER && max_rows == 0) {
         // chunked count -> scan -> emit (brg_pairs.cu): offsets per 256-row chunk, staged coalesced emission
         const uint64_t n_chunks = pairs_chunk_count(n);
-        if ((rc = l->scratch_b.ensure((n_chunks + 1) * 8))) return fail(rc);
+        if ((rc = l->scratch_b.ensure((n_chunks + 1) * 8)) || (rc = l->scratch_a.ensure(n * 8))) return fail(rc);
         uint64_t* chunk_base = l->scratch_b.as<uint64_t>();
-        if ((rc = launch_pairs_chunk_offsets(ix->view, dk, ds, de, n, chunk_base, st))) return fail(rc);
+        uint64_t* row_rng = l->scratch_a.as<uint64_t>();
+        if ((rc = launch_pairs_chunk_offsets(ix->view, dk, ds, de, n, chunk_base, row_rng, st))) return fail(rc);
         uint64_t total = 0;
         cudaError_t e = cudaMemcpyAsync(&total, chunk_base + n_chunks, 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -846,7 +848,7 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
             return fail(rc);
         if ((rc = pinned_get(ctx, total * 4, &r->blk_probe)) || (rc = pinned_get(ctx, total * 4, &r->blk_build))) return fail(rc);
         if (total) {
-            if ((rc = launch_pairs_fill(ix->view, dk, ds, de, n, chunk_base, l->out1[0].as<uint32_t>(), l->out0[0].as<uint32_t>(), st)))
+            if ((rc = launch_pairs_fill(ix->view, ds, n, chunk_base, row_rng, l->out1[0].as<uint32_t>(), l->out0[0].as<uint32_t>(), st)))
                 return fail(rc);
             e = cudaMemcpyAsync(r->blk_probe.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_build.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);

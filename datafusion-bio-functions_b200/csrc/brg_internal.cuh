@@ -151,9 +151,9 @@ int launch_pairs_emit(const IndexView& ix, const uint32_t* key, const int32_t* s
 // chunked pair pipeline: chunk_base[c] = first output slot of 256-row chunk c, chunk_base[n_chunks] = total
 uint64_t pairs_chunk_count(uint64_t n);
 int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
-                               uint64_t* chunk_base /*n_chunks + 1*/, cudaStream_t st);
-int launch_pairs_fill(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
-                      const uint64_t* chunk_base, uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
+                               uint64_t* chunk_base /*n_chunks + 1*/, uint64_t* row_rng /*n*/, cudaStream_t st);
+int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const uint64_t* chunk_base, const uint64_t* row_rng,
+                      uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
 int launch_semi_anti_flags(const uint32_t* counts, uint64_t n, int anti, uint32_t* flags, cudaStream_t st);
 int launch_compact_rows(const uint32_t* flags, const uint64_t* offsets, uint64_t n, uint32_t* probe_idx,
                         cudaStream_t st);

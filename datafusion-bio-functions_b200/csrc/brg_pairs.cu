@@ -78,103 +78,80 @@ __global__ void __launch_bounds__(PR_THREADS) pairs_emit_kernel(IndexView ix, co
 // ---------------------------------------------------------------------------------------------------
 // Chunked pair pipeline (the fast path of BRG_PAIRS_INNER): the unit of the count -> scan -> emit scheme is a
 // 256-row probe chunk, not a row.
-//   pass 1  pairs_total_kernel_tiled : per chunk, sum of  #(start <= qe) - #(end < qs)  (the count_overlaps identity,
-//           exact for build rows with start <= end and probes with qs <= qe; other rows walk their candidate range)
+//   pass 1  pairs_ranges_kernel_tiled : per row, the candidate range [i0, n_le) of the start-sorted build rows
+//           (i0 = first row whose prefix_max_end >= qs, n_le = #(start <= qe)), written as one u64 per row; per chunk,
+//           the number of pairs = sum of  #(start <= qe) - #(end < qs)  (the count_overlaps identity, exact for build
+//           rows with start <= end and probes with qs <= qe; other rows count by walking their range).
+//           Probe columns arrive through the per-warp TMA rings of brg_tile.cuh, all ranks of a chunk come from
+//           inverse searches keyed on the (sorted) probe starts.  Chunks that do not fit the pattern go to a
+//           one-row-per-thread kernel through the to-do list.
 //   scan    exclusive scan of the n/256 chunk totals (tiny)
-//   pass 2  pairs_emit_kernel_tiled  : recomputes the per-row counts of the chunk, prefix-sums them inside the warp,
-//           walks each row's candidate range [first prefix_max_end >= qs, #(start <= qe)) and STAGES the matches in
-//           shared memory so that the chunk leaves the SM as full, coalesced runs of build_idx / probe_idx
-//           (per-row direct stores touch every 32 B sector up to eight times -- the old emit kernel's limit).
-// Both passes read the probe columns through the per-warp TMA rings of brg_tile.cuh and find all ranks of a chunk with
-// inverse searches keyed on the (sorted) probe starts.  Chunks that do not fit the pattern go to one-row-per-thread
-// kernels through the to-do list; a chunk is always handled by exactly one of the two in each pass.
+//   pass 2  pairs_emit_kernel_flat : no searching.  A warp FLATTENS the candidate slots of its chunk (row-major, so the
+//           output stays probe-major): a byte map slot -> row is built with one scattered store per row and a packed
+//           prefix-max; then 32 slots are tested per step (`end >= qs`), compacted with a ballot and written as one
+//           contiguous run of build_idx / probe_idx.  No lane ever walks a range alone, so skewed rows cost nothing
+//           extra and the stores of a step are adjacent (the per-row emit kernel touched every 32 B sector up to eight
+//           times).
 // ---------------------------------------------------------------------------------------------------
-constexpr int PT_THREADS = 128;  // emit pass: 4 warps per CTA, 3 CTAs per SM (shared-memory bound)
-constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_CAP = 1536;     // staged output slots per warp and round
-struct __align__(16) PairStage {
-    uint32_t b[PT_CAP];  // build row ids
-    uint8_t p[PT_CAP];   // probe row within the chunk
-};
-struct __align__(128) PairSmem {
-    WarpRing w[PT_WARPS];
-    PairStage st[PT_WARPS];
-};
-
-// matches of one probe inside its candidate range (degenerate probes / generic fallback)
 __device__ __forceinline__ uint32_t walk_count(const IndexView& ix, uint32_t i0, uint32_t i1, int32_t qs) {
     uint32_t c = 0;
     for (uint32_t i = i0; i < i1; i++) c += (__ldg(ix.s_end + i) >= qs) ? 1u : 0u;
     return c;
 }
 
-// ranks of one full chunk; false = defer the chunk
-struct PairCursors {
-    WarpCursor cs, cp, ce;
-    KeyDir ks, kp, ke;
-    uint32_t kd_key;
-    __device__ __forceinline__ void reset() { cs.reset(); cp.reset(); ce.reset(); kd_key = 0xFFFFFFFFu; }
-    __device__ __forceinline__ void invalidate() { cs.valid = false; cp.valid = false; ce.valid = false; }
-};
-
-template <bool NEED_I0>
-__device__ __forceinline__ bool pair_chunk_ranks(const IndexView& ix, PairCursors& pc, const ProbeTile& t, uint32_t* aux0,
-                                                 uint32_t* aux1, uint32_t* aux2, uint32_t (&n_le)[PV], uint32_t (&i0)[PV],
-                                                 uint32_t (&cnt)[PV]) {
-    uint32_t kuni;
-    if (!warp_uniform_key(t.key, t.active, ix.n_keys, &kuni)) return false;
-    if (kuni != pc.kd_key) {
-        pc.kd_key = kuni;
-        pc.ks = load_keydir(ix.d_sstart.kd, kuni);
-        pc.kp = load_keydir(ix.d_pme.kd, kuni);
-        pc.ke = load_keydir(ix.d_eend.kd, kuni);
-    }
-    const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-    uint32_t ended[PV];
-    if (!warp_ranks_le_end(pc.cs, ix.d_sstart, pc.ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le))
-        return false;
-    if (!warp_window_ranks<true>(pc.ce, ix.d_eend, pc.ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, ended)) return false;
-    bool degenerate = false;
-#pragma unroll
-    for (int j = 0; j < PV; j++) degenerate |= t.qe[j] < t.qs[j];
-    const bool any_deg = __any_sync(0xFFFFFFFFu, degenerate);
-    if (NEED_I0 || any_deg) {
-        if (!warp_window_ranks<true>(pc.cp, ix.d_pme, pc.kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, i0)) return false;
-    }
-#pragma unroll
-    for (int j = 0; j < PV; j++) {
-        // start <= end on the build side (checked at build time): every row that ends before qs also starts before qe
-        cnt[j] = n_le[j] - ended[j];
-        if (t.qe[j] < t.qs[j]) cnt[j] = (i0[j] < n_le[j]) ? walk_count(ix, i0[j], n_le[j], t.qs[j]) : 0u;  // unguarded closed predicate
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(TP_THREADS, 2) pairs_total_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
-                                                                          const int32_t* __restrict__ start,
-                                                                          const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                          uint32_t* __restrict__ chunk_tot, TodoList todo) {
+__global__ void __launch_bounds__(TP_THREADS, 2) pairs_ranges_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                           const int32_t* __restrict__ start,
+                                                                           const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                           uint64_t* __restrict__ row_rng,
+                                                                           uint32_t* __restrict__ chunk_tot, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
     ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256: every chunk is full
     ProbeTile t;
-    PairCursors pc;
-    pc.reset();
+    WarpCursor cs, cp, ce;
+    cs.reset(); cp.reset(); ce.reset();
+    KeyDir ks, kp, ke;
+    uint32_t kd_key = 0xFFFFFFFFu;
     uint32_t fails = 0;
     while (pipe.next(t)) {
-        uint32_t n_le[PV], i0[PV], cnt[PV];
-        if (pair_chunk_ranks<false>(ix, pc, t, aux0, aux1, aux2, n_le, i0, cnt)) {
+        uint32_t kuni;
+        bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
+        uint32_t n_le[PV], i0[PV], ended[PV];
+        if (ok) {
+            if (kuni != kd_key) {
+                kd_key = kuni;
+                ks = load_keydir(ix.d_sstart.kd, kuni);
+                kp = load_keydir(ix.d_pme.kd, kuni);
+                ke = load_keydir(ix.d_eend.kd, kuni);
+            }
+            const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, n_le);
+            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i0);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, ended);
+        }
+        if (ok) {
             uint32_t tot = 0;
+            ulonglong2* out = reinterpret_cast<ulonglong2*>(row_rng + t.row0);
 #pragma unroll
-            for (int j = 0; j < PV; j++) tot += cnt[j];
+            for (int j = 0; j < PV; j++) {
+                // start <= end on the build side (checked at build time): a row that ends before qs also starts before qe
+                uint32_t c = n_le[j] - ended[j];
+                if (t.qe[j] < t.qs[j]) c = (i0[j] < n_le[j]) ? walk_count(ix, i0[j], n_le[j], t.qs[j]) : 0u;  // unguarded predicate
+                tot += c;
+            }
+#pragma unroll
+            for (int j = 0; j < PV; j += 2)
+                __stcs(out + j / 2, make_ulonglong2((uint64_t)i0[j] | ((uint64_t)n_le[j] << 32),
+                                                    (uint64_t)i0[j + 1] | ((uint64_t)n_le[j + 1] << 32)));
             tot = __reduce_add_sync(0xFFFFFFFFu, tot);
             if ((threadIdx.x & 31) == 0) chunk_tot[t.chunk] = tot;
             fails = 0;
         } else {
-            pc.invalidate();
+            cs.valid = false; cp.valid = false; ce.valid = false;
             todo_push(todo, t.chunk);
             fails++;
         }
@@ -183,111 +160,13 @@ __global__ void __launch_bounds__(TP_THREADS, 2) pairs_total_kernel_tiled(IndexV
     }
 }
 
-// writes the matches of the PV rows a lane owns, `o` = first output slot of the lane
-template <bool DIRECT>
-__device__ __forceinline__ void pair_walk(const IndexView& ix, const uint32_t (&i0)[PV], const uint32_t (&cnt)[PV],
-                                          const int32_t (&qs)[PV], uint32_t o, PairStage& stg, uint32_t* gb, uint32_t* gp,
-                                          uint32_t row0) {
-    const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < PV; j++) {
-        uint32_t left = cnt[j];
-        uint32_t i = i0[j];
-        while (left) {
-            if (__ldg(ix.s_end + i) >= qs[j]) {
-                const uint32_t pos = __ldg(ix.s_pos + i);
-                if (DIRECT) { gb[o] = pos; gp[o] = row0 + lane * PV + j; }
-                else { stg.b[o] = pos; stg.p[o] = (uint8_t)(lane * PV + j); }
-                o++;
-                left--;
-            }
-            i++;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(PT_THREADS, 3) pairs_emit_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
-                                                                         const int32_t* __restrict__ start,
-                                                                         const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                         const uint64_t* __restrict__ chunk_base,
-                                                                         uint32_t* __restrict__ build_idx,
-                                                                         uint32_t* __restrict__ probe_idx, TodoList todo) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PairSmem* sm = reinterpret_cast<PairSmem*>(smem_raw);
-    const int warp = threadIdx.x >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t* aux0 = sm->w[warp].aux[0];
-    uint32_t* aux1 = sm->w[warp].aux[1];
-    uint32_t* aux2 = sm->w[warp].aux[2];
-    PairStage& stg = sm->st[warp];
-    ProbePipe pipe(sm->w, key, start, end, n_rows);  // full chunks only
-    ProbeTile t;
-    PairCursors pc;
-    pc.reset();
-    uint32_t fails = 0;
-    while (pipe.next(t)) {
-        uint32_t n_le[PV], i0[PV], cnt[PV];
-        if (pair_chunk_ranks<true>(ix, pc, t, aux0, aux1, aux2, n_le, i0, cnt)) {
-            fails = 0;
-            uint32_t lane_tot = 0;
-#pragma unroll
-            for (int j = 0; j < PV; j++) lane_tot += cnt[j];
-            uint32_t incl = lane_tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= (uint32_t)o) incl += y;
-            }
-            const uint32_t lane_off = incl - lane_tot;
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (total) {
-                const uint64_t base = chunk_base[t.chunk];
-                uint32_t* gb = build_idx + base;
-                uint32_t* gp = probe_idx + base;
-                const uint32_t row0 = (uint32_t)(t.chunk * TP_WTILE);
-                uint32_t first = 0;  // lanes [0, first) are done (warp-uniform)
-                while (first < 32) {
-                    const uint32_t rb = __shfl_sync(0xFFFFFFFFu, lane_off, first);  // first slot of this round
-                    const bool over = lane >= first && (incl - rb) > (uint32_t)PT_CAP;
-                    const uint32_t nf = __ballot_sync(0xFFFFFFFFu, over);
-                    const uint32_t stop = nf ? (uint32_t)(__ffs(nf) - 1) : 32u;     // first lane that no longer fits
-                    if (stop == first) {  // one lane alone exceeds the stage: it writes straight to global memory
-                        if (lane == first) pair_walk<true>(ix, i0, cnt, t.qs, lane_off, stg, gb, gp, row0);
-                        first++;
-                        continue;
-                    }
-                    const uint32_t next_off = __shfl_sync(0xFFFFFFFFu, lane_off, stop & 31u);
-                    const uint32_t rend = (stop == 32u) ? total : next_off;
-                    if (lane >= first && lane < stop) pair_walk<false>(ix, i0, cnt, t.qs, lane_off - rb, stg, gb, gp, row0);
-                    __syncwarp();
-                    for (uint32_t u = lane; u < rend - rb; u += 32) {
-                        __stcs(gb + rb + u, stg.b[u]);
-                        __stcs(gp + rb + u, row0 + stg.p[u]);
-                    }
-                    __syncwarp();
-                    first = stop;
-                }
-            }
-        } else {
-            pc.invalidate();
-            todo_push(todo, t.chunk);
-            fails++;
-        }
-        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
-        pipe.release();
-    }
-}
-
-// deferred chunks (and the partial last chunk, and everything when the tiled kernels cannot run): one row per thread
-template <bool EMIT>
-__global__ void __launch_bounds__(TP_WTILE) pairs_chunk_todo_kernel(IndexView ix, const uint32_t* __restrict__ key,
-                                                                    const int32_t* __restrict__ start,
-                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                    uint32_t* __restrict__ chunk_tot,
-                                                                    const uint64_t* __restrict__ chunk_base,
-                                                                    uint32_t* __restrict__ build_idx,
-                                                                    uint32_t* __restrict__ probe_idx, TodoList todo,
-                                                                    uint32_t all_chunks, uint32_t tail_chunk) {
+// deferred chunks (and the partial last chunk, and everything when the tiled kernel cannot run): one row per thread
+__global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                                     const int32_t* __restrict__ start,
+                                                                     const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                     uint64_t* __restrict__ row_rng,
+                                                                     uint32_t* __restrict__ chunk_tot, TodoList todo,
+                                                                     uint32_t all_chunks, uint32_t tail_chunk) {
     __shared__ uint32_t wsum[TP_WTILE / 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_list = todo.count ? *todo.count : all_chunks;
@@ -295,42 +174,187 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_chunk_todo_kernel(IndexView ix
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t chunk = item < n_list ? (todo.count ? todo.chunks[item] : item) : tail_chunk;
         const uint64_t i = (uint64_t)chunk * TP_WTILE + threadIdx.x;
-        uint32_t i0 = 0, i1 = 0, cnt = 0;
-        int32_t qs = 0;
+        uint32_t cnt = 0;
         if (i < n_rows) {
-            qs = ld_stream(start + i);
-            const int32_t qe = ld_stream(end + i);
+            const int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
             const uint32_t c = key ? ld_stream(key + i) : 0u;
+            uint32_t i0, i1;
             pair_range(ix, c, qs, qe, &i0, &i1);
             cnt = walk_count(ix, i0, i1, qs);
+            row_rng[i] = (uint64_t)i0 | ((uint64_t)i1 << 32);
         }
-        uint32_t incl = cnt;
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) wsum[warp] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < TP_WTILE / 32; w++) total += wsum[w];
+            chunk_tot[chunk] = total;
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int PF_THREADS = 256;
+constexpr int PF_WARPS = PF_THREADS / 32;
+constexpr int PF_U = 4;       // slot steps in flight per iteration of the emit loop
+constexpr int PF_CAP = 2560;  // candidate slots a warp flattens at a time (bytes of the slot -> row map)
+struct __align__(16) FlatWarp {
+    uint4 row[TP_WTILE + 1];    // per row {P = exclusive prefix of the candidate counts, i0, qs, -}; row[256].x = total
+    uint8_t rowof[PF_CAP];
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 4) pairs_emit_kernel_flat(IndexView ix, const int32_t* __restrict__ start,
+                                                                        uint64_t n_rows, uint64_t n_chunks,
+                                                                        const uint64_t* __restrict__ row_rng,
+                                                                        const uint64_t* __restrict__ chunk_base,
+                                                                        uint32_t* __restrict__ build_idx,
+                                                                        uint32_t* __restrict__ probe_idx) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FlatWarp& sm = reinterpret_cast<FlatWarp*>(smem_raw)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint64_t n_warps = (uint64_t)gridDim.x * PF_WARPS;
+    for (uint64_t chunk = (uint64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5); chunk < n_chunks; chunk += n_warps) {
+        const uint64_t base = __ldg(chunk_base + chunk);
+        if (__ldg(chunk_base + chunk + 1) == base) continue;  // no pairs in this chunk (warp-uniform)
+        const uint64_t row = chunk * TP_WTILE + lane * PV;
+        uint32_t i0[PV], cand[PV];
+        int32_t qs[PV];
+        if (row + PV <= n_rows) {
+            const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(row_rng + row);
+            const int4* pq = reinterpret_cast<const int4*>(start + row);
+#pragma unroll
+            for (int j = 0; j < PV; j += 2) {
+                const ulonglong2 v = __ldcs(pr + j / 2);
+                i0[j] = (uint32_t)v.x; cand[j] = (uint32_t)(v.x >> 32);
+                i0[j + 1] = (uint32_t)v.y; cand[j + 1] = (uint32_t)(v.y >> 32);
+            }
+            const int4 a = __ldcs(pq), b = __ldcs(pq + 1);
+            qs[0] = a.x; qs[1] = a.y; qs[2] = a.z; qs[3] = a.w; qs[4] = b.x; qs[5] = b.y; qs[6] = b.z; qs[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < PV; j++) {
+                const bool v = row + j < n_rows;
+                const uint64_t r = v ? __ldcs(row_rng + row + j) : 0ull;
+                i0[j] = (uint32_t)r; cand[j] = (uint32_t)(r >> 32);
+                qs[j] = v ? __ldcs(start + row + j) : 0;
+            }
+        }
+        uint32_t lane_tot = 0;
+#pragma unroll
+        for (int j = 0; j < PV; j++) { cand[j] = cand[j] > i0[j] ? cand[j] - i0[j] : 0u; lane_tot += cand[j]; }
+        uint32_t incl = lane_tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= (uint32_t)o) incl += y;
         }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
+        uint32_t pj[PV];
+        pj[0] = incl - lane_tot;
 #pragma unroll
-        for (int w = 0; w < TP_WTILE / 32; w++) {
-            const uint32_t v = wsum[w];
-            before += (uint32_t)w < warp ? v : 0u;
-            total += v;
-        }
-        __syncthreads();
-        if (!EMIT) {
-            if (threadIdx.x == 0) chunk_tot[chunk] = total;
-        } else if (cnt) {
-            uint64_t o = chunk_base[chunk] + before + incl - cnt;
-            for (uint32_t j = i0; j < i1; j++) {
-                if (__ldg(ix.s_end + j) >= qs) {
-                    build_idx[o] = __ldg(ix.s_pos + j);
-                    probe_idx[o] = (uint32_t)i;
-                    o++;
+        for (int j = 1; j < PV; j++) pj[j] = pj[j - 1] + cand[j - 1];
+        __syncwarp();  // the previous chunk's readers are done with the shared arrays
+#pragma unroll
+        for (int j = 0; j < PV; j++) sm.row[lane * PV + j] = make_uint4(pj[j], i0[j], (uint32_t)qs[j], 0u);
+        if (lane == 31) sm.row[TP_WTILE] = make_uint4(incl, 0u, 0u, 0u);
+        __syncwarp();
+        uint32_t* gb = build_idx + base;
+        uint32_t* gp = probe_idx + base;
+        const uint32_t row0 = (uint32_t)(chunk * TP_WTILE);
+        uint32_t run = 0;  // pairs of this chunk written so far (warp-uniform)
+        uint32_t ra = 0;   // rows [0, ra) are done (warp-uniform)
+        while (ra < (uint32_t)TP_WTILE) {
+            const uint32_t Pa = sm.row[ra].x;
+            // rows [ra, rb) whose candidates fit the slot map together (their prefix is monotone)
+            uint32_t fit = 0;
+#pragma unroll
+            for (int j = 0; j < PV; j++) fit += (lane * PV + j >= ra && pj[j] + cand[j] - Pa <= (uint32_t)PF_CAP) ? 1u : 0u;
+            fit = __reduce_add_sync(0xFFFFFFFFu, fit);
+            if (fit == 0) {
+                // one row alone exceeds the map: the warp sweeps its range 32 candidates at a time
+                const uint32_t rI0 = sm.row[ra].y, rN = sm.row[ra + 1].x - Pa;
+                const int32_t rQ = (int32_t)sm.row[ra].z;
+                for (uint32_t sb = 0; sb < rN; sb += 32) {
+                    const uint32_t s = sb + lane;
+                    const bool m = s < rN && __ldg(ix.s_end + rI0 + s) >= rQ;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m);
+                    if (m) {
+                        const uint32_t o = run + __popc(bal & lt_mask);
+                        __stcs(gb + o, __ldg(ix.s_pos + rI0 + s));
+                        __stcs(gp + o, row0 + ra);
+                    }
+                    run += __popc(bal);
+                }
+                ra++;
+                continue;
+            }
+            const uint32_t rb = ra + fit;
+            const uint32_t n_slots = sm.row[rb].x - Pa;
+            if (n_slots) {
+                // ---- slot -> row map: zero, one byte per non-empty row at its first slot, packed prefix-max ---------
+                const uint32_t n_words = (n_slots + 3) >> 2;
+                uint32_t* w32 = reinterpret_cast<uint32_t*>(sm.rowof);
+                for (uint32_t x = lane; x < n_words; x += 32) w32[x] = 0u;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < PV; j++) {
+                    const uint32_t r = lane * PV + j;
+                    if (r >= ra && r < rb && cand[j]) sm.rowof[pj[j] - Pa] = (uint8_t)r;
+                }
+                __syncwarp();
+                const uint32_t per = ((n_words + 31) >> 5) | 1u;  // odd word stride per lane: conflict-free
+                uint32_t carry = 0;
+                for (uint32_t x = lane * per, e = min(lane * per + per, n_words); x < e; x++) {
+                    uint32_t v = w32[x];
+                    v = __vmaxu4(v, v << 8);
+                    v = __vmaxu4(v, v << 16);
+                    v = __vmaxu4(v, carry * 0x01010101u);
+                    w32[x] = v;
+                    carry = v >> 24;
+                }
+                uint32_t before = carry;  // exclusive prefix-max of the lanes' last bytes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, before, o);
+                    if (lane >= (uint32_t)o) before = max(before, y);
+                }
+                before = __shfl_up_sync(0xFFFFFFFFu, before, 1);
+                if (lane == 0) before = 0;
+                if (before) {
+                    const uint32_t bb = before * 0x01010101u;
+                    for (uint32_t x = lane * per, e = min(lane * per + per, n_words); x < e; x++) w32[x] = __vmaxu4(w32[x], bb);
+                }
+                __syncwarp();
+                // ---- test 32 candidate slots per step, compact, write one contiguous run ---------------------------
+                // (PF_U steps are software-pipelined: all their loads are issued before the first ballot)
+                for (uint32_t sb = 0; sb < n_slots; sb += 32 * PF_U) {
+                    uint32_t rr[PF_U], pos[PF_U];
+                    bool mt[PF_U];
+#pragma unroll
+                    for (int u = 0; u < PF_U; u++) {
+                        const uint32_t s = sb + u * 32 + lane;
+                        const bool v = s < n_slots;
+                        rr[u] = v ? sm.rowof[s] : ra;
+                        const uint4 rw = sm.row[rr[u]];
+                        const uint32_t i = rw.y + (s + Pa - rw.x);
+                        mt[u] = v && __ldg(ix.s_end + i) >= (int32_t)rw.z;
+                        pos[u] = v ? __ldg(ix.s_pos + i) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF_U; u++) {
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mt[u]);
+                        if (mt[u]) {
+                            const uint32_t o = run + __popc(bal & lt_mask);
+                            __stcs(gb + o, pos[u]);
+                            __stcs(gp + o, row0 + rr[u]);
+                        }
+                        run += __popc(bal);
+                    }
                 }
             }
+            ra = rb;
         }
     }
 }
@@ -421,7 +445,7 @@ static int todo_list_alloc(uint64_t chunks, TodoList* td, cudaStream_t st) {
 uint64_t pairs_chunk_count(uint64_t n) { return (n + TP_WTILE - 1) / TP_WTILE; }
 
 int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
-                               uint64_t* chunk_base, cudaStream_t st) {
+                               uint64_t* chunk_base, uint64_t* row_rng, cudaStream_t st) {
     const ChunkPlan p = plan_chunks(ix, key, s, e, n);
     if (p.n_chunks == 0) { BRG_CUDA(cudaMemsetAsync(chunk_base, 0, sizeof(uint64_t), st)); return 0; }
     uint32_t* tot = nullptr;
@@ -432,19 +456,17 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
     if (p.tiled) {
         TodoList todo;
         if ((rc = todo_list_alloc(p.n_chunks, &todo, st))) return rc;
-        BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_total_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
+        BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_ranges_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
         const uint64_t tiles = p.full_rows / TP_TILE + 1;
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * 2));
-        pairs_total_kernel_tiled<<<grid, TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, p.full_rows, tot, todo);
+        pairs_ranges_kernel_tiled<<<grid, TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, p.full_rows, row_rng, tot, todo);
         BRG_LAUNCH_CHECK();
-        pairs_chunk_todo_kernel<false><<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, tot, nullptr, nullptr, nullptr,
-                                                                                     todo, 0u, p.tail_chunk);
+        pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, todo, 0u, p.tail_chunk);
         BRG_LAUNCH_CHECK();
         BRG_CUDA(cudaFreeAsync(todo.count, st));
     } else {
-        pairs_chunk_todo_kernel<false><<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, tot, nullptr, nullptr, nullptr,
-                                                                                     TodoList{nullptr, nullptr}, (uint32_t)p.n_chunks,
-                                                                                     0xFFFFFFFFu);
+        pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, TodoList{nullptr, nullptr},
+                                                                               (uint32_t)p.n_chunks, 0xFFFFFFFFu);
         BRG_LAUNCH_CHECK();
     }
     if ((rc = exclusive_scan_u32_to_u64(tot, chunk_base, p.n_chunks, scratch, st))) return rc;
@@ -453,30 +475,17 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
     return 0;
 }
 
-int launch_pairs_fill(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
-                      const uint64_t* chunk_base, uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st) {
-    const ChunkPlan p = plan_chunks(ix, key, s, e, n);
-    if (p.n_chunks == 0) return 0;
-    int rc = 0;
-    if (p.tiled) {
-        TodoList todo;
-        if ((rc = todo_list_alloc(p.n_chunks, &todo, st))) return rc;
-        BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_emit_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
-        const uint64_t per_cta = (uint64_t)PT_WARPS * TP_WTILE;
-        const uint64_t tiles = p.full_rows / per_cta + 1;
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * 3));
-        pairs_emit_kernel_tiled<<<grid, PT_THREADS, sizeof(PairSmem), st>>>(ix, key, s, e, p.full_rows, chunk_base, build_idx, probe_idx, todo);
-        BRG_LAUNCH_CHECK();
-        pairs_chunk_todo_kernel<true><<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, nullptr, chunk_base, build_idx,
-                                                                                    probe_idx, todo, 0u, p.tail_chunk);
-        BRG_LAUNCH_CHECK();
-        BRG_CUDA(cudaFreeAsync(todo.count, st));
-    } else {
-        pairs_chunk_todo_kernel<true><<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, nullptr, chunk_base, build_idx,
-                                                                                    probe_idx, TodoList{nullptr, nullptr},
-                                                                                    (uint32_t)p.n_chunks, 0xFFFFFFFFu);
-        BRG_LAUNCH_CHECK();
-    }
+int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const uint64_t* chunk_base, const uint64_t* row_rng,
+                      uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st) {
+    const uint64_t n_chunks = pairs_chunk_count(n);
+    if (n_chunks == 0) return 0;
+    BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_emit_kernel_flat, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(FlatWarp) * PF_WARPS)));
+    const uint64_t ctas = (n_chunks + PF_WARPS - 1) / PF_WARPS;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctas, (uint64_t)kSMs * 4));
+    pairs_emit_kernel_flat<<<grid, PF_THREADS, sizeof(FlatWarp) * PF_WARPS, st>>>(ix, s, n, n_chunks, row_rng, chunk_base, build_idx,
+                                                                                 probe_idx);
+    BRG_LAUNCH_CHECK();
     return 0;
 }
 

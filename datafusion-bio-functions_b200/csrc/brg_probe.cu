@@ -22,6 +22,10 @@
 namespace brg {
 
 constexpr int PB_THREADS = 256;
+#ifndef BRG_CC_CTAS
+#define BRG_CC_CTAS 2  // resident CTAs per SM of the count / coverage tiled kernels: 128 registers per thread, no spills
+                       // (3 CTAs = 80 registers spilled in the hot loop: 0.73 ms vs 0.59 ms per 125M probes on B200)
+#endif
 
 __device__ __forceinline__ uint32_t load_key(const uint32_t* key, uint64_t i) { return key ? ld_stream(key + i) : 0u; }
 
@@ -56,7 +60,7 @@ __device__ __forceinline__ void store8_i64(int64_t* out, const long long (&v)[PV
     for (int j = 0; j < PV / 2; j++) __stcs(o + j, make_longlong2(v[2 * j], v[2 * j + 1]));
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+__global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
                                                                     const int32_t* __restrict__ start,
                                                                     const int32_t* __restrict__ end, uint64_t n_rows,
                                                                     int strict, int64_t* __restrict__ out, TodoList todo) {
@@ -64,6 +68,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     ProbePipe pipe(ring, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cs, ce;
@@ -85,8 +90,8 @@ __global__ void __launch_bounds__(TP_THREADS, 3) count_kernel_tiled(IndexView ix
             }
             // seg_begin + #(starts <= qe)  and  seg_begin + #(ends < qs)
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, started);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, ended);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, started);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, ended);
         }
         if (ok) {
             long long cnt[PV];
@@ -191,7 +196,7 @@ __device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint
     return (lo < hi) ? acc : 0;
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+__global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
                                                                        const int32_t* __restrict__ start,
                                                                        const int32_t* __restrict__ end, uint64_t n_rows,
                                                                        int strict, int64_t* __restrict__ out, TodoList todo) {
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     ProbePipe pipe(ring, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cl, cf;
@@ -220,8 +226,8 @@ __global__ void __launch_bounds__(TP_THREADS, 3) coverage_kernel_tiled(IndexView
             }
             // merged intervals overlapping [qs,qe] are exactly [first j with last_j >= qs, first j with first_j > qe)
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, lo);
-            ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, hi);
+            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, win, lo);
+            ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, win, hi);
         }
         if (ok) {
             long long cov[PV];
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
+    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
     ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256 here: every chunk is full
     ProbeTile t;
@@ -402,9 +409,9 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);
-            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i_pme);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, l_idx);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, n_le);
+            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i_pme);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, l_idx);
         }
         if (ok) {
             uint32_t pos[PV];
@@ -572,7 +579,7 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k_kernel(IndexView ix, con
 // launchers
 // ---------------------------------------------------------------------------------------------------
 // persistent grid for the tiled kernels: 3 CTAs per SM (shared-memory bound), never more CTAs than tiles
-static inline unsigned tiled_grid(uint64_t rows, int per_sm = 3) {
+static inline unsigned tiled_grid(uint64_t rows, int per_sm = BRG_CC_CTAS) {
     uint64_t tiles = (rows + TP_TILE - 1) / TP_TILE;
     uint64_t cap = (uint64_t)kSMs * per_sm;
     return (unsigned)std::max<uint64_t>(1, std::min(tiles, cap));

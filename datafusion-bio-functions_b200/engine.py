@@ -225,20 +225,21 @@ class Index:
         A.check(A.lib().brg_pairs_emit_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
                                            _tptr(offsets), _tptr(build_idx), _tptr(probe_idx), st))
 
-    def pairs_chunk_offsets_dev(self, key, start, end, chunk_base):
-        """chunk_base: int64[ceil(n/256)+1]; [c] = first output slot of 256-row chunk c, [-1] = total pairs"""
+    def pairs_chunk_offsets_dev(self, key, start, end, chunk_base, row_ranges):
+        """pass 1.  chunk_base: int64[ceil(n/256)+1] ([c] = first output slot of 256-row chunk c, [-1] = total pairs);
+        row_ranges: int64[n] (candidate range of every probe row, consumed by pairs_fill_dev)"""
         import torch
 
         st = torch.cuda.current_stream().cuda_stream
         A.check(A.lib().brg_pairs_chunk_offsets_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
-                                                    _tptr(chunk_base), st))
+                                                    _tptr(chunk_base), _tptr(row_ranges), st))
 
-    def pairs_fill_dev(self, key, start, end, chunk_base, build_idx, probe_idx):
+    def pairs_fill_dev(self, start, chunk_base, row_ranges, build_idx, probe_idx):
         import torch
 
         st = torch.cuda.current_stream().cuda_stream
-        A.check(A.lib().brg_pairs_fill_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(),
-                                           _tptr(chunk_base), _tptr(build_idx), _tptr(probe_idx), st))
+        A.check(A.lib().brg_pairs_fill_dev(self.ctx._h, self._h, _tptr(start), start.numel(), _tptr(chunk_base),
+                                           _tptr(row_ranges), _tptr(build_idx), _tptr(probe_idx), st))
 
 
 _default = {}

@@ -152,13 +152,16 @@ BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* idx, const uint32_
                        uint32_t* d_probe_idx, void* stream);
 
 /* chunked device form (the fast path): the unit of count -> scan -> emit is a chunk of brg_pairs_chunk_rows() (256)
- * probe rows.  d_chunk_base has ceil(n/256)+1 u64 entries: [c] = first output slot of chunk c, [last] = total pairs.
- * The fill pass stages each chunk's pairs in shared memory and writes full coalesced runs. */
+ * probe rows.  Pass 1 writes d_chunk_base (ceil(n/256)+1 u64: [c] = first output slot of chunk c, [last] = total pairs)
+ * and d_row_ranges (n u64: the candidate range of every probe row in the start-sorted build rows).  Pass 2 needs only
+ * the probe start column and those two arrays: it flattens each chunk's candidates across a warp and writes the pairs
+ * as contiguous runs (probe-major; matches of one probe in (start, end, row id) order). */
 BRG_API uint32_t brg_pairs_chunk_rows(void);
 BRG_API int brg_pairs_chunk_offsets_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
-                                const int32_t* d_end, uint64_t n, uint64_t* d_chunk_base, void* stream);
-BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
-                       const int32_t* d_end, uint64_t n, const uint64_t* d_chunk_base, uint32_t* d_build_idx,
+                                const int32_t* d_end, uint64_t n, uint64_t* d_chunk_base, uint64_t* d_row_ranges,
+                                void* stream);
+BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* idx, const int32_t* d_start, uint64_t n,
+                       const uint64_t* d_chunk_base, const uint64_t* d_row_ranges, uint32_t* d_build_idx,
                        uint32_t* d_probe_idx, void* stream);
 
 /* ---- variable-length results ------------------------------------------------------------------------ */

@@ -265,13 +265,14 @@ def test_gpu_large_scale_properties(ctx):
         else:
             qk, qs, qe = pk, ps, pe
         cb = torch.empty((npb + 255) // 256 + 1, dtype=torch.int64, device="cuda")
-        ix.pairs_chunk_offsets_dev(qk, qs, qe, cb)
+        rr = torch.empty(npb, dtype=torch.int64, device="cuda")
+        ix.pairs_chunk_offsets_dev(qk, qs, qe, cb, rr)
         torch.cuda.synchronize()
         assert int(cb[-1].item()) == total_pairs
         assert torch.equal(cb[:-1], offsets[:-1:256])
         bi2 = torch.full((total_pairs,), -1, dtype=torch.int32, device="cuda")
         pi2 = torch.full((total_pairs,), -1, dtype=torch.int32, device="cuda")
-        ix.pairs_fill_dev(qk, qs, qe, cb, bi2, pi2)
+        ix.pairs_fill_dev(qs, cb, rr, bi2, pi2)
         torch.cuda.synchronize()
         assert torch.equal(bi2, bi) and torch.equal(pi2, pi)
 
