@@ -376,15 +376,24 @@ def main():
     h_pe = torch.empty(n, dtype=torch.int32).pin_memory(); h_pe.copy_(pe)
     npk, nps, npe = h_pk.numpy().view(np.uint32), h_ps.numpy(), h_pe.numpy()
     e2e_steps = max(3, min(args.steps, 5))
+    # The contig column travels in run-length form (brg_*_runs): the host's contig-cache loop (interval_tree.rs:258-265)
+    # yields runs on a coordinate-sorted table; a shuffled table has no runs to speak of and sends the id column.
+    run_key, run_end = brg._cabi.key_runs(npk)
+    use_runs = len(run_key) <= max(1024, n // 4096)
     if name in ("count", "coverage"):
         h_out = torch.empty(n, dtype=torch.int64).pin_memory()
-        hfn = ix.count_overlaps if name == "count" else ix.coverage
-        estep = lambda: hfn(npk, nps, npe, out=h_out.numpy())
-        h2d, d2h, e_units = n * 12, n * 8, n
+        if use_runs:
+            hfn = ix.count_overlaps_runs if name == "count" else ix.coverage_runs
+            estep = lambda: hfn(run_key, run_end, nps, npe, out=h_out.numpy())
+        else:
+            hfn = ix.count_overlaps if name == "count" else ix.coverage
+            estep = lambda: hfn(npk, nps, npe, out=h_out.numpy())
+        h2d, d2h, e_units = n * (8 if use_runs else 12), n * 8, n
     elif name == "nearest":
-        estep = lambda: ix.nearest_k1(npk, nps, npe)
-        h2d, d2h, e_units = n * 12, n * 12 + n // 8, n
+        estep = (lambda: ix.nearest_k1_runs(run_key, run_end, nps, npe)) if use_runs else (lambda: ix.nearest_k1(npk, nps, npe))
+        h2d, d2h, e_units = n * (8 if use_runs else 12), n * 12 + n // 8, n
     else:
+        use_runs = False
         estep = lambda: ix.overlap_pairs(npk, nps, npe)
         h2d, d2h, e_units = n * 12, units_per_step * 8, units_per_step
     estep()
@@ -400,7 +409,8 @@ def main():
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / e2e_steps
     e2e = {"value": sum_over_ranks(e_units) / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_ms, "api": {"count": "brg_count_overlaps", "coverage": "brg_coverage", "nearest": "brg_nearest_k1",
-                                          "pairs": "brg_overlap_pairs"}[name] + " (host buffers, pinned)"}
+                                          "pairs": "brg_overlap_pairs"}[name] + ("_runs (host buffers, pinned; contig column as key runs)"
+                                                                                if use_runs else " (host buffers, pinned)")}
     # parity spot check of the timed result against the oracle (rank 0, small sample) -- the checker, not the product
     parity = None
     if rank == 0 and name in ("count", "coverage") and not args.no_cpu:

@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "brg_pinned_alloc", "brg_pinned_free", "brg_build", "brg_build_dev", "brg_index_destroy", "brg_index_rows",
     "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_count_overlaps",
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
+    "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
     "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
     "brg_pairs_fill_dev", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
@@ -67,6 +68,9 @@ def lib():
     L.brg_index_import.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.brg_count_overlaps.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
     L.brg_coverage.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
+    L.brg_count_overlaps_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, vp]
+    L.brg_coverage_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, vp]
+    L.brg_nearest_k1_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, i32, vp, vp, vp]
     L.brg_count_overlaps_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
     L.brg_coverage_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
     L.brg_nearest_k1.argtypes = [vp, vp, vp, vp, vp, u64, i32, i32, vp, vp, vp]
@@ -109,6 +113,18 @@ def as_key(a):
     if a is None:
         return None
     return np.ascontiguousarray(np.asarray(a), dtype=np.uint32)
+
+
+def key_runs(key):
+    """run-length form of a per-row key column: (run_key u32[r], run_end u64[r]) -- what the host's contig-cache loop
+    produces while it walks a coordinate-sorted table"""
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    n = len(key)
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint64)
+    cut = np.flatnonzero(key[1:] != key[:-1]) + 1
+    starts = np.concatenate([[0], cut])
+    return key[starts].copy(), np.concatenate([cut, [n]]).astype(np.uint64)
 
 
 def copy_from(ptr, n, dtype):

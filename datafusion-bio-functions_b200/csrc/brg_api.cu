@@ -128,6 +128,19 @@ __global__ void pack_bits_kernel(const uint32_t* __restrict__ v, uint64_t n, uin
     uint32_t b = __ballot_sync(0xFFFFFFFFu, i < n && v[i] != 0);
     if ((threadIdx.x & 31) == 0) bits[i >> 5] = b;
 }
+// key column of rows [row0, row0 + m) from run-length form: run r covers rows [run_end[r-1], run_end[r])
+__global__ void expand_runs_kernel(const uint32_t* __restrict__ run_key, const unsigned long long* __restrict__ run_end,
+                                   uint32_t n_runs, uint64_t row0, uint64_t m, uint32_t* __restrict__ key_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long row = row0 + i;
+    uint32_t lo = 0, hi = n_runs;  // first run whose end is > row
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(run_end + mid) <= row) lo = mid + 1; else hi = mid;
+    }
+    key_out[i] = lo < n_runs ? __ldg(run_key + lo) : 0xFFFFFFFFu;
+}
 // largest m in [1, n] with offsets[m] <= max_rows (at least one probe row is always consumed)
 __global__ void find_cut_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t max_rows, uint64_t* out) {
     uint64_t lo = 1, hi = n;  // answer in [lo, hi]
@@ -687,20 +700,39 @@ extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, con
 // ---------------------------------------------------------------------------------------------------
 enum FixedOp { OP_COUNT, OP_COVERAGE, OP_NEAREST1 };
 
+struct KeyRuns {  // run-length form of the probe key column (NULL run_key = not used)
+    const uint32_t* run_key = nullptr;
+    const uint64_t* run_end = nullptr;
+    uint64_t n_runs = 0;
+};
+
 static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32_t* key, const int32_t* start,
                      const int32_t* end, uint64_t n, int include_overlaps, int strict, int64_t* out_i64,
-                     uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist) {
+                     uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist, KeyRuns runs = KeyRuns()) {
     if (n == 0) return BRG_OK;
     if (!start || !end) { set_error("probe: NULL column"); return BRG_ERR_INVALID; }
+    const bool by_runs = runs.run_key != nullptr;
+    if (by_runs) {
+        if (!runs.run_end || runs.n_runs == 0 || runs.n_runs > 0xFFFFFFFFull || runs.run_end[runs.n_runs - 1] != n) {
+            set_error("probe: key runs must be non-empty and end at the row count");
+            return BRG_ERR_INVALID;
+        }
+    }
     BRG_CUDA(cudaSetDevice(ctx->device));
     LaneGuard g(ctx);
     int rc;
     if ((rc = g.acquire())) return rc;
     Lane* l = g.l;
+    if (by_runs) {  // the runs travel once (a few bytes per contig); the per-row key column is expanded on the device
+        if ((rc = l->scratch_a.ensure(runs.n_runs * 4)) || (rc = l->scratch_b.ensure(runs.n_runs * 8))) return rc;
+        BRG_CUDA(cudaMemcpyAsync(l->scratch_a.p, runs.run_key, runs.n_runs * 4, cudaMemcpyHostToDevice, l->k));
+        BRG_CUDA(cudaMemcpyAsync(l->scratch_b.p, runs.run_end, runs.n_runs * 8, cudaMemcpyHostToDevice, l->k));
+    }
+    const bool dev_key = key != nullptr || by_runs;
     // chunk rows are a multiple of 32 so that validity bitmap words never straddle chunks
     const uint64_t C = std::min<uint64_t>((ctx->chunk_rows + 31) & ~31ull, (n + 31) & ~31ull);
     for (int b = 0; b < Lane::NBUF; b++) {
-        if (key && (rc = l->in_key[b].ensure(C * 4))) return rc;
+        if (dev_key && (rc = l->in_key[b].ensure(C * 4))) return rc;
         if ((rc = l->in_s[b].ensure(C * 4)) || (rc = l->in_e[b].ensure(C * 4))) return rc;
         if (op == OP_NEAREST1) {
             if ((rc = l->out0[b].ensure(C * 4)) || (rc = l->out1[b].ensure(C / 8 + 4))) return rc;
@@ -715,14 +747,20 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
         const uint64_t m = std::min<uint64_t>(C, n - done);
         // inputs of buffer b may be overwritten once the kernel that read them has finished
         BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
-        if (key) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
+        if (key && !by_runs) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
         BRG_CUDA(cudaMemcpyAsync(l->in_s[b].p, start + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
         BRG_CUDA(cudaMemcpyAsync(l->in_e[b].p, end + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
         BRG_CUDA(cudaEventRecord(l->ev_in[b], l->h2d));
         // kernel: after its inputs landed and after the previous results of buffer b left the device
         BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_in[b], 0));
         BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_out[b], 0));
-        const uint32_t* dk = key ? l->in_key[b].as<uint32_t>() : nullptr;
+        const uint32_t* dk = dev_key ? l->in_key[b].as<uint32_t>() : nullptr;
+        if (by_runs) {  // (the k stream already waited for the previous kernel that read this buffer)
+            expand_runs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->k>>>(l->scratch_a.as<uint32_t>(),
+                                                                              l->scratch_b.as<unsigned long long>(),
+                                                                              (uint32_t)runs.n_runs, done, m, l->in_key[b].as<uint32_t>());
+            g_launches.fetch_add(1);
+        }
         if (op == OP_COUNT)
             rc = launch_count(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
         else if (op == OP_COVERAGE)
@@ -754,6 +792,33 @@ extern "C" BRG_API int brg_count_overlaps(brg_ctx* ctx, const brg_index* ix, con
     if (rc) return rc;
     if (n && !out) { set_error("brg_count_overlaps: NULL output"); return BRG_ERR_INVALID; }
     return run_fixed(ctx, ix, OP_COUNT, key, start, end, n, 0, strict, out, nullptr, nullptr, nullptr);
+}
+extern "C" BRG_API int brg_count_overlaps_runs(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                       uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int strict,
+                                       int64_t* out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COUNT | BRG_WANT_NEAREST, "brg_count_overlaps_runs");
+    if (rc) return rc;
+    if (n && (!out || !run_key)) { set_error("brg_count_overlaps_runs: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_COUNT, nullptr, start, end, n, 0, strict, out, nullptr, nullptr, nullptr, kr);
+}
+extern "C" BRG_API int brg_coverage_runs(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                 uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int strict, int64_t* out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COVERAGE, "brg_coverage_runs");
+    if (rc) return rc;
+    if (n && (!out || !run_key)) { set_error("brg_coverage_runs: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_COVERAGE, nullptr, start, end, n, 0, strict, out, nullptr, nullptr, nullptr, kr);
+}
+extern "C" BRG_API int brg_nearest_k1_runs(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                   uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int include_overlaps,
+                                   int strict, uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist) {
+    int rc = check_probe(ctx, ix, BRG_WANT_NEAREST, "brg_nearest_k1_runs");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("right row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!out_left || !out_bits || !run_key)) { set_error("brg_nearest_k1_runs: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_NEAREST1, nullptr, start, end, n, include_overlaps, strict, nullptr, out_left, out_bits, out_dist, kr);
 }
 extern "C" BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
                             const int32_t* end, uint64_t n, int strict, int64_t* out) {

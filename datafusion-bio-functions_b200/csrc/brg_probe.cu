@@ -274,19 +274,18 @@ struct Cand {
     int32_t s, e;
     uint32_t pos;
 };
-// nearest_index.rs:252-260
+// nearest_index.rs:252-260 (same precedence of the two tests, written as selects: no divergent branches)
 __device__ __forceinline__ int64_t cand_distance(int32_t qs, int32_t qe, int32_t is, int32_t ie) {
-    if (qe < is) return (int64_t)is - (int64_t)qe;
-    if (ie < qs) return (int64_t)qs - (int64_t)ie;
-    return 0;
+    const int64_t right = (int64_t)is - (int64_t)qe, left = (int64_t)qs - (int64_t)ie;
+    const int64_t d = (ie < qs) ? left : 0;
+    return (qe < is) ? right : d;
 }
 // cmp_candidate(a,b) <= 0  (nearest_index.rs:262-266): (distance, start, end, position)
 __device__ __forceinline__ bool cand_le(int32_t qs, int32_t qe, const Cand& a, const Cand& b) {
-    int64_t ad = cand_distance(qs, qe, a.s, a.e), bd = cand_distance(qs, qe, b.s, b.e);
-    if (ad != bd) return ad < bd;
-    if (a.s != b.s) return a.s < b.s;
-    if (a.e != b.e) return a.e < b.e;
-    return a.pos <= b.pos;
+    const int64_t ad = cand_distance(qs, qe, a.s, a.e), bd = cand_distance(qs, qe, b.s, b.e);
+    const bool tail = (a.e != b.e) ? a.e < b.e : a.pos <= b.pos;
+    const bool mid = (a.s != b.s) ? a.s < b.s : tail;
+    return (ad != bd) ? ad < bd : mid;
 }
 __device__ __forceinline__ Cand load_s(const IndexView& ix, uint32_t i) {
     const int4 r = __ldg(ix.s_rec + i);

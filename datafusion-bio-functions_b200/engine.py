@@ -137,6 +137,38 @@ class Index:
                                            int(strict), A.np_ptr(out)))
         return out
 
+    def count_overlaps_runs(self, run_key, run_end, start, end, strict=False, out=None):
+        """count_overlaps with the probe key column in run-length form (see brg_count_overlaps_runs)"""
+        start, end = A.as_i32(start), A.as_i32(end)
+        run_key = np.ascontiguousarray(run_key, np.uint32)
+        run_end = np.ascontiguousarray(run_end, np.uint64)
+        out = np.empty(len(start), np.int64) if out is None else out
+        A.check(A.lib().brg_count_overlaps_runs(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key),
+                                                A.np_ptr(start), A.np_ptr(end), len(start), int(strict), A.np_ptr(out)))
+        return out
+
+    def coverage_runs(self, run_key, run_end, start, end, strict=False, out=None):
+        start, end = A.as_i32(start), A.as_i32(end)
+        run_key = np.ascontiguousarray(run_key, np.uint32)
+        run_end = np.ascontiguousarray(run_end, np.uint64)
+        out = np.empty(len(start), np.int64) if out is None else out
+        A.check(A.lib().brg_coverage_runs(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key),
+                                          A.np_ptr(start), A.np_ptr(end), len(start), int(strict), A.np_ptr(out)))
+        return out
+
+    def nearest_k1_runs(self, run_key, run_end, start, end, include_overlaps=True, strict=False, compute_distance=True):
+        start, end = A.as_i32(start), A.as_i32(end)
+        run_key = np.ascontiguousarray(run_key, np.uint32)
+        run_end = np.ascontiguousarray(run_end, np.uint64)
+        n = len(start)
+        left = np.empty(n, np.uint32)
+        bits = np.zeros(((n + 31) // 32) * 4, np.uint8)
+        dist = np.empty(n, np.int64) if compute_distance else None
+        A.check(A.lib().brg_nearest_k1_runs(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key),
+                                            A.np_ptr(start), A.np_ptr(end), n, int(include_overlaps), int(strict),
+                                            A.np_ptr(left), A.np_ptr(bits), A.np_ptr(dist)))
+        return left, A.unpack_bits(bits, n), dist
+
     def coverage(self, key, start, end, strict=False, out=None):
         key, start, end = self._cols(key, start, end)
         out = np.empty(len(start), np.int64) if out is None else out

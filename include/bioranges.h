@@ -110,6 +110,21 @@ BRG_API int brg_count_overlaps(brg_ctx* ctx, const brg_index* idx, const uint32_
 BRG_API int brg_count_overlaps_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
                            const int32_t* d_end, uint64_t n, int strict, int64_t* d_out_count, void* stream);
 
+/* Run-length form of the probe key column.  The reference's row loops resolve the contig of a row by comparing it with
+ * the previous row's (cached_contig, interval_tree.rs:258-265; nearest.rs:346-352): on a coordinate-sorted table that
+ * loop produces a handful of runs, not a column.  run r covers probe rows [run_end[r-1], run_end[r]) (run_end ascending,
+ * run_end[n_runs-1] == n) with key run_key[r] (BRG_KEY_ABSENT allowed).  Only the runs cross PCIe; the per-row key
+ * column the kernels read is expanded on the device.  Saves a third of the host->device bytes of a probe call. */
+BRG_API int brg_count_overlaps_runs(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                            uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int strict,
+                            int64_t* out_count);
+BRG_API int brg_coverage_runs(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                      uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int strict,
+                      int64_t* out_coverage);
+BRG_API int brg_nearest_k1_runs(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                        uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int include_overlaps,
+                        int strict, uint32_t* out_left_idx, uint8_t* out_valid_bits, int64_t* out_distance);
+
 /* ---- coverage (replaces get_coverage + get_stream's row loop, interval_tree.rs:145-152, 155-221) ------ */
 BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
                  const int32_t* end, uint64_t n, int strict, int64_t* out_coverage);

@@ -125,6 +125,30 @@ def test_gpu_sorted_probe_regimes(ctx, regime):
     _compare_all(ctx, bk, bs, be, pk, ps, pe, nk, ks=(3,))
 
 
+def test_gpu_key_runs_entry_points(ctx):
+    """run-length key column (what the host's contig-cache loop yields) == per-row key column"""
+    import bio_ranges_b200 as brg
+
+    rng = np.random.default_rng(21)
+    nk = 6
+    bk, bs, be = _rand(rng, 30_000, nk, 0, 1_000_000, 700)
+    pk, ps, pe = _sorted_probes(rng, 100_003, nk, 1_000_000, 1, 600, absent_runs=True)
+    rk, rend = brg._cabi.key_runs(pk)
+    assert rend[-1] == len(pk) and len(rk) < 40
+    gi = ctx.build(bk, bs, be, nk)
+    for strict in (False, True):
+        assert (gi.count_overlaps_runs(rk, rend, ps, pe, strict=strict) == gi.count_overlaps(pk, ps, pe, strict=strict)).all()
+        assert (gi.coverage_runs(rk, rend, ps, pe, strict=strict) == gi.coverage(pk, ps, pe, strict=strict)).all()
+        a = gi.nearest_k1_runs(rk, rend, ps, pe, strict=strict)
+        b = gi.nearest_k1(pk, ps, pe, strict=strict)
+        assert all((x == y).all() for x, y in zip(a, b))
+    oi = O.OracleIndex(bk, bs, be, nk)
+    assert (gi.count_overlaps_runs(rk, rend, ps, pe) == oi.count_overlaps(pk, ps, pe)).all()
+    with pytest.raises(brg.BioRangesError):
+        gi.count_overlaps_runs(rk[:-1], rend[:-1], ps, pe)  # runs do not cover the rows
+    gi.close()
+
+
 def test_gpu_edge_cases(ctx):
     rng = np.random.default_rng(77)
     # empty build side, keys without rows, empty probe side
