@@ -1,0 +1,132 @@
+"""Host layer (include/bioranges_host.h) pieces that need no GPU: BioConfig / Algorithm parsing, the table functions'
+argument grammar and errors, column resolution (PosArray::resolve) and `take`.  Texts are the reference's
+(session_context.rs, table_function.rs, array_utils.rs)."""
+import os
+import re
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import bio_ranges_b200 as brg
+from bio_ranges_b200 import session as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _err(fn, *a, **kw):
+    with pytest.raises(brg.BioRangesError) as ei:
+        fn(*a, **kw)
+    return ei.value.status, str(ei.value)
+
+
+def test_host_header_and_binding_agree():
+    src = open(os.path.join(ROOT, "include", "bioranges_host.h")).read()
+    declared = sorted(set(re.findall(r"BRG_API[^;(]*?\b(brgh_\w+)\s*\(", src)))
+    assert declared == sorted(S.HOST_SYMBOLS)
+    L = brg._cabi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_bio_config_set_show():
+    """session_context.rs:48-110 -- defaults, case-insensitive Algorithm parsing, Display names, parse error text"""
+    ctx = S.create_bio_session()
+    assert ctx.get("bio.interval_join_algorithm") == "Coitrees"
+    assert ctx.get("bio.prefer_interval_join") == "true"
+    assert ctx.get("bio.interval_join_low_memory") == "false"
+    for text, shown in [("lapper", "Lapper"), ("INTERVALTREE", "IntervalTree"), ("ArrayIntervalTree", "ArrayIntervalTree"),
+                        ("superintervals", "SuperIntervals"), ("CoitreesNearest", "CoitreesNearest"),
+                        ("coitreescountoverlaps", "CoitreesCountOverlaps"), ("Coitrees", "Coitrees")]:
+        ctx.set("bio.interval_join_algorithm", text)
+        assert ctx.get("bio.interval_join_algorithm") == shown
+        assert ctx.explain_interval_join().endswith(f"alg={shown}")  # EXPLAIN text the reference's tests grep (TEST:129,223)
+    st, msg = _err(ctx.set, "bio.interval_join_algorithm", "btree")
+    assert st == S.EXTERNAL and "Can't parse 'btree' as Algorithm" in msg
+    ctx.set("bio.interval_join_low_memory", "true")
+    assert ctx.get("bio.interval_join_low_memory") == "true"
+    assert _err(ctx.set, "bio.no_such_option", "1")[0] == S.EXTERNAL
+    ctx.close()
+
+
+def _tbl(rows, names=("contig", "pos_start", "pos_end"), pos_type=pa.int32()):
+    return pa.table({names[0]: pa.array([r[0] for r in rows], pa.string()),
+                     names[1]: pa.array([r[1] for r in rows], pos_type),
+                     names[2]: pa.array([r[2] for r in rows], pos_type)})
+
+
+def test_udtf_argument_grammar_errors():
+    """table_function.rs:59-214 -- errors are raised before any device work"""
+    ctx = S.create_bio_session()
+    ctx.register_table("a", _tbl([("chr1", 1, 5)]))
+    ctx.register_table("b", _tbl([("chr1", 2, 3)]))
+    st, msg = _err(ctx.count_overlaps, "a", "b", "contig", "pos_start")
+    assert st == S.PLAN and "count_overlaps() expects 0, 3, or 6 column name arguments (got 2)" in msg
+    assert "Usage: count_overlaps('left_table', 'right_table' [, col1, col2, col3 [, col4, col5, col6]] [, 'strict'|'weak'])" in msg
+    st, msg = _err(ctx.coverage, "a", "b", "c`x", "s", "e")
+    assert st == S.PLAN and "coverage() column name must not contain backtick characters, got: c`x" in msg
+    st, msg = _err(ctx.nearest, "a", "b", k=0)
+    assert st == S.PLAN and "nearest() k must be >= 1" in msg
+    st, msg = _err(ctx.count_overlaps, "a", "nope")
+    assert st == S.PLAN and "table 'nope' not found" in msg
+    # column errors (array_utils.rs:178-300)
+    st, msg = _err(ctx.count_overlaps, "a", "b", "chrom", "pos_start", "pos_end")
+    assert st == S.PLAN and "contig column 'chrom' not found in batch with columns: [\"contig\", \"pos_start\", \"pos_end\"]" in msg
+    ctx.register_table("f", pa.table({"contig": ["chr1"], "pos_start": pa.array([1.5], pa.float64()), "pos_end": pa.array([2], pa.int32())}))
+    st, msg = _err(ctx.count_overlaps, "f", "b")
+    assert st == S.NOT_IMPLEMENTED
+    assert "unsupported data type Float64 for start column 'pos_start'; expected Int32, Int64, UInt32, or UInt64" in msg
+    ctx.register_table("g", pa.table({"contig": pa.array([7], pa.int32()), "pos_start": pa.array([1], pa.int32()), "pos_end": pa.array([2], pa.int32())}))
+    st, msg = _err(ctx.count_overlaps, "g", "b")
+    assert st == S.NOT_IMPLEMENTED and "unsupported data type Int32 for contig column 'contig'; expected Utf8, LargeUtf8, or Utf8View" in msg
+    ctx.close()
+
+
+def test_resolve_positions_like_posarray_resolve():
+    """array_utils.rs:73-131"""
+    b = pa.record_batch({"i32": pa.array([1, -5, 2**31 - 1], pa.int32()), "i64": pa.array([1, 2, 3], pa.int64()),
+                         "u32": pa.array([0, 7, 2**31 - 1], pa.uint32()), "u64": pa.array([5, 6, 7], pa.uint64()),
+                         "big": pa.array([1, 2**31, 3], pa.int64()), "ubig": pa.array([1, 2, 2**32 + 5], pa.uint64()),
+                         "nul": pa.array([1, None, 3], pa.int64()), "txt": pa.array(["a", "b", "c"])})
+    assert list(S.resolve_positions(b, "i32")) == [1, -5, 2**31 - 1]
+    assert list(S.resolve_positions(b, "i64")) == [1, 2, 3]
+    assert list(S.resolve_positions(b, "u32")) == [0, 7, 2**31 - 1]
+    assert list(S.resolve_positions(b, "u64")) == [5, 6, 7]
+    st, msg = _err(S.resolve_positions, b, "big")
+    assert st == S.EXECUTION and "coordinate value 2147483648 at row 1 overflows i32 (max 2147483647)" in msg
+    st, msg = _err(S.resolve_positions, b, "ubig")
+    assert st == S.EXECUTION and "coordinate value 4294967301 at row 2 overflows i32 (max 2147483647)" in msg
+    st, msg = _err(S.resolve_positions, b, "nul")
+    assert st == S.EXECUTION and "coordinate column contains null values" in msg
+    st, msg = _err(S.resolve_positions, b, "txt", "end")
+    assert st == S.NOT_IMPLEMENTED and "unsupported data type Utf8 for end column 'txt'" in msg
+    # a sliced batch (non-zero offset)
+    assert list(S.resolve_positions(b.slice(1, 2), "i64")) == [2, 3]
+
+
+def test_take_matches_arrow_compute():
+    import pyarrow.compute as pc
+
+    rng = np.random.default_rng(0)
+    n = 1000
+    b = pa.record_batch({
+        "s": pa.array([None if i % 17 == 0 else f"chr{i % 23}_{'x' * (i % 5)}" for i in range(n)], pa.string()),
+        "ls": pa.array([f"L{i}" for i in range(n)], pa.large_string()),
+        "i32": pa.array(rng.integers(-100, 100, n), pa.int32()),
+        "i64": pa.array([None if i % 11 == 0 else int(i) * 10**10 for i in range(n)], pa.int64()),
+        "f64": pa.array(rng.random(n), pa.float64()),
+        "u8": pa.array(rng.integers(0, 255, n), pa.uint8()),
+        "flag": pa.array([bool(i % 3) for i in range(n)], pa.bool_()),
+    })
+    idx = rng.integers(0, n, 5000).astype(np.uint32)
+    valid = rng.random(5000) > 0.2
+    for src in (b, b.slice(100, 700)):
+        ii = idx % src.num_rows
+        got = S.take(src, ii, valid, prefix="left_")
+        want_idx = pa.array([int(v) if ok else None for v, ok in zip(ii, valid)], pa.uint32())
+        for name in src.schema.names:
+            assert got.column("left_" + name).equals(pc.take(src.column(name), want_idx)), name
+        got2 = S.take(src, ii)
+        assert got2.column("s").equals(pc.take(src.column("s"), pa.array(ii, pa.uint32())))
+    st, msg = _err(S.take, b, np.array([n], np.uint32))
+    assert st == S.ARROW and "index out of bounds" in msg.lower()
