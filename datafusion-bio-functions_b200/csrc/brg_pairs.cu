@@ -198,14 +198,20 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
 
 constexpr int PF_THREADS = 256;
 constexpr int PF_WARPS = PF_THREADS / 32;
-constexpr int PF_U = 4;       // slot steps in flight per iteration of the emit loop
+#ifndef BRG_PF_U
+#define BRG_PF_U 4
+#endif
+#ifndef BRG_PF_CTAS
+#define BRG_PF_CTAS 4
+#endif
+constexpr int PF_U = BRG_PF_U;  // slot steps in flight per iteration of the emit loop
 constexpr int PF_CAP = 2560;  // candidate slots a warp flattens at a time (bytes of the slot -> row map)
 struct __align__(16) FlatWarp {
     uint4 row[TP_WTILE + 1];    // per row {P = exclusive prefix of the candidate counts, i0, qs, -}; row[256].x = total
     uint8_t rowof[PF_CAP];
 };
 
-__global__ void __launch_bounds__(PF_THREADS, 4) pairs_emit_kernel_flat(IndexView ix, const int32_t* __restrict__ start,
+__global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_flat(IndexView ix, const int32_t* __restrict__ start,
                                                                         uint64_t n_rows, uint64_t n_chunks,
                                                                         const uint64_t* __restrict__ row_rng,
                                                                         const uint64_t* __restrict__ chunk_base,
@@ -482,7 +488,7 @@ int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const u
     BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_emit_kernel_flat, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(FlatWarp) * PF_WARPS)));
     const uint64_t ctas = (n_chunks + PF_WARPS - 1) / PF_WARPS;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctas, (uint64_t)kSMs * 4));
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctas, (uint64_t)kSMs * BRG_PF_CTAS));
     pairs_emit_kernel_flat<<<grid, PF_THREADS, sizeof(FlatWarp) * PF_WARPS, st>>>(ix, s, n, n_chunks, row_rng, chunk_base, build_idx,
                                                                                  probe_idx);
     BRG_LAUNCH_CHECK();

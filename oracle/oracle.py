@@ -153,7 +153,14 @@ def merge_intervals(first, last):
 
 
 def max_threads():
-    return lib().brgo_max_threads()
+    """host cores this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently turn the multi-threaded CPU baseline into a single-threaded one."""
+    import os
+
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
 
 
 # ---------------------------------------------------------------------------------------------
