@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(In
             }
             // seg_begin + #(starts <= qe)  and  seg_begin + #(ends < qs)
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, started);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, ended);
+            // both searches interleaved when both windows are short (the common case), else one after the other
+            if (!(mono_s && mono_e &&
+                  warp_window_ranks2<false, true>(cs, ix.d_sstart, ks, t.qe, t.s_qe, aux0, started, ce, ix.d_eend, ke, t.qs, t.s_qs,
+                                                  aux1, ended, kuni))) {
+                ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, started);
+                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, ended);
+            }
         }
         if (ok) {
             long long cnt[PV];
@@ -226,8 +231,12 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled
             }
             // merged intervals overlapping [qs,qe] are exactly [first j with last_j >= qs, first j with first_j > qe)
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, win, lo);
-            ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, win, hi);
+            if (!(mono_s && mono_e &&
+                  warp_window_ranks2<true, false>(cl, ix.d_mlast, kl, t.qs, t.s_qs, aux0, lo, cf, ix.d_mfirst, kf, t.qe, t.s_qe, aux1,
+                                                  hi, kuni))) {
+                ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, win, lo);
+                ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, win, hi);
+            }
         }
         if (ok) {
             long long cov[PV];

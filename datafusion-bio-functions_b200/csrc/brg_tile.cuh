@@ -463,6 +463,68 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
     return false;
 }
 
+// Two inverse searches at once.  The common case of the sparse regime -- both windows fit one round of 32 elements --
+// is a chain of dependent shared-memory accesses (8 search steps, histogram atomics, prefix sums): running the chains
+// of the two arrays interleaved doubles the instruction-level parallelism of the warp.  Returns false WITHOUT touching
+// cursors or results when the case does not apply (a cursor in dense mode, a window wider than one round); the caller
+// then runs the two searches one after the other.  Preconditions: full chunk, q0 and q1 non-decreasing.
+template <bool LT0, bool LT1>
+__device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView& d0, const KeyDir& k0, const int32_t (&q0)[PV],
+                                                   const int32_t* Q0, uint32_t* aux0, uint32_t (&r0)[PV], WarpCursor& c1,
+                                                   const DirView& d1, const KeyDir& k1, const int32_t (&q1)[PV],
+                                                   const int32_t* Q1, uint32_t* aux1, uint32_t (&r1)[PV], uint32_t kid) {
+    if (c0.dense || c1.dense) return false;
+    const int lane = threadIdx.x & 31;
+    const int32_t mn0 = __shfl_sync(0xFFFFFFFFu, q0[0], 0), mx0 = __shfl_sync(0xFFFFFFFFu, q0[PV - 1], 31);
+    const int32_t mn1 = __shfl_sync(0xFFFFFFFFu, q1[0], 0), mx1 = __shfl_sync(0xFFFFFFFFu, q1[PV - 1], 31);
+    const bool reuse0 = c0.valid && c0.key == kid && mn0 >= c0.bound;
+    const bool reuse1 = c1.valid && c1.key == kid && mn1 >= c1.bound;
+    if (!(reuse0 && reuse1)) return false;  // (first chunk of a run: the single searches consult the directory)
+    const uint32_t lo0 = c0.pos, lo1 = c1.pos;
+    const int32_t v0 = c0.pre, v1 = c1.pre;
+    const bool in0 = lo0 + lane < k0.seg_end && (LT0 ? v0 < mx0 : v0 <= mx0);
+    const bool in1 = lo1 + lane < k1.seg_end && (LT1 ? v1 < mx1 : v1 <= mx1);
+    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
+    if (m0 == 0xFFFFFFFFu || m1 == 0xFFFFFFFFu) return false;  // a window continues past this round
+    uint4* a0 = reinterpret_cast<uint4*>(aux0) + 2 * lane;
+    uint4* a1 = reinterpret_cast<uint4*>(aux1) + 2 * lane;
+    a0[0] = make_uint4(0, 0, 0, 0); a0[1] = make_uint4(0, 0, 0, 0);
+    a1[0] = make_uint4(0, 0, 0, 0); a1[1] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    if (m0 | m1) {
+        uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+        for (uint32_t step = 128; step; step >>= 1) {
+            const int32_t x0 = Q0[p0 + step - 1], x1 = Q1[p1 + step - 1];
+            p0 += (LT0 ? (x0 <= v0) : (x0 < v0)) ? step : 0u;
+            p1 += (LT1 ? (x1 <= v1) : (x1 < v1)) ? step : 0u;
+        }
+        if (in0) atomicAdd(&aux0[p0], 1u);
+        if (in1) atomicAdd(&aux1[p1], 1u);
+    }
+    __syncwarp();
+    c0.pos = lo0 + __popc(m0); c0.bound = mx0; c0.dense = false;
+    c1.pos = lo1 + __popc(m1); c1.bound = mx1; c1.dense = false;
+    c0.pre = (c0.pos + lane < k0.seg_end) ? __ldg(d0.A + c0.pos + lane) : INT32_MAX;
+    c1.pre = (c1.pos + lane < k1.seg_end) ? __ldg(d1.A + c1.pos + lane) : INT32_MAX;
+    const uint4 h00 = a0[0], h01 = a0[1], h10 = a1[0], h11 = a1[1];
+    uint32_t e0[PV] = {h00.x, h00.y, h00.z, h00.w, h01.x, h01.y, h01.z, h01.w};
+    uint32_t e1[PV] = {h10.x, h10.y, h10.z, h10.w, h11.x, h11.y, h11.z, h11.w};
+#pragma unroll
+    for (int j = 1; j < PV; j++) { e0[j] += e0[j - 1]; e1[j] += e1[j - 1]; }
+    uint32_t i0 = e0[PV - 1], i1 = e1[PV - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), y1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+        if (lane >= o) { i0 += y0; i1 += y1; }
+    }
+    const uint32_t b0 = lo0 + i0 - e0[PV - 1], b1 = lo1 + i1 - e1[PV - 1];
+#pragma unroll
+    for (int j = 0; j < PV; j++) { r0[j] = b0 + e0[j]; r1[j] = b1 + e1[j]; }
+    __syncwarp();
+    return true;
+}
+
 // r[j] = seg_begin + #(A <= qe[j]) for a chunk of a START-sorted probe table.  Interval ends are only sorted when all
 // probes have the same length, so the search is keyed on the (sorted) starts whenever the ends are not monotone:
 //   dense window  : dense_ranks stages the window up to the largest end and binary-searches the ends in shared memory

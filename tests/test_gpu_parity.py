@@ -317,3 +317,41 @@ def test_gpu_index_export_import_roundtrip(ctx):
     assert (ix.coverage(pk, ps, pe) == ix2.coverage(pk, ps, pe)).all()
     a, b = ix.nearest_k1(pk, ps, pe), ix2.nearest_k1(pk, ps, pe)
     assert all((x == y).all() for x, y in zip(a, b))
+
+
+def test_gpu_concurrent_probes_share_one_index(ctx):
+    """the reference shares one build result across partitions polled on several threads (joins/utils.rs:73-107,
+    count_overlaps.rs:127-153): probe entry points are re-entrant against an immutable index"""
+    import threading
+
+    rng = np.random.default_rng(12)
+    nk = 4
+    bk, bs, be = _rand(rng, 80_000, nk, 0, 5_000_000, 900)
+    gi = ctx.build(bk, bs, be, nk)
+    oi = O.OracleIndex(bk, bs, be, nk)
+    parts = [_sorted_probes(np.random.default_rng(100 + t), 300_000 + 1000 * t, nk, 5_000_000, 1, 700) for t in range(6)]
+    want = [(oi.count_overlaps(*p, threads=O.max_threads()), oi.coverage(*p, threads=O.max_threads()), oi.nearest_k1(*p, threads=O.max_threads()))
+            for p in parts]
+    got, errs = [None] * len(parts), []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                got[t] = (gi.count_overlaps(*parts[t]), gi.coverage(*parts[t]), gi.nearest_k1(*parts[t]),
+                          gi.overlap_pairs(*parts[t]))
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(len(parts))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t, p in enumerate(parts):
+        assert (got[t][0] == want[t][0]).all() and (got[t][1] == want[t][1]).all()
+        assert all((a == b).all() for a, b in zip(got[t][2], want[t][2]))
+        gb, gp = O.canonical_pairs(*got[t][3])
+        ob, op = O.canonical_pairs(*oi.overlap_pairs(*p))
+        assert (gb == ob).all() and (gp == op).all()
+    gi.close()
