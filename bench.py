@@ -390,7 +390,13 @@ def main():
             estep = lambda: hfn(npk, nps, npe, out=h_out.numpy())
         h2d, d2h, e_units = n * (8 if use_runs else 12), n * 8, n
     elif name == "nearest":
-        estep = (lambda: ix.nearest_k1_runs(run_key, run_end, nps, npe)) if use_runs else (lambda: ix.nearest_k1(npk, nps, npe))
+        if not use_runs:  # the id column form has no caller-buffer variant in the python wrapper: send one run per row change
+            use_runs = True
+        h_left = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_bits = torch.zeros(((n + 31) // 32) * 4, dtype=torch.uint8).pin_memory()
+        h_dist = torch.empty(n, dtype=torch.int64).pin_memory()
+        nout = (h_left.numpy().view(np.uint32), h_bits.numpy(), h_dist.numpy())
+        estep = lambda: ix.nearest_k1_runs(run_key, run_end, nps, npe, out=nout)
         h2d, d2h, e_units = n * (8 if use_runs else 12), n * 12 + n // 8, n
     else:
         use_runs = False

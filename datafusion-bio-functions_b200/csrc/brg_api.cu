@@ -695,6 +695,12 @@ extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, con
     return launch_pairs_fill(ix->view, s, n, d_chunk_base, d_row_ranges, d_build_idx, d_probe_idx, (cudaStream_t)stream);
 }
 
+extern "C" BRG_API int brg_take_dev(brg_ctx* ctx, const void* d_src, uint32_t elem_bytes, const uint32_t* d_idx,
+                            const uint32_t* d_valid_bits, uint64_t n, void* d_out, void* stream) {
+    if (!ctx || (n && (!d_src || !d_idx || !d_out))) { set_error("brg_take: NULL argument"); return BRG_ERR_INVALID; }
+    return launch_take(d_src, elem_bytes, d_idx, d_valid_bits, n, d_out, (cudaStream_t)stream) ? BRG_ERR_INVALID : BRG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-buffer probes with fixed-size outputs: chunked, double-buffered H2D / kernel / D2H pipeline
 // ---------------------------------------------------------------------------------------------------

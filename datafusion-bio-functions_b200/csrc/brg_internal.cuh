@@ -154,6 +154,8 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
                                uint64_t* chunk_base /*n_chunks + 1*/, uint64_t* row_rng /*n*/, cudaStream_t st);
 int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const uint64_t* chunk_base, const uint64_t* row_rng,
                       uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
+int launch_take(const void* src, uint32_t elem_bytes, const uint32_t* idx, const uint32_t* valid_bits, uint64_t n, void* out,
+                cudaStream_t st);
 int launch_semi_anti_flags(const uint32_t* counts, uint64_t n, int anti, uint32_t* flags, cudaStream_t st);
 int launch_compact_rows(const uint32_t* flags, const uint64_t* offsets, uint64_t n, uint32_t* probe_idx,
                         cudaStream_t st);

@@ -99,7 +99,10 @@ __device__ __forceinline__ uint32_t walk_count(const IndexView& ix, uint32_t i0,
     return c;
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 2) pairs_ranges_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+#ifndef BRG_PR_CTAS
+#define BRG_PR_CTAS 2
+#endif
+__global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
                                                                            const int32_t* __restrict__ start,
                                                                            const int32_t* __restrict__ end, uint64_t n_rows,
                                                                            uint64_t* __restrict__ row_rng,
@@ -365,6 +368,39 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Output materialisation on the device: arrow::compute::take of a fixed-width column by the emitted index column
+// (interval_join.rs:1655-1667, nearest.rs:456-482).  One element per thread; the index column of a probe-major pair list
+// is non-decreasing on the probe side and locally clustered on the build side, so the gathers hit L1/L2.
+// NULL indices (validity bit clear) produce zeroed elements; the output validity is the index validity.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void take_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ valid_bits,
+                            uint64_t n, T* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool ok = !valid_bits || ((__ldg(valid_bits + (i >> 5)) >> (i & 31)) & 1u);
+        T v{};
+        if (ok) v = __ldg(src + __ldcs(idx + i));
+        __stcs(out + i, v);
+    }
+}
+int launch_take(const void* src, uint32_t elem_bytes, const uint32_t* idx, const uint32_t* valid_bits, uint64_t n, void* out,
+                cudaStream_t st) {
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)kSMs * 32));
+    switch (elem_bytes) {
+        case 1: take_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, idx, valid_bits, n, (uint8_t*)out); break;
+        case 2: take_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, idx, valid_bits, n, (uint16_t*)out); break;
+        case 4: take_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)src, idx, valid_bits, n, (uint32_t*)out); break;
+        case 8: take_kernel<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long*)src, idx, valid_bits, n, (unsigned long long*)out); break;
+        case 16: take_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)src, idx, valid_bits, n, (uint4*)out); break;
+        default: set_error("brg_take: element width must be 1, 2, 4, 8 or 16 bytes"); return 1;
+    }
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
 // RightSemi / RightAnti (interval_join.rs:1433-1463): keep probe rows with (no) match
 __global__ void semi_anti_flags_kernel(const uint32_t* __restrict__ counts, uint64_t n, int anti,
                                        uint32_t* __restrict__ flags) {
@@ -464,7 +500,7 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
         if ((rc = todo_list_alloc(p.n_chunks, &todo, st))) return rc;
         BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_ranges_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
         const uint64_t tiles = p.full_rows / TP_TILE + 1;
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * 2));
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * BRG_PR_CTAS));
         pairs_ranges_kernel_tiled<<<grid, TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, p.full_rows, row_rng, tot, todo);
         BRG_LAUNCH_CHECK();
         pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, todo, 0u, p.tail_chunk);

@@ -283,15 +283,19 @@ struct Cand {
     int32_t s, e;
     uint32_t pos;
 };
-// nearest_index.rs:252-260 (same precedence of the two tests, written as selects: no divergent branches)
-__device__ __forceinline__ int64_t cand_distance(int32_t qs, int32_t qe, int32_t is, int32_t ie) {
-    const int64_t right = (int64_t)is - (int64_t)qe, left = (int64_t)qs - (int64_t)ie;
-    const int64_t d = (ie < qs) ? left : 0;
+// nearest_index.rs:252-260 (same precedence of the two tests, written as selects: no divergent branches).  Both
+// differences are taken where they are positive, so they are exact in 32-bit unsigned arithmetic (< 2^32).
+__device__ __forceinline__ uint32_t cand_distance_u32(int32_t qs, int32_t qe, int32_t is, int32_t ie) {
+    const uint32_t right = (uint32_t)is - (uint32_t)qe, left = (uint32_t)qs - (uint32_t)ie;
+    const uint32_t d = (ie < qs) ? left : 0u;
     return (qe < is) ? right : d;
+}
+__device__ __forceinline__ int64_t cand_distance(int32_t qs, int32_t qe, int32_t is, int32_t ie) {
+    return (int64_t)cand_distance_u32(qs, qe, is, ie);
 }
 // cmp_candidate(a,b) <= 0  (nearest_index.rs:262-266): (distance, start, end, position)
 __device__ __forceinline__ bool cand_le(int32_t qs, int32_t qe, const Cand& a, const Cand& b) {
-    const int64_t ad = cand_distance(qs, qe, a.s, a.e), bd = cand_distance(qs, qe, b.s, b.e);
+    const uint32_t ad = cand_distance_u32(qs, qe, a.s, a.e), bd = cand_distance_u32(qs, qe, b.s, b.e);
     const bool tail = (a.e != b.e) ? a.e < b.e : a.pos <= b.pos;
     const bool mid = (a.s != b.s) ? a.s < b.s : tail;
     return (ad != bd) ? ad < bd : mid;
@@ -417,9 +421,14 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            // the two start-keyed searches interleaved when both windows are short, else one after the other
+            const bool dual = mono_s && warp_window_ranks2<true, true>(cp, ix.d_pme, kp, t.qs, t.s_qs, aux1, i_pme, ce, ix.d_eend, ke,
+                                                                       t.qs, t.s_qs, aux2, l_idx, kuni);
             ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, n_le);
-            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i_pme);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, l_idx);
+            if (!dual) {
+                ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i_pme);
+                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, l_idx);
+            }
         }
         if (ok) {
             uint32_t pos[PV];

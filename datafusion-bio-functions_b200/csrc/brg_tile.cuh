@@ -31,7 +31,10 @@ constexpr int TP_STAGES = 2;
 constexpr int TP_WCAP = 256;                // words of per-array scratch (histogram bins / window copy of the fallback)
 constexpr int TP_NWIN = 3;                  // scratch buffers per warp (one per sorted array searched)
 constexpr int TP_WMAX = 1024;               // widest window the inverse search walks before the chunk is deferred
-constexpr int TP_WBATCH = 4;                // rounds of a dense window fetched per batch of independent loads
+#ifndef BRG_WBATCH
+#define BRG_WBATCH 8  // (pairs 10M x 10M: 0.45 ms per step with 8 rounds per batch, 0.49 ms with 4)
+#endif
+constexpr int TP_WBATCH = BRG_WBATCH;                // rounds of a dense window fetched per batch of independent loads
 constexpr int TP_SCAN_MAX = 12;             // forward-scan steps before a row falls back to the rank directory
 constexpr int TP_FWCAP = TP_NWIN * TP_WCAP; // words of the per-warp scratch area = capacity of a staged (dense) window
 constexpr int TP_DENSE_ON = 96;             // window sizes at which the search switches to / from the forward search

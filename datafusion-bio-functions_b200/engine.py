@@ -32,6 +32,15 @@ class Context:
         except Exception:
             pass
 
+    def take_dev(self, src, idx, out, valid_bits=None):
+        """out[i] = src[idx[i]] on the device (fixed-width column gather by an emitted index column)"""
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().brg_take_dev(self._h, _tptr(src), src.element_size(), _tptr(idx), _tptr(valid_bits), idx.numel(),
+                                     _tptr(out), st))
+        return out
+
     # ---- build ------------------------------------------------------------------------------------------
     def build(self, key, start, end, n_keys, want=A.WANT_ALL):
         key = A.as_key(key)
@@ -156,17 +165,25 @@ class Index:
                                           A.np_ptr(start), A.np_ptr(end), len(start), int(strict), A.np_ptr(out)))
         return out
 
-    def nearest_k1_runs(self, run_key, run_end, start, end, include_overlaps=True, strict=False, compute_distance=True):
+    def nearest_k1_runs(self, run_key, run_end, start, end, include_overlaps=True, strict=False, compute_distance=True,
+                        out=None):
+        """out: optional (left_idx u32[n], valid_bits u8[4*ceil(n/32)], distance i64[n]) caller buffers (e.g. pinned);
+        with `out` the packed Arrow validity bitmap is returned as is"""
         start, end = A.as_i32(start), A.as_i32(end)
         run_key = np.ascontiguousarray(run_key, np.uint32)
         run_end = np.ascontiguousarray(run_end, np.uint64)
         n = len(start)
-        left = np.empty(n, np.uint32)
-        bits = np.zeros(((n + 31) // 32) * 4, np.uint8)
-        dist = np.empty(n, np.int64) if compute_distance else None
+        if out is None:
+            left = np.empty(n, np.uint32)
+            bits = np.zeros(((n + 31) // 32) * 4, np.uint8)
+            dist = np.empty(n, np.int64) if compute_distance else None
+        else:
+            left, bits, dist = out
         A.check(A.lib().brg_nearest_k1_runs(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key),
                                             A.np_ptr(start), A.np_ptr(end), n, int(include_overlaps), int(strict),
                                             A.np_ptr(left), A.np_ptr(bits), A.np_ptr(dist)))
+        if out is not None:
+            return left, bits, dist
         return left, A.unpack_bits(bits, n), dist
 
     def coverage(self, key, start, end, strict=False, out=None):

@@ -179,6 +179,12 @@ BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* idx, const int32_t
                        const uint64_t* d_chunk_base, const uint64_t* d_row_ranges, uint32_t* d_build_idx,
                        uint32_t* d_probe_idx, void* stream);
 
+/* ---- output materialisation on the device (replaces arrow::compute::take of a fixed-width column by the emitted
+ *      index column, interval_join.rs:1655-1667, nearest.rs:456-482): d_out[i] = d_src[d_idx[i]], zero where the
+ *      validity bit of i is clear (d_valid_bits may be NULL = all valid).  elem_bytes in {1, 2, 4, 8, 16}. */
+BRG_API int brg_take_dev(brg_ctx* ctx, const void* d_src, uint32_t elem_bytes, const uint32_t* d_idx,
+                 const uint32_t* d_valid_bits, uint64_t n, void* d_out, void* stream);
+
 /* ---- variable-length results ------------------------------------------------------------------------ */
 BRG_API uint64_t brg_rows_len(const brg_rows* r);
 BRG_API const uint32_t* brg_rows_build_idx(const brg_rows* r); /* NULL for SEMI/ANTI                   */

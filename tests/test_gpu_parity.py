@@ -355,3 +355,25 @@ def test_gpu_concurrent_probes_share_one_index(ctx):
         ob, op = O.canonical_pairs(*oi.overlap_pairs(*p))
         assert (gb == ob).all() and (gp == op).all()
     gi.close()
+
+
+def test_gpu_take_dev_matches_index_select(ctx):
+    """device-side `take` of fixed-width columns by the emitted pair indices (interval_join.rs:1655-1667)"""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_src, n = 1_000_003, 3_000_001
+    idx = torch.randint(0, n_src, (n,), device="cuda", generator=g, dtype=torch.int32)
+    valid = torch.rand(n, device="cuda", generator=g) > 0.1
+    pad = (-n) % 32
+    vb = torch.cat([valid, torch.zeros(pad, dtype=torch.bool, device="cuda")]).view(-1, 32).to(torch.int64)
+    bits = (vb << torch.arange(32, device="cuda")).sum(1).to(torch.int32)  # LSB-first validity words
+    for dtype in (torch.uint8, torch.int16, torch.int32, torch.int64):
+        src = torch.randint(0, 100, (n_src,), device="cuda", generator=g).to(dtype)
+        out = torch.empty(n, dtype=dtype, device="cuda")
+        ctx.take_dev(src, idx, out)
+        torch.cuda.synchronize()
+        assert torch.equal(out, src[idx.long()])
+        ctx.take_dev(src, idx, out, valid_bits=bits)
+        torch.cuda.synchronize()
+        assert torch.equal(out, torch.where(valid, src[idx.long()], torch.zeros((), dtype=dtype, device="cuda")))
