@@ -321,6 +321,7 @@ __device__ __forceinline__ bool nearest_one(const IndexView& ix, uint32_t c, int
         *best = load_s(ix, idx);
         return true;
     }
+    if (include_overlaps == 2) return false;                            // overlaps only (BRG_NEAREST_OVERLAP_ONLY)
     KeyDir ke = load_keydir(ix.d_eend.kd, c);                           // nearest_non_overlap_one (:192-220)
     const uint32_t left_idx = rank_lt_kd(ix.d_eend, ke, qs);            // partition_point(last < start)
     const bool has_left = left_idx > ke.seg_begin, has_right = n_le < ks.seg_end;
@@ -383,7 +384,7 @@ __device__ __forceinline__ bool nearest_from_ranks(const IndexView& ix, uint32_t
     Cand c = take_left ? l : r;
     if (ov) c = Cand{ro.x, ro.y, (uint32_t)ro.z};
     *best = c;
-    return ov || has_left || has_right;
+    return ov || (include_overlaps != 2 && (has_left || has_right));  // 2 = overlaps only
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,

@@ -835,10 +835,11 @@ static Err run_join(brgh_session* s, const Table& lt, const Table& rt, const cha
     }
     // `l.end > r.start` compares against l.end - 1 (intervals.rs:85-115: minus_one on the side of the strict comparison)
     if (gt_strict) for (auto& v : ben) v = (int32_t)((uint32_t)v - 1u);
-    const bool nearest_mode = s->algorithm == CoitreesNearest;
-    if (s->algorithm == CoitreesCountOverlaps)
-        return notimpl("bio.interval_join_algorithm = CoitreesCountOverlaps emits the first interval the tree visits, an order the "
-                       "reference leaves unspecified (interval_join.rs:1627-1636); it has no GPU equivalent");
+    // one-row-per-probe modes (interval_join.rs:1627-1636): CoitreesNearest = nearest_one(start, end, true);
+    // CoitreesCountOverlaps = the first overlapping interval or NULL.  The reference takes the first interval its tree
+    // visits (order unspecified); here it is the first in (start, end, row id) order.
+    const bool nearest_mode = s->algorithm == CoitreesNearest || s->algorithm == CoitreesCountOverlaps;
+    const int nearest_overlaps = s->algorithm == CoitreesCountOverlaps ? BRG_NEAREST_OVERLAP_ONLY : 1;
     brg_ctx* ctx;
     BRGH_TRY(session_ctx(s, &ctx));
     IndexGuard ig;
@@ -869,7 +870,7 @@ static Err run_join(brgh_session* s, const Table& lt, const Table& rt, const cha
             // one row per probe row: nearest_one(start, end, true), NULL left when the key has no index (interval_join.rs:864-870)
             std::vector<uint32_t> li(n);
             std::vector<uint8_t> bits(((n + 31) / 32) * 4, 0);
-            if (n) BRGH_TRY(from_abi(brg_nearest_k1(ctx, ig.ix, pk.data(), pst.data(), pen.data(), n, 1, 0, li.data(), bits.data(), nullptr)));
+            if (n) BRGH_TRY(from_abi(brg_nearest_k1(ctx, ig.ix, pk.data(), pst.data(), pen.data(), n, nearest_overlaps, 0, li.data(), bits.data(), nullptr)));
             int64_t nulls = 0;
             for (uint64_t i = 0; i < n; i++) nulls += ((bits[i >> 3] >> (i & 7)) & 1) ? 0 : 1;
             std::vector<uint32_t> ri(n);

@@ -137,6 +137,11 @@ BRG_API int brg_coverage_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t*
  *      out_valid_bits = Arrow validity bitmap (LSB-first, ceil(n/8) bytes, padded to 4 bytes) shared by the
  *      left columns and the distance column; out_distance (may be NULL) from RAW probe coordinates
  *      (nearest.rs:367-375), 0 where invalid. */
+/* include_overlaps: 0 = neighbours only, 1 = first overlap else nearest neighbour (the reference's two settings),
+ * BRG_NEAREST_OVERLAP_ONLY = first overlap in (start, end, row id) order else NULL -- the one-row-per-probe mode of the
+ * CoitreesCountOverlaps join arm (interval_join.rs:1627-1636; the reference emits the first interval its tree VISITS, an
+ * order it leaves unspecified, so which of several overlapping intervals is reported is not pinned). */
+#define BRG_NEAREST_OVERLAP_ONLY 2
 BRG_API int brg_nearest_k1(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
                    const int32_t* end, uint64_t n, int include_overlaps, int strict, uint32_t* out_left_idx,
                    uint8_t* out_valid_bits, int64_t* out_distance);

@@ -97,6 +97,23 @@ def test_join_coitrees_nearest_two_column_key(ctx):
     assert rows == sorted(want, key=repr)
 
 
+# ---- interval_join.rs:1627-1636: CoitreesCountOverlaps = one row per probe row, an overlapping interval or NULL --------------
+def test_join_coitrees_count_overlaps_mode(ctx):
+    init_ranges_tables(ctx)
+    ctx.set("bio.interval_join_algorithm", "CoitreesCountOverlaps")
+    out = ctx.interval_join("reads", "targets", [("contig", "contig")], ("pos_start", "pos_end"), ("pos_start", "pos_end"))
+    t = pa.Table.from_batches(out)
+    assert t.num_rows == len(RANGES_TARGETS)  # exactly one row per probe row, in probe order
+    rows = list(zip(*[t.column(i).to_pylist() for i in range(6)]))
+    for row, probe in zip(rows, RANGES_TARGETS):
+        assert row[3:] == probe
+        hits = [a for a in RANGES_READS if a[0] == probe[0] and a[1] <= probe[2] and a[2] >= probe[1]]
+        if hits:  # which overlapping interval is unpinned in the reference; here: smallest (start, end, row)
+            assert row[:3] == min(hits, key=lambda a: (a[1], a[2]))
+        else:
+            assert row[:3] == (None, None, None)
+
+
 # ---- TEST:608-657 count_overlaps, TEST:664-717 coverage (ranges fixtures; also with shared / separate column names) --------
 @pytest.mark.parametrize("pos_type", [pa.int64(), pa.int32(), pa.uint32(), pa.uint64()])
 @pytest.mark.parametrize("contig_type", [pa.string(), pa.large_string(), pa.string_view()])
