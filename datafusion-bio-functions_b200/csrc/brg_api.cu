@@ -74,6 +74,10 @@ struct IndexHeader {
     uint64_t off_s_start, off_s_end, off_s_pos, off_pme, off_e_end, off_m_first, off_m_last, off_m_pre, off_s_rec, off_e_rec,
         off_m_rec;
     DirDesc dir[5];  // 0 s_start, 1 e_end, 2 pme, 3 m_first, 4 m_last
+    // compact rank index of s_start / e_end (per-row count path): samples, delta blocks, directory over the samples
+    uint64_t off_cS[2], off_cB[2];
+    DirDesc cdir[2];
+    uint32_t n_blocks, pad_;
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
 static const uint64_t kNone = ~0ull;
@@ -103,6 +107,16 @@ static IndexView make_view(const IndexHeader& h, void* slab) {
         dv[i]->D = (const uint32_t*)P(h.dir[i].off_D);
         dv[i]->A = arrs[i];
         dv[i]->shift = h.dir[i].shift;
+    }
+    CompactView* cv[2] = {&v.c_sstart, &v.c_eend};
+    const int32_t* plain[2] = {v.s_start, v.e_end};
+    for (int a = 0; a < 2; a++) {
+        cv[a]->blocks = (const uint4*)P(h.off_cB[a]);
+        cv[a]->A = plain[a];
+        cv[a]->d.kd = (const KeyDir*)P(h.cdir[a].off_kd);
+        cv[a]->d.D = (const uint32_t*)P(h.cdir[a].off_D);
+        cv[a]->d.A = (const int32_t*)P(h.off_cS[a]);
+        cv[a]->d.shift = h.cdir[a].shift;
     }
     return v;
 }
@@ -306,7 +320,7 @@ static const uint32_t kTargetPerBin = 4;
 
 // phase 1 of a directory: key ranges + choice of the bin width
 static int dir_plan(const int32_t* A, const uint32_t* off, uint32_t n_keys, uint64_t n_elems, DirBuild* db,
-                    unsigned long long* d_bins, uint32_t* d_total, cudaStream_t st) {
+                    unsigned long long* d_bins, uint32_t* d_total, cudaStream_t st, uint64_t bins_wanted = 0) {
     int rc = db->kd.ensure((uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
     if (rc) return rc;
     rc = dir_key_ranges(A, off, n_keys, db->kd.as<KeyDir>(), d_bins, st);
@@ -314,7 +328,7 @@ static int dir_plan(const int32_t* A, const uint32_t* off, uint32_t n_keys, uint
     unsigned long long bins[32];
     BRG_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof(bins), cudaMemcpyDeviceToHost, st));
     BRG_CUDA(cudaStreamSynchronize(st));
-    uint64_t budget = std::max<uint64_t>(n_elems / kTargetPerBin, 2ull * n_keys);
+    uint64_t budget = std::max<uint64_t>(bins_wanted ? bins_wanted : n_elems / kTargetPerBin, 2ull * n_keys);
     budget = std::max<uint64_t>(budget, 64);
     uint32_t shift = 31;
     for (uint32_t s = 0; s < 32; s++)
@@ -480,9 +494,35 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         if ((rc = dir_plan(dirA[i], dirOff[i], n_keys, dirN[i], &db[i], d_bins, d_scalar, st))) return rc;
     }
 
+    // ---- compact rank index of s_start / e_end: the L2-resident structure of the per-row count kernels -------
+    const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0;
+    DevBuf boff_d, cS[2], cB[2];
+    DirBuild cdb[2];
+    uint32_t n_blocks = 0;
+    if (need_ci) {
+        std::vector<uint32_t> h_off((size_t)n_keys + 1), h_boff((size_t)n_keys + 1);
+        BRG_CUDA(cudaMemcpyAsync(h_off.data(), off.p, ((uint64_t)n_keys + 1) * 4, cudaMemcpyDeviceToHost, st));
+        BRG_CUDA(cudaStreamSynchronize(st));
+        uint64_t acc = 0;
+        for (uint32_t k = 0; k < n_keys; k++) { h_boff[k] = (uint32_t)acc; acc += ((uint64_t)(h_off[k + 1] - h_off[k]) + CI_BLOCK - 1) / CI_BLOCK; }
+        h_boff[n_keys] = (uint32_t)acc;
+        n_blocks = (uint32_t)acc;
+        if ((rc = boff_d.ensure(((uint64_t)n_keys + 2) * 4))) return rc;
+        BRG_CUDA(cudaMemcpyAsync(boff_d.p, h_boff.data(), ((uint64_t)n_keys + 1) * 4, cudaMemcpyHostToDevice, st));
+        for (int a = 0; a < 2; a++) {
+            if ((rc = cS[a].ensure((uint64_t)n_blocks * 4)) || (rc = cB[a].ensure((uint64_t)n_blocks * 16))) return rc;
+            if ((rc = ci_build(dirA[a], off.as<uint32_t>(), boff_d.as<uint32_t>(), n_keys, n_blocks, cS[a].as<int32_t>(), cB[a].as<uint4>(), st)))
+                return rc;
+            // up to 2 bins per block (the bin width is a power of two: 1..2 in practice)
+            if ((rc = dir_plan(cS[a].as<int32_t>(), boff_d.as<uint32_t>(), n_keys, n_blocks, &cdb[a], d_bins, d_scalar, st, 2ull * n_blocks))) return rc;
+            if ((rc = ci_patch_keydir(cdb[a].kd.as<KeyDir>(), off.as<uint32_t>(), n_keys, st))) return rc;
+        }
+        BRG_CUDA(cudaStreamSynchronize(st));  // h_boff is read by the copy above
+    }
+
     // ---- lay out and fill the slab -------------------------------------------------------------------------
     IndexHeader h{};
-    h.magic = kMagic; h.version = 2;
+    h.magic = kMagic; h.version = 3;
     h.n_keys = n_keys; h.n = n_valid; h.n_merged = n_merged; h.flags = want | idx_props;
     uint64_t cur = 0;
     auto place = [&](bool on, uint64_t bytes) -> uint64_t {
@@ -508,6 +548,15 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         h.dir[i].off_D = place(need_dir[i], ((uint64_t)db[i].entries + 1) * 4);
         h.dir[i].shift = db[i].shift;
         h.dir[i].entries = db[i].entries;
+    }
+    h.n_blocks = n_blocks;
+    for (int a = 0; a < 2; a++) {
+        h.off_cS[a] = kNone;
+        h.off_cB[a] = place(need_ci, (uint64_t)n_blocks * 16);
+        h.cdir[a].off_kd = place(need_ci, (uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+        h.cdir[a].off_D = place(need_ci, ((uint64_t)cdb[a].entries + 1) * 4);
+        h.cdir[a].shift = cdb[a].shift;
+        h.cdir[a].entries = cdb[a].entries;
     }
     h.slab_bytes = std::max<uint64_t>(cur, 256);
 
@@ -536,12 +585,26 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     chk(copy_in(h.off_m_pre, m_pre.p, ((uint64_t)n_merged + 1) * 4));
     for (int i = 0; i < 5; i++)
         if (need_dir[i]) chk(copy_in(h.dir[i].off_kd, db[i].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
+    if (need_ci)
+        for (int a = 0; a < 2; a++) {
+            chk(copy_in(h.off_cB[a], cB[a].p, (uint64_t)n_blocks * 16));
+            chk(copy_in(h.cdir[a].off_kd, cdb[a].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
+        }
     if (ce != cudaSuccess) { cudaFree(slab); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
     for (int i = 0; i < 5; i++) {
         if (!need_dir[i]) continue;
         rc = dir_fill(dirA[i], db[i].kd.as<KeyDir>(), n_keys, db[i].shift, (uint32_t*)(base + h.dir[i].off_D), db[i].entries, st);
         if (rc) { cudaFree(slab); return rc; }
     }
+    if (need_ci)
+        for (int a = 0; a < 2; a++) {
+            DevBuf dtmp;  // plain table first, then packed into the slab
+            if ((rc = dtmp.ensure(((uint64_t)cdb[a].entries + 1) * 4))) { cudaFree(slab); return rc; }
+            rc = dir_fill(cS[a].as<int32_t>(), cdb[a].kd.as<KeyDir>(), n_keys, cdb[a].shift, dtmp.as<uint32_t>(), cdb[a].entries, st);
+            if (!rc) rc = ci_pack_table(dtmp.as<uint32_t>(), cdb[a].entries, (uint32_t*)(base + h.cdir[a].off_D), st);
+            if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("compact table: sync failed"); rc = BRG_ERR_CUDA; }
+            if (rc) { cudaFree(slab); return rc; }
+        }
     {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { cudaFree(slab); set_error(std::string("build sync: ") + cudaGetErrorString(e)); return BRG_ERR_CUDA; }
@@ -603,7 +666,7 @@ extern "C" BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64
     if (header_len != sizeof(IndexHeader)) { set_error("brg_index_import: header size mismatch"); return BRG_ERR_INVALID; }
     IndexHeader h;
     memcpy(&h, header, sizeof(h));
-    if (h.magic != kMagic || h.version != 2) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
+    if (h.magic != kMagic || h.version != 3) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
     BRG_CUDA(cudaSetDevice(ctx->device));
     void* slab = nullptr;
     cudaError_t e = cudaMalloc(&slab, h.slab_bytes);

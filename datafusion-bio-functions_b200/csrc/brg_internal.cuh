@@ -62,6 +62,33 @@ constexpr uint32_t BRG_IDX_INVERTED = 1u << 8;  // some build row has start > en
 // any row with start > end?  (sets *flag to 1)
 int flag_inverted_rows(const int32_t* start, const int32_t* end, uint64_t n, uint32_t* d_flag, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------------
+// Compact rank index: the search structure of the one-row-per-thread kernels (unsorted probe tables).
+// A random rank query against the plain arrays costs ~8 divergent load instructions (KeyDir, two directory words, a
+// binary search over a bin of A) and touches sectors that do not stay in L2 next to the probe stream
+// (profiles/r1_count_todo_v1_ncu.txt: 9.9 GB of DRAM reads for 1.5 GB of probe columns).  Fully divergent loads are
+// paid per lane in the L1 pipeline, so the structure below is built to need THREE of them per query:
+//   blocks : every key segment cut into runs of 7 consecutive elements, 16 bytes each:
+//            { int32 first element F ; u16 delta[6] of the next 6 elements from F }
+//            delta[0] == 0xFFFF marks a block whose deltas do not fit (the query then searches A itself);
+//            missing tail elements are 0xFFFE, above every clamped query; real deltas are <= 0xFFFD.
+//   P      : direct-address table over the VALUES: P[bin] = (first block starting in the bin) << 2 | min(#block starts
+//            in the bin, 3), about one bin per block.
+//   keys   : the per-key constants, copied to shared memory by the kernels when they fit.
+// Query = P[bin] -> the block before the bin, or the (1-2) blocks starting in it -> 16-byte block -> SIMD compare.
+// KeyDir of `d`: seg_begin/seg_end are block indices; pad[0]/pad[1] hold the ELEMENT range of the key in A.
+// ------------------------------------------------------------------------------------------------
+constexpr int CI_BLOCK = 7;
+struct CompactView {
+    DirView d;            // d.kd = per-key constants, d.D = packed table P, d.shift = bin width; d.A unused
+    const uint4* blocks;  // one uint4 per block; nullptr = structure absent
+    const int32_t* A;     // the plain sorted array (wide blocks)
+};
+struct CompactKey {       // per-key constants of a CompactView (32 bytes, same layout as KeyDir)
+    int32_t lo;
+    uint32_t nb, base, blk_begin, blk_end, eb, ee, pad;
+};
+
 // Device view of an index (pointers into the single HBM slab)
 struct IndexView {
     uint32_t n_keys;
@@ -87,6 +114,7 @@ struct IndexView {
     const int4* e_rec;
     const int4* m_rec;
     DirView d_sstart, d_eend, d_pme, d_mfirst, d_mlast;
+    CompactView c_sstart, c_eend;  // per-row path of count_overlaps
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +151,12 @@ int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uin
 // 16-byte records: out[i] = {a[i], b[i], c[i], d ? d[i] : 0}
 int pack_records(const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d, uint64_t n, int4* out,
                  cudaStream_t st);
+// compact rank index: S[j] / blocks[j] of every 16-element block; boff = per-key block offsets (n_keys + 1)
+int ci_build(const int32_t* A, const uint32_t* off, const uint32_t* boff, uint32_t n_keys, uint32_t n_blocks, int32_t* S,
+             uint4* blocks, cudaStream_t st);
+int ci_patch_keydir(KeyDir* kd, const uint32_t* off, uint32_t n_keys, cudaStream_t st);
+// P[i] = D[i] << 2 | min(D[i + 1] - D[i], 3)
+int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaStream_t st);
 // rank directory
 int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
                    cudaStream_t st);
@@ -189,6 +223,59 @@ __device__ __forceinline__ uint32_t rank_le_kd(const DirView& d, const KeyDir& k
 __device__ __forceinline__ uint32_t rank_lt_kd(const DirView& d, const KeyDir& k, int32_t q) {
     if (q == INT32_MIN) return k.seg_begin;
     return rank_le_kd(d, k, q - 1);
+}
+
+// seg_begin(A) + #(A <= q) within a key, through the compact index; k = the key's constants (shared or global memory)
+__device__ __forceinline__ uint32_t rank_le_compact(const CompactView& c, const CompactKey& k, int32_t q) {
+    if (k.nb == 0 || q < k.lo) return k.eb;
+    // J = last block whose first element is <= q
+    const uint32_t bin = ((uint32_t)q - (uint32_t)k.lo) >> c.d.shift;
+    uint32_t J;
+    uint4 w;
+    if (bin >= k.nb) {
+        J = k.blk_end - 1;
+        w = __ldg(c.blocks + J);
+    } else {
+        const uint32_t e = __ldg(c.d.D + k.base + bin);
+        const uint32_t j0 = e >> 2;
+        uint32_t cnt = e & 3u;
+        J = j0 - 1;  // (j0 > blk_begin whenever no block starting in this bin is <= q, see the builder)
+        bool found = false;
+        if (cnt) {
+            if (cnt == 3u) cnt = (__ldg(c.d.D + k.base + bin + 1) >> 2) - j0;  // saturated: the real count
+            for (uint32_t j = j0; j < j0 + cnt; j++) {  // block starts inside the bin: one, seldom more
+                const uint4 t = __ldg(c.blocks + j);
+                if ((int32_t)t.x > q) break;
+                J = j; w = t; found = true;
+            }
+        }
+        if (!found) w = __ldg(c.blocks + J);
+    }
+    const uint32_t e0 = k.eb + (J - k.blk_begin) * CI_BLOCK;
+    if ((w.y & 0xFFFFu) == 0xFFFFu) {  // wide block: search the elements themselves
+        uint32_t lo = e0, hi = min(e0 + CI_BLOCK, k.ee);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(c.A + mid) <= q) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+    const uint32_t t = min((uint32_t)q - w.x, 0xFFFDu);
+    const uint32_t tt = t | (t << 16);
+    const uint32_t bits = __popc(__vcmpleu2(w.y, tt)) + __popc(__vcmpleu2(w.z, tt)) + __popc(__vcmpleu2(w.w, tt));
+    return e0 + 1 + (bits >> 4);  // the block's first element + 16 bits per matching halfword
+}
+__device__ __forceinline__ uint32_t rank_lt_compact(const CompactView& c, const CompactKey& k, int32_t q) {
+    if (q == INT32_MIN) return k.eb;
+    return rank_le_compact(c, k, q - 1);
+}
+__device__ __forceinline__ CompactKey load_compact_key(const CompactView& c, uint32_t key) {
+    const int4* p = reinterpret_cast<const int4*>(c.d.kd + key);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    CompactKey k;
+    k.lo = a.x; k.nb = (uint32_t)a.y; k.base = (uint32_t)a.z; k.blk_begin = (uint32_t)a.w;
+    k.blk_end = (uint32_t)b.x; k.eb = (uint32_t)b.y; k.ee = (uint32_t)b.z; k.pad = 0;
+    return k;
 }
 
 // ------------------------------------------------------------------------------------------------

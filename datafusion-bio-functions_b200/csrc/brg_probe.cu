@@ -32,10 +32,38 @@ __device__ __forceinline__ uint32_t load_key(const uint32_t* key, uint64_t i) { 
 // ---------------------------------------------------------------------------------------------------
 // count_overlaps
 // ---------------------------------------------------------------------------------------------------
+// #(starts <= qe) - #(ends < qs) of one row of key c: through the compact index when the build made one.
+// skeys = the compact index' per-key constants in shared memory ([0] starts, [n_keys] ends), or nullptr.
+constexpr uint32_t CI_SMEM_KEYS = 256;  // keys whose constants the per-row kernels keep in shared memory (2 x 8 KB)
+__device__ __forceinline__ int64_t count_one_row(const IndexView& ix, const CompactKey* skeys, uint32_t c, int32_t qs, int32_t qe) {
+    if (ix.c_sstart.blocks) {
+        if (skeys)
+            return (int64_t)rank_le_compact(ix.c_sstart, skeys[c], qe) - (int64_t)rank_lt_compact(ix.c_eend, skeys[ix.n_keys + c], qs);
+        return (int64_t)rank_le_compact(ix.c_sstart, load_compact_key(ix.c_sstart, c), qe) -
+               (int64_t)rank_lt_compact(ix.c_eend, load_compact_key(ix.c_eend, c), qs);
+    }
+    const KeyDir ks = load_keydir(ix.d_sstart.kd, c);
+    const KeyDir ke = load_keydir(ix.d_eend.kd, c);
+    return (int64_t)rank_le_kd(ix.d_sstart, ks, qe) - (int64_t)rank_lt_kd(ix.d_eend, ke, qs);  // (both ranks include seg_begin)
+}
+// copies the compact index' per-key constants to shared memory (all threads of the CTA; returns nullptr when they do not fit)
+__device__ __forceinline__ const CompactKey* stage_compact_keys(const IndexView& ix, CompactKey* smem) {
+    if (!ix.c_sstart.blocks || ix.n_keys > CI_SMEM_KEYS) return nullptr;
+    const uint32_t words = ix.n_keys * (uint32_t)(sizeof(CompactKey) / 4);
+    const uint32_t* g0 = reinterpret_cast<const uint32_t*>(ix.c_sstart.d.kd);
+    const uint32_t* g1 = reinterpret_cast<const uint32_t*>(ix.c_eend.d.kd);
+    uint32_t* s = reinterpret_cast<uint32_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) { s[i] = __ldg(g0 + i); s[words + i] = __ldg(g1 + i); }
+    __syncthreads();
+    return smem;
+}
+
 __global__ void __launch_bounds__(PB_THREADS) count_kernel(IndexView ix, const uint32_t* __restrict__ key,
                                                            const int32_t* __restrict__ start,
                                                            const int32_t* __restrict__ end, uint64_t n, int strict,
                                                            int64_t* __restrict__ out) {
+    __shared__ CompactKey skeys_buf[2 * CI_SMEM_KEYS];
+    const CompactKey* skeys = stage_compact_keys(ix, skeys_buf);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
@@ -43,11 +71,7 @@ __global__ void __launch_bounds__(PB_THREADS) count_kernel(IndexView ix, const u
         if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }  // interval_tree.rs:253-256
         int64_t cnt = 0;
         if (c < ix.n_keys && !(qe < qs)) {                    // unknown contig -> 0 (:265); guard (:42-44)
-            KeyDir ks = load_keydir(ix.d_sstart.kd, c);
-            KeyDir ke = load_keydir(ix.d_eend.kd, c);
-            uint32_t started = rank_le_kd(ix.d_sstart, ks, qe);       // seg_begin + #(starts <= qe)
-            uint32_t ended_before = rank_lt_kd(ix.d_eend, ke, qs);    // seg_begin + #(ends < qs)
-            cnt = (int64_t)started - (int64_t)ended_before;
+            cnt = count_one_row(ix, skeys, c, qs, qe);
         }
         st_stream(out + i, cnt);
     }
@@ -124,6 +148,9 @@ __global__ void __launch_bounds__(TP_WTILE) count_kernel_todo(IndexView ix, cons
                                                               const int32_t* __restrict__ end, uint64_t n_rows, int strict,
                                                               int64_t* __restrict__ out, TodoList todo) {
     const uint32_t n_todo = *todo.count;
+    if (blockIdx.x >= n_todo) return;  // (nothing was deferred: skip staging the key constants)
+    __shared__ CompactKey skeys_buf[2 * CI_SMEM_KEYS];
+    const CompactKey* skeys = stage_compact_keys(ix, skeys_buf);
     for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {
         const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
         if (i >= n_rows) continue;
@@ -131,11 +158,7 @@ __global__ void __launch_bounds__(TP_WTILE) count_kernel_todo(IndexView ix, cons
         const uint32_t k = load_key(key, i);
         if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
         int64_t cnt = 0;
-        if (k < ix.n_keys && !(qe < qs)) {
-            const KeyDir ks = load_keydir(ix.d_sstart.kd, k);
-            const KeyDir ke = load_keydir(ix.d_eend.kd, k);
-            cnt = (int64_t)rank_le_kd(ix.d_sstart, ks, qe) - (int64_t)rank_lt_kd(ix.d_eend, ke, qs);
-        }
+        if (k < ix.n_keys && !(qe < qs)) cnt = count_one_row(ix, skeys, k, qs, qe);
         st_stream(out + i, cnt);
     }
 }

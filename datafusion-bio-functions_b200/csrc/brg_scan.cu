@@ -330,6 +330,75 @@ int segment_offsets(const uint32_t* sorted_key, uint64_t n, uint32_t n_keys, uin
 }
 
 // ---------------------------------------------------------------------------------------------------
+// compact rank index (see brg_internal.cuh): one thread per 16-element block
+// ---------------------------------------------------------------------------------------------------
+__global__ void ci_build_kernel(const int32_t* __restrict__ A, const uint32_t* __restrict__ off,
+                                const uint32_t* __restrict__ boff, uint32_t n_keys, uint32_t n_blocks,
+                                int32_t* __restrict__ S, uint4* __restrict__ blocks) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_blocks) return;
+    uint32_t lo = 0, hi = n_keys;  // key = last k with boff[k] <= g (keys without blocks share their successor's offset)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (boff[mid + 1] <= g) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t k = lo;
+    const uint32_t e0 = off[k] + (g - boff[k]) * CI_BLOCK, e1 = min(e0 + CI_BLOCK, off[k + 1]);
+    const int32_t base = A[e0];
+    S[g] = base;
+    uint32_t d[CI_BLOCK - 1];
+    bool wide = false;
+#pragma unroll
+    for (int t = 1; t < CI_BLOCK; t++) {
+        const uint32_t idx = e0 + t;
+        if (idx < e1) {
+            const uint32_t v = (uint32_t)A[idx] - (uint32_t)base;
+            wide |= v > 0xFFFDu;
+            d[t - 1] = v & 0xFFFFu;
+        } else {
+            d[t - 1] = 0xFFFEu;
+        }
+    }
+    if (wide) d[0] = 0xFFFFu;
+    blocks[g] = make_uint4((uint32_t)base, d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16));
+}
+int ci_build(const int32_t* A, const uint32_t* off, const uint32_t* boff, uint32_t n_keys, uint32_t n_blocks, int32_t* S,
+             uint4* blocks, cudaStream_t st) {
+    if (n_blocks == 0) return 0;
+    ci_build_kernel<<<(n_blocks + 255) / 256, 256, 0, st>>>(A, off, boff, n_keys, n_blocks, S, blocks);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+__global__ void ci_patch_keydir_kernel(KeyDir* __restrict__ kd, const uint32_t* __restrict__ off, uint32_t n_keys) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_keys) return;
+    kd[c].pad[0] = off[c];
+    kd[c].pad[1] = off[c + 1];
+}
+// reads D[i + 1] while other threads overwrite it: the packed value keeps the original in its upper 30 bits, but to stay
+// free of races the kernel writes to a second buffer
+__global__ void ci_pack_table_kernel(const uint32_t* __restrict__ D, uint32_t total, uint32_t* __restrict__ P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t a = D[i];
+    const uint32_t b = (i + 1 < total) ? D[i + 1] : a;
+    const uint32_t cnt = b >= a ? min(b - a, 3u) : 0u;  // (b < a only across a key boundary: that entry is never read)
+    P[i] = (a << 2) | cnt;
+}
+int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaStream_t st) {
+    if (total_entries == 0) return 0;
+    ci_pack_table_kernel<<<(total_entries + 255) / 256, 256, 0, st>>>(D, total_entries, P);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int ci_patch_keydir(KeyDir* kd, const uint32_t* off, uint32_t n_keys, cudaStream_t st) {
+    if (n_keys == 0) return 0;
+    ci_patch_keydir_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(kd, off, n_keys);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // rank directory construction
 // ---------------------------------------------------------------------------------------------------
 __global__ void dir_key_ranges_kernel(const int32_t* __restrict__ A, const uint32_t* __restrict__ off, uint32_t n_keys,
