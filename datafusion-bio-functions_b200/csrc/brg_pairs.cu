@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
     ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256: every chunk is full
     ProbeTile t;
@@ -132,9 +131,9 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, n_le);
-            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i0);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, ended);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);
+            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i0);
+            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, ended);
         }
         if (ok) {
             uint32_t tot = 0;
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
             todo_push(todo, t.chunk);
             fails++;
         }
-        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
+        if (fails >= TP_BAIL || cs.wide || cp.wide || ce.wide) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -183,7 +182,16 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
             const uint32_t c = key ? ld_stream(key + i) : 0u;
             uint32_t i0, i1;
             pair_range(ix, c, qs, qe, &i0, &i1);
-            cnt = walk_count(ix, i0, i1, qs);
+            if (i0 < i1) {
+                // count identity (no build row with start > end, qs <= qe): matches = #(start <= qe) - #(end < qs);
+                // otherwise count by walking the candidate range
+                if (!(ix.flags & BRG_IDX_INVERTED) && !(qe < qs)) {
+                    const KeyDir ke = load_keydir(ix.d_eend.kd, c);
+                    cnt = i1 - rank_lt_kd(ix.d_eend, ke, qs);
+                } else {
+                    cnt = walk_count(ix, i0, i1, qs);
+                }
+            }
             row_rng[i] = (uint64_t)i0 | ((uint64_t)i1 << 32);
         }
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);

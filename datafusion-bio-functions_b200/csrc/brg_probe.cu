@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(In
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     ProbePipe pipe(ring, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cs, ce;
@@ -118,8 +117,8 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(In
             if (!(mono_s && mono_e &&
                   warp_window_ranks2<false, true>(cs, ix.d_sstart, ks, t.qe, t.s_qe, aux0, started, ce, ix.d_eend, ke, t.qs, t.s_qs,
                                                   aux1, ended, kuni))) {
-                ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, started);
-                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, ended);
+                ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, started);
+                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, ended);
             }
         }
         if (ok) {
@@ -137,7 +136,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(In
             todo_push(todo, t.chunk);
             fails++;
         }
-        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
+        if (fails >= TP_BAIL || cs.wide || ce.wide) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -232,7 +231,6 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     ProbePipe pipe(ring, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cl, cf;
@@ -257,8 +255,8 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled
             if (!(mono_s && mono_e &&
                   warp_window_ranks2<true, false>(cl, ix.d_mlast, kl, t.qs, t.s_qs, aux0, lo, cf, ix.d_mfirst, kf, t.qe, t.s_qe, aux1,
                                                   hi, kuni))) {
-                ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, win, lo);
-                ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, win, hi);
+                ok = warp_window_ranks<true>(cl, ix.d_mlast, kl, kuni, t.qs, t.active, mono_s, t.s_qs, aux0, lo);
+                ok = ok && warp_ranks_le_end(cf, ix.d_mfirst, kf, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux1, hi);
             }
         }
         if (ok) {
@@ -273,7 +271,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled
             todo_push(todo, t.chunk);
             fails++;
         }
-        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
+        if (fails >= TP_BAIL || cl.wide || cf.wide) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }
@@ -421,7 +419,6 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
     uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    int32_t* win = reinterpret_cast<int32_t*>(ring->w[threadIdx.x >> 5].aux[0]);  // whole scratch area (dense windows)
     uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
     ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256 here: every chunk is full
     ProbeTile t;
@@ -448,10 +445,10 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
             // the two start-keyed searches interleaved when both windows are short, else one after the other
             const bool dual = mono_s && warp_window_ranks2<true, true>(cp, ix.d_pme, kp, t.qs, t.s_qs, aux1, i_pme, ce, ix.d_eend, ke,
                                                                        t.qs, t.s_qs, aux2, l_idx, kuni);
-            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, win, n_le);
+            ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);
             if (!dual) {
-                ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, win, i_pme);
-                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, win, l_idx);
+                ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i_pme);
+                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, l_idx);
             }
         }
         if (ok) {
@@ -483,7 +480,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
             todo_push(todo, t.chunk);
             fails++;
         }
-        if (fails >= TP_BAIL) { pipe.bail_out(todo); break; }
+        if (fails >= TP_BAIL || cs.wide || cp.wide || ce.wide) { pipe.bail_out(todo); break; }
         pipe.release();
     }
 }

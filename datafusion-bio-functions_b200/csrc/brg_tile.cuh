@@ -29,17 +29,16 @@ constexpr int TP_WTILE = 32 * PV;           // 256 consecutive rows per warp chu
 constexpr int TP_TILE = TP_THREADS * PV;    // rows in flight per CTA step
 constexpr int TP_STAGES = 2;
 constexpr int TP_WCAP = 256;                // words of per-array scratch (histogram bins / window copy of the fallback)
-constexpr int TP_NWIN = 3;                  // scratch buffers per warp (one per sorted array searched)
-constexpr int TP_WMAX = 1024;               // widest window the inverse search walks before the chunk is deferred
-#ifndef BRG_WBATCH
-#define BRG_WBATCH 8  // (pairs 10M x 10M: 0.45 ms per step with 8 rounds per batch, 0.49 ms with 4)
+#ifndef BRG_NWIN
+#define BRG_NWIN 3
 #endif
-constexpr int TP_WBATCH = BRG_WBATCH;                // rounds of a dense window fetched per batch of independent loads
+constexpr int TP_NWIN = BRG_NWIN;                  // scratch buffers per warp (one per sorted array searched)
+constexpr int TP_WMAX = 128;                // widest window (elements) the inverse search walks; beyond it the chunk is
+                                            // deferred: with the build side about as dense as the probe side the
+                                            // one-row-per-thread kernels win (10M x 10M sorted, B200: nearest 0.16 ms vs
+                                            // 0.34 ms for a staged-window search, coverage 0.083 vs 0.113, count 0.16 vs 0.16)
 constexpr int TP_SCAN_MAX = 12;             // forward-scan steps before a row falls back to the rank directory
-constexpr int TP_FWCAP = TP_NWIN * TP_WCAP; // words of the per-warp scratch area = capacity of a staged (dense) window
-constexpr int TP_DENSE_ON = 96;             // window sizes at which the search switches to / from the forward search
-constexpr int TP_DENSE_OFF = 64;
-constexpr uint32_t TP_BAIL = 8;             // consecutive deferred chunks after which a warp stops trying windows
+constexpr uint32_t TP_BAIL = 3;             // consecutive deferred chunks after which a warp stops trying windows
 
 #ifdef __CUDACC__
 // ---- TMA / mbarrier primitives (inline PTX) -----------------------------------------------------------------
@@ -264,9 +263,9 @@ struct WarpCursor {
     int32_t bound;
     uint32_t key;
     bool valid;
-    bool dense;   // the last window was wide (build side about as dense as the probe side): use the forward search
+    bool wide;    // the last failure was a window wider than TP_WMAX: a property of the region, not of one chunk
     int32_t pre;  // prefetched A[pos + lane] (or +inf past the segment): the first 32 window candidates of the next chunk
-    __device__ __forceinline__ void reset() { valid = false; dense = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; pre = INT32_MAX; }
+    __device__ __forceinline__ void reset() { valid = false; wide = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; pre = INT32_MAX; }
 };
 
 // are the chunk's 256 query values non-decreasing in row order?  (only full chunks qualify)
@@ -280,80 +279,15 @@ __device__ __forceinline__ bool chunk_mono(const int32_t (&q)[PV], bool full) {
     return __all_sync(0xFFFFFFFFu, up);
 }
 
-// ---- dense windows: staged window + interleaved binary searches ------------------------------------------------------
-// When the build side is about as dense as the probe side the window of a chunk holds hundreds of elements and the
-// inverse search (one 8-step binary search per window element) loses to the plain thing: stage the window in shared
-// memory with batched, independent, coalesced loads and let every lane run the binary searches of its PV rows
-// interleaved (PV independent shared-memory chains, no divergence).  The staged area is filled up to 2*top-1 entries
-// (top = largest power of two <= window size) with the elements that follow the window -- all larger than every query --
-// so the classic branch-free search needs no bound checks.
-// Queries need not be sorted here; only the CURSOR follows `cursor_mx` (the largest probe start of the chunk), which
-// lets the same routine rank the probe ENDS of a start-sorted table (load_bound = largest end).
-// Returns false when the window does not fit `win` (TP_FWCAP words).
-template <bool LT>
-__device__ __forceinline__ bool dense_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
-                                            const int32_t (&q)[PV], int32_t cursor_mx, int32_t load_bound, uint32_t lo,
-                                            bool reuse, int32_t* win, uint32_t (&r)[PV]) {
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t wn = 0, wn_cur = 0, stored = 0;
-    bool open = true;
-#pragma unroll 1
-    for (; open && stored + 32 * TP_WBATCH <= (uint32_t)TP_FWCAP; stored += 32 * TP_WBATCH) {
-        int32_t vb[TP_WBATCH];
-#pragma unroll
-        for (int rr = 0; rr < TP_WBATCH; rr++) {
-            const uint32_t idx = lo + stored + rr * 32 + lane;
-            if (rr == 0 && stored == 0 && reuse) vb[rr] = cur.pre;
-            else vb[rr] = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
-            win[stored + rr * 32 + lane] = vb[rr];
-        }
-#pragma unroll
-        for (int rr = 0; rr < TP_WBATCH; rr++) {
-            const bool seg = lo + stored + rr * 32 + lane < k.seg_end;
-            const bool in = seg && (LT ? vb[rr] < load_bound : vb[rr] <= load_bound);
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, open && in);
-            wn += __popc(m);
-            wn_cur += __popc(__ballot_sync(0xFFFFFFFFu, open && seg && (LT ? vb[rr] < cursor_mx : vb[rr] <= cursor_mx)));
-            open = open && (m == 0xFFFFFFFFu);
-        }
-    }
-    if (open) { __syncwarp(); return false; }  // (the cursor is left untouched: the caller tries another strategy)
-    const uint32_t top = wn ? 1u << (31 - __clz(wn)) : 0u;
-    if (2 * top > (uint32_t)TP_FWCAP) { __syncwarp(); return false; }
-    for (; stored + 1 < 2 * top; stored += 32) {  // padding up to 2*top-1 entries (elements beyond the window)
-        const uint32_t idx = lo + stored + lane;
-        win[stored + lane] = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
-    }
-    __syncwarp();
-    uint32_t pos[PV];
-#pragma unroll
-    for (int j = 0; j < PV; j++) pos[j] = 0;
-    for (uint32_t step = top; step; step >>= 1) {
-#pragma unroll
-        for (int j = 0; j < PV; j++) {
-            const int32_t v = win[pos[j] + step - 1];
-            pos[j] += (LT ? (v < q[j]) : (v <= q[j])) ? step : 0u;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < PV; j++) r[j] = lo + min(pos[j], wn);  // (a query of INT32_MAX can count the padding)
-    cur.pos = lo + wn_cur; cur.bound = cursor_mx; cur.key = kid; cur.valid = true;
-    cur.dense = wn_cur > (uint32_t)TP_DENSE_OFF;
-    cur.pre = (cur.pos + lane < k.seg_end) ? __ldg(d.A + cur.pos + lane) : INT32_MAX;
-    __syncwarp();
-    return true;
-}
-
 // r[j] = global index of the first element of key k's segment that is  > q[j] (LT = false)  or  >= q[j] (LT = true).
 // Must be called by all 32 lanes; `k`/`kid` warp-uniform.  Lanes with active == false contribute nothing and get
 // unspecified ranks.  Returns false when the chunk's window does not fit the shared buffers (the caller defers the chunk
 // to the per-row kernel).  mono = chunk_mono(q).  Q = the chunk's 256 query values in shared memory (same values as q,
-// row-major), only read when mono.  aux = this warp's 256-word scratch for this array, win = the warp's whole scratch
-// area (TP_FWCAP words, contains aux; only used between calls as scratch).
+// row-major), only read when mono.  aux = this warp's 256-word scratch for this array.
 template <bool LT>
 __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
                                                   const int32_t (&q)[PV], bool active, bool mono, const int32_t* Q,
-                                                  uint32_t* aux, int32_t* win, uint32_t (&r)[PV]) {
+                                                  uint32_t* aux, uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
     int32_t mn, mx;
     if (mono) {
@@ -375,9 +309,16 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
     if (reuse) lo = cur.pos;
     else lo = LT ? rank_lt_kd(d, k, mn) : rank_le_kd(d, k, mn);
 
-    if (mono && cur.dense && dense_ranks<LT>(cur, d, k, kid, q, mx, mx, lo, reuse, win, r)) return true;
-    // (a window too wide to stage falls through to the inverse search, which walks it in place)
     if (mono) {
+        // ---- too wide for the inverse search?  One load decides, before any work is spent on the chunk: the element
+        // TP_WMAX places after the window start.  (Dense build sides are the per-row kernels' job, see TP_WMAX.)
+        {
+            const uint32_t far = lo + (uint32_t)TP_WMAX - 1;
+            if (far < k.seg_end) {
+                const int32_t vf = __ldg(d.A + far);
+                if (LT ? vf < mx : vf <= mx) { cur.valid = false; cur.wide = true; return false; }
+            }
+        }
         // ---- inverse search ---------------------------------------------------------------------------------------
         uint4* a4 = reinterpret_cast<uint4*>(aux) + 2 * lane;
         a4[0] = make_uint4(0, 0, 0, 0);
@@ -410,7 +351,6 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
         __syncwarp();
         if (!open) {
             cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
-            cur.dense = wn > (uint32_t)TP_DENSE_ON;
             cur.pre = (cur.pos + lane < k.seg_end) ? __ldg(d.A + cur.pos + lane) : INT32_MAX;
             const uint4 h0 = a4[0], h1 = a4[1];
             uint32_t c[PV] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -469,14 +409,13 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
 // Two inverse searches at once.  The common case of the sparse regime -- both windows fit one round of 32 elements --
 // is a chain of dependent shared-memory accesses (8 search steps, histogram atomics, prefix sums): running the chains
 // of the two arrays interleaved doubles the instruction-level parallelism of the warp.  Returns false WITHOUT touching
-// cursors or results when the case does not apply (a cursor in dense mode, a window wider than one round); the caller
+// cursors or results when the case does not apply (a cursor that cannot be reused, a window wider than one round); the caller
 // then runs the two searches one after the other.  Preconditions: full chunk, q0 and q1 non-decreasing.
 template <bool LT0, bool LT1>
 __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView& d0, const KeyDir& k0, const int32_t (&q0)[PV],
                                                    const int32_t* Q0, uint32_t* aux0, uint32_t (&r0)[PV], WarpCursor& c1,
                                                    const DirView& d1, const KeyDir& k1, const int32_t (&q1)[PV],
                                                    const int32_t* Q1, uint32_t* aux1, uint32_t (&r1)[PV], uint32_t kid) {
-    if (c0.dense || c1.dense) return false;
     const int lane = threadIdx.x & 31;
     const int32_t mn0 = __shfl_sync(0xFFFFFFFFu, q0[0], 0), mx0 = __shfl_sync(0xFFFFFFFFu, q0[PV - 1], 31);
     const int32_t mn1 = __shfl_sync(0xFFFFFFFFu, q1[0], 0), mx1 = __shfl_sync(0xFFFFFFFFu, q1[PV - 1], 31);
@@ -506,8 +445,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
         if (in1) atomicAdd(&aux1[p1], 1u);
     }
     __syncwarp();
-    c0.pos = lo0 + __popc(m0); c0.bound = mx0; c0.dense = false;
-    c1.pos = lo1 + __popc(m1); c1.bound = mx1; c1.dense = false;
+    c0.pos = lo0 + __popc(m0); c0.bound = mx0;
+    c1.pos = lo1 + __popc(m1); c1.bound = mx1;
     c0.pre = (c0.pos + lane < k0.seg_end) ? __ldg(d0.A + c0.pos + lane) : INT32_MAX;
     c1.pre = (c1.pos + lane < k1.seg_end) ? __ldg(d1.A + c1.pos + lane) : INT32_MAX;
     const uint4 h00 = a0[0], h01 = a0[1], h10 = a1[0], h11 = a1[1];
@@ -530,34 +469,16 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
 
 // r[j] = seg_begin + #(A <= qe[j]) for a chunk of a START-sorted probe table.  Interval ends are only sorted when all
 // probes have the same length, so the search is keyed on the (sorted) starts whenever the ends are not monotone:
-//   dense window  : dense_ranks stages the window up to the largest end and binary-searches the ends in shared memory
-//                   while the cursor follows the starts;
-//   sparse window : inverse search on the starts (r0 = #(A <= qs)), then every row walks forward over the few elements
+//   inverse search on the starts (r0 = #(A <= qs)), then every row walks forward over the few elements
 //                   in (qs, qe] -- their number is the number of build values inside the probe interval.  Rows that need
 //                   more than TP_SCAN_MAX steps, and degenerate rows (qe < qs), ask the rank directory.
 // Same contract as warp_window_ranks.
 __device__ __forceinline__ bool warp_ranks_le_end(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
                                                   const int32_t (&qs)[PV], const int32_t (&qe)[PV], bool active, bool mono_s,
                                                   bool mono_e, const int32_t* Qs, const int32_t* Qe, uint32_t* aux,
-                                                  int32_t* win, uint32_t (&r)[PV]) {
-    if (mono_e || !mono_s) return warp_window_ranks<false>(cur, d, k, kid, qe, active, mono_e, Qe, aux, win, r);
-    if (cur.dense) {
-        const int32_t mn = __shfl_sync(0xFFFFFFFFu, qs[0], 0);
-        const int32_t mx = __shfl_sync(0xFFFFFFFFu, qs[PV - 1], 31);
-        int32_t mxe = qe[0];
-#pragma unroll
-        for (int j = 1; j < PV; j++) mxe = max(mxe, qe[j]);
-        mxe = max(__reduce_max_sync(0xFFFFFFFFu, mxe), mx);
-        const bool reuse = cur.valid && cur.key == kid && mn >= cur.bound;
-        const uint32_t lo = reuse ? cur.pos : rank_le_kd(d, k, mn);
-        if (dense_ranks<false>(cur, d, k, kid, qe, mx, mxe, lo, reuse, win, r)) {
-#pragma unroll
-            for (int j = 0; j < PV; j++)
-                if (qe[j] < qs[j]) r[j] = rank_le_kd(d, k, qe[j]);  // degenerate row: its end may lie before the window
-            return true;
-        }
-    }
-    if (!warp_window_ranks<false>(cur, d, k, kid, qs, active, true, Qs, aux, win, r)) return false;
+                                                  uint32_t (&r)[PV]) {
+    if (mono_e || !mono_s) return warp_window_ranks<false>(cur, d, k, kid, qe, active, mono_e, Qe, aux, r);
+    if (!warp_window_ranks<false>(cur, d, k, kid, qs, active, true, Qs, aux, r)) return false;
     uint32_t live = (1u << PV) - 1u;
 #pragma unroll
     for (int j = 0; j < PV; j++)
