@@ -219,6 +219,33 @@ __device__ __forceinline__ uint32_t rank_le_kd(const DirView& d, const KeyDir& k
     }
     return lo;
 }
+// The directory step of rank_le_kd alone: [lo, hi) = the part of the key's segment that still has to be searched for q
+// (lo == hi when the directory already decides the rank).  Several independent rank queries of one row can take this
+// step together and then run their bin searches in lock step (rank_search3), so their memory latencies overlap.
+__device__ __forceinline__ void rank_le_bin(const DirView& d, const KeyDir& k, int32_t q, uint32_t* lo, uint32_t* hi) {
+    if (k.nb == 0 || q < k.lo) { *lo = *hi = k.seg_begin; return; }
+    const uint32_t b = ((uint32_t)q - (uint32_t)k.lo) >> d.shift;
+    if (b >= k.nb) { *lo = *hi = k.seg_end; return; }
+    *lo = __ldg(d.D + k.base + b);
+    *hi = __ldg(d.D + k.base + b + 1);
+}
+__device__ __forceinline__ void rank_lt_bin(const DirView& d, const KeyDir& k, int32_t q, uint32_t* lo, uint32_t* hi) {
+    if (q == INT32_MIN) { *lo = *hi = k.seg_begin; return; }
+    rank_le_bin(d, k, q - 1, lo, hi);
+}
+// three bin searches in lock step: on return lo_i = rank (first element of A_i in [lo_i, hi_i) that is > q_i)
+__device__ __forceinline__ void rank_search3(const int32_t* A0, int32_t q0, uint32_t& lo0, uint32_t hi0, const int32_t* A1,
+                                             int32_t q1, uint32_t& lo1, uint32_t hi1, const int32_t* A2, int32_t q2,
+                                             uint32_t& lo2, uint32_t hi2) {
+    while ((lo0 < hi0) | (lo1 < hi1) | (lo2 < hi2)) {
+        const uint32_t m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1;
+        const bool a0 = lo0 < hi0, a1 = lo1 < hi1, a2 = lo2 < hi2;
+        const int32_t v0 = a0 ? __ldg(A0 + m0) : 0, v1 = a1 ? __ldg(A1 + m1) : 0, v2 = a2 ? __ldg(A2 + m2) : 0;
+        if (a0) { if (v0 <= q0) lo0 = m0 + 1; else hi0 = m0; }
+        if (a1) { if (v1 <= q1) lo1 = m1 + 1; else hi1 = m1; }
+        if (a2) { if (v2 <= q2) lo2 = m2 + 1; else hi2 = m2; }
+    }
+}
 // global index of the first element that is >= q (== seg_begin + #(A < q))
 __device__ __forceinline__ uint32_t rank_lt_kd(const DirView& d, const KeyDir& k, int32_t q) {
     if (q == INT32_MIN) return k.seg_begin;

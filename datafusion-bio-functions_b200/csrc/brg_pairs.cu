@@ -180,16 +180,22 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
         if (i < n_rows) {
             const int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
             const uint32_t c = key ? ld_stream(key + i) : 0u;
-            uint32_t i0, i1;
-            pair_range(ix, c, qs, qe, &i0, &i1);
-            if (i0 < i1) {
-                // count identity (no build row with start > end, qs <= qe): matches = #(start <= qe) - #(end < qs);
-                // otherwise count by walking the candidate range
-                if (!(ix.flags & BRG_IDX_INVERTED) && !(qe < qs)) {
-                    const KeyDir ke = load_keydir(ix.d_eend.kd, c);
-                    cnt = i1 - rank_lt_kd(ix.d_eend, ke, qs);
-                } else {
-                    cnt = walk_count(ix, i0, i1, qs);
+            uint32_t i0 = 0, i1 = 0;
+            if (c < ix.n_keys) {
+                // the three rank queries of the row are independent: directory steps together, bin searches in lock step
+                //   n_le = #(start <= qe),  p0 = first row with prefix_max_end >= qs,  ended = #(end < qs)
+                const KeyDir ks = load_keydir(ix.d_sstart.kd, c), kp = load_keydir(ix.d_pme.kd, c), ke = load_keydir(ix.d_eend.kd, c);
+                uint32_t n_le, h0, p0, h1, ended, h2;
+                rank_le_bin(ix.d_sstart, ks, qe, &n_le, &h0);
+                rank_lt_bin(ix.d_pme, kp, qs, &p0, &h1);
+                rank_lt_bin(ix.d_eend, ke, qs, &ended, &h2);
+                rank_search3(ix.d_sstart.A, qe, n_le, h0, ix.d_pme.A, wsub(qs, 1), p0, h1, ix.d_eend.A, wsub(qs, 1), ended, h2);
+                if (p0 < n_le) {  // (rows before p0 end before qs, rows from n_le on start after qe)
+                    i0 = p0; i1 = n_le;
+                    // count identity (no build row with start > end, qs <= qe): matches = #(start <= qe) - #(end < qs);
+                    // otherwise count by walking the candidate range
+                    if (!(ix.flags & BRG_IDX_INVERTED) && !(qe < qs)) cnt = n_le - ended;
+                    else cnt = walk_count(ix, i0, i1, qs);
                 }
             }
             row_rng[i] = (uint64_t)i0 | ((uint64_t)i1 << 32);
