@@ -305,61 +305,6 @@ __device__ __forceinline__ CompactKey load_compact_key(const CompactView& c, uin
     return k;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Finger search: rank queries of CONSECUTIVE probe rows handled by one thread.  Genomic probe tables are
-// coordinate-sorted (the reference counts on it too: nearest.rs:320-322), so the rank of the next probe is
-// almost always the rank of the previous one or a few elements further.  The finger keeps the current rank r
-// and a window [lo, hi) of query values for which r is still the answer; a hit costs two compares and no
-// memory access.  A near miss walks at most FINGER_G elements; anything else (unsorted input, key change)
-// falls back to the rank directory, so the result is exact for any input order.
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t FINGER_G = 4;
-struct Finger {
-    uint32_t r;    // rank_le of the last query (global index)
-    int64_t lo;    // r is valid for every q with lo <= q < hi
-    int64_t hi;
-    bool local;    // the last directory lookup landed near the previous rank: try neighbours first
-    __device__ __forceinline__ void reset() { r = 0; lo = 1; hi = 0; local = false; }
-
-    __device__ __forceinline__ uint32_t seek(const DirView& d, const KeyDir& k, int32_t q) {
-        const int64_t q64 = q;
-        if (q64 >= lo && q64 < hi) return r;
-        const int64_t kInf = (int64_t)1 << 40;
-        if (local && lo <= hi) {
-            if (q64 >= hi) {  // forward; hi is finite here, so r < seg_end
-                uint32_t far = min(r + FINGER_G, k.seg_end - 1);
-                int32_t vfar = __ldg(d.A + far);
-                if (q < vfar) {
-                    int32_t v;
-                    do { r++; v = __ldg(d.A + r); } while (v <= q);  // A[far] > q bounds the walk
-                    lo = q64; hi = v;
-                    return r;
-                }
-                if (far == k.seg_end - 1) { r = k.seg_end; lo = q64; hi = kInf; return r; }
-            } else {          // backward: q < lo
-                uint32_t near = (r - k.seg_begin > FINGER_G) ? r - FINGER_G : k.seg_begin;
-                if (near == k.seg_begin || __ldg(d.A + near - 1) <= q) {
-                    uint32_t rr = r;
-                    int64_t h = (rr < k.seg_end) ? (int64_t)__ldg(d.A + rr) : kInf;
-                    while (rr > near) {
-                        int32_t v = __ldg(d.A + rr - 1);
-                        if (v <= q) break;
-                        rr--; h = v;
-                    }
-                    r = rr; lo = q64; hi = h;
-                    return r;
-                }
-            }
-        }
-        const uint32_t r_old = r;
-        r = rank_le_kd(d, k, q);
-        local = (r >= r_old ? r - r_old : r_old - r) <= 4 * FINGER_G;
-        lo = q64;
-        hi = (r < k.seg_end) ? (int64_t)__ldg(d.A + r) : kInf;
-        return r;
-    }
-};
-
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 

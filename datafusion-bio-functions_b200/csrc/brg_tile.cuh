@@ -1,22 +1,23 @@
-// brg_tile.cuh -- tile pipeline and warp-window rank search shared by the probe kernels (sm_100a).
+// brg_tile.cuh -- tile pipeline and warp-window rank search shared by the tiled probe kernels (sm_100a).
 //
 // Data movement: the probe columns are streamed with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx,
-// L2 evict-first) into a shared-memory ring, issued by one thread per CTA, so HBM requests stay in flight
-// independently of what the warps are doing.  (The first version of the kernels issued per-thread 4-byte loads and
-// was latency-bound: 29 % DRAM throughput with every warp stalled on its probe loads, profiles/r1_count_v0_ncu.txt.)
+// L2 evict-first) into a per-warp shared-memory ring, issued by one lane, so HBM requests stay in flight independently
+// of what the warp is doing.  (The first version of the kernels issued per-thread 4-byte loads and was latency-bound:
+// 29 % DRAM throughput with every warp stalled on its probe loads, profiles/r1_count_v0_ncu.txt.)
 //
-// Search: every thread owns PV consecutive probe rows, a warp owns a contiguous range of 256-row chunks.  Genomic
-// probe tables are coordinate-sorted (the reference relies on that locality too, nearest.rs:320-322), so the ranks of
-// one chunk fall into a short window of the sorted build array and the window of the next chunk starts where the
-// previous one ended.  Per sorted array the warp keeps a cursor (WarpCursor).  A chunk then costs
+// Search: every thread owns PV consecutive probe rows, a warp owns a contiguous range of 256-row chunks.  Genomic probe
+// tables are coordinate-sorted (the reference relies on that locality too, nearest.rs:320-322), so the ranks of one
+// chunk fall into a short window of the sorted build array and the window of the next chunk starts where the previous
+// one ended.  Per sorted array the warp keeps a cursor (WarpCursor).  A chunk then costs
 //   * one coalesced load of the next few dozen build values (they ARE the window) + a ballot to find its end,
 //   * an INVERSE search: each of the (few) window elements binary-searches the (many) probe values of the chunk in
 //     shared memory, drops a 1 into a 256-bin shared histogram at its insertion point, and an inclusive prefix sum
 //     of the histogram (8 serial adds per lane + one warp scan) yields the rank of all 256 rows at once.
 // That is ~100 instructions per lane for 8 rows instead of 8 independent searches.  It needs the chunk's query values
-// to be non-decreasing (checked with one vote).  Anything that breaks the pattern -- unsorted rows, a key change
-// inside the chunk, a partial chunk, a window wider than the shared buffer -- falls back to a per-row search over a
-// shared-memory copy of the window or to the rank directory (brg_internal.cuh), so results are exact for any input.
+// to be non-decreasing (checked with one vote).  Anything that breaks the pattern -- unsorted rows, a key change inside
+// the chunk, a partial chunk, a window wider than TP_WMAX (a build side about as dense as the probe side) -- makes the
+// warp defer the chunk (or, for a wide window, its whole remaining range) to a one-row-per-thread kernel through a
+// to-do list, so results are exact for any input.
 #pragma once
 #include "brg_internal.cuh"
 
