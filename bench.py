@@ -450,6 +450,7 @@ def main():
             extras[f"count_{alt}"] = quick_device_run(torch, brg, ctx, "count", alt, args.scale, device, peak, 5)
             for other in ("coverage", "nearest", "pairs"):
                 extras[other] = quick_device_run(torch, brg, ctx, other, args.order, args.scale, device, peak, 5)
+            extras["merge"] = quick_merge_run(torch, ctx, args.scale, device)
         except Exception as ex:  # extras never invalidate the headline
             extras["error"] = repr(ex)
 
@@ -464,6 +465,21 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def quick_merge_run(torch, ctx, scale, device):
+    """merge UDTF core through the host-buffer entry point brg_merge: 10M intervals, 24 contigs"""
+    n = max(1024, int(10_000_000 * scale))
+    k, s, e = gen_intervals(torch, n, 44, 1, 1550, device)
+    hk, hs, he = (to_np(k).astype(np.uint32), to_np(s), to_np(e))
+    ctx.merge(hk, hs, he, len(HG38))
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        out = ctx.merge(hk, hs, he, len(HG38))
+    dt = (time.perf_counter() - t0) / reps
+    return {"workload": f"merge {n} intervals, 24 contigs, min_dist 0 (host buffers -> sort -> running max -> compact -> host)",
+            "value": n / dt, "unit": "intervals/s", "ms_per_step": dt * 1e3, "merged_rows": int(len(out[0]))}
 
 
 def quick_device_run(torch, brg, ctx, name, order, scale, device, peak, steps):

@@ -1042,6 +1042,98 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     return BRG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// merge (the first of the sort + sweep table functions; reuses K1 and K2)
+// ---------------------------------------------------------------------------------------------------
+struct brg_merged {
+    brg_ctx* ctx = nullptr;
+    uint64_t len = 0;
+    PinnedBlock key{}, start{}, end{}, count{};
+};
+extern "C" BRG_API uint64_t brg_merged_len(const brg_merged* m) { return m ? m->len : 0; }
+extern "C" BRG_API const uint32_t* brg_merged_key(const brg_merged* m) { return m ? (const uint32_t*)m->key.p : nullptr; }
+extern "C" BRG_API const int32_t* brg_merged_start(const brg_merged* m) { return m ? (const int32_t*)m->start.p : nullptr; }
+extern "C" BRG_API const int32_t* brg_merged_end(const brg_merged* m) { return m ? (const int32_t*)m->end.p : nullptr; }
+extern "C" BRG_API const uint32_t* brg_merged_count(const brg_merged* m) { return m ? (const uint32_t*)m->count.p : nullptr; }
+extern "C" BRG_API void brg_merged_release(brg_merged* m) {
+    if (!m) return;
+    pinned_put(m->ctx, m->key); pinned_put(m->ctx, m->start); pinned_put(m->ctx, m->end); pinned_put(m->ctx, m->count);
+    delete m;
+}
+
+extern "C" BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                         uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out) {
+    if (!ctx || !out) { set_error("brg_merge: NULL ctx/out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (n > 0 && (!start || !end)) { set_error("brg_merge: NULL column"); return BRG_ERR_INVALID; }
+    if (n >= 0xFFFFFFFFull) { set_error("brg_merge: row count exceeds UInt32 capacity"); return BRG_ERR_OVERFLOW; }
+    if (n_keys == 0 || n_keys == BRG_KEY_ABSENT) { set_error("brg_merge: bad n_keys"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    brg_merged* r = new brg_merged();
+    r->ctx = ctx;
+    if (n == 0) { *out = r; return BRG_OK; }
+    cudaStream_t st = ctx->build_stream;
+    DevBuf in[3], setA[4], setB[4], hist, scan, small, pme, flags, midx, m_key, m_first, m_last, m_row0, m_count;
+    int rc;
+    auto fail = [&](int code) { cudaStreamSynchronize(st); brg_merged_release(r); return code; };
+    for (int i = 0; i < 3; i++) if ((rc = in[i].ensure(n * 4))) return fail(rc);
+    for (int i = 0; i < 4; i++) if ((rc = setA[i].ensure(n * 4)) || (rc = setB[i].ensure(n * 4))) return fail(rc);
+    if ((rc = hist.ensure(radix_hist_words(n) * 4)) || (rc = small.ensure(4096)) ||
+        (rc = scan.ensure((scan_scratch_words(std::max<uint64_t>(radix_hist_words(n), n)) + 16) * 4)))
+        return fail(rc);
+    if (key) BRG_CUDA(cudaMemcpyAsync(in[0].p, key, n * 4, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(in[1].p, start, n * 4, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(in[2].p, end, n * 4, cudaMemcpyHostToDevice, st));
+    uint32_t* a[4] = {setA[0].as<uint32_t>(), setA[1].as<uint32_t>(), setA[2].as<uint32_t>(), setA[3].as<uint32_t>()};
+    uint32_t* b[4] = {setB[0].as<uint32_t>(), setB[1].as<uint32_t>(), setB[2].as<uint32_t>(), setB[3].as<uint32_t>()};
+    init_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key ? in[0].as<uint32_t>() : nullptr, in[1].as<int32_t>(),
+                                                                  in[2].as<int32_t>(), n, a[0], a[1], a[2], a[3]);
+    g_launches.fetch_add(1);
+    // intervals.sort_unstable() per contig (grouped_stream.rs:92-94): rows ordered by (key, start, end)
+    std::vector<SortPass> passes;
+    int key_passes = 0;
+    for (uint64_t v = n_keys; v > 0; v >>= 8) key_passes++;
+    for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
+    for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
+    for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
+    int res = 0;
+    if ((rc = radix_sort_rows(a, b, 3, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4, scan.as<uint32_t>(), st, &res)))
+        return fail(rc);
+    uint32_t** S = res == 0 ? a : b;
+    uint32_t* d_scalar = small.as<uint32_t>();
+    // rows with start > end break the equivalence "run end == running max": the sequential sweep has no parallel form then
+    if ((rc = flag_inverted_rows((const int32_t*)S[1], (const int32_t*)S[2], n, d_scalar + 8, st))) return fail(rc);
+    if ((rc = pme.ensure(n * 4)) || (rc = flags.ensure(n * 4)) || (rc = midx.ensure(n * 4)) || (rc = m_key.ensure(n * 4)) ||
+        (rc = m_first.ensure(n * 4)) || (rc = m_last.ensure(n * 4)) || (rc = m_row0.ensure(n * 4)) || (rc = m_count.ensure(n * 4)))
+        return fail(rc);
+    if ((rc = segmented_running_max(S[0], (const int32_t*)S[2], pme.as<int32_t>(), n, scan.as<int32_t>(), st))) return fail(rc);
+    if ((rc = merge_runs(S[0], (const int32_t*)S[1], pme.as<int32_t>(), n, (long long)min_dist, strict, flags.as<uint32_t>(),
+                         midx.as<uint32_t>(), scan.as<uint32_t>(), m_key.as<uint32_t>(), m_first.as<int32_t>(),
+                         m_last.as<int32_t>(), m_row0.as<uint32_t>(), d_scalar, st)))
+        return fail(rc);
+    uint32_t host_vals[9] = {0};
+    {
+        cudaError_t e = cudaMemcpyAsync(host_vals, d_scalar, sizeof(host_vals), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("merge: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    if (host_vals[8]) { set_error("merge: intervals with start > end are not supported on the GPU path"); return fail(BRG_ERR_UNSUPPORTED); }
+    const uint64_t m = host_vals[0];
+    if ((rc = merge_counts(m_row0.as<uint32_t>(), m, n, m_count.as<uint32_t>(), st))) return fail(rc);
+    r->len = m;
+    if ((rc = pinned_get(ctx, m * 4, &r->key)) || (rc = pinned_get(ctx, m * 4, &r->start)) || (rc = pinned_get(ctx, m * 4, &r->end)) ||
+        (rc = pinned_get(ctx, m * 4, &r->count)))
+        return fail(rc);
+    cudaError_t e = cudaMemcpyAsync(r->key.p, m_key.p, m * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->start.p, m_first.p, m * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->end.p, m_last.p, m * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->count.p, m_count.p, m * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(std::string("merge D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    *out = r;
+    return BRG_OK;
+}
+
 extern "C" BRG_API int brg_nearest(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
                            const int32_t* end, uint64_t n, uint32_t k, int include_overlaps, int compute_distance,
                            int strict, brg_rows** out) {

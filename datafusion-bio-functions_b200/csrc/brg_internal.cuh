@@ -144,6 +144,11 @@ int segmented_running_max(const uint32_t* key, const int32_t* val, int32_t* out,
 int merge_sorted_intervals(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme, uint64_t n,
                            uint32_t* d_flags /*n*/, uint32_t* d_midx /*n*/, uint32_t* scan_scratch, int32_t* m_first,
                            int32_t* m_last, uint32_t* m_key, uint32_t* d_n_merged, cudaStream_t st);
+// merge UDTF: runs of rows sorted by (key, start, end); writes run heads and *d_n_merged, then the row counts
+int merge_runs(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme, uint64_t n, long long min_dist, int strict,
+               uint32_t* d_flags, uint32_t* d_midx, uint32_t* scan_scratch, uint32_t* m_key, int32_t* m_first, int32_t* m_last,
+               uint32_t* m_row0, uint32_t* d_n_merged, cudaStream_t st);
+int merge_counts(const uint32_t* m_row0, uint64_t m, uint64_t n, uint32_t* m_count, cudaStream_t st);
 int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t n_merged, uint32_t* widths_tmp,
                         int32_t* m_pre /*n_merged+1*/, uint32_t* scan_scratch, cudaStream_t st);
 // segment offsets off[0..n_keys] from a sorted key array (keys >= n_keys are the invalid tail)

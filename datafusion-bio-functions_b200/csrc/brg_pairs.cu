@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
                                                                         const uint64_t* __restrict__ row_rng,
                                                                         const uint64_t* __restrict__ chunk_base,
                                                                         uint32_t* __restrict__ build_idx,
-                                                                        uint32_t* __restrict__ probe_idx) {
+                                                                        uint32_t* __restrict__ probe_idx, int vec_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FlatWarp& sm = reinterpret_cast<FlatWarp*>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
         const uint64_t row = chunk * TP_WTILE + lane * PV;
         uint32_t i0[PV], cand[PV];
         int32_t qs[PV];
-        if (row + PV <= n_rows) {
+        if (vec_ok && row + PV <= n_rows) {  // (vec_ok: both columns are 16-byte aligned)
             const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(row_rng + row);
             const int4* pq = reinterpret_cast<const int4*>(start + row);
 #pragma unroll
@@ -539,8 +539,9 @@ int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const u
                                   (int)(sizeof(FlatWarp) * PF_WARPS)));
     const uint64_t ctas = (n_chunks + PF_WARPS - 1) / PF_WARPS;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ctas, (uint64_t)kSMs * BRG_PF_CTAS));
+    const int vec_ok = aligned16p(s) && aligned16p(row_rng);
     pairs_emit_kernel_flat<<<grid, PF_THREADS, sizeof(FlatWarp) * PF_WARPS, st>>>(ix, s, n, n_chunks, row_rng, chunk_base, build_idx,
-                                                                                 probe_idx);
+                                                                                 probe_idx, vec_ok);
     BRG_LAUNCH_CHECK();
     return 0;
 }

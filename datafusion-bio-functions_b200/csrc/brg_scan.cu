@@ -8,6 +8,8 @@
 //
 // Scans are reduce-then-scan with warp-shuffle block scans: tile reduce -> one-CTA scan of the tile
 // aggregates -> tile scan with carry-in.  All of it is HBM-bound streaming (2 reads + 1 write per element).
+#include <climits>
+
 #include "brg_internal.cuh"
 
 namespace brg {
@@ -266,6 +268,65 @@ int merge_sorted_intervals(const uint32_t* s_key, const int32_t* s_start, const 
     int rc = exclusive_scan_u32_total(d_flags, d_midx, n, scan_scratch, d_n_merged, st);
     if (rc) return rc;
     merge_write_kernel<<<g, 256, 0, st>>>(s_key, s_start, pme, d_flags, d_midx, n, m_first, m_last, m_key);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge UDTF (merge.rs:260-358) on rows sorted by (key, start, end): an interval joins the current run when
+// start <= run_end + min_dist (strict: <), boundary with a saturating i64 add.  With start <= end on every row the run's
+// end equals the per-key running max (a new run starts above everything before it), so runs are found in parallel:
+// flag -> scan -> compact; n_intervals = distance between consecutive run heads.
+// ---------------------------------------------------------------------------------------------------
+__global__ void merge_dist_flags_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ s_start,
+                                        const int32_t* __restrict__ pme, uint64_t n, long long min_dist, int strict,
+                                        uint32_t* __restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool head = (i == 0 || key[i] != key[i - 1]);
+    if (!head) {
+        const long long ce = pme[i - 1];
+        long long boundary;  // ce.saturating_add(min_dist)
+        if (min_dist > 0 && ce > LLONG_MAX - min_dist) boundary = LLONG_MAX;
+        else if (min_dist < 0 && ce < LLONG_MIN - min_dist) boundary = LLONG_MIN;
+        else boundary = ce + min_dist;
+        const long long s = s_start[i];
+        head = !(strict ? s < boundary : s <= boundary);
+    }
+    flags[i] = head ? 1u : 0u;
+}
+__global__ void merge_heads_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ s_start,
+                                   const int32_t* __restrict__ pme, const uint32_t* __restrict__ flags,
+                                   const uint32_t* __restrict__ midx, uint64_t n, uint32_t* __restrict__ m_key,
+                                   int32_t* __restrict__ m_first, int32_t* __restrict__ m_last, uint32_t* __restrict__ m_row0) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t h = flags[i];
+    const uint32_t mi = midx[i] + h - 1;
+    if (h) { m_first[mi] = s_start[i]; m_key[mi] = key[i]; m_row0[mi] = (uint32_t)i; }
+    if (i + 1 == n || flags[i + 1]) m_last[mi] = pme[i];
+}
+__global__ void merge_counts_kernel(const uint32_t* __restrict__ m_row0, uint64_t m, uint64_t n, uint32_t* __restrict__ m_count) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    m_count[j] = (uint32_t)((j + 1 < m ? m_row0[j + 1] : (uint32_t)n) - m_row0[j]);
+}
+int merge_runs(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme, uint64_t n, long long min_dist, int strict,
+               uint32_t* d_flags, uint32_t* d_midx, uint32_t* scan_scratch, uint32_t* m_key, int32_t* m_first, int32_t* m_last,
+               uint32_t* m_row0, uint32_t* d_n_merged, cudaStream_t st) {
+    if (n == 0) { BRG_CUDA(cudaMemsetAsync(d_n_merged, 0, 4, st)); return 0; }
+    const unsigned g = (unsigned)((n + 255) / 256);
+    merge_dist_flags_kernel<<<g, 256, 0, st>>>(s_key, s_start, pme, n, min_dist, strict, d_flags);
+    BRG_LAUNCH_CHECK();
+    int rc = exclusive_scan_u32_total(d_flags, d_midx, n, scan_scratch, d_n_merged, st);
+    if (rc) return rc;
+    merge_heads_kernel<<<g, 256, 0, st>>>(s_key, s_start, pme, d_flags, d_midx, n, m_key, m_first, m_last, m_row0);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+int merge_counts(const uint32_t* m_row0, uint64_t m, uint64_t n, uint32_t* m_count, cudaStream_t st) {
+    if (m == 0) return 0;
+    merge_counts_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m_row0, m, n, m_count);
     BRG_LAUNCH_CHECK();
     return 0;
 }

@@ -391,6 +391,33 @@ static Err resolve_positions(const Batch& b, const std::string& name, const char
     return kOk;
 }
 
+// PosArray::resolve_i64 (array_utils.rs:137-171): Int32 / Int64 / UInt32 widen, UInt64 is checked against i64::MAX
+static Err resolve_positions_i64(const Batch& b, const std::string& name, const char* label, std::vector<int64_t>* out) {
+    const Column* c = b.find(name);
+    if (!c) return plan(std::string(label) + " column '" + name + "' not found in batch with columns: " + b.names());
+    const std::string& f = c->f.format;
+    if (f != "i" && f != "l" && f != "I" && f != "L")
+        return notimpl("unsupported data type " + type_name(f) + " for " + label + " column '" + name +
+                       "'; expected Int32, Int64, UInt32, or UInt64");
+    if (c->null_count > 0) return exec("coordinate column contains null values; requires non-null coordinates");
+    const int64_t n = c->length;
+    const size_t base = out->size();
+    out->resize(base + (size_t)n);
+    int64_t* dst = out->data() + base;
+    if (f == "i") { const int32_t* s = (const int32_t*)c->buffers[1] + c->offset; for (int64_t i = 0; i < n; i++) dst[i] = s[i]; }
+    else if (f == "l") { if (n) memcpy(dst, (const int64_t*)c->buffers[1] + c->offset, (size_t)n * 8); }
+    else if (f == "I") { const uint32_t* s = (const uint32_t*)c->buffers[1] + c->offset; for (int64_t i = 0; i < n; i++) dst[i] = s[i]; }
+    else {
+        const uint64_t* s = (const uint64_t*)c->buffers[1] + c->offset;
+        for (int64_t i = 0; i < n; i++) {
+            if (s[i] > (uint64_t)INT64_MAX)
+                return exec("coordinate value " + std::to_string(s[i]) + " at row " + std::to_string(i) + " overflows i64 (max 9223372036854775807)");
+            dst[i] = (int64_t)s[i];
+        }
+    }
+    return kOk;
+}
+
 // ---- take (arrow::compute::take over a chunked source) ------------------------------------------------------------------------
 // idx[i] is a row of the concatenation of `src` batches; idx_valid (LSB-first bitmap, may be NULL) marks NULL indices
 static Err take_column(const std::vector<const Column*>& src, const std::vector<int64_t>& batch_first_row, const uint32_t* idx,
@@ -655,6 +682,106 @@ static void probe_key_runs(const ContigArray& ca, int64_t rows, const KeyDict& d
         if (!run_key->empty() && run_key->back() == cached_id && run_end->back() == row_base + (uint64_t)i) run_end->back()++;
         else { run_key->push_back(cached_id); run_end->push_back(row_base + (uint64_t)i + 1); }
     }
+}
+
+// ---- merge (merge.rs; table_function.rs:430-520) --------------------------------------------------------------------------------
+static Column make_utf8(const std::string& name, const std::vector<std::string_view>& vals) {
+    auto ob = std::make_shared<OwnedBuffers>();
+    int64_t total = 0;
+    for (auto& v : vals) total += (int64_t)v.size();
+    int32_t* offs = (int32_t*)ob->alloc((vals.size() + 1) * 4);
+    char* data = (char*)ob->alloc((size_t)total);
+    int64_t pos = 0;
+    for (size_t i = 0; i < vals.size(); i++) { offs[i] = (int32_t)pos; if (!vals[i].empty()) memcpy(data + pos, vals[i].data(), vals[i].size()); pos += (int64_t)vals[i].size(); }
+    offs[vals.size()] = (int32_t)pos;
+    Column c;
+    c.f = Field{name, "u", false};
+    c.length = (int64_t)vals.size();
+    c.buffers = {nullptr, offs, data};
+    c.keep = ob;
+    return c;
+}
+
+static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result* res) {
+    if (min_dist < 0) return plan("merge() min_dist must be >= 0, got " + std::to_string(min_dist));  // table_function.rs:236-241
+    // parse_merge_col_args (table_function.rs:472-520): 0 or 3 column names, optional trailing 'strict' / 'weak'
+    std::vector<std::string> a;
+    for (int i = 0; i < n_args; i++) a.push_back(args[i] ? args[i] : "");
+    bool strict = false;
+    if (!a.empty()) {
+        const std::string l = lower(a.back());
+        if (l == "strict") { strict = true; a.pop_back(); }
+        else if (l == "weak") { a.pop_back(); }
+    }
+    ColTriple cols{kDefaultCols[0], kDefaultCols[1], kDefaultCols[2]};
+    if (a.size() == 3) {
+        for (auto& v : a) BRGH_TRY(check_name(v, "column name", "merge"));
+        cols = ColTriple{a[0], a[1], a[2]};
+    } else if (!a.empty()) {
+        return plan("merge() expects 0 or 3 column name arguments (got " + std::to_string(a.size()) +
+                    "). Usage: merge('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])");
+    }
+    const Table* t;
+    BRGH_TRY(find_table(s, table, &t));
+    // StreamCollector (grouped_stream.rs:48-98): group rows by contig; groups are emitted in contig-name order
+    KeyDict dict;
+    std::vector<std::string_view> names;  // first-seen order
+    std::vector<uint32_t> key;
+    std::vector<int64_t> st64, en64;
+    for (auto& b : t->batches) {
+        if (b.rows == 0) continue;
+        ContigArray ca;
+        BRGH_TRY(contig_array(b, cols.contig, &ca));
+        BRGH_TRY(resolve_positions_i64(b, cols.start, "start", &st64));
+        BRGH_TRY(resolve_positions_i64(b, cols.end, "end", &en64));
+        for (int64_t i = 0; i < b.rows; i++) {
+            const std::string_view v = ca.value(i);
+            const uint32_t id = dict.get_or_add(v);
+            if (id == names.size()) names.push_back(v);
+            key.push_back(id);
+        }
+    }
+    std::vector<uint32_t> order(names.size()), rank(names.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return names[x] < names[y]; });  // String::cmp = bytes
+    for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
+    std::vector<int32_t> st(key.size()), en(key.size());
+    for (size_t i = 0; i < key.size(); i++) {
+        key[i] = rank[key[i]];
+        if (st64[i] < INT32_MIN || st64[i] > INT32_MAX || en64[i] < INT32_MIN || en64[i] > INT32_MAX)
+            return notimpl("merge: coordinate value " + std::to_string(st64[i] < INT32_MIN || st64[i] > INT32_MAX ? st64[i] : en64[i]) +
+                           " at row " + std::to_string(i) + " does not fit the 32-bit coordinates of the GPU path");
+        st[i] = (int32_t)st64[i];
+        en[i] = (int32_t)en64[i];
+    }
+    brg_merged* m = nullptr;
+    if (!key.empty()) {
+        brg_ctx* ctx;
+        BRGH_TRY(session_ctx(s, &ctx));
+        BRGH_TRY(from_abi(brg_merge(ctx, key.data(), st.data(), en.data(), key.size(), (uint32_t)names.size(), min_dist, strict ? 1 : 0, &m)));
+    }
+    const uint64_t total = brg_merged_len(m);
+    const uint64_t batch_size = 8192;  // the session's batch size: MergeStream flushes its builders at this many rows
+    for (uint64_t r0 = 0; r0 < total; r0 += batch_size) {
+        const uint64_t r1 = std::min(total, r0 + batch_size);
+        std::vector<std::string_view> cn;
+        std::vector<int64_t> cs, ce, cc;
+        for (uint64_t i = r0; i < r1; i++) {
+            cn.push_back(names[order[brg_merged_key(m)[i]]]);
+            cs.push_back(brg_merged_start(m)[i]);
+            ce.push_back(brg_merged_end(m)[i]);
+            cc.push_back(brg_merged_count(m)[i]);
+        }
+        Batch ob;
+        ob.rows = (int64_t)(r1 - r0);
+        ob.cols.push_back(make_utf8(cols.contig, cn));
+        ob.cols.push_back(make_primitive<int64_t>(cols.start, "l", false, std::move(cs), nullptr, 0));
+        ob.cols.push_back(make_primitive<int64_t>(cols.end, "l", false, std::move(ce), nullptr, 0));
+        ob.cols.push_back(make_primitive<int64_t>("n_intervals", "l", false, std::move(cc), nullptr, 0));
+        res->batches.push_back(std::move(ob));
+    }
+    brg_merged_release(m);
+    return kOk;
 }
 
 // ---- count_overlaps / coverage (count_overlaps.rs:107-169; interval_tree.rs:155-280) ----------------------------------------
@@ -998,6 +1125,11 @@ BRG_API int brgh_coverage(brgh_session* s, const char* left, const char* right, 
     if (!s || !out) return finish(internal("brgh_coverage: NULL argument"));
     auto* r = new brgh_result();
     return run_to_result(run_count(s, left, right, args, n_args, true, r), r, out);
+}
+BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result** out) {
+    if (!s || !out) return finish(internal("brgh_merge: NULL argument"));
+    auto* r = new brgh_result();
+    return run_to_result(run_merge(s, table, min_dist, args, n_args, r), r, out);
 }
 BRG_API int brgh_nearest(brgh_session* s, const char* left, const char* right, int64_t k, int include_overlaps,
                          int compute_distance, const char* const* args, int n_args, brgh_result** out) {

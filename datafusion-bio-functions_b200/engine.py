@@ -41,6 +41,22 @@ class Context:
                                      _tptr(out), st))
         return out
 
+    def merge(self, key, start, end, n_keys, min_dist=0, strict=False):
+        """merge UDTF core: (key u32[m], start i32[m], end i32[m], n_intervals u32[m]) ordered by key id, then start"""
+        key = A.as_key(key)
+        start, end = A.as_i32(start), A.as_i32(end)
+        h = C.c_void_p()
+        A.check(A.lib().brg_merge(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys), int(min_dist),
+                                  int(bool(strict)), C.byref(h)))
+        try:
+            L = A.lib()
+            m = L.brg_merged_len(h)
+            out = (A.copy_from(L.brg_merged_key(h), m, np.uint32), A.copy_from(L.brg_merged_start(h), m, np.int32),
+                   A.copy_from(L.brg_merged_end(h), m, np.int32), A.copy_from(L.brg_merged_count(h), m, np.uint32))
+        finally:
+            A.lib().brg_merged_release(h)
+        return out
+
     # ---- build ------------------------------------------------------------------------------------------
     def build(self, key, start, end, n_keys, want=A.WANT_ALL):
         key = A.as_key(key)

@@ -198,6 +198,22 @@ BRG_API const uint8_t* brg_rows_valid_bits(const brg_rows* r); /* NULL when ever
 BRG_API const int64_t* brg_rows_distance(const brg_rows* r);   /* NULL unless nearest with distance    */
 BRG_API void brg_rows_release(brg_rows* r);
 
+/* ---- merge (replaces the sweep of MergeStream + the per-contig sort of StreamCollector, merge.rs:260-358,
+ *      grouped_stream.rs:48-98; SURVEY 8f rank 3: same sort + scan kernels as the index build).  Rows of one key are
+ *      sorted by (start, end); a row joins the current run when start <= run_end + min_dist (strict: <), the boundary a
+ *      saturating i64 add.  Result rows (key, run start, run end, n_intervals) come out ordered by key id, then start.
+ *      Coordinates are i32 here (the reference sweeps i64): the caller narrows and refuses what does not fit.  Rows with
+ *      start > end make the sweep inherently sequential: BRG_ERR_UNSUPPORTED. */
+typedef struct brg_merged brg_merged;
+BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
+              uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out);
+BRG_API uint64_t brg_merged_len(const brg_merged* m);
+BRG_API const uint32_t* brg_merged_key(const brg_merged* m);
+BRG_API const int32_t* brg_merged_start(const brg_merged* m);
+BRG_API const int32_t* brg_merged_end(const brg_merged* m);
+BRG_API const uint32_t* brg_merged_count(const brg_merged* m);
+BRG_API void brg_merged_release(brg_merged* m);
+
 /* ---- instrumentation: kernels launched by this library on the calling process (bench `gpu_launches`) -- */
 BRG_API uint64_t brg_kernel_launches(void);
 

@@ -87,6 +87,13 @@ BRG_API int brgh_nearest(brgh_session* s, const char* left, const char* right, i
 BRG_API int brgh_overlap(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args,
                  brgh_result** out);
 
+/* merge(table [, min_dist] [, col1, col2, col3] [, 'strict'|'weak']) (table_function.rs:430-520, merge.rs): output =
+ * (<contig col> Utf8, <start col> Int64, <end col> Int64, n_intervals Int64), all NOT NULL, contigs in name order, batches
+ * of 8192 rows.  min_dist < 0 -> BRGH_ERR_PLAN.  Coordinates beyond i32 -> BRGH_ERR_NOT_IMPLEMENTED (the reference sweeps
+ * i64; the GPU path is 32-bit). */
+BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args,
+               brgh_result** out);
+
 /* ---- the range join IntervalJoinExec executes ---------------------------------------------------------------------------
  *   SELECT * FROM left l JOIN right r ON l.<on_left[i]> = r.<on_right[i]> ...
  *        AND l.<left_start> <[=] r.<right_end> AND l.<left_end> >[=] r.<right_start>

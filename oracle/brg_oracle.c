@@ -457,6 +457,49 @@ uint64_t brgo_merge_intervals(const int32_t *first, const int32_t *last, uint64_
     return k;
 }
 
+/* ---- merge (merge.rs:260-358 + grouped_stream.rs:48-98): per contig, intervals sorted by (start, end); an interval joins
+ * the current run when start <= cur_end + min_dist (strict: <), the boundary computed with a saturating i64 add;
+ * output rows (contig, cur_start, cur_end, n_intervals), contigs in id order (the caller assigns ids in name order). */
+typedef struct { int64_t s, e; } iv64_t;
+static int cmp_iv64(const void *a, const void *b) {
+    const iv64_t *x = a, *y = b;
+    if (x->s != y->s) return x->s < y->s ? -1 : 1;
+    if (x->e != y->e) return x->e < y->e ? -1 : 1;
+    return 0;
+}
+static int64_t sat_add_i64(int64_t a, int64_t b) {
+    if (b > 0 && a > INT64_MAX - b) return INT64_MAX;
+    if (b < 0 && a < INT64_MIN - b) return INT64_MIN;
+    return a + b;
+}
+uint64_t brgo_merge(const uint32_t *key, const int64_t *start, const int64_t *end, uint64_t n, uint32_t n_keys,
+                    int64_t min_dist, int strict, uint32_t *out_key, int64_t *out_start, int64_t *out_end, int64_t *out_count) {
+    uint64_t *cnt = calloc((size_t)n_keys + 1, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) cnt[(key ? key[i] : 0) + 1]++;
+    for (uint32_t k = 0; k < n_keys; k++) cnt[k + 1] += cnt[k];
+    iv64_t *rows = malloc((n ? n : 1) * sizeof(iv64_t));
+    uint64_t *fill = malloc(((size_t)n_keys + 1) * sizeof(uint64_t));
+    memcpy(fill, cnt, ((size_t)n_keys + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) { iv64_t r = {start[i], end[i]}; rows[fill[key ? key[i] : 0]++] = r; }
+    uint64_t m = 0;
+    for (uint32_t k = 0; k < n_keys; k++) {
+        iv64_t *g = rows + cnt[k];
+        const uint64_t gn = cnt[k + 1] - cnt[k];
+        if (!gn) continue;
+        qsort(g, gn, sizeof(iv64_t), cmp_iv64);
+        int64_t cs = g[0].s, ce = g[0].e, cc = 1;
+        for (uint64_t i = 1; i < gn; i++) {
+            const int64_t boundary = sat_add_i64(ce, min_dist);
+            const int join = strict ? g[i].s < boundary : g[i].s <= boundary;
+            if (join) { if (g[i].e > ce) ce = g[i].e; cc++; }
+            else { out_key[m] = k; out_start[m] = cs; out_end[m] = ce; out_count[m] = cc; m++; cs = g[i].s; ce = g[i].e; cc = 1; }
+        }
+        out_key[m] = k; out_start[m] = cs; out_end[m] = ce; out_count[m] = cc; m++;
+    }
+    free(cnt); free(rows); free(fill);
+    return m;
+}
+
 void brgo_free(void *p) { free(p); }
 int brgo_max_threads(void) {
 #ifdef _OPENMP

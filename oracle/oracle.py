@@ -152,6 +152,22 @@ def merge_intervals(first, last):
     return of[:m].copy(), ol[:m].copy()
 
 
+def merge(key, start, end, n_keys, min_dist=0, strict=False):
+    """merge UDTF core (merge.rs:260-358): returns (key u32[m], start i64[m], end i64[m], n_intervals i64[m])"""
+    L = lib()
+    L.brgo_merge.restype = C.c_uint64
+    L.brgo_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_void_p]
+    start = np.ascontiguousarray(start, np.int64)
+    end = np.ascontiguousarray(end, np.int64)
+    key = None if key is None else np.ascontiguousarray(key, np.uint32)
+    n = len(start)
+    ok, os_, oe, oc = np.empty(n, np.uint32), np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64)
+    m = L.brgo_merge(None if key is None else key.ctypes.data, start.ctypes.data, end.ctypes.data, n, int(n_keys), int(min_dist),
+                     int(bool(strict)), ok.ctypes.data, os_.ctypes.data, oe.ctypes.data, oc.ctypes.data)
+    return ok[:m].copy(), os_[:m].copy(), oe[:m].copy(), oc[:m].copy()
+
+
 def max_threads():
     """host cores this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
     which would silently turn the multi-threaded CPU baseline into a single-threaded one."""

@@ -299,6 +299,25 @@ def test_gpu_large_scale_properties(ctx):
         ix.pairs_fill_dev(qs, cb, rr, bi2, pi2)
         torch.cuda.synchronize()
         assert torch.equal(bi2, bi) and torch.equal(pi2, pi)
+    # (6) device entry points accept columns that are not 16-byte aligned (views at odd offsets): scalar paths
+    m = 1_000_001
+    qk, qs, qe = pk[1:m + 1], ps[1:m + 1], pe[1:m + 1]
+    o1 = torch.empty(m + 1, dtype=torch.int64, device="cuda")[1:]
+    ix.count_overlaps_dev(qk, qs, qe, o1)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, out[1:m + 1])
+    cb = torch.empty((m + 255) // 256 + 1, dtype=torch.int64, device="cuda")
+    rr = torch.empty(m + 1, dtype=torch.int64, device="cuda")[1:]
+    ix.pairs_chunk_offsets_dev(qk, qs, qe, cb, rr)
+    torch.cuda.synchronize()
+    tot = int(cb[-1].item())
+    assert tot == int(out[1:m + 1].sum().item())
+    b3 = torch.empty(tot, dtype=torch.int32, device="cuda")
+    p3 = torch.empty(tot, dtype=torch.int32, device="cuda")
+    ix.pairs_fill_dev(qs, cb, rr, b3, p3)
+    torch.cuda.synchronize()
+    b64, p64 = b3.long(), p3.long()
+    assert bool(((bk[b64] == qk[p64]) & (bs[b64] <= qe[p64]) & (be[b64] >= qs[p64])).all())
 
 
 def test_gpu_index_export_import_roundtrip(ctx):

@@ -1,0 +1,138 @@
+"""merge: the oracle pinned to the reference's merge tests (tests/integration_test.rs:2062-2410,
+testing/data/merge/input.csv), the CUDA path against the oracle, and the table function through the host layer."""
+import numpy as np
+import pytest
+
+from _fixtures import RANGES_READS
+
+# testing/data/merge/input.csv (test data, 22 rows)
+MERGE_INPUT = [
+    ("chr1", 150, 250), ("chr1", 190, 300), ("chr1", 300, 501), ("chr1", 500, 700), ("chr1", 22000, 22300), ("chr1", 15000, 15001),
+    ("chr2", 150, 250), ("chr2", 190, 300), ("chr2", 300, 500), ("chr2", 500, 700), ("chr2", 22000, 22300), ("chr2", 15000, 15001),
+    ("chr1", 100, 190), ("chr1", 200, 290), ("chr1", 400, 600), ("chr1", 10000, 20000), ("chr1", 22100, 22101),
+    ("chr2", 100, 190), ("chr2", 200, 290), ("chr2", 400, 600), ("chr2", 10000, 20000), ("chr2", 22100, 22101),
+]
+# TEST:2104-2116 (strict), TEST:2335-2346 (reads.csv, weak)
+EXPECTED_BIOFRAME = [("chr1", 100, 300, 4), ("chr1", 300, 700, 3), ("chr1", 10000, 20000, 2), ("chr1", 22000, 22300, 2),
+                     ("chr2", 100, 300, 4), ("chr2", 300, 700, 3), ("chr2", 10000, 20000, 2), ("chr2", 22000, 22300, 2)]
+EXPECTED_READS = [("chr1", 150, 700, 4), ("chr1", 15000, 15000, 1), ("chr1", 22000, 22300, 1), ("chr2", 150, 700, 4),
+                  ("chr2", 15000, 15000, 1), ("chr2", 22000, 22300, 1), ("chr3", 234, 300, 1)]
+LITERALS = [  # (rows, min_dist, strict, expected)  TEST:2123-2404
+    ([("a", 100, 200), ("a", 150, 250), ("a", 300, 400)], 0, False, [("a", 100, 250, 2), ("a", 300, 400, 1)]),
+    ([("a", 100, 200), ("a", 201, 300)], 0, False, [("a", 100, 200, 1), ("a", 201, 300, 1)]),
+    ([("a", 100, 200), ("a", 201, 300)], 1, False, [("a", 100, 300, 2)]),
+    ([("a", 100, 300), ("a", 150, 250), ("a", 200, 400)], 0, False, [("a", 100, 400, 3)]),
+    ([("a", 100, 200)], 0, False, [("a", 100, 200, 1)]),
+    ([], 0, False, []),
+    ([("a", 100, 150), ("a", 150, 200)], 0, True, [("a", 100, 150, 1), ("a", 150, 200, 1)]),
+    ([("a", 100, 150), ("a", 150, 200)], 0, False, [("a", 100, 200, 2)]),
+    (MERGE_INPUT, 0, True, EXPECTED_BIOFRAME),
+    (RANGES_READS, 0, False, EXPECTED_READS),
+]
+
+
+def _encode_sorted(rows):
+    names = sorted({r[0] for r in rows})
+    ids = {n: i for i, n in enumerate(names)}
+    return names, np.array([ids[r[0]] for r in rows], np.uint32), np.array([r[1] for r in rows], np.int64), np.array([r[2] for r in rows], np.int64)
+
+
+def _decode(names, out):
+    k, s, e, c = out
+    return [(names[int(a)], int(b), int(cc), int(d)) for a, b, cc, d in zip(k, s, e, c)]
+
+
+@pytest.mark.parametrize("case", range(len(LITERALS)))
+def test_oracle_merge_reference_literals(case):
+    from oracle import oracle as O
+
+    rows, min_dist, strict, want = LITERALS[case]
+    names, k, s, e = _encode_sorted(rows)
+    got = _decode(names, O.merge(k, s, e, max(1, len(names)), min_dist, strict))
+    assert got == want  # contigs in name order, runs in coordinate order
+
+
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    nk = int(rng.choice([1, 3, 30]))
+    n = int(rng.choice([1, 40, 3000, 200_000]))
+    span = int(rng.choice([500, 100_000, 2_000_000_000]))
+    k = rng.integers(0, nk, n).astype(np.uint32)
+    s = rng.integers(-span if seed % 2 else 0, span, n).astype(np.int64)
+    e = np.minimum(s + rng.integers(0, int(rng.choice([1, 50, 5000])), n), 2**31 - 1)
+    md = int(rng.choice([0, 0, 1, 17, 10_000, 2**40]))
+    return nk, k, s, e, md, bool(seed % 3 == 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_merge_vs_oracle(seed):
+    import bio_ranges_b200 as brg
+    from oracle import oracle as O
+
+    nk, k, s, e, md, strict = _random_case(seed)
+    ctx = brg.default_context(0)
+    gk, gs, ge, gc = ctx.merge(k, s.astype(np.int32), e.astype(np.int32), nk, md, strict)
+    ok, os_, oe, oc = O.merge(k, s, e, nk, md, strict)
+    assert len(gk) == len(ok)
+    assert (gk == ok).all() and (gs == os_).all() and (ge == oe).all() and (gc == oc).all()
+    assert int(gc.sum()) == len(k)
+
+
+@pytest.mark.gpu
+def test_gpu_merge_rejects_inverted_intervals():
+    import bio_ranges_b200 as brg
+
+    ctx = brg.default_context(0)
+    with pytest.raises(brg.BioRangesError) as ei:
+        ctx.merge(np.zeros(3, np.uint32), np.array([10, 50, 70], np.int32), np.array([20, 40, 80], np.int32), 1)
+    assert ei.value.status == 5 and "start > end" in str(ei.value)
+
+
+@pytest.mark.gpu
+def test_merge_udtf_through_session():
+    """TEST:2062-2404 through the host layer: argument grammar, output schema, contig order, strictness, min_dist"""
+    import pyarrow as pa
+
+    import bio_ranges_b200 as brg
+    from bio_ranges_b200.session import NOT_IMPLEMENTED, PLAN, create_bio_session
+
+    def tbl(rows, names=("contig", "pos_start", "pos_end"), t=pa.int64()):
+        return pa.table({names[0]: pa.array([r[0] for r in rows], pa.string()), names[1]: pa.array([r[1] for r in rows], t),
+                         names[2]: pa.array([r[2] for r in rows], t)})
+
+    def rows_of(batches):
+        t = pa.Table.from_batches(batches) if batches else None
+        return [] if t is None else list(zip(*[t.column(i).to_pylist() for i in range(4)]))
+
+    ctx = create_bio_session()
+    for rows, md, strict, want in LITERALS:
+        ctx.register_table("intervals", tbl(rows, t=pa.int32()))
+        args = ("contig", "pos_start", "pos_end", "strict") if strict else ()
+        assert rows_of(ctx.merge("intervals", *args, min_dist=md)) == want
+    out = ctx.merge("intervals")
+    t = pa.Table.from_batches(out)
+    assert t.schema.names == ["contig", "pos_start", "pos_end", "n_intervals"]
+    assert [str(f.type) for f in t.schema] == ["string", "int64", "int64", "int64"] and not any(f.nullable for f in t.schema)
+    # TEST:2285-2317 custom column names come from the arguments
+    ctx.register_table("c", tbl([("a", 100, 200), ("a", 150, 250)], names=("chr", "s", "e"), t=pa.int32()))
+    t = pa.Table.from_batches(ctx.merge("c", "chr", "s", "e", min_dist=0))
+    assert t.schema.names == ["chr", "s", "e", "n_intervals"] and rows_of([t.to_batches()[0]]) == [("a", 100, 250, 2)]
+    # batches of the session batch size
+    rng = np.random.default_rng(0)
+    st = np.sort(rng.integers(0, 10**9, 50_000)) * 2
+    ctx.register_table("big", pa.table({"contig": pa.array(["x"] * len(st)), "pos_start": pa.array(st, pa.int64()), "pos_end": pa.array(st, pa.int64())}))
+    out = ctx.merge("big")
+    assert [b.num_rows for b in out][:2] == [8192, 8192] and sum(b.num_rows for b in out) == len(np.unique(st))
+    # errors
+    with pytest.raises(brg.BioRangesError) as ei:
+        ctx.merge("intervals", min_dist=-1)
+    assert ei.value.status == PLAN and "merge() min_dist must be >= 0, got -1" in str(ei.value)
+    with pytest.raises(brg.BioRangesError) as ei:
+        ctx.merge("intervals", "a", "b")
+    assert ei.value.status == PLAN and "merge() expects 0 or 3 column name arguments (got 2)" in str(ei.value)
+    ctx.register_table("wide", tbl([("a", 1, 2**40)]))
+    with pytest.raises(brg.BioRangesError) as ei:
+        ctx.merge("wide")
+    assert ei.value.status == NOT_IMPLEMENTED
+    ctx.close()
