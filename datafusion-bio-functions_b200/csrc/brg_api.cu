@@ -1061,8 +1061,18 @@ extern "C" BRG_API void brg_merged_release(brg_merged* m) {
     delete m;
 }
 
+static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out);
 extern "C" BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
                          uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out) {
+    return merge_pipeline(ctx, key, start, end, n, n_keys, min_dist, strict, false, out);
+}
+extern "C" BRG_API int brg_cluster(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                           uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out) {
+    return merge_pipeline(ctx, key, start, end, n, n_keys, min_dist, strict, true, out);
+}
+static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out) {
     if (!ctx || !out) { set_error("brg_merge: NULL ctx/out"); return BRG_ERR_INVALID; }
     *out = nullptr;
     if (n > 0 && (!start || !end)) { set_error("brg_merge: NULL column"); return BRG_ERR_INVALID; }
@@ -1097,7 +1107,8 @@ extern "C" BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key, const int32_
     for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
     for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
     int res = 0;
-    if ((rc = radix_sort_rows(a, b, 3, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4, scan.as<uint32_t>(), st, &res)))
+    // (cluster carries the row ids along: ties keep input order, like the reference's (start, end, row) tuples)
+    if ((rc = radix_sort_rows(a, b, cluster ? 4 : 3, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4, scan.as<uint32_t>(), st, &res)))
         return fail(rc);
     uint32_t** S = res == 0 ? a : b;
     uint32_t* d_scalar = small.as<uint32_t>();
@@ -1118,8 +1129,25 @@ extern "C" BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key, const int32_
         if (e != cudaSuccess) { set_error(std::string("merge: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
     }
     if (host_vals[8]) { set_error("merge: intervals with start > end are not supported on the GPU path"); return fail(BRG_ERR_UNSUPPORTED); }
-    const uint64_t m = host_vals[0];
-    if ((rc = merge_counts(m_row0.as<uint32_t>(), m, n, m_count.as<uint32_t>(), st))) return fail(rc);
+    uint64_t m = host_vals[0];
+    if (cluster) {
+        // one result row per input row, in (key, start, end, row) order:
+        //   key -> original row id, start / end -> extent of the row's run, count -> run id (global, key order)
+        // flags / midx stay as they are; the run heads move out of the way first (m_count, m_row0, pme as outputs)
+        DevBuf c_start, c_end;
+        if ((rc = c_start.ensure(n * 4)) || (rc = c_end.ensure(n * 4))) return fail(rc);
+        if ((rc = cluster_rows(flags.as<uint32_t>(), midx.as<uint32_t>(), m_first.as<int32_t>(), m_last.as<int32_t>(), n,
+                               m_count.as<uint32_t>(), c_start.as<int32_t>(), c_end.as<int32_t>(), st)))
+            return fail(rc);
+        cudaError_t ce = cudaMemcpyAsync(m_key.p, S[3], n * 4, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m_first.p, c_start.p, n * 4, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m_last.p, c_end.p, n * 4, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { set_error(std::string("cluster: ") + cudaGetErrorString(ce)); return fail(BRG_ERR_CUDA); }
+        m = n;
+    } else if ((rc = merge_counts(m_row0.as<uint32_t>(), m, n, m_count.as<uint32_t>(), st))) {
+        return fail(rc);
+    }
     r->len = m;
     if ((rc = pinned_get(ctx, m * 4, &r->key)) || (rc = pinned_get(ctx, m * 4, &r->start)) || (rc = pinned_get(ctx, m * 4, &r->end)) ||
         (rc = pinned_get(ctx, m * 4, &r->count)))

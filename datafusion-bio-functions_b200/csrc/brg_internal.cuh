@@ -149,6 +149,8 @@ int merge_runs(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme
                uint32_t* d_flags, uint32_t* d_midx, uint32_t* scan_scratch, uint32_t* m_key, int32_t* m_first, int32_t* m_last,
                uint32_t* m_row0, uint32_t* d_n_merged, cudaStream_t st);
 int merge_counts(const uint32_t* m_row0, uint64_t m, uint64_t n, uint32_t* m_count, cudaStream_t st);
+int cluster_rows(const uint32_t* flags, const uint32_t* midx, const int32_t* m_first, const int32_t* m_last, uint64_t n,
+                 uint32_t* cluster, int32_t* c_start, int32_t* c_end, cudaStream_t st);
 int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t n_merged, uint32_t* widths_tmp,
                         int32_t* m_pre /*n_merged+1*/, uint32_t* scan_scratch, cudaStream_t st);
 // segment offsets off[0..n_keys] from a sorted key array (keys >= n_keys are the invalid tail)

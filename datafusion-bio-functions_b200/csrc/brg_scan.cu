@@ -324,6 +324,24 @@ int merge_runs(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme
     BRG_LAUNCH_CHECK();
     return 0;
 }
+// cluster UDTF (cluster.rs:560-720): every sorted row gets the id and the extent of its run
+__global__ void cluster_rows_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ midx,
+                                    const int32_t* __restrict__ m_first, const int32_t* __restrict__ m_last, uint64_t n,
+                                    uint32_t* __restrict__ cluster, int32_t* __restrict__ c_start, int32_t* __restrict__ c_end) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mi = midx[i] + flags[i] - 1;
+    cluster[i] = mi;
+    c_start[i] = m_first[mi];
+    c_end[i] = m_last[mi];
+}
+int cluster_rows(const uint32_t* flags, const uint32_t* midx, const int32_t* m_first, const int32_t* m_last, uint64_t n,
+                 uint32_t* cluster, int32_t* c_start, int32_t* c_end, cudaStream_t st) {
+    if (n == 0) return 0;
+    cluster_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, midx, m_first, m_last, n, cluster, c_start, c_end);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
 int merge_counts(const uint32_t* m_row0, uint64_t m, uint64_t n, uint32_t* m_count, cudaStream_t st) {
     if (m == 0) return 0;
     merge_counts_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m_row0, m, n, m_count);

@@ -702,8 +702,10 @@ static Column make_utf8(const std::string& name, const std::vector<std::string_v
     return c;
 }
 
-static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result* res) {
-    if (min_dist < 0) return plan("merge() min_dist must be >= 0, got " + std::to_string(min_dist));  // table_function.rs:236-241
+static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, bool cluster,
+                     brgh_result* res) {
+    const std::string fn = cluster ? "cluster" : "merge";
+    if (min_dist < 0) return plan(fn + "() min_dist must be >= 0, got " + std::to_string(min_dist));  // table_function.rs:236-241
     // parse_merge_col_args (table_function.rs:472-520): 0 or 3 column names, optional trailing 'strict' / 'weak'
     std::vector<std::string> a;
     for (int i = 0; i < n_args; i++) a.push_back(args[i] ? args[i] : "");
@@ -715,11 +717,11 @@ static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const
     }
     ColTriple cols{kDefaultCols[0], kDefaultCols[1], kDefaultCols[2]};
     if (a.size() == 3) {
-        for (auto& v : a) BRGH_TRY(check_name(v, "column name", "merge"));
+        for (auto& v : a) BRGH_TRY(check_name(v, "column name", fn));
         cols = ColTriple{a[0], a[1], a[2]};
     } else if (!a.empty()) {
-        return plan("merge() expects 0 or 3 column name arguments (got " + std::to_string(a.size()) +
-                    "). Usage: merge('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])");
+        return plan(fn + "() expects 0 or 3 column name arguments (got " + std::to_string(a.size()) + "). Usage: " + fn +
+                    "('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])");
     }
     const Table* t;
     BRGH_TRY(find_table(s, table, &t));
@@ -749,7 +751,7 @@ static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const
     for (size_t i = 0; i < key.size(); i++) {
         key[i] = rank[key[i]];
         if (st64[i] < INT32_MIN || st64[i] > INT32_MAX || en64[i] < INT32_MIN || en64[i] > INT32_MAX)
-            return notimpl("merge: coordinate value " + std::to_string(st64[i] < INT32_MIN || st64[i] > INT32_MAX ? st64[i] : en64[i]) +
+            return notimpl(fn + ": coordinate value " + std::to_string(st64[i] < INT32_MIN || st64[i] > INT32_MAX ? st64[i] : en64[i]) +
                            " at row " + std::to_string(i) + " does not fit the 32-bit coordinates of the GPU path");
         st[i] = (int32_t)st64[i];
         en[i] = (int32_t)en64[i];
@@ -758,7 +760,49 @@ static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const
     if (!key.empty()) {
         brg_ctx* ctx;
         BRGH_TRY(session_ctx(s, &ctx));
-        BRGH_TRY(from_abi(brg_merge(ctx, key.data(), st.data(), en.data(), key.size(), (uint32_t)names.size(), min_dist, strict ? 1 : 0, &m)));
+        auto f = cluster ? brg_cluster : brg_merge;
+        BRGH_TRY(from_abi(f(ctx, key.data(), st.data(), en.data(), key.size(), (uint32_t)names.size(), min_dist, strict ? 1 : 0, &m)));
+    }
+    if (cluster) {
+        // ClusterProvider's schema (cluster.rs:40-72): a 3-column input is rebuilt as (Utf8, Int64, Int64), a wider one keeps
+        // all its fields (arrow take by row); then cluster / cluster_start / cluster_end Int64 NOT NULL.  Rows come out in
+        // (contig, start, end, row) order, in batches of the session batch size.
+        const uint64_t total = brg_merged_len(m), batch_size = 8192;
+        const bool extra = t->schema.size() > 3;
+        Err e = kOk;
+        for (uint64_t r0 = 0; r0 < total && !e.code; r0 += batch_size) {
+            const uint64_t r1 = std::min(total, r0 + batch_size);
+            const uint32_t* rows = brg_merged_key(m) + r0;
+            Batch ob;
+            ob.rows = (int64_t)(r1 - r0);
+            if (extra) {
+                e = take_table(*t, rows, nullptr, ob.rows, "", -1, &ob.cols);
+            } else {
+                std::vector<std::string_view> cn;
+                std::vector<int64_t> cs, ce;
+                for (uint64_t i = r0; i < r1; i++) {
+                    const uint32_t row = brg_merged_key(m)[i];
+                    cn.push_back(names[order[key[row]]]);
+                    cs.push_back(st64[row]);
+                    ce.push_back(en64[row]);
+                }
+                ob.cols.push_back(make_utf8(cols.contig, cn));
+                ob.cols.push_back(make_primitive<int64_t>(cols.start, "l", false, std::move(cs), nullptr, 0));
+                ob.cols.push_back(make_primitive<int64_t>(cols.end, "l", false, std::move(ce), nullptr, 0));
+            }
+            std::vector<int64_t> cid, cst, cen;
+            for (uint64_t i = r0; i < r1; i++) {
+                cid.push_back(brg_merged_count(m)[i]);
+                cst.push_back(brg_merged_start(m)[i]);
+                cen.push_back(brg_merged_end(m)[i]);
+            }
+            ob.cols.push_back(make_primitive<int64_t>("cluster", "l", false, std::move(cid), nullptr, 0));
+            ob.cols.push_back(make_primitive<int64_t>("cluster_start", "l", false, std::move(cst), nullptr, 0));
+            ob.cols.push_back(make_primitive<int64_t>("cluster_end", "l", false, std::move(cen), nullptr, 0));
+            res->batches.push_back(std::move(ob));
+        }
+        brg_merged_release(m);
+        return e;
     }
     const uint64_t total = brg_merged_len(m);
     const uint64_t batch_size = 8192;  // the session's batch size: MergeStream flushes its builders at this many rows
@@ -1129,7 +1173,12 @@ BRG_API int brgh_coverage(brgh_session* s, const char* left, const char* right, 
 BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result** out) {
     if (!s || !out) return finish(internal("brgh_merge: NULL argument"));
     auto* r = new brgh_result();
-    return run_to_result(run_merge(s, table, min_dist, args, n_args, r), r, out);
+    return run_to_result(run_merge(s, table, min_dist, args, n_args, false, r), r, out);
+}
+BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result** out) {
+    if (!s || !out) return finish(internal("brgh_cluster: NULL argument"));
+    auto* r = new brgh_result();
+    return run_to_result(run_merge(s, table, min_dist, args, n_args, true, r), r, out);
 }
 BRG_API int brgh_nearest(brgh_session* s, const char* left, const char* right, int64_t k, int include_overlaps,
                          int compute_distance, const char* const* args, int n_args, brgh_result** out) {

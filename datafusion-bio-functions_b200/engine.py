@@ -41,12 +41,17 @@ class Context:
                                      _tptr(out), st))
         return out
 
-    def merge(self, key, start, end, n_keys, min_dist=0, strict=False):
+    def cluster(self, key, start, end, n_keys, min_dist=0, strict=False):
+        """cluster UDTF core, one row per input row in (key, start, end, row) order:
+        (row_id u32[n], cluster_start i32[n], cluster_end i32[n], cluster_id u32[n])"""
+        return self.merge(key, start, end, n_keys, min_dist, strict, _fn="brg_cluster")
+
+    def merge(self, key, start, end, n_keys, min_dist=0, strict=False, _fn="brg_merge"):
         """merge UDTF core: (key u32[m], start i32[m], end i32[m], n_intervals u32[m]) ordered by key id, then start"""
         key = A.as_key(key)
         start, end = A.as_i32(start), A.as_i32(end)
         h = C.c_void_p()
-        A.check(A.lib().brg_merge(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys), int(min_dist),
+        A.check(getattr(A.lib(), _fn)(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys), int(min_dist),
                                   int(bool(strict)), C.byref(h)))
         try:
             L = A.lib()

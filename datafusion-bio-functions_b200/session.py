@@ -20,7 +20,7 @@ JOIN_INNER, JOIN_RIGHT_SEMI, JOIN_RIGHT_ANTI = 0, 1, 2
 HOST_SYMBOLS = [
     "brgh_create_bio_session", "brgh_session_destroy", "brgh_session_set", "brgh_session_get", "brgh_session_set_coalesce_rows",
     "brgh_register_batch", "brgh_deregister_table", "brgh_count_overlaps", "brgh_coverage", "brgh_nearest", "brgh_overlap",
-    "brgh_merge", "brgh_interval_join", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
+    "brgh_merge", "brgh_cluster", "brgh_interval_join", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
     "brgh_result_release", "brgh_resolve_positions", "brgh_take",
 ]
 
@@ -47,6 +47,7 @@ def _lib():
     L.brgh_nearest.argtypes = [vp, cp, cp, i64, i32, i32, strs, i32, C.POINTER(vp)]
     L.brgh_overlap.argtypes = [vp, cp, cp, strs, i32, C.POINTER(vp)]
     L.brgh_merge.argtypes = [vp, cp, i64, strs, i32, C.POINTER(vp)]
+    L.brgh_cluster.argtypes = [vp, cp, i64, strs, i32, C.POINTER(vp)]
     L.brgh_interval_join.argtypes = [vp, cp, cp, strs, strs, i32, cp, cp, cp, cp, i32, i32, i32, C.POINTER(vp)]
     L.brgh_explain_interval_join.argtypes = [vp, i32, cp, u64]
     L.brgh_result_num_batches.argtypes = [vp]
@@ -163,6 +164,12 @@ class BioSession:
         """SELECT * FROM merge('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])"""
         res = C.c_void_p()
         A.check(_lib().brgh_merge(self._h, table.encode(), int(min_dist), _cstrs(args), len(args), C.byref(res)))
+        return self._collect(res)
+
+    def cluster(self, table, *args, min_dist=0):
+        """SELECT * FROM cluster('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])"""
+        res = C.c_void_p()
+        A.check(_lib().brgh_cluster(self._h, table.encode(), int(min_dist), _cstrs(args), len(args), C.byref(res)))
         return self._collect(res)
 
     def nearest(self, left, right, *args, k=1, overlap=True, compute_distance=True):

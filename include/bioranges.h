@@ -207,6 +207,12 @@ BRG_API void brg_rows_release(brg_rows* r);
 typedef struct brg_merged brg_merged;
 BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
               uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out);
+/* cluster (replaces the sweep of ClusterStream, cluster.rs:560-720, and the id offsets of ClusterIdCoordinator::build_offsets,
+ * cluster.rs:383-414): same runs as brg_merge, but one result row per INPUT row, ordered by (key, start, end, row):
+ * brg_merged_key = original row id, brg_merged_start / _end = extent of the row's run, brg_merged_count = run id,
+ * numbered globally in key order (ids of key k start after all runs of keys < k). */
+BRG_API int brg_cluster(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
+                uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out);
 BRG_API uint64_t brg_merged_len(const brg_merged* m);
 BRG_API const uint32_t* brg_merged_key(const brg_merged* m);
 BRG_API const int32_t* brg_merged_start(const brg_merged* m);

@@ -94,6 +94,12 @@ BRG_API int brgh_overlap(brgh_session* s, const char* left, const char* right, c
 BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args,
                brgh_result** out);
 
+/* cluster(table [, min_dist] [, col1, col2, col3] [, 'strict'|'weak']) (table_function.rs, cluster.rs:30-72): every input
+ * row plus `cluster`, `cluster_start`, `cluster_end` Int64 NOT NULL; a 3-column input is rebuilt as (Utf8, Int64, Int64), a
+ * wider one keeps all its columns; cluster ids are global, numbered in contig-name order (cluster.rs:383-414). */
+BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args,
+                 brgh_result** out);
+
 /* ---- the range join IntervalJoinExec executes ---------------------------------------------------------------------------
  *   SELECT * FROM left l JOIN right r ON l.<on_left[i]> = r.<on_right[i]> ...
  *        AND l.<left_start> <[=] r.<right_end> AND l.<left_end> >[=] r.<right_start>

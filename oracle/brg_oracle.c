@@ -500,6 +500,48 @@ uint64_t brgo_merge(const uint32_t *key, const int64_t *start, const int64_t *en
     return m;
 }
 
+/* ---- cluster (cluster.rs:560-720; ids: ClusterIdCoordinator::build_offsets, cluster.rs:383-414): same sweep as merge, one
+ * output row per input row in (contig id, start, end, row) order; cluster ids are numbered globally in contig order. */
+typedef struct { int64_t s, e; uint64_t row; } ivr64_t;
+static int cmp_ivr64(const void *a, const void *b) {
+    const ivr64_t *x = a, *y = b;
+    if (x->s != y->s) return x->s < y->s ? -1 : 1;
+    if (x->e != y->e) return x->e < y->e ? -1 : 1;
+    return x->row < y->row ? -1 : (x->row > y->row ? 1 : 0);
+}
+void brgo_cluster(const uint32_t *key, const int64_t *start, const int64_t *end, uint64_t n, uint32_t n_keys, int64_t min_dist,
+                  int strict, uint64_t *out_row, int64_t *out_cluster, int64_t *out_cstart, int64_t *out_cend) {
+    uint64_t *cnt = calloc((size_t)n_keys + 1, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) cnt[(key ? key[i] : 0) + 1]++;
+    for (uint32_t k = 0; k < n_keys; k++) cnt[k + 1] += cnt[k];
+    ivr64_t *rows = malloc((n ? n : 1) * sizeof(ivr64_t));
+    uint64_t *fill = malloc(((size_t)n_keys + 1) * sizeof(uint64_t));
+    memcpy(fill, cnt, ((size_t)n_keys + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) { ivr64_t r = {start[i], end[i], i}; rows[fill[key ? key[i] : 0]++] = r; }
+    uint64_t o = 0;
+    int64_t cluster_id = 0;
+    for (uint32_t k = 0; k < n_keys; k++) {
+        ivr64_t *g = rows + cnt[k];
+        const uint64_t gn = cnt[k + 1] - cnt[k];
+        if (!gn) continue;
+        qsort(g, gn, sizeof(ivr64_t), cmp_ivr64);
+        uint64_t first = 0;  /* first row of the pending cluster */
+        int64_t cs = g[0].s, ce = g[0].e;
+        for (uint64_t i = 1; i <= gn; i++) {
+            int join = 0;
+            if (i < gn) {
+                const int64_t boundary = sat_add_i64(ce, min_dist);
+                join = strict ? g[i].s < boundary : g[i].s <= boundary;
+            }
+            if (join) { if (g[i].e > ce) ce = g[i].e; continue; }
+            for (uint64_t j = first; j < i; j++) { out_row[o] = g[j].row; out_cluster[o] = cluster_id; out_cstart[o] = cs; out_cend[o] = ce; o++; }
+            cluster_id++;
+            if (i < gn) { first = i; cs = g[i].s; ce = g[i].e; }
+        }
+    }
+    free(cnt); free(rows); free(fill);
+}
+
 void brgo_free(void *p) { free(p); }
 int brgo_max_threads(void) {
 #ifdef _OPENMP

@@ -168,6 +168,23 @@ def merge(key, start, end, n_keys, min_dist=0, strict=False):
     return ok[:m].copy(), os_[:m].copy(), oe[:m].copy(), oc[:m].copy()
 
 
+def cluster(key, start, end, n_keys, min_dist=0, strict=False):
+    """cluster UDTF core (cluster.rs:560-720): (row u64[n], cluster i64[n], cluster_start i64[n], cluster_end i64[n]) in
+    (contig id, start, end, row) order"""
+    L = lib()
+    L.brgo_cluster.restype = None
+    L.brgo_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+    start = np.ascontiguousarray(start, np.int64)
+    end = np.ascontiguousarray(end, np.int64)
+    key = None if key is None else np.ascontiguousarray(key, np.uint32)
+    n = len(start)
+    orow, oc, os_, oe = np.empty(n, np.uint64), np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64)
+    L.brgo_cluster(None if key is None else key.ctypes.data, start.ctypes.data, end.ctypes.data, n, int(n_keys), int(min_dist),
+                   int(bool(strict)), orow.ctypes.data, oc.ctypes.data, os_.ctypes.data, oe.ctypes.data)
+    return orow, oc, os_, oe
+
+
 def max_threads():
     """host cores this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
     which would silently turn the multi-threaded CPU baseline into a single-threaded one."""

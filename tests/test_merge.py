@@ -136,3 +136,84 @@ def test_merge_udtf_through_session():
         ctx.merge("wide")
     assert ei.value.status == NOT_IMPLEMENTED
     ctx.close()
+
+
+# ---- cluster (tests/integration_test.rs:2410-2760, 3594-3626) ------------------------------------------------------------
+CLUSTER_LITERALS = [  # (rows, min_dist, strict, expected rows sorted by (contig, start, end))
+    ([("a", 100, 200), ("a", 150, 250), ("a", 400, 500)], 0, False,
+     [("a", 100, 200, 0, 100, 250), ("a", 150, 250, 0, 100, 250), ("a", 400, 500, 1, 400, 500)]),
+    ([("a", 100, 200), ("a", 210, 300)], 0, False, [("a", 100, 200, 0, 100, 200), ("a", 210, 300, 1, 210, 300)]),
+    ([("a", 100, 200), ("a", 210, 300)], 10, False, [("a", 100, 200, 0, 100, 300), ("a", 210, 300, 0, 100, 300)]),
+    ([("a", 100, 200), ("a", 150, 250), ("b", 100, 200), ("b", 300, 400)], 0, False,
+     [("a", 100, 200, 0, 100, 250), ("a", 150, 250, 0, 100, 250), ("b", 100, 200, 1, 100, 200), ("b", 300, 400, 2, 300, 400)]),
+    ([("a", 100, 200)], 0, False, [("a", 100, 200, 0, 100, 200)]),
+    ([], 0, False, []),
+    ([("a", 100, 150), ("a", 150, 200)], 0, False, [("a", 100, 150, 0, 100, 200), ("a", 150, 200, 0, 100, 200)]),
+    ([("a", 100, 150), ("a", 150, 200)], 0, True, [("a", 100, 150, 0, 100, 150), ("a", 150, 200, 1, 150, 200)]),
+    (RANGES_READS, 0, False, [
+        ("chr1", 150, 250, 0, 150, 700), ("chr1", 190, 300, 0, 150, 700), ("chr1", 300, 501, 0, 150, 700), ("chr1", 500, 700, 0, 150, 700),
+        ("chr1", 15000, 15000, 1, 15000, 15000), ("chr1", 22000, 22300, 2, 22000, 22300),
+        ("chr2", 150, 250, 3, 150, 700), ("chr2", 190, 300, 3, 150, 700), ("chr2", 300, 500, 3, 150, 700), ("chr2", 500, 700, 3, 150, 700),
+        ("chr2", 15000, 15000, 4, 15000, 15000), ("chr2", 22000, 22300, 5, 22000, 22300), ("chr3", 234, 300, 6, 234, 300)]),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CLUSTER_LITERALS)))
+def test_oracle_cluster_reference_literals(case):
+    from oracle import oracle as O
+
+    rows, min_dist, strict, want = CLUSTER_LITERALS[case]
+    names, k, s, e = _encode_sorted(rows)
+    row, cid, cs, ce = O.cluster(k, s, e, max(1, len(names)), min_dist, strict)
+    got = [(rows[int(r)][0], rows[int(r)][1], rows[int(r)][2], int(c), int(a), int(b)) for r, c, a, b in zip(row, cid, cs, ce)]
+    assert got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_cluster_vs_oracle(seed):
+    import bio_ranges_b200 as brg
+    from oracle import oracle as O
+
+    nk, k, s, e, md, strict = _random_case(seed)
+    ctx = brg.default_context(0)
+    grow, gcs, gce, gcid = ctx.cluster(k, s.astype(np.int32), e.astype(np.int32), nk, md, strict)
+    orow, ocid, ocs, oce = O.cluster(k, s, e, nk, md, strict)
+    assert (grow == orow).all() and (gcid == ocid).all() and (gcs == ocs).all() and (gce == oce).all()
+
+
+@pytest.mark.gpu
+def test_cluster_udtf_through_session():
+    import pyarrow as pa
+
+    import bio_ranges_b200 as brg
+    from bio_ranges_b200.session import NOT_IMPLEMENTED, create_bio_session
+
+    ctx = create_bio_session()
+    for rows, md, strict, want in CLUSTER_LITERALS:
+        ctx.register_table("intervals", pa.table({"contig": pa.array([r[0] for r in rows], pa.string()),
+                                                  "pos_start": pa.array([r[1] for r in rows], pa.int32()),
+                                                  "pos_end": pa.array([r[2] for r in rows], pa.int32())}))
+        args = ("contig", "pos_start", "pos_end", "strict") if strict else ()
+        out = ctx.cluster("intervals", *args, min_dist=md)
+        got = [] if not out else list(zip(*[pa.Table.from_batches(out).column(i).to_pylist() for i in range(6)]))
+        assert got == want
+    t = pa.Table.from_batches(ctx.cluster("intervals"))
+    assert t.schema.names == ["contig", "pos_start", "pos_end", "cluster", "cluster_start", "cluster_end"]
+    assert [str(f.type) for f in t.schema] == ["string"] + ["int64"] * 5  # a 3-column input is rebuilt as Utf8 / Int64
+    # TEST:3594-3626 extra columns are preserved with their types
+    ctx.register_table("x", pa.table({"contig": ["a", "a", "a"], "pos_start": pa.array([400, 100, 150], pa.int32()),
+                                      "pos_end": pa.array([500, 200, 250], pa.int32()), "gene": ["TP53", "BRCA1", "BRCA2"],
+                                      "score": pa.array([0.75, 0.95, 0.85], pa.float64())}))
+    t = pa.Table.from_batches(ctx.cluster("x"))
+    assert t.schema.names == ["contig", "pos_start", "pos_end", "gene", "score", "cluster", "cluster_start", "cluster_end"]
+    assert t.schema.field("pos_start").type == pa.int32()
+    assert list(zip(*[t.column(i).to_pylist() for i in range(8)])) == [
+        ("a", 100, 200, "BRCA1", 0.95, 0, 100, 250), ("a", 150, 250, "BRCA2", 0.85, 0, 100, 250), ("a", 400, 500, "TP53", 0.75, 1, 400, 500)]
+    # TEST:2638-2688 needs 64-bit coordinates: declared unsupported on the 32-bit GPU path
+    ctx.register_table("w", pa.table({"contig": ["a", "a"], "pos_start": pa.array([2**63 - 8, 2**63 - 1], pa.int64()),
+                                      "pos_end": pa.array([2**63 - 2, 2**63 - 1], pa.int64())}))
+    with pytest.raises(brg.BioRangesError) as ei:
+        ctx.cluster("w", min_dist=100)
+    assert ei.value.status == NOT_IMPLEMENTED
+    ctx.close()
