@@ -21,7 +21,8 @@ ABI_SYMBOLS = [
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
     "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
-    "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_merged_len", "brg_merged_key", "brg_merged_start",
+    "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
+    "brg_merged_len", "brg_merged_key", "brg_merged_start",
     "brg_merged_end", "brg_merged_count", "brg_merged_release", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
 ]
@@ -86,6 +87,11 @@ def lib():
     L.brg_take_dev.argtypes = [vp, vp, u32, vp, vp, u64, vp, vp]
     L.brg_merge.argtypes = [vp, vp, vp, vp, u64, u32, C.c_int64, i32, C.POINTER(vp)]
     L.brg_cluster.argtypes = [vp, vp, vp, vp, u64, u32, C.c_int64, i32, C.POINTER(vp)]
+    L.brg_subtract.argtypes = [vp, vp, vp, vp, vp, u64, i32, C.POINTER(vp)]
+    L.brg_sort_rows.argtypes = [vp, vp, vp, vp, u64, u32, vp]
+    for f in (L.brg_rows_piece_start, L.brg_rows_piece_end):
+        f.argtypes = [vp]
+        f.restype = vp
     L.brg_merged_len.argtypes = [vp]
     L.brg_merged_len.restype = u64
     for f in (L.brg_merged_key, L.brg_merged_start, L.brg_merged_end, L.brg_merged_count):

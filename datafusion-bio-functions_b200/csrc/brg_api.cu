@@ -912,15 +912,18 @@ extern "C" BRG_API int brg_nearest_k1(brg_ctx* ctx, const brg_index* ix, const u
 struct brg_rows {
     brg_ctx* ctx = nullptr;
     uint64_t len = 0;
-    PinnedBlock blk_build{}, blk_probe{}, blk_bits{}, blk_dist{};
+    PinnedBlock blk_build{}, blk_probe{}, blk_bits{}, blk_dist{}, blk_ps{}, blk_pe{};
 };
 extern "C" BRG_API uint64_t brg_rows_len(const brg_rows* r) { return r ? r->len : 0; }
 extern "C" BRG_API const uint32_t* brg_rows_build_idx(const brg_rows* r) { return r ? (const uint32_t*)r->blk_build.p : nullptr; }
 extern "C" BRG_API const uint32_t* brg_rows_probe_idx(const brg_rows* r) { return r ? (const uint32_t*)r->blk_probe.p : nullptr; }
 extern "C" BRG_API const uint8_t* brg_rows_valid_bits(const brg_rows* r) { return r ? (const uint8_t*)r->blk_bits.p : nullptr; }
 extern "C" BRG_API const int64_t* brg_rows_distance(const brg_rows* r) { return r ? (const int64_t*)r->blk_dist.p : nullptr; }
+extern "C" BRG_API const int32_t* brg_rows_piece_start(const brg_rows* r) { return r ? (const int32_t*)r->blk_ps.p : nullptr; }
+extern "C" BRG_API const int32_t* brg_rows_piece_end(const brg_rows* r) { return r ? (const int32_t*)r->blk_pe.p : nullptr; }
 extern "C" BRG_API void brg_rows_release(brg_rows* r) {
     if (!r) return;
+    pinned_put(r->ctx, r->blk_ps); pinned_put(r->ctx, r->blk_pe);
     pinned_put(r->ctx, r->blk_build); pinned_put(r->ctx, r->blk_probe);
     pinned_put(r->ctx, r->blk_bits); pinned_put(r->ctx, r->blk_dist);
     delete r;
@@ -1039,6 +1042,102 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
         if (e != cudaSuccess) { set_error(std::string("pairs D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
     }
     *out = r;
+    return BRG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// subtract: count -> scan -> emit over the merged intervals of the right side's coverage index
+// ---------------------------------------------------------------------------------------------------
+extern "C" BRG_API int brg_subtract(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start, const int32_t* end,
+                            uint64_t n, int strict, brg_rows** out) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COVERAGE, "brg_subtract");
+    if (rc) return rc;
+    if (!out) { set_error("brg_subtract: NULL out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (n > 0xFFFFFFFFull) { set_error("left row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!start || !end)) { set_error("brg_subtract: NULL column"); return BRG_ERR_INVALID; }
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    brg_rows* r = new brg_rows();
+    r->ctx = ctx;
+    if (n == 0) { *out = r; return BRG_OK; }
+    LaneGuard g(ctx);
+    if ((rc = g.acquire())) { delete r; return rc; }
+    Lane* l = g.l;
+    cudaStream_t st = l->k;
+    auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };
+    if ((rc = upload_probe(l, key, start, end, n))) return fail(rc);
+    if ((rc = pairs_scratch(l, n))) return fail(rc);
+    if ((rc = l->scratch_b.ensure((n + 1) * 8))) return fail(rc);
+    const uint32_t* dk = key ? l->in_key[0].as<uint32_t>() : nullptr;
+    const int32_t* ds = l->in_s[0].as<int32_t>();
+    const int32_t* de = l->in_e[0].as<int32_t>();
+    uint32_t* counts = l->scratch_a.as<uint32_t>();
+    uint64_t* offsets = l->scratch_b.as<uint64_t>();
+    if ((rc = launch_subtract(ix->view, dk, ds, de, n, strict, counts, nullptr, nullptr, nullptr, nullptr, st))) return fail(rc);
+    if ((rc = exclusive_scan_u32_to_u64(counts, offsets, n, l->scratch_c.as<uint64_t>(), st))) return fail(rc);
+    uint64_t total = 0;
+    {
+        cudaError_t e = cudaMemcpyAsync(&total, offsets + n, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("subtract total: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    r->len = total;
+    const uint64_t tb = std::max<uint64_t>(total, 1) * 4;
+    if ((rc = l->out0[0].ensure(tb)) || (rc = l->out1[0].ensure(tb)) || (rc = l->out2[0].ensure(tb))) return fail(rc);
+    if ((rc = pinned_get(ctx, total * 4, &r->blk_probe)) || (rc = pinned_get(ctx, total * 4, &r->blk_ps)) ||
+        (rc = pinned_get(ctx, total * 4, &r->blk_pe)))
+        return fail(rc);
+    if (total) {
+        if ((rc = launch_subtract(ix->view, dk, ds, de, n, strict, nullptr, offsets, l->out0[0].as<uint32_t>(), l->out1[0].as<int32_t>(),
+                                  l->out2[0].as<int32_t>(), st)))
+            return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(r->blk_probe.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_ps.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_pe.p, l->out2[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(std::string("subtract D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+    }
+    *out = r;
+    return BRG_OK;
+}
+
+// row order of a table sorted by (key, start, end, row): the order in which the sort + sweep table functions walk their
+// input (grouped_stream.rs:92-94, 228-237 with contig ids assigned in name order)
+extern "C" BRG_API int brg_sort_rows(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                             uint32_t n_keys, uint32_t* out_row_order) {
+    if (!ctx || (n && (!start || !end || !out_row_order))) { set_error("brg_sort_rows: NULL argument"); return BRG_ERR_INVALID; }
+    if (n >= 0xFFFFFFFFull) { set_error("brg_sort_rows: row count exceeds UInt32 capacity"); return BRG_ERR_OVERFLOW; }
+    if (n_keys == 0 || n_keys == BRG_KEY_ABSENT) { set_error("brg_sort_rows: bad n_keys"); return BRG_ERR_INVALID; }
+    if (n == 0) return BRG_OK;
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->build_stream;
+    DevBuf in[3], setA[4], setB[4], hist, scan;
+    int rc;
+    for (int i = 0; i < 3; i++) if ((rc = in[i].ensure(n * 4))) return rc;
+    for (int i = 0; i < 4; i++) if ((rc = setA[i].ensure(n * 4)) || (rc = setB[i].ensure(n * 4))) return rc;
+    if ((rc = hist.ensure(radix_hist_words(n) * 4)) ||
+        (rc = scan.ensure((scan_scratch_words(std::max<uint64_t>(radix_hist_words(n), n)) + 16) * 4)))
+        return rc;
+    if (key) BRG_CUDA(cudaMemcpyAsync(in[0].p, key, n * 4, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(in[1].p, start, n * 4, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(in[2].p, end, n * 4, cudaMemcpyHostToDevice, st));
+    uint32_t* a[4] = {setA[0].as<uint32_t>(), setA[1].as<uint32_t>(), setA[2].as<uint32_t>(), setA[3].as<uint32_t>()};
+    uint32_t* b[4] = {setB[0].as<uint32_t>(), setB[1].as<uint32_t>(), setB[2].as<uint32_t>(), setB[3].as<uint32_t>()};
+    init_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key ? in[0].as<uint32_t>() : nullptr, in[1].as<int32_t>(),
+                                                                  in[2].as<int32_t>(), n, a[0], a[1], a[2], a[3]);
+    g_launches.fetch_add(1);
+    std::vector<SortPass> passes;
+    int key_passes = 0;
+    for (uint64_t v = n_keys; v > 0; v >>= 8) key_passes++;
+    for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
+    for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
+    for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
+    int res = 0;
+    if ((rc = radix_sort_rows(a, b, 4, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4, scan.as<uint32_t>(), st, &res)))
+        return rc;
+    uint32_t** S = res == 0 ? a : b;
+    BRG_CUDA(cudaMemcpyAsync(out_row_order, S[3], n * 4, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
     return BRG_OK;
 }
 

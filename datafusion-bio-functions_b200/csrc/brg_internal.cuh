@@ -179,6 +179,10 @@ int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, 
 int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
                       int include_overlaps, int strict, uint32_t* left_idx, uint32_t* valid_bits, int64_t* dist,
                       cudaStream_t st);
+// subtract: offsets == nullptr -> count pass (counts), else emit pass
+int launch_subtract(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
+                    uint32_t* counts, const uint64_t* offsets, uint32_t* out_row, int32_t* out_start, int32_t* out_end,
+                    cudaStream_t st);
 int launch_nearest_k_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,
                            uint32_t k, int include_overlaps, int strict, uint32_t* counts, cudaStream_t st);
 int launch_nearest_k_emit(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,

@@ -614,6 +614,49 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k_kernel(IndexView ix, con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// subtract (subtract.rs:395-440): the pieces of a left interval [ls, le] that no right interval covers.  The reference
+// sweeps the right intervals of the contig in (start, end) order with a cursor; gaps open exactly between consecutive
+// MERGED right intervals (`next.start <= cur.end` merges, interval_tree.rs:52-73 -- the same rule as `rs > cursor`), so the
+// sweep runs over the merged intervals of the coverage index:
+//   skip runs ending before ls (strict: at or before), stop at runs starting after le (strict: at or after).
+// ---------------------------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(PB_THREADS) subtract_kernel(IndexView ix, const uint32_t* __restrict__ key,
+                                                              const int32_t* __restrict__ start,
+                                                              const int32_t* __restrict__ end, uint64_t n, int strict,
+                                                              uint32_t* __restrict__ counts,
+                                                              const uint64_t* __restrict__ offsets,
+                                                              uint32_t* __restrict__ out_row, int32_t* __restrict__ out_start,
+                                                              int32_t* __restrict__ out_end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t ls = ld_stream(start + i), le = ld_stream(end + i);
+        const uint32_t c = load_key(key, i);
+        uint64_t o = EMIT ? offsets[i] : 0;
+        uint32_t m = 0;
+        int32_t cursor = ls;
+        if (c < ix.n_keys) {
+            const KeyDir kl = load_keydir(ix.d_mlast.kd, c), kf = load_keydir(ix.d_mfirst.kd, c);
+            const uint32_t lo = strict ? rank_le_kd(ix.d_mlast, kl, ls) : rank_lt_kd(ix.d_mlast, kl, ls);
+            const uint32_t hi = strict ? rank_lt_kd(ix.d_mfirst, kf, le) : rank_le_kd(ix.d_mfirst, kf, le);
+            for (uint32_t j = lo; j < hi; j++) {
+                const int4 r = __ldg(ix.m_rec + j);  // {first, last, ..}
+                if (r.x > cursor) {
+                    if (EMIT) { out_row[o] = (uint32_t)i; out_start[o] = cursor; out_end[o] = r.x; o++; }
+                    m++;
+                }
+                if (r.y > cursor) cursor = r.y;
+            }
+        }
+        if (cursor < le) {
+            if (EMIT) { out_row[o] = (uint32_t)i; out_start[o] = cursor; out_end[o] = le; }
+            m++;
+        }
+        if (!EMIT) counts[i] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
 // persistent grid for the tiled kernels: 3 CTAs per SM (shared-memory bound), never more CTAs than tiles
@@ -734,6 +777,17 @@ int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s
             valid_bits + done / 32, dist ? dist + done : nullptr);
         BRG_LAUNCH_CHECK();
     }
+    return 0;
+}
+int launch_subtract(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
+                    uint32_t* counts, const uint64_t* offsets, uint32_t* out_row, int32_t* out_start, int32_t* out_end,
+                    cudaStream_t st) {
+    if (n == 0) return 0;
+    if (offsets)
+        subtract_kernel<true><<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, nullptr, offsets, out_row, out_start, out_end);
+    else
+        subtract_kernel<false><<<probe_grid(n, 32), PB_THREADS, 0, st>>>(ix, key, s, e, n, strict, counts, nullptr, nullptr, nullptr, nullptr);
+    BRG_LAUNCH_CHECK();
     return 0;
 }
 int launch_nearest_k_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n,

@@ -828,6 +828,93 @@ static Err run_merge(brgh_session* s, const char* table, int64_t min_dist, const
     return kOk;
 }
 
+// ---- subtract (subtract.rs; table_function.rs) -----------------------------------------------------------------------------------
+static Err run_subtract(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args, brgh_result* res) {
+    UdtfArgs ua;
+    BRGH_TRY(parse_col_args(args, n_args, "subtract", &ua));
+    const Table *lt, *rt;
+    BRGH_TRY(find_table(s, left, &lt));
+    BRGH_TRY(find_table(s, right, &rt));
+    // right side: merged intervals per contig on the device (the sweep walks them, see brg_subtract)
+    KeyDict rdict;
+    IndexGuard ig;
+    BRGH_TRY(build_from_table(s, *rt, ua.right, BRG_WANT_COVERAGE, &rdict, &ig));
+    // left side: rows in (contig name, start, end, row) order (FullBatchCollector::take_groups, grouped_stream.rs:228-237)
+    KeyDict ldict;
+    std::vector<std::string_view> names;
+    std::vector<uint32_t> sort_key, probe_key;
+    std::vector<int64_t> st64, en64;
+    for (auto& b : lt->batches) {
+        if (b.rows == 0) continue;
+        ContigArray ca;
+        BRGH_TRY(contig_array(b, ua.left.contig, &ca));
+        BRGH_TRY(resolve_positions_i64(b, ua.left.start, "start", &st64));
+        BRGH_TRY(resolve_positions_i64(b, ua.left.end, "end", &en64));
+        for (int64_t i = 0; i < b.rows; i++) {
+            const std::string_view v = ca.value(i);
+            const uint32_t id = ldict.get_or_add(v);
+            if (id == names.size()) names.push_back(v);
+            sort_key.push_back(id);
+            probe_key.push_back(rdict.lookup(v));
+        }
+    }
+    const uint64_t n = sort_key.size();
+    std::vector<uint32_t> name_order(names.size()), rank(names.size());
+    for (uint32_t i = 0; i < name_order.size(); i++) name_order[i] = i;
+    std::sort(name_order.begin(), name_order.end(), [&](uint32_t x, uint32_t y) { return names[x] < names[y]; });
+    for (uint32_t r = 0; r < name_order.size(); r++) rank[name_order[r]] = r;
+    std::vector<int32_t> st(n), en(n);
+    for (uint64_t i = 0; i < n; i++) {
+        sort_key[i] = rank[sort_key[i]];
+        if (st64[i] < INT32_MIN || st64[i] > INT32_MAX || en64[i] < INT32_MIN || en64[i] > INT32_MAX)
+            return notimpl("subtract: coordinate value " + std::to_string(st64[i] < INT32_MIN || st64[i] > INT32_MAX ? st64[i] : en64[i]) +
+                           " at row " + std::to_string(i) + " does not fit the 32-bit coordinates of the GPU path");
+        st[i] = (int32_t)st64[i];
+        en[i] = (int32_t)en64[i];
+    }
+    if (n == 0) return kOk;
+    std::vector<uint32_t> order(n);
+    BRGH_TRY(from_abi(brg_sort_rows(s->ctx, sort_key.data(), st.data(), en.data(), n, std::max<uint32_t>(1, (uint32_t)names.size()), order.data())));
+    std::vector<uint32_t> pk(n);
+    std::vector<int32_t> ps(n), pe(n);
+    for (uint64_t i = 0; i < n; i++) { pk[i] = probe_key[order[i]]; ps[i] = st[order[i]]; pe[i] = en[order[i]]; }
+    brg_rows* rows = nullptr;
+    BRGH_TRY(from_abi(brg_subtract(s->ctx, ig.ix, pk.data(), ps.data(), pe.data(), n, ua.strict ? 1 : 0, &rows)));
+    // output: a 3-column left table is rebuilt as (Utf8, Int64, Int64); a wider one keeps its columns, with the start / end
+    // columns replaced by the Int64 pieces (subtract.rs:48-75)
+    const uint64_t total = brg_rows_len(rows), batch_size = 8192;
+    const bool extra = lt->schema.size() > 3;
+    Err e = kOk;
+    for (uint64_t r0 = 0; r0 < total && !e.code; r0 += batch_size) {
+        const uint64_t r1 = std::min(total, r0 + batch_size);
+        std::vector<uint32_t> src(r1 - r0);
+        std::vector<int64_t> cs, ce;
+        for (uint64_t i = r0; i < r1; i++) {
+            src[i - r0] = order[brg_rows_probe_idx(rows)[i]];
+            cs.push_back(brg_rows_piece_start(rows)[i]);
+            ce.push_back(brg_rows_piece_end(rows)[i]);
+        }
+        Batch ob;
+        ob.rows = (int64_t)(r1 - r0);
+        if (extra) {
+            e = take_table(*lt, src.data(), nullptr, ob.rows, "", -1, &ob.cols);
+            for (auto& c : ob.cols) {
+                if (c.f.name == ua.left.start) c = make_primitive<int64_t>(c.f.name, "l", c.f.nullable, std::move(cs), nullptr, 0);
+                else if (c.f.name == ua.left.end) c = make_primitive<int64_t>(c.f.name, "l", c.f.nullable, std::move(ce), nullptr, 0);
+            }
+        } else {
+            std::vector<std::string_view> cn;
+            for (uint32_t row : src) cn.push_back(names[name_order[sort_key[row]]]);
+            ob.cols.push_back(make_utf8(ua.left.contig, cn));
+            ob.cols.push_back(make_primitive<int64_t>(ua.left.start, "l", false, std::move(cs), nullptr, 0));
+            ob.cols.push_back(make_primitive<int64_t>(ua.left.end, "l", false, std::move(ce), nullptr, 0));
+        }
+        res->batches.push_back(std::move(ob));
+    }
+    brg_rows_release(rows);
+    return e;
+}
+
 // ---- count_overlaps / coverage (count_overlaps.rs:107-169; interval_tree.rs:155-280) ----------------------------------------
 static Err run_count(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args, bool coverage,
                      brgh_result* res) {
@@ -1174,6 +1261,12 @@ BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, con
     if (!s || !out) return finish(internal("brgh_merge: NULL argument"));
     auto* r = new brgh_result();
     return run_to_result(run_merge(s, table, min_dist, args, n_args, false, r), r, out);
+}
+BRG_API int brgh_subtract(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args,
+                          brgh_result** out) {
+    if (!s || !out) return finish(internal("brgh_subtract: NULL argument"));
+    auto* r = new brgh_result();
+    return run_to_result(run_subtract(s, left, right, args, n_args, r), r, out);
 }
 BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result** out) {
     if (!s || !out) return finish(internal("brgh_cluster: NULL argument"));

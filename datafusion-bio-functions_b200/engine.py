@@ -41,6 +41,14 @@ class Context:
                                      _tptr(out), st))
         return out
 
+    def sort_rows(self, key, start, end, n_keys):
+        """row order by (key, start, end, row) -> uint32[n]"""
+        key = A.as_key(key)
+        start, end = A.as_i32(start), A.as_i32(end)
+        out = np.empty(len(start), np.uint32)
+        A.check(A.lib().brg_sort_rows(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys), A.np_ptr(out)))
+        return out
+
     def cluster(self, key, start, end, n_keys, min_dist=0, strict=False):
         """cluster UDTF core, one row per input row in (key, start, end, row) order:
         (row_id u32[n], cluster_start i32[n], cluster_end i32[n], cluster_id u32[n])"""
@@ -239,6 +247,21 @@ class Index:
         finally:
             A.lib().brg_rows_release(r)
         return left, A.unpack_bits(bits, m), right, dist
+
+    def subtract(self, key, start, end, strict=False):
+        """pieces of the given (left) intervals not covered by this (right, WANT_COVERAGE) index:
+        (left_row u32[m], piece_start i32[m], piece_end i32[m]), left-row-major"""
+        key, start, end = self._cols(key, start, end)
+        r = C.c_void_p()
+        A.check(A.lib().brg_subtract(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(strict), C.byref(r)))
+        try:
+            L = A.lib()
+            m = L.brg_rows_len(r)
+            out = (A.copy_from(L.brg_rows_probe_idx(r), m, np.uint32), A.copy_from(L.brg_rows_piece_start(r), m, np.int32),
+                   A.copy_from(L.brg_rows_piece_end(r), m, np.int32))
+        finally:
+            A.lib().brg_rows_release(r)
+        return out
 
     def overlap_pairs(self, key, start, end, mode=A.PAIRS_INNER, max_rows=0, return_consumed=False):
         key, start, end = self._cols(key, start, end)

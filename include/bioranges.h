@@ -220,6 +220,20 @@ BRG_API const int32_t* brg_merged_end(const brg_merged* m);
 BRG_API const uint32_t* brg_merged_count(const brg_merged* m);
 BRG_API void brg_merged_release(brg_merged* m);
 
+/* ---- subtract (replaces the sweep of SubtractStream, subtract.rs:395-440): the pieces of every left interval [start, end]
+ *      that no right interval covers.  `idx` is the index of the RIGHT table built with BRG_WANT_COVERAGE (its merged
+ *      intervals are what the sweep walks).  Result rows, left-row-major, pieces of one row in coordinate order:
+ *      brg_rows_probe_idx = left row, brg_rows_piece_start / _end = the piece.  strict: a right interval ending AT the left
+ *      start / starting AT the left end does not touch it (subtract.rs:399-404, 414-417). */
+BRG_API int brg_subtract(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start, const int32_t* end,
+                 uint64_t n, int strict, brg_rows** out);
+BRG_API const int32_t* brg_rows_piece_start(const brg_rows* r);
+BRG_API const int32_t* brg_rows_piece_end(const brg_rows* r);
+/* row order of a table sorted by (key, start, end, row): the order in which the sort + sweep table functions walk and emit
+ * their input (grouped_stream.rs:92-94, 228-237).  out_row_order: host buffer of n u32. */
+BRG_API int brg_sort_rows(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
+                  uint32_t n_keys, uint32_t* out_row_order);
+
 /* ---- instrumentation: kernels launched by this library on the calling process (bench `gpu_launches`) -- */
 BRG_API uint64_t brg_kernel_launches(void);
 

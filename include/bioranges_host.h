@@ -100,6 +100,12 @@ BRG_API int brgh_merge(brgh_session* s, const char* table, int64_t min_dist, con
 BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args,
                  brgh_result** out);
 
+/* subtract(left, right [, cols...] [, 'strict'|'weak']) (subtract.rs): the pieces of every left interval that no right
+ * interval covers, left rows walked in (contig name, start, end, row) order.  A 3-column left table is rebuilt as
+ * (Utf8, Int64, Int64); a wider one keeps its columns with start / end replaced by the Int64 pieces (subtract.rs:48-75). */
+BRG_API int brgh_subtract(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args,
+                  brgh_result** out);
+
 /* ---- the range join IntervalJoinExec executes ---------------------------------------------------------------------------
  *   SELECT * FROM left l JOIN right r ON l.<on_left[i]> = r.<on_right[i]> ...
  *        AND l.<left_start> <[=] r.<right_end> AND l.<left_end> >[=] r.<right_start>

@@ -542,6 +542,48 @@ void brgo_cluster(const uint32_t *key, const int64_t *start, const int64_t *end,
     free(cnt); free(rows); free(fill);
 }
 
+/* ---- subtract (subtract.rs:395-440 / 560-640): per contig, left intervals in (start, end, row) order, right intervals in
+ * (start, end) order, the reference's cursor sweep restated literally (persistent right_cursor included).
+ * Returns the number of pieces; only the first `cap` are written (call once with cap = 0 to size the outputs). */
+uint64_t brgo_subtract(const uint32_t *lkey, const int64_t *lstart, const int64_t *lend, uint64_t nl, const uint32_t *rkey,
+                       const int64_t *rstart, const int64_t *rend, uint64_t nr, uint32_t n_keys, int strict,
+                       uint64_t *out_row, int64_t *out_start, int64_t *out_end, uint64_t cap) {
+    uint64_t *lc = calloc((size_t)n_keys + 2, sizeof(uint64_t)), *rc = calloc((size_t)n_keys + 2, sizeof(uint64_t));
+    for (uint64_t i = 0; i < nl; i++) lc[lkey[i] + 1]++;
+    for (uint64_t i = 0; i < nr; i++) if (rkey[i] < n_keys) rc[rkey[i] + 1]++;
+    for (uint32_t k = 0; k < n_keys; k++) { lc[k + 1] += lc[k]; rc[k + 1] += rc[k]; }
+    ivr64_t *L = malloc((nl ? nl : 1) * sizeof(ivr64_t));
+    iv64_t *R = malloc((nr ? nr : 1) * sizeof(iv64_t));
+    uint64_t *lf = malloc(((size_t)n_keys + 1) * sizeof(uint64_t)), *rf = malloc(((size_t)n_keys + 1) * sizeof(uint64_t));
+    memcpy(lf, lc, ((size_t)n_keys + 1) * sizeof(uint64_t));
+    memcpy(rf, rc, ((size_t)n_keys + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < nl; i++) { ivr64_t r = {lstart[i], lend[i], i}; L[lf[lkey[i]]++] = r; }
+    for (uint64_t i = 0; i < nr; i++) if (rkey[i] < n_keys) { iv64_t r = {rstart[i], rend[i]}; R[rf[rkey[i]]++] = r; }
+    uint64_t o = 0;
+    for (uint32_t k = 0; k < n_keys; k++) {
+        ivr64_t *lg = L + lc[k];
+        iv64_t *rg = R + rc[k];
+        const uint64_t ln = lc[k + 1] - lc[k], rn = rc[k + 1] - rc[k];
+        qsort(lg, ln, sizeof(ivr64_t), cmp_ivr64);
+        qsort(rg, rn, sizeof(iv64_t), cmp_iv64);
+        uint64_t right_cursor = 0;
+        for (uint64_t i = 0; i < ln; i++) {
+            const int64_t ls = lg[i].s, le = lg[i].e;
+            while (right_cursor < rn && (strict ? rg[right_cursor].e <= ls : rg[right_cursor].e < ls)) right_cursor++;
+            int64_t cursor = ls;
+            for (uint64_t j = right_cursor; j < rn; j++) {
+                const int64_t rs = rg[j].s, re = rg[j].e;
+                if (strict ? rs >= le : rs > le) break;
+                if (rs > cursor) { if (o < cap) { out_row[o] = lg[i].row; out_start[o] = cursor; out_end[o] = rs; } o++; }
+                if (re > cursor) cursor = re;
+            }
+            if (cursor < le) { if (o < cap) { out_row[o] = lg[i].row; out_start[o] = cursor; out_end[o] = le; } o++; }
+        }
+    }
+    free(lc); free(rc); free(L); free(R); free(lf); free(rf);
+    return o;
+}
+
 void brgo_free(void *p) { free(p); }
 int brgo_max_threads(void) {
 #ifdef _OPENMP

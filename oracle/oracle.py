@@ -185,6 +185,23 @@ def cluster(key, start, end, n_keys, min_dist=0, strict=False):
     return orow, oc, os_, oe
 
 
+def subtract(lkey, lstart, lend, rkey, rstart, rend, n_keys, strict=False):
+    """subtract UDTF core (subtract.rs:395-440): (left_row u64[m], piece_start i64[m], piece_end i64[m]); left rows are walked
+    in (key, start, end, row) order.  Keys are ids over the LEFT contigs; right rows with key >= n_keys are ignored."""
+    L = lib()
+    L.brgo_subtract.restype = C.c_uint64
+    L.brgo_subtract.argtypes = [C.c_void_p] * 3 + [C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64, C.c_uint32, C.c_int] + [C.c_void_p] * 3 + [C.c_uint64]
+    lkey, rkey = np.ascontiguousarray(lkey, np.uint32), np.ascontiguousarray(rkey, np.uint32)
+    ls, le = np.ascontiguousarray(lstart, np.int64), np.ascontiguousarray(lend, np.int64)
+    rs, re = np.ascontiguousarray(rstart, np.int64), np.ascontiguousarray(rend, np.int64)
+    call = lambda o, a, b, cap: L.brgo_subtract(lkey.ctypes.data, ls.ctypes.data, le.ctypes.data, len(ls), rkey.ctypes.data, rs.ctypes.data,
+                                                re.ctypes.data, len(rs), int(n_keys), int(bool(strict)), o, a, b, cap)
+    m = call(None, None, None, 0)  # sizing pass
+    orow, os_, oe = np.empty(m, np.uint64), np.empty(m, np.int64), np.empty(m, np.int64)
+    call(orow.ctypes.data, os_.ctypes.data, oe.ctypes.data, m)
+    return orow, os_, oe
+
+
 def max_threads():
     """host cores this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
     which would silently turn the multi-threaded CPU baseline into a single-threaded one."""

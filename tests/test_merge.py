@@ -217,3 +217,100 @@ def test_cluster_udtf_through_session():
         ctx.cluster("w", min_dist=100)
     assert ei.value.status == NOT_IMPLEMENTED
     ctx.close()
+
+
+# ---- subtract (tests/integration_test.rs:3185-3712) ----------------------------------------------------------------------
+SUBTRACT_LITERALS = [  # (left rows, right rows, strict, expected pieces)
+    ([("a", 100, 400)], [("a", 200, 300)], False, [("a", 100, 200), ("a", 300, 400)]),
+    ([("a", 100, 200)], [("a", 300, 400)], False, [("a", 100, 200)]),
+    ([("a", 100, 200)], [("a", 50, 300)], False, []),
+    ([("a", 100, 500)], [("a", 150, 200), ("a", 300, 350)], False, [("a", 100, 150), ("a", 200, 300), ("a", 350, 500)]),
+    ([("a", 100, 300), ("b", 100, 300)], [("a", 150, 250)], False, [("a", 100, 150), ("a", 250, 300), ("b", 100, 300)]),
+    ([], [("a", 1, 2)], False, []),
+    ([("a", 100, 200)], [], False, [("a", 100, 200)]),
+    ([("a", 100, 300)], [("a", 300, 400)], False, [("a", 100, 300)]),
+    ([("a", 100, 300)], [("a", 300, 400)], True, [("a", 100, 300)]),
+    ([("a", 100, 500)], [("a", 150, 250), ("a", 200, 350)], False, [("a", 100, 150), ("a", 350, 500)]),
+]
+
+
+def _encode_two(left, right):
+    names = sorted({r[0] for r in left})
+    ids = {n: i for i, n in enumerate(names)}
+    enc = lambda rows: (np.array([ids.get(r[0], 0xFFFFFFFF) for r in rows], np.uint32), np.array([r[1] for r in rows], np.int64),
+                        np.array([r[2] for r in rows], np.int64))
+    return names, enc(left), enc(right)
+
+
+@pytest.mark.parametrize("case", range(len(SUBTRACT_LITERALS)))
+def test_oracle_subtract_reference_literals(case):
+    from oracle import oracle as O
+
+    left, right, strict, want = SUBTRACT_LITERALS[case]
+    names, (lk, ls, le), (rk, rs, re) = _encode_two(left, right)
+    row, ps, pe = O.subtract(lk, ls, le, rk, rs, re, max(1, len(names)), strict)
+    assert [(left[int(r)][0], int(a), int(b)) for r, a, b in zip(row, ps, pe)] == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_subtract_vs_oracle(seed):
+    import bio_ranges_b200 as brg
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(100 + seed)
+    nk = int(rng.choice([1, 4, 40]))
+    nl, nr = int(rng.choice([1, 300, 50_000])), int(rng.choice([0, 1, 500, 80_000]))
+    span = int(rng.choice([2000, 300_000, 1_000_000_000]))
+    mk = lambda n, maxlen: (rng.integers(0, nk + (1 if seed % 4 == 0 else 0), n).astype(np.uint32), rng.integers(0, span, n).astype(np.int64))
+    lk, ls = mk(nl, 0)
+    lk = np.minimum(lk, nk - 1)
+    le = ls + rng.integers(0, int(rng.choice([1, 100, 20000])), nl)
+    rk, rs = mk(nr, 0)
+    re = rs + rng.integers(0, int(rng.choice([1, 60, 9000])), nr)
+    strict = bool(seed % 2)
+    ctx = brg.default_context(0)
+    gi = ctx.build(rk, rs.astype(np.int32), re.astype(np.int32), nk + 1, brg.WANT_COVERAGE)
+    order = ctx.sort_rows(lk, ls.astype(np.int32), le.astype(np.int32), nk)
+    idx, ps, pe = gi.subtract(lk[order], ls[order].astype(np.int32), le[order].astype(np.int32), strict=strict)
+    orow, ops, ope = O.subtract(lk, ls, le, np.where(rk < nk, rk, 0xFFFFFFFF).astype(np.uint32), rs, re, nk, strict)
+    assert len(idx) == len(orow)
+    assert (order[idx] == orow).all() and (ps == ops).all() and (pe == ope).all()
+    gi.close()
+
+
+@pytest.mark.gpu
+def test_subtract_udtf_through_session():
+    import pyarrow as pa
+
+    from bio_ranges_b200.session import create_bio_session
+
+    def tbl(rows, names=("contig", "pos_start", "pos_end")):
+        return pa.table({names[0]: pa.array([r[0] for r in rows], pa.string()), names[1]: pa.array([r[1] for r in rows], pa.int32()),
+                         names[2]: pa.array([r[2] for r in rows], pa.int32())})
+
+    ctx = create_bio_session()
+    for left, right, strict, want in SUBTRACT_LITERALS:
+        ctx.register_table("left_t", tbl(left))
+        ctx.register_table("right_t", tbl(right))
+        args = ("contig", "pos_start", "pos_end", "strict") if strict else ()
+        out = ctx.subtract("left_t", "right_t", *args)
+        got = [] if not out else list(zip(*[pa.Table.from_batches(out).column(i).to_pylist() for i in range(3)]))
+        assert got == want
+        if out:
+            assert [str(f.type) for f in out[0].schema] == ["string", "int64", "int64"]
+    # TEST:3628-3712 extra columns preserved, start / end replaced by the Int64 pieces
+    ctx.register_table("left_multi", pa.table({"contig": ["a"], "pos_start": pa.array([100], pa.int32()), "pos_end": pa.array([600], pa.int32()),
+                                               "gene": ["BRCA1"], "score": pa.array([0.95], pa.float64())}))
+    ctx.register_table("right_multi", tbl([("a", 200, 300), ("a", 400, 500)]))
+    t = pa.Table.from_batches(ctx.subtract("left_multi", "right_multi"))
+    assert t.schema.names == ["contig", "pos_start", "pos_end", "gene", "score"]
+    assert t.schema.field("pos_start").type == pa.int64() and t.schema.field("score").type == pa.float64()
+    assert list(zip(*[t.column(i).to_pylist() for i in range(5)])) == [
+        ("a", 100, 200, "BRCA1", 0.95), ("a", 300, 400, "BRCA1", 0.95), ("a", 500, 600, "BRCA1", 0.95)]
+    # TEST:3453-3495 separate column names per side
+    ctx.register_table("lc", tbl([("a", 100, 400)], names=("chr", "s", "e")))
+    ctx.register_table("rc", tbl([("a", 200, 300)], names=("c2", "s2", "e2")))
+    t = pa.Table.from_batches(ctx.subtract("lc", "rc", "chr", "s", "e", "c2", "s2", "e2"))
+    assert t.schema.names == ["chr", "s", "e"] and t.column("s").to_pylist() == [100, 300]
+    ctx.close()
