@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
     "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
-    "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
+    "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_complement", "brg_gaps_len", "brg_gaps_view", "brg_gaps_start", "brg_gaps_end", "brg_gaps_release", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
     "brg_merged_len", "brg_merged_key", "brg_merged_start",
     "brg_merged_end", "brg_merged_count", "brg_merged_release", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
@@ -89,6 +89,14 @@ def lib():
     L.brg_cluster.argtypes = [vp, vp, vp, vp, u64, u32, C.c_int64, i32, C.POINTER(vp)]
     L.brg_subtract.argtypes = [vp, vp, vp, vp, vp, u64, i32, C.POINTER(vp)]
     L.brg_sort_rows.argtypes = [vp, vp, vp, vp, u64, u32, vp]
+    L.brg_complement.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, vp, u64, i32, C.POINTER(vp)]
+    L.brg_gaps_len.argtypes = [vp]
+    L.brg_gaps_len.restype = u64
+    for f in (L.brg_gaps_view, L.brg_gaps_start, L.brg_gaps_end):
+        f.argtypes = [vp]
+        f.restype = vp
+    L.brg_gaps_release.argtypes = [vp]
+    L.brg_gaps_release.restype = None
     for f in (L.brg_rows_piece_start, L.brg_rows_piece_end):
         f.argtypes = [vp]
         f.restype = vp

@@ -1160,8 +1160,48 @@ extern "C" BRG_API void brg_merged_release(brg_merged* m) {
     delete m;
 }
 
+struct brg_gaps {
+    brg_ctx* ctx = nullptr;
+    uint64_t len = 0;
+    PinnedBlock view{}, start{}, end{};
+};
+extern "C" BRG_API uint64_t brg_gaps_len(const brg_gaps* g) { return g ? g->len : 0; }
+extern "C" BRG_API const uint32_t* brg_gaps_view(const brg_gaps* g) { return g ? (const uint32_t*)g->view.p : nullptr; }
+extern "C" BRG_API const int64_t* brg_gaps_start(const brg_gaps* g) { return g ? (const int64_t*)g->start.p : nullptr; }
+extern "C" BRG_API const int64_t* brg_gaps_end(const brg_gaps* g) { return g ? (const int64_t*)g->end.p : nullptr; }
+extern "C" BRG_API void brg_gaps_release(brg_gaps* g) {
+    if (!g) return;
+    pinned_put(g->ctx, g->view); pinned_put(g->ctx, g->start); pinned_put(g->ctx, g->end);
+    delete g;
+}
+struct ViewArgs {  // complement: the view rows and where the gaps go
+    const uint32_t* key;
+    const int64_t *start, *end;
+    uint64_t n;
+    brg_gaps* gaps;
+};
+
 static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
-                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out);
+                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out,
+                          const ViewArgs* views = nullptr);
+extern "C" BRG_API int brg_complement(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
+                              uint32_t n_keys, const uint32_t* view_key, const int64_t* view_start, const int64_t* view_end,
+                              uint64_t n_views, int strict, brg_gaps** out) {
+    if (!ctx || !out) { set_error("brg_complement: NULL ctx/out"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    if (n_views && (!view_key || !view_start || !view_end)) { set_error("brg_complement: NULL view column"); return BRG_ERR_INVALID; }
+    if (n_views >= 0xFFFFFFFFull) { set_error("brg_complement: view row count exceeds UInt32 capacity"); return BRG_ERR_OVERFLOW; }
+    brg_gaps* g = new brg_gaps();
+    g->ctx = ctx;
+    if (n_views == 0) { *out = g; return BRG_OK; }
+    ViewArgs va{view_key, view_start, view_end, n_views, g};
+    brg_merged* unused = nullptr;
+    const int rc = merge_pipeline(ctx, key, start, end, n, n_keys ? n_keys : 1u, 0, strict, false, &unused, &va);
+    if (unused) brg_merged_release(unused);
+    if (rc) { brg_gaps_release(g); return rc; }
+    *out = g;
+    return BRG_OK;
+}
 extern "C" BRG_API int brg_merge(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
                          uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out) {
     return merge_pipeline(ctx, key, start, end, n, n_keys, min_dist, strict, false, out);
@@ -1170,8 +1210,49 @@ extern "C" BRG_API int brg_cluster(brg_ctx* ctx, const uint32_t* key, const int3
                            uint32_t n_keys, int64_t min_dist, int strict, brg_merged** out) {
     return merge_pipeline(ctx, key, start, end, n, n_keys, min_dist, strict, true, out);
 }
+// complement with the merged intervals (m of them, key order) on the device: count -> scan -> emit over the views
+static int complement_views(brg_ctx* ctx, const uint32_t* m_key, const int32_t* m_first, const int32_t* m_last, uint64_t m,
+                            uint32_t n_keys, const ViewArgs& va, uint32_t* scan_scratch, cudaStream_t st) {
+    DevBuf v_key, v_start, v_end, m_off, g_tmp, G, plan, counts, offsets, scan64, o_view, o_start, o_end;
+    int rc;
+    const uint64_t nv = va.n;
+    if ((rc = v_key.ensure(nv * 4)) || (rc = v_start.ensure(nv * 8)) || (rc = v_end.ensure(nv * 8)) ||
+        (rc = m_off.ensure(((uint64_t)n_keys + 1) * 4)) || (rc = g_tmp.ensure(std::max<uint64_t>(m, 1) * 4)) ||
+        (rc = G.ensure((m + 1) * 4)) || (rc = plan.ensure(nv * 16)) || (rc = counts.ensure(nv * 4)) ||
+        (rc = offsets.ensure((nv + 1) * 8)) || (rc = scan64.ensure((scan_scratch_words(nv) + 16) * 8)))
+        return rc;
+    BRG_CUDA(cudaMemcpyAsync(v_key.p, va.key, nv * 4, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(v_start.p, va.start, nv * 8, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemcpyAsync(v_end.p, va.end, nv * 8, cudaMemcpyHostToDevice, st));
+    BRG_CUDA(cudaMemsetAsync(G.p, 0, (m + 1) * 4, st));
+    if ((rc = complement_plan(m_key, m_first, m_last, m, n_keys, v_key.as<uint32_t>(), v_start.as<long long>(), v_end.as<long long>(),
+                              nv, m_off.as<uint32_t>(), g_tmp.as<uint32_t>(), G.as<uint32_t>(), scan_scratch, plan.as<uint4>(),
+                              counts.as<uint32_t>(), st)))
+        return rc;
+    if ((rc = exclusive_scan_u32_to_u64(counts.as<uint32_t>(), offsets.as<uint64_t>(), nv, scan64.as<uint64_t>(), st))) return rc;
+    uint64_t total = 0;
+    BRG_CUDA(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + nv, 8, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
+    brg_gaps* g = va.gaps;
+    g->len = total;
+    if (total == 0) return 0;
+    if ((rc = o_view.ensure(total * 4)) || (rc = o_start.ensure(total * 8)) || (rc = o_end.ensure(total * 8))) return rc;
+    if ((rc = pinned_get(ctx, total * 4, &g->view)) || (rc = pinned_get(ctx, total * 8, &g->start)) ||
+        (rc = pinned_get(ctx, total * 8, &g->end)))
+        return rc;
+    if ((rc = complement_emit(v_start.as<long long>(), v_end.as<long long>(), nv, offsets.as<uint64_t>(), m_first, m_last,
+                              G.as<uint32_t>(), plan.as<uint4>(), total, o_view.as<uint32_t>(), o_start.as<long long>(),
+                              o_end.as<long long>(), st)))
+        return rc;
+    BRG_CUDA(cudaMemcpyAsync(g->view.p, o_view.p, total * 4, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaMemcpyAsync(g->start.p, o_start.p, total * 8, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaMemcpyAsync(g->end.p, o_end.p, total * 8, cudaMemcpyDeviceToHost, st));
+    BRG_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* start, const int32_t* end, uint64_t n,
-                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out) {
+                          uint32_t n_keys, int64_t min_dist, int strict, bool cluster, brg_merged** out, const ViewArgs* views) {
     if (!ctx || !out) { set_error("brg_merge: NULL ctx/out"); return BRG_ERR_INVALID; }
     *out = nullptr;
     if (n > 0 && (!start || !end)) { set_error("brg_merge: NULL column"); return BRG_ERR_INVALID; }
@@ -1180,8 +1261,16 @@ static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* star
     BRG_CUDA(cudaSetDevice(ctx->device));
     brg_merged* r = new brg_merged();
     r->ctx = ctx;
-    if (n == 0) { *out = r; return BRG_OK; }
     cudaStream_t st = ctx->build_stream;
+    if (n == 0) {
+        *out = r;
+        if (!views) return BRG_OK;
+        DevBuf scan0;  // no input rows: no merged intervals, every view is answered from its own bounds
+        int rc0 = scan0.ensure(64);
+        if (!rc0) rc0 = complement_views(ctx, nullptr, nullptr, nullptr, 0, n_keys, *views, scan0.as<uint32_t>(), st);
+        if (rc0) cudaStreamSynchronize(st);
+        return rc0;
+    }
     DevBuf in[3], setA[4], setB[4], hist, scan, small, pme, flags, midx, m_key, m_first, m_last, m_row0, m_count;
     int rc;
     auto fail = [&](int code) { cudaStreamSynchronize(st); brg_merged_release(r); return code; };
@@ -1229,6 +1318,13 @@ static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* star
     }
     if (host_vals[8]) { set_error("merge: intervals with start > end are not supported on the GPU path"); return fail(BRG_ERR_UNSUPPORTED); }
     uint64_t m = host_vals[0];
+    if (views) {
+        if ((rc = complement_views(ctx, m_key.as<uint32_t>(), m_first.as<int32_t>(), m_last.as<int32_t>(), m, n_keys, *views,
+                                   scan.as<uint32_t>(), st)))
+            return fail(rc);
+        *out = r;
+        return BRG_OK;
+    }
     if (cluster) {
         // one result row per input row, in (key, start, end, row) order:
         //   key -> original row id, start / end -> extent of the row's run, count -> run id (global, key order)

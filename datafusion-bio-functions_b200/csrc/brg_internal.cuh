@@ -151,6 +151,14 @@ int merge_runs(const uint32_t* s_key, const int32_t* s_start, const int32_t* pme
 int merge_counts(const uint32_t* m_row0, uint64_t m, uint64_t n, uint32_t* m_count, cudaStream_t st);
 int cluster_rows(const uint32_t* flags, const uint32_t* midx, const int32_t* m_first, const int32_t* m_last, uint64_t n,
                  uint32_t* cluster, int32_t* c_start, int32_t* c_end, cudaStream_t st);
+// complement UDTF: per-view row counts + plan (count pass), then one output row per thread (emit pass)
+int complement_plan(const uint32_t* m_key, const int32_t* m_first, const int32_t* m_last, uint64_t m, uint32_t n_keys,
+                    const uint32_t* v_key, const long long* v_start, const long long* v_end, uint64_t n_views,
+                    uint32_t* m_off /*n_keys+1*/, uint32_t* g_tmp /*m*/, uint32_t* G /*m+1*/, uint32_t* scan_scratch,
+                    uint4* plan /*n_views*/, uint32_t* counts /*n_views*/, cudaStream_t st);
+int complement_emit(const long long* v_start, const long long* v_end, uint64_t n_views, const uint64_t* offsets,
+                    const int32_t* m_first, const int32_t* m_last, const uint32_t* G, const uint4* plan, uint64_t total,
+                    uint32_t* out_view, long long* out_start, long long* out_end, cudaStream_t st);
 int merged_width_prefix(const int32_t* m_first, const int32_t* m_last, uint64_t n_merged, uint32_t* widths_tmp,
                         int32_t* m_pre /*n_merged+1*/, uint32_t* scan_scratch, cudaStream_t st);
 // segment offsets off[0..n_keys] from a sorted key array (keys >= n_keys are the invalid tail)

@@ -574,4 +574,130 @@ int dir_fill(const int32_t* A, const KeyDir* kd, uint32_t n_keys, uint32_t shift
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// complement UDTF (complement.rs:297-358): the gaps of a contig's merged input intervals inside each of its view
+// intervals [vs, ve).  The reference walks, per view, the merged intervals with me > vs and ms < ve (a contiguous range
+// [j0, j1) because ms and me are both non-decreasing), emits [cursor, max(ms, vs)) when that is non-empty, moves the
+// cursor to min(me, ve), and finally emits [cursor, ve).  Inside the range a gap precedes merged interval j > j0 iff
+// ms[j] > me[j-1] (always, unless `strict` left two touching runs unmerged), so with G = exclusive prefix sum of those
+// flags a view's row count is  [ms[j0] > vs] + G[j1] - G[j0+1] + [cursor < ve]:  count -> scan -> emit, and the emit
+// pass is parallel over OUTPUT rows (a chromosome-sized view holds millions of gaps): each output slot finds its view
+// by a search in the view offsets and its gap by a search in G.
+// Views whose key is absent from the input (view-only contigs, complement.rs:437-457) come out whole and unconditionally.
+// ---------------------------------------------------------------------------------------------------
+__global__ void gap_flags_kernel(const uint32_t* __restrict__ m_key, const int32_t* __restrict__ m_first,
+                                 const int32_t* __restrict__ m_last, uint64_t m, uint32_t* __restrict__ g) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    g[j] = (j > 0 && m_key[j] == m_key[j - 1] && m_first[j] > m_last[j - 1]) ? 1u : 0u;
+}
+__global__ void complement_count_kernel(const uint32_t* __restrict__ v_key, const long long* __restrict__ v_start,
+                                        const long long* __restrict__ v_end, uint64_t n_views,
+                                        const uint32_t* __restrict__ m_off, uint32_t n_keys,
+                                        const int32_t* __restrict__ m_first, const int32_t* __restrict__ m_last,
+                                        const uint32_t* __restrict__ G, uint4* __restrict__ plan,
+                                        uint32_t* __restrict__ counts) {
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_views) return;
+    const uint32_t k = v_key[v];
+    const long long vs = v_start[v], ve = v_end[v];
+    uint32_t j0 = 0, j1 = 0, lead = 0, tail = 0, mid = 0;
+    if (k >= n_keys || m_off[k] == m_off[k + 1]) {
+        tail = 1;  // view-only contig (no input rows): (view_start, view_end) as is
+    } else if (vs < ve) {
+        uint32_t lo = m_off[k], hi = m_off[k + 1];
+        const uint32_t seg_end = hi;
+        while (lo < hi) {  // first merged interval with me > vs
+            const uint32_t mid_j = (lo + hi) >> 1;
+            if ((long long)m_last[mid_j] > vs) hi = mid_j; else lo = mid_j + 1;
+        }
+        j0 = lo;
+        hi = seg_end;
+        while (lo < hi) {  // first merged interval with ms >= ve
+            const uint32_t mid_j = (lo + hi) >> 1;
+            if ((long long)m_first[mid_j] >= ve) hi = mid_j; else lo = mid_j + 1;
+        }
+        j1 = lo;
+        long long cursor = vs;
+        if (j1 > j0) {
+            lead = (long long)m_first[j0] > vs ? 1u : 0u;
+            mid = G[j1] - G[j0 + 1];
+            cursor = min((long long)m_last[j1 - 1], ve);
+        }
+        tail = cursor < ve ? 1u : 0u;
+    }
+    plan[v] = make_uint4(j0, j1, lead, tail);
+    counts[v] = lead + mid + tail;
+}
+__global__ void complement_emit_kernel(const long long* __restrict__ v_start, const long long* __restrict__ v_end,
+                                       uint64_t n_views, const uint64_t* __restrict__ offsets,
+                                       const int32_t* __restrict__ m_first, const int32_t* __restrict__ m_last,
+                                       const uint32_t* __restrict__ G, const uint4* __restrict__ plan, uint64_t total,
+                                       uint32_t* __restrict__ out_view, long long* __restrict__ out_start,
+                                       long long* __restrict__ out_end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        uint64_t lo = 0, hi = n_views;  // last view whose first slot is <= t (views without rows share their successor's offset)
+        while (hi - lo > 1) {
+            const uint64_t mid_v = (lo + hi) >> 1;
+            if (offsets[mid_v] <= t) lo = mid_v; else hi = mid_v;
+        }
+        const uint64_t v = lo;
+        uint32_t r = (uint32_t)(t - offsets[v]);
+        const uint4 p = plan[v];
+        const long long vs = v_start[v], ve = v_end[v];
+        long long s, e;
+        if (p.z && r == 0) {
+            s = vs; e = m_first[p.x];
+        } else {
+            r -= p.z;
+            const uint32_t mid = p.y > p.x ? G[p.y] - G[p.x + 1] : 0u;
+            if (r < mid) {
+                const uint32_t target = G[p.x + 1] + r;  // the flagged j with exactly `r` flagged intervals before it in (j0, j1)
+                uint32_t a = p.x + 1, b = p.y;           // = the last j with G[j] <= target
+                while (b - a > 1) {
+                    const uint32_t c = (a + b) >> 1;
+                    if (G[c] <= target) a = c; else b = c;
+                }
+                s = m_last[a - 1]; e = m_first[a];
+            } else {
+                s = p.y > p.x ? min((long long)m_last[p.y - 1], ve) : vs;
+                e = ve;
+            }
+        }
+        out_view[t] = (uint32_t)v;
+        out_start[t] = s;
+        out_end[t] = e;
+    }
+}
+int complement_plan(const uint32_t* m_key, const int32_t* m_first, const int32_t* m_last, uint64_t m, uint32_t n_keys,
+                    const uint32_t* v_key, const long long* v_start, const long long* v_end, uint64_t n_views,
+                    uint32_t* m_off /*n_keys+1*/, uint32_t* g_tmp /*m*/, uint32_t* G /*m+1*/, uint32_t* scan_scratch,
+                    uint4* plan /*n_views*/, uint32_t* counts /*n_views*/, cudaStream_t st) {
+    int rc = segment_offsets(m_key, m, n_keys, m_off, st);
+    if (rc) return rc;
+    if (m) {
+        gap_flags_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m_key, m_first, m_last, m, g_tmp);
+        BRG_LAUNCH_CHECK();
+        if ((rc = exclusive_scan_u32_total(g_tmp, G, m, scan_scratch, G + m, st))) return rc;
+    }
+    if (n_views) {
+        complement_count_kernel<<<(unsigned)((n_views + 255) / 256), 256, 0, st>>>(v_key, v_start, v_end, n_views, m_off, n_keys,
+                                                                                  m_first, m_last, G, plan, counts);
+        BRG_LAUNCH_CHECK();
+    }
+    return 0;
+}
+int complement_emit(const long long* v_start, const long long* v_end, uint64_t n_views, const uint64_t* offsets,
+                    const int32_t* m_first, const int32_t* m_last, const uint32_t* G, const uint4* plan, uint64_t total,
+                    uint32_t* out_view, long long* out_start, long long* out_end, cudaStream_t st) {
+    if (total == 0) return 0;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)kSMs * 16));
+    complement_emit_kernel<<<grid, 256, 0, st>>>(v_start, v_end, n_views, offsets, m_first, m_last, G, plan, total, out_view,
+                                                 out_start, out_end);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+
 }  // namespace brg

@@ -915,6 +915,138 @@ static Err run_subtract(brgh_session* s, const char* left, const char* right, co
     return e;
 }
 
+// ---- complement (complement.rs; table_function.rs:602-767) -------------------------------------------------------------------
+static Err run_complement(brgh_session* s, const char* table, const char* const* args, int n_args, brgh_result* res) {
+    const std::string fn = "complement";
+    // argument grammar of ComplementTableFunction::call (table_function.rs:615-767): after the table name, an optional trailing
+    // 'strict' / 'weak', then 0 / 1 (view table) / 3 (columns) / 4 (view + columns) / 7 (view + columns + view columns) strings
+    std::vector<std::string> a;
+    for (int i = 0; i < n_args; i++) a.push_back(args[i] ? args[i] : "");
+    bool strict = false;
+    if (!a.empty()) {
+        const std::string l = lower(a.back());
+        if (l == "strict") { strict = true; a.pop_back(); }
+        else if (l == "weak") { a.pop_back(); }
+    }
+    ColTriple cols{kDefaultCols[0], kDefaultCols[1], kDefaultCols[2]};
+    ColTriple vcols = cols;
+    std::string view_table;
+    bool has_view = false;
+    switch (a.size()) {
+        case 0: break;
+        case 1: view_table = a[0]; has_view = true; break;
+        case 3: cols = vcols = ColTriple{a[0], a[1], a[2]}; break;
+        case 4: view_table = a[0]; has_view = true; cols = vcols = ColTriple{a[1], a[2], a[3]}; break;
+        case 7: view_table = a[0]; has_view = true; cols = ColTriple{a[1], a[2], a[3]}; vcols = ColTriple{a[4], a[5], a[6]}; break;
+        default:
+            return plan(fn + "() unexpected number of arguments (" + std::to_string(a.size()) + " extra args after table name). Usage: " + fn +
+                        "('table' [, 'view_table'] [, col1, col2, col3 [, vcol1, vcol2, vcol3]] [, 'strict'|'weak'])");
+    }
+    const Table *t, *vt = nullptr;
+    BRGH_TRY(find_table(s, table, &t));
+    if (has_view) BRGH_TRY(find_table(s, view_table.c_str(), &vt));
+    // input rows grouped by contig (StreamCollector, grouped_stream.rs:48-98); groups are walked in contig-name order
+    KeyDict dict;
+    std::vector<std::string_view> names;
+    std::vector<uint32_t> key;
+    std::vector<int64_t> st64, en64;
+    for (auto& b : t->batches) {
+        if (b.rows == 0) continue;
+        ContigArray ca;
+        BRGH_TRY(contig_array(b, cols.contig, &ca));
+        BRGH_TRY(resolve_positions_i64(b, cols.start, "start", &st64));
+        BRGH_TRY(resolve_positions_i64(b, cols.end, "end", &en64));
+        for (int64_t i = 0; i < b.rows; i++) {
+            const std::string_view v = ca.value(i);
+            const uint32_t id = dict.get_or_add(v);
+            if (id == names.size()) names.push_back(v);
+            key.push_back(id);
+        }
+    }
+    std::vector<uint32_t> order(names.size()), rank(names.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return names[x] < names[y]; });
+    for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
+    std::vector<int32_t> st(key.size()), en(key.size());
+    for (size_t i = 0; i < key.size(); i++) {
+        key[i] = rank[key[i]];
+        if (st64[i] < INT32_MIN || st64[i] > INT32_MAX || en64[i] < INT32_MIN || en64[i] > INT32_MAX)
+            return notimpl(fn + ": coordinate value " + std::to_string(st64[i] < INT32_MIN || st64[i] > INT32_MAX ? st64[i] : en64[i]) +
+                           " at row " + std::to_string(i) + " does not fit the 32-bit coordinates of the GPU path");
+        st[i] = (int32_t)st64[i];
+        en[i] = (int32_t)en64[i];
+    }
+    // view rows per contig, each contig's rows in (start, end) order (take_groups_as_map after sort_unstable)
+    KeyDict vdict;
+    std::vector<std::string_view> vnames;
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> vgroups;
+    if (vt) {
+        std::vector<int64_t> vs64, ve64;
+        for (auto& b : vt->batches) {
+            if (b.rows == 0) continue;
+            ContigArray ca;
+            BRGH_TRY(contig_array(b, vcols.contig, &ca));
+            vs64.clear(); ve64.clear();
+            BRGH_TRY(resolve_positions_i64(b, vcols.start, "start", &vs64));
+            BRGH_TRY(resolve_positions_i64(b, vcols.end, "end", &ve64));
+            for (int64_t i = 0; i < b.rows; i++) {
+                const std::string_view v = ca.value(i);
+                const uint32_t id = vdict.get_or_add(v);
+                if (id == vnames.size()) { vnames.push_back(v); vgroups.emplace_back(); }
+                vgroups[id].emplace_back(vs64[i], ve64[i]);
+            }
+        }
+        for (auto& g : vgroups) std::sort(g.begin(), g.end());
+    }
+    // emission order (complement.rs:396-457): input contigs by name, each with its views or the implicit (0, i64::MAX);
+    // then the view-only contigs by name, whole
+    std::vector<uint32_t> vkey;
+    std::vector<int64_t> vstart, vend;
+    std::vector<std::string_view> vcontig;
+    for (uint32_t r = 0; r < order.size(); r++) {
+        const std::string_view nm = names[order[r]];
+        const uint32_t vid = vdict.lookup(nm);
+        if (vid == BRG_KEY_ABSENT) {
+            vkey.push_back(r); vstart.push_back(0); vend.push_back(INT64_MAX); vcontig.push_back(nm);
+        } else {
+            for (auto& pr : vgroups[vid]) { vkey.push_back(r); vstart.push_back(pr.first); vend.push_back(pr.second); vcontig.push_back(nm); }
+        }
+    }
+    std::vector<uint32_t> vorder(vnames.size());
+    for (uint32_t i = 0; i < vorder.size(); i++) vorder[i] = i;
+    std::sort(vorder.begin(), vorder.end(), [&](uint32_t x, uint32_t y) { return vnames[x] < vnames[y]; });
+    for (uint32_t vi : vorder) {
+        if (dict.lookup(vnames[vi]) != BRG_KEY_ABSENT) continue;
+        for (auto& pr : vgroups[vi]) { vkey.push_back(BRG_KEY_ABSENT); vstart.push_back(pr.first); vend.push_back(pr.second); vcontig.push_back(vnames[vi]); }
+    }
+    if (vkey.empty()) return kOk;
+    brg_ctx* ctx;
+    BRGH_TRY(session_ctx(s, &ctx));
+    brg_gaps* g = nullptr;
+    BRGH_TRY(from_abi(brg_complement(ctx, key.data(), st.data(), en.data(), key.size(), std::max<uint32_t>(1, (uint32_t)names.size()),
+                                     vkey.data(), vstart.data(), vend.data(), vkey.size(), strict ? 1 : 0, &g)));
+    // ComplementProvider's schema (complement.rs:46-50): (contig Utf8, start Int64, end Int64) NOT NULL, named after the input columns
+    const uint64_t total = brg_gaps_len(g), batch_size = 8192;
+    for (uint64_t r0 = 0; r0 < total; r0 += batch_size) {
+        const uint64_t r1 = std::min(total, r0 + batch_size);
+        std::vector<std::string_view> cn;
+        std::vector<int64_t> cs, ce;
+        for (uint64_t i = r0; i < r1; i++) {
+            cn.push_back(vcontig[brg_gaps_view(g)[i]]);
+            cs.push_back(brg_gaps_start(g)[i]);
+            ce.push_back(brg_gaps_end(g)[i]);
+        }
+        Batch ob;
+        ob.rows = (int64_t)(r1 - r0);
+        ob.cols.push_back(make_utf8(cols.contig, cn));
+        ob.cols.push_back(make_primitive<int64_t>(cols.start, "l", false, std::move(cs), nullptr, 0));
+        ob.cols.push_back(make_primitive<int64_t>(cols.end, "l", false, std::move(ce), nullptr, 0));
+        res->batches.push_back(std::move(ob));
+    }
+    brg_gaps_release(g);
+    return kOk;
+}
+
 // ---- count_overlaps / coverage (count_overlaps.rs:107-169; interval_tree.rs:155-280) ----------------------------------------
 static Err run_count(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args, bool coverage,
                      brgh_result* res) {
@@ -1267,6 +1399,11 @@ BRG_API int brgh_subtract(brgh_session* s, const char* left, const char* right, 
     if (!s || !out) return finish(internal("brgh_subtract: NULL argument"));
     auto* r = new brgh_result();
     return run_to_result(run_subtract(s, left, right, args, n_args, r), r, out);
+}
+BRG_API int brgh_complement(brgh_session* s, const char* table, const char* const* args, int n_args, brgh_result** out) {
+    if (!s || !out) return finish(internal("brgh_complement: NULL argument"));
+    auto* r = new brgh_result();
+    return run_to_result(run_complement(s, table, args, n_args, r), r, out);
 }
 BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, const char* const* args, int n_args, brgh_result** out) {
     if (!s || !out) return finish(internal("brgh_cluster: NULL argument"));

@@ -70,6 +70,25 @@ class Context:
             A.lib().brg_merged_release(h)
         return out
 
+    def complement(self, key, start, end, n_keys, view_key, view_start, view_end, strict=False):
+        """complement UDTF core: gaps of the merged input intervals inside each view [view_start, view_end) (i64), views
+        answered in the order given -> (view_row u32[m], gap_start i64[m], gap_end i64[m])"""
+        key = A.as_key(key)
+        start, end = A.as_i32(start), A.as_i32(end)
+        vk = np.ascontiguousarray(view_key, np.uint32)
+        vs, ve = np.ascontiguousarray(view_start, np.int64), np.ascontiguousarray(view_end, np.int64)
+        h = C.c_void_p()
+        A.check(A.lib().brg_complement(self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start), int(n_keys), A.np_ptr(vk),
+                                       A.np_ptr(vs), A.np_ptr(ve), len(vk), int(bool(strict)), C.byref(h)))
+        try:
+            L = A.lib()
+            m = L.brg_gaps_len(h)
+            out = (A.copy_from(L.brg_gaps_view(h), m, np.uint32), A.copy_from(L.brg_gaps_start(h), m, np.int64),
+                   A.copy_from(L.brg_gaps_end(h), m, np.int64))
+        finally:
+            A.lib().brg_gaps_release(h)
+        return out
+
     # ---- build ------------------------------------------------------------------------------------------
     def build(self, key, start, end, n_keys, want=A.WANT_ALL):
         key = A.as_key(key)

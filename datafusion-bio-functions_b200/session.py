@@ -20,7 +20,7 @@ JOIN_INNER, JOIN_RIGHT_SEMI, JOIN_RIGHT_ANTI = 0, 1, 2
 HOST_SYMBOLS = [
     "brgh_create_bio_session", "brgh_session_destroy", "brgh_session_set", "brgh_session_get", "brgh_session_set_coalesce_rows",
     "brgh_register_batch", "brgh_deregister_table", "brgh_count_overlaps", "brgh_coverage", "brgh_nearest", "brgh_overlap",
-    "brgh_merge", "brgh_cluster", "brgh_subtract", "brgh_interval_join", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
+    "brgh_merge", "brgh_cluster", "brgh_subtract", "brgh_complement", "brgh_interval_join", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
     "brgh_result_release", "brgh_resolve_positions", "brgh_take",
 ]
 
@@ -49,6 +49,7 @@ def _lib():
     L.brgh_merge.argtypes = [vp, cp, i64, strs, i32, C.POINTER(vp)]
     L.brgh_cluster.argtypes = [vp, cp, i64, strs, i32, C.POINTER(vp)]
     L.brgh_subtract.argtypes = [vp, cp, cp, strs, i32, C.POINTER(vp)]
+    L.brgh_complement.argtypes = [vp, cp, strs, i32, C.POINTER(vp)]
     L.brgh_interval_join.argtypes = [vp, cp, cp, strs, strs, i32, cp, cp, cp, cp, i32, i32, i32, C.POINTER(vp)]
     L.brgh_explain_interval_join.argtypes = [vp, i32, cp, u64]
     L.brgh_result_num_batches.argtypes = [vp]
@@ -164,6 +165,12 @@ class BioSession:
     def subtract(self, left, right, *args):
         """SELECT * FROM subtract('left', 'right' [, cols...] [, 'strict'|'weak'])"""
         return self._udtf(_lib().brgh_subtract, left, right, args)
+
+    def complement(self, table, *args):
+        """SELECT * FROM complement('table' [, 'view_table'] [, col1, col2, col3 [, vcol1, vcol2, vcol3]] [, 'strict'|'weak'])"""
+        res = C.c_void_p()
+        A.check(_lib().brgh_complement(self._h, table.encode(), _cstrs(args), len(args), C.byref(res)))
+        return self._collect(res)
 
     def merge(self, table, *args, min_dist=0):
         """SELECT * FROM merge('table' [, min_dist] [, col1, col2, col3] [, 'strict'|'weak'])"""

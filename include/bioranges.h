@@ -234,6 +234,23 @@ BRG_API const int32_t* brg_rows_piece_end(const brg_rows* r);
 BRG_API int brg_sort_rows(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
                   uint32_t n_keys, uint32_t* out_row_order);
 
+/* ---- complement (replaces ComplementStream::merge_intervals + emit_contig_complement and the view-only pass,
+ *      complement.rs:297-358, 437-457): the gaps that the merged input intervals (run rule of brg_merge with min_dist 0:
+ *      start <= run_end joins, strict: <) leave inside each view interval [view_start, view_end).  Views are i64 (the implicit
+ *      view of a contig without one is (0, i64::MAX), complement.rs:403-406) and are answered in the order given; a view whose
+ *      key is BRG_KEY_ABSENT (or >= n_keys: a contig with no input rows) comes out whole.  Result rows, view-major, gaps
+ *      of one view in coordinate order: brg_gaps_view = view row, brg_gaps_start / _end = the gap (half-open as in the
+ *      reference: the end of one merged interval to the start of the next). */
+typedef struct brg_gaps brg_gaps;
+BRG_API int brg_complement(brg_ctx* ctx, const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n,
+                   uint32_t n_keys, const uint32_t* view_key, const int64_t* view_start, const int64_t* view_end,
+                   uint64_t n_views, int strict, brg_gaps** out);
+BRG_API uint64_t brg_gaps_len(const brg_gaps* g);
+BRG_API const uint32_t* brg_gaps_view(const brg_gaps* g);
+BRG_API const int64_t* brg_gaps_start(const brg_gaps* g);
+BRG_API const int64_t* brg_gaps_end(const brg_gaps* g);
+BRG_API void brg_gaps_release(brg_gaps* g);
+
 /* ---- instrumentation: kernels launched by this library on the calling process (bench `gpu_launches`) -- */
 BRG_API uint64_t brg_kernel_launches(void);
 

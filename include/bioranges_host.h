@@ -106,6 +106,13 @@ BRG_API int brgh_cluster(brgh_session* s, const char* table, int64_t min_dist, c
 BRG_API int brgh_subtract(brgh_session* s, const char* left, const char* right, const char* const* args, int n_args,
                   brgh_result** out);
 
+/* complement(table [, view_table] [, col1, col2, col3 [, vcol1, vcol2, vcol3]] [, 'strict'|'weak']) (complement.rs;
+ * table_function.rs:602-767): the gaps the merged input intervals leave inside each view interval of their contig (a contig
+ * without a view gets (0, i64::MAX)); contigs that only the view table names come out whole, after the others.  `args` are
+ * the arguments AFTER the table name, view table included.  Output (contig Utf8, start Int64, end Int64) NOT NULL, named
+ * after the input columns. */
+BRG_API int brgh_complement(brgh_session* s, const char* table, const char* const* args, int n_args, brgh_result** out);
+
 /* ---- the range join IntervalJoinExec executes ---------------------------------------------------------------------------
  *   SELECT * FROM left l JOIN right r ON l.<on_left[i]> = r.<on_right[i]> ...
  *        AND l.<left_start> <[=] r.<right_end> AND l.<left_end> >[=] r.<right_start>

@@ -584,6 +584,63 @@ uint64_t brgo_subtract(const uint32_t *lkey, const int64_t *lstart, const int64_
     return o;
 }
 
+/* ---- complement (complement.rs:297-358, 396-457): per contig, the input intervals sorted by (start, end)
+ * (grouped_stream.rs:92-94) and merged with ComplementStream::merge_intervals (s <= cur_end joins; strict: s < cur_end),
+ * then emit_contig_complement restated literally for each view in the order given (the caller lists a contig's views in
+ * (start, end) order, as StreamCollector leaves them).  A view whose key has no input rows is a "trailing" view-only contig
+ * (complement.rs:437-457): emitted whole, unconditionally.  Returns the number of gaps; the first `cap` are written. */
+uint64_t brgo_complement(const uint32_t *key, const int64_t *start, const int64_t *end, uint64_t n, uint32_t n_keys,
+                         const uint32_t *vkey, const int64_t *vstart, const int64_t *vend, uint64_t nv, int strict,
+                         uint64_t *out_view, int64_t *out_start, int64_t *out_end, uint64_t cap) {
+    uint64_t *cnt = calloc((size_t)n_keys + 2, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) cnt[(key ? key[i] : 0) + 1]++;
+    for (uint32_t k = 0; k < n_keys; k++) cnt[k + 1] += cnt[k];
+    iv64_t *rows = malloc((n ? n : 1) * sizeof(iv64_t));
+    uint64_t *fill = malloc(((size_t)n_keys + 1) * sizeof(uint64_t));
+    uint64_t *mcnt = calloc((size_t)n_keys + 1, sizeof(uint64_t)); /* merged intervals of key k: rows[cnt[k] .. cnt[k] + mcnt[k]) */
+    memcpy(fill, cnt, ((size_t)n_keys + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) { iv64_t r = {start[i], end[i]}; rows[fill[key ? key[i] : 0]++] = r; }
+    for (uint32_t k = 0; k < n_keys; k++) {
+        iv64_t *g = rows + cnt[k];
+        const uint64_t gn = cnt[k + 1] - cnt[k];
+        if (!gn) continue;
+        qsort(g, gn, sizeof(iv64_t), cmp_iv64);
+        uint64_t m = 0; /* merge in place (complement.rs:297-320) */
+        int64_t cs = g[0].s, ce = g[0].e;
+        for (uint64_t i = 1; i < gn; i++) {
+            const int join = strict ? g[i].s < ce : g[i].s <= ce;
+            if (join) { if (g[i].e > ce) ce = g[i].e; }
+            else { g[m].s = cs; g[m].e = ce; m++; cs = g[i].s; ce = g[i].e; }
+        }
+        g[m].s = cs; g[m].e = ce; m++;
+        mcnt[k] = m;
+    }
+    uint64_t o = 0;
+    for (uint64_t v = 0; v < nv; v++) {
+        const int64_t view_start = vstart[v], view_end = vend[v];
+        const uint32_t k = vkey[v];
+        if (k >= n_keys || cnt[k + 1] == cnt[k]) { /* view-only contig */
+            if (o < cap) { out_view[o] = v; out_start[o] = view_start; out_end[o] = view_end; }
+            o++;
+            continue;
+        }
+        const iv64_t *mg = rows + cnt[k];
+        int64_t cursor = view_start; /* complement.rs:330-356 */
+        for (uint64_t j = 0; j < mcnt[k]; j++) {
+            const int64_t ms = mg[j].s, me = mg[j].e;
+            if (me <= view_start) continue;
+            if (ms >= view_end) break;
+            const int64_t interval_start = ms > view_start ? ms : view_start;
+            const int64_t interval_end = me < view_end ? me : view_end;
+            if (interval_start > cursor) { if (o < cap) { out_view[o] = v; out_start[o] = cursor; out_end[o] = interval_start; } o++; }
+            cursor = interval_end;
+        }
+        if (cursor < view_end) { if (o < cap) { out_view[o] = v; out_start[o] = cursor; out_end[o] = view_end; } o++; }
+    }
+    free(cnt); free(rows); free(fill); free(mcnt);
+    return o;
+}
+
 void brgo_free(void *p) { free(p); }
 int brgo_max_threads(void) {
 #ifdef _OPENMP

@@ -202,6 +202,24 @@ def subtract(lkey, lstart, lend, rkey, rstart, rend, n_keys, strict=False):
     return orow, os_, oe
 
 
+def complement(key, start, end, n_keys, vkey, vstart, vend, strict=False):
+    """complement UDTF core (complement.rs:297-358, 396-457): (view_row u64[m], gap_start i64[m], gap_end i64[m]), views
+    answered in the order given; a view whose key has no input rows comes out whole."""
+    L = lib()
+    L.brgo_complement.restype = C.c_uint64
+    L.brgo_complement.argtypes = [C.c_void_p] * 3 + [C.c_uint64, C.c_uint32] + [C.c_void_p] * 3 + [C.c_uint64, C.c_int] + [C.c_void_p] * 3 + [C.c_uint64]
+    s, e = np.ascontiguousarray(start, np.int64), np.ascontiguousarray(end, np.int64)
+    key = None if key is None else np.ascontiguousarray(key, np.uint32)
+    vk = np.ascontiguousarray(vkey, np.uint32)
+    vs, ve = np.ascontiguousarray(vstart, np.int64), np.ascontiguousarray(vend, np.int64)
+    call = lambda o, a, b, cap: L.brgo_complement(None if key is None else key.ctypes.data, s.ctypes.data, e.ctypes.data, len(s), int(n_keys),
+                                                  vk.ctypes.data, vs.ctypes.data, ve.ctypes.data, len(vk), int(bool(strict)), o, a, b, cap)
+    m = call(None, None, None, 0)  # sizing pass
+    ov, os_, oe = np.empty(m, np.uint64), np.empty(m, np.int64), np.empty(m, np.int64)
+    call(ov.ctypes.data, os_.ctypes.data, oe.ctypes.data, m)
+    return ov, os_, oe
+
+
 def max_threads():
     """host cores this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
     which would silently turn the multi-threaded CPU baseline into a single-threaded one."""

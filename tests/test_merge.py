@@ -314,3 +314,137 @@ def test_subtract_udtf_through_session():
     t = pa.Table.from_batches(ctx.subtract("lc", "rc", "chr", "s", "e", "c2", "s2", "e2"))
     assert t.schema.names == ["chr", "s", "e"] and t.column("s").to_pylist() == [100, 300]
     ctx.close()
+
+
+# ---- complement (tests/integration_test.rs:2821-3180, 3803-3882) -----------------------------------------------------------
+I64MAX = 2**63 - 1
+COMPLEMENT_LITERALS = [  # (input rows, view rows or None, strict, expected gaps)
+    ([("a", 100, 200), ("a", 300, 400)], None, False, [("a", 0, 100), ("a", 200, 300), ("a", 400, I64MAX)]),
+    ([("a", 100, 200), ("b", 300, 400)], None, False, [("a", 0, 100), ("a", 200, I64MAX), ("b", 0, 300), ("b", 400, I64MAX)]),
+    ([("a", 100, 200), ("a", 300, 400)], [("a", 0, 500)], False, [("a", 0, 100), ("a", 200, 300), ("a", 400, 500)]),
+    ([("a", 0, 500)], [("a", 0, 500)], False, []),
+    ([], [("a", 0, 500)], False, [("a", 0, 500)]),
+    ([("a", 100, 200), ("b", 300, 400)], [("a", 0, 500), ("b", 0, 600)], False, [("a", 0, 100), ("a", 200, 500), ("b", 0, 300), ("b", 400, 600)]),
+    ([("a", 100, 250), ("a", 200, 400)], [("a", 0, 500)], False, [("a", 0, 100), ("a", 400, 500)]),
+    ([("a", 100, 200)], [("a", 0, 500), ("b", 0, 300)], False, [("a", 0, 100), ("a", 200, 500), ("b", 0, 300)]),
+    # the partitioned-parquet test (TEST:3760-3882): two input files, one view file
+    ([("chr1", 0, 10), ("chr1", 20, 30), ("chr2", 10, 20), ("chr1", 8, 25), ("chr2", 30, 40)], [("chr1", 0, 40), ("chr2", 0, 50)], False,
+     [("chr1", 30, 40), ("chr2", 0, 10), ("chr2", 20, 30), ("chr2", 40, 50)]),
+    ([("chr1", 0, 10), ("chr1", 20, 30), ("chr2", 10, 20), ("chr1", 8, 25), ("chr2", 30, 40)], None, False,
+     [("chr1", 30, I64MAX), ("chr2", 0, 10), ("chr2", 20, 30), ("chr2", 40, I64MAX)]),
+]
+
+
+def _encode_complement(rows, views):
+    """contig ids in name order; views in emission order: input contigs by name with their views sorted by (start, end) or
+    the implicit (0, i64::MAX), then view-only contigs by name"""
+    names = sorted({r[0] for r in rows})
+    ids = {n: i for i, n in enumerate(names)}
+    k = np.array([ids[r[0]] for r in rows], np.uint32)
+    s, e = np.array([r[1] for r in rows], np.int64), np.array([r[2] for r in rows], np.int64)
+    vrows = []
+    for n in names:
+        mine = sorted((v[1], v[2]) for v in (views or []) if v[0] == n)
+        vrows += [(ids[n], n, a, b) for a, b in mine] if mine else [(ids[n], n, 0, I64MAX)]
+    for n in sorted({v[0] for v in (views or [])} - set(names)):
+        vrows += [(0xFFFFFFFF, n, a, b) for a, b in sorted((v[1], v[2]) for v in views if v[0] == n)]
+    vk = np.array([v[0] for v in vrows], np.uint32)
+    vs, ve = np.array([v[2] for v in vrows], np.int64), np.array([v[3] for v in vrows], np.int64)
+    return names, (k, s, e), [v[1] for v in vrows], (vk, vs, ve)
+
+
+@pytest.mark.parametrize("case", range(len(COMPLEMENT_LITERALS)))
+def test_oracle_complement_reference_literals(case):
+    from oracle import oracle as O
+
+    rows, views, strict, want = COMPLEMENT_LITERALS[case]
+    names, (k, s, e), vcontig, (vk, vs, ve) = _encode_complement(rows, views)
+    ov, gs, ge = O.complement(k, s, e, max(1, len(names)), vk, vs, ve, strict)
+    assert [(vcontig[int(v)], int(a), int(b)) for v, a, b in zip(ov, gs, ge)] == want
+
+
+def test_oracle_complement_strict_keeps_touching_runs_apart():
+    from oracle import oracle as O
+
+    # strict: s < cur_end merges, so [100,150] and [150,200] stay two runs; no gap between them either way
+    k, s, e = np.zeros(2, np.uint32), np.array([100, 150], np.int64), np.array([150, 200], np.int64)
+    for strict in (False, True):
+        ov, gs, ge = O.complement(k, s, e, 1, np.zeros(1, np.uint32), np.array([0], np.int64), np.array([300], np.int64), strict)
+        assert list(zip(gs.tolist(), ge.tolist())) == [(0, 100), (200, 300)]
+    # a zero-width run splits the gap it sits in (interval_start > cursor, cursor = interval_end)
+    ov, gs, ge = O.complement(np.zeros(1, np.uint32), [50], [50], 1, np.zeros(1, np.uint32), [0], [100], False)
+    assert list(zip(gs.tolist(), ge.tolist())) == [(0, 50), (50, 100)]
+    # a degenerate view of an input contig yields nothing; of a view-only contig it comes out as is
+    ov, gs, ge = O.complement(np.zeros(1, np.uint32), [50], [60], 1, np.array([0, 0xFFFFFFFF], np.uint32), [70, 70], [20, 20], False)
+    assert list(zip(ov.tolist(), gs.tolist(), ge.tolist())) == [(1, 70, 20)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(14))
+def test_gpu_complement_vs_oracle(seed):
+    import bio_ranges_b200 as brg
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(300 + seed)
+    nk = int(rng.choice([1, 4, 40]))
+    n = int(rng.choice([0, 1, 300, 50_000, 400_000]))
+    nv = int(rng.choice([1, 5, 200, 20_000]))
+    span = int(rng.choice([2000, 300_000, 1_000_000_000]))
+    k = rng.integers(0, nk, n).astype(np.uint32)
+    s = rng.integers(0, span, n).astype(np.int64)
+    e = s + rng.integers(0, int(rng.choice([1, 100, 20000])), n)
+    # views: some keys absent (>= nk or the ABSENT id), some degenerate, some implicit whole-contig, overlapping each other
+    vk = rng.integers(0, nk + 2, nv).astype(np.uint32)
+    vk[vk == nk + 1] = 0xFFFFFFFF
+    vs = rng.integers(-50, span, nv).astype(np.int64)
+    ve = vs + rng.integers(-5, int(rng.choice([10, 5000, span])), nv)
+    whole = rng.random(nv) < 0.1
+    vs[whole], ve[whole] = 0, I64MAX
+    order = np.lexsort((ve, vs, vk))
+    vk, vs, ve = vk[order], vs[order], ve[order]
+    strict = bool(seed % 2)
+    ctx = brg.default_context(0)
+    gv, gs, ge = ctx.complement(k, s.astype(np.int32), e.astype(np.int32), nk, vk, vs, ve, strict=strict)
+    ov, os_, oe = O.complement(k, s, e, nk, vk, vs, ve, strict)
+    assert len(gv) == len(ov)
+    assert (gv == ov).all() and (gs == os_).all() and (ge == oe).all()
+
+
+@pytest.mark.gpu
+def test_complement_udtf_through_session():
+    import pyarrow as pa
+
+    from bio_ranges_b200.session import create_bio_session
+
+    def tbl(rows, names=("contig", "pos_start", "pos_end")):
+        return pa.table({names[0]: pa.array([r[0] for r in rows], pa.string()), names[1]: pa.array([r[1] for r in rows], pa.int32()),
+                         names[2]: pa.array([r[2] for r in rows], pa.int32())})
+
+    ctx = create_bio_session()
+    for rows, views, strict, want in COMPLEMENT_LITERALS:
+        ctx.register_table("intervals", tbl(rows))
+        args = []
+        if views is not None:
+            ctx.register_table("chromsizes", tbl(views))
+            args.append("chromsizes")
+        if strict:
+            args.append("strict")
+        out = ctx.complement("intervals", *args)
+        got = [] if not out else list(zip(*[pa.Table.from_batches(out).column(i).to_pylist() for i in range(3)]))
+        assert got == want  # already in the reference's emission order (contig name, view, coordinate)
+        if out:
+            assert [str(f.type) for f in out[0].schema] == ["string", "int64", "int64"]
+            assert not any(f.nullable for f in out[0].schema)
+    # TEST:3093-3135 custom column names, used for both tables; the output takes the input's names
+    ctx.register_table("iv", tbl([("a", 100, 200)], names=("chr", "s", "e")))
+    ctx.register_table("cs", tbl([("a", 0, 500)], names=("chr", "s", "e")))
+    t = pa.Table.from_batches(ctx.complement("iv", "cs", "chr", "s", "e"))
+    assert t.schema.names == ["chr", "s", "e"] and list(zip(t.column("s").to_pylist(), t.column("e").to_pylist())) == [(0, 100), (200, 500)]
+    # separate view column names (table_function.rs:748-766)
+    ctx.register_table("cs2", tbl([("a", 0, 500)], names=("vc", "vs", "ve")))
+    t = pa.Table.from_batches(ctx.complement("iv", "cs2", "chr", "s", "e", "vc", "vs", "ve"))
+    assert t.schema.names == ["chr", "s", "e"] and t.num_rows == 2
+    # argument-count error text (table_function.rs:757-763)
+    with pytest.raises(Exception, match=r"complement\(\) unexpected number of arguments \(2 extra args after table name\)"):
+        ctx.complement("iv", "cs", "chr")
+    ctx.close()
