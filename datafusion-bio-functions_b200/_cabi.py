@@ -20,12 +20,24 @@ ABI_SYMBOLS = [
     "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_count_overlaps",
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
+    "brg_count_overlaps_arrow", "brg_coverage_arrow", "brg_nearest_k1_arrow",
     "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
     "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_complement", "brg_gaps_len", "brg_gaps_view", "brg_gaps_start", "brg_gaps_end", "brg_gaps_release", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
     "brg_merged_len", "brg_merged_key", "brg_merged_start",
     "brg_merged_end", "brg_merged_count", "brg_merged_release", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
 ]
+
+
+POS_TYPES = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.uint32): 2, np.dtype(np.uint64): 3}  # BRG_POS_*
+
+
+def as_pos(a):
+    """a position column in its Arrow width (Int32 / Int64 / UInt32 / UInt64) -> (contiguous array, BRG_POS_* code)"""
+    a = np.ascontiguousarray(a)
+    if a.dtype not in POS_TYPES:
+        raise TypeError(f"unsupported position dtype {a.dtype}; expected int32, int64, uint32 or uint64")
+    return a, POS_TYPES[a.dtype]
 
 
 class BioRangesError(RuntimeError):
@@ -73,6 +85,9 @@ def lib():
     L.brg_count_overlaps_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, vp]
     L.brg_coverage_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, vp]
     L.brg_nearest_k1_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, i32, vp, vp, vp]
+    L.brg_count_overlaps_arrow.argtypes = [vp, vp, vp, vp, u64, vp, i32, vp, i32, u64, i32, vp, vp]
+    L.brg_coverage_arrow.argtypes = [vp, vp, vp, vp, u64, vp, i32, vp, i32, u64, i32, vp, vp]
+    L.brg_nearest_k1_arrow.argtypes = [vp, vp, vp, vp, u64, vp, i32, vp, i32, u64, i32, i32, vp, vp, vp, vp]
     L.brg_count_overlaps_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
     L.brg_coverage_dev.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp, vp]
     L.brg_nearest_k1.argtypes = [vp, vp, vp, vp, vp, u64, i32, i32, vp, vp, vp]

@@ -47,6 +47,7 @@ struct Lane {
     DevBuf in_key[NBUF], in_s[NBUF], in_e[NBUF], out0[NBUF], out1[NBUF], out2[NBUF];
     cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
     DevBuf scratch_a, scratch_b, scratch_c, scratch_d;  // counts / offsets / scan scratch / flags
+    DevBuf raw_s[NBUF], raw_e[NBUF], bad_rows;          // Arrow ingest: position columns in their native width; first bad rows
     bool busy = false;
 };
 
@@ -155,6 +156,56 @@ __global__ void expand_runs_kernel(const uint32_t* __restrict__ run_key, const u
     }
     key_out[i] = lo < n_runs ? __ldg(run_key + lo) : 0xFFFFFFFFu;
 }
+// Arrow ingest: PosArray::resolve (array_utils.rs:73-131) on the device.  A position column that crossed
+// PCIe in its native width (Int64 / UInt32 / UInt64) is narrowed to the i32 the kernels read; the first row whose value
+// does not fit (i32::try_from fails) is recorded with an atomicMin and reported by the host after the call.
+// One 16-byte load per thread and step.
+template <typename T> __device__ __forceinline__ bool fits_i32(T v);
+template <> __device__ __forceinline__ bool fits_i32<long long>(long long v) { return v >= INT32_MIN && v <= INT32_MAX; }
+template <> __device__ __forceinline__ bool fits_i32<unsigned int>(unsigned int v) { return v <= (unsigned int)INT32_MAX; }
+template <> __device__ __forceinline__ bool fits_i32<unsigned long long>(unsigned long long v) { return v <= (unsigned long long)INT32_MAX; }
+template <typename T>
+__global__ void narrow_positions_kernel(const T* __restrict__ src, uint64_t m, uint64_t row0, int32_t* __restrict__ dst,
+                                        unsigned long long* __restrict__ first_bad) {
+    constexpr int V = 16 / sizeof(T);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_vec = m / V;
+    unsigned long long bad = ~0ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+        T v[V];
+        memcpy(v, &raw, 16);
+        int32_t o[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            o[j] = (int32_t)v[j];
+            if (!fits_i32<T>(v[j]) && bad == ~0ull) bad = row0 + i * V + j;
+        }
+        if (V == 2) *reinterpret_cast<int2*>(dst + i * V) = make_int2(o[0], o[V - 1]);
+        else *reinterpret_cast<int4*>(dst + i * V) = make_int4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+    }
+    const uint64_t t = n_vec * V + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // scalar tail
+    if (t < m) {
+        const T v = src[t];
+        dst[t] = (int32_t)v;
+        if (!fits_i32<T>(v) && row0 + t < bad) bad = row0 + t;
+    }
+    if (bad != ~0ull) atomicMin(first_bad, bad);
+}
+static int launch_narrow(const void* src, int pos_type, uint64_t m, uint64_t row0, int32_t* dst, unsigned long long* first_bad,
+                         cudaStream_t st) {
+    if (m == 0) return 0;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m / 2 + 255) / 256 + 1, (uint64_t)kSMs * 16));
+    switch (pos_type) {
+        case BRG_POS_INT64: narrow_positions_kernel<long long><<<grid, 256, 0, st>>>((const long long*)src, m, row0, dst, first_bad); break;
+        case BRG_POS_UINT32: narrow_positions_kernel<unsigned int><<<grid, 256, 0, st>>>((const unsigned int*)src, m, row0, dst, first_bad); break;
+        case BRG_POS_UINT64: narrow_positions_kernel<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long*)src, m, row0, dst, first_bad); break;
+        default: set_error("probe: unknown position column type"); return BRG_ERR_INVALID;
+    }
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+static inline uint64_t pos_width(int t) { return (t == BRG_POS_INT64 || t == BRG_POS_UINT64) ? 8 : 4; }
 // largest m in [1, n] with offsets[m] <= max_rows (at least one probe row is always consumed)
 __global__ void find_cut_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t max_rows, uint64_t* out) {
     uint64_t lo = 1, hi = n;  // answer in [lo, hi]
@@ -775,11 +826,27 @@ struct KeyRuns {  // run-length form of the probe key column (NULL run_key = not
     uint64_t n_runs = 0;
 };
 
-static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32_t* key, const int32_t* start,
-                     const int32_t* end, uint64_t n, int include_overlaps, int strict, int64_t* out_i64,
-                     uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist, KeyRuns runs = KeyRuns()) {
+struct PosTypes {  // Arrow ingest: native width of the start / end value buffers, and where the first bad rows are reported
+    int s_type = BRG_POS_INT32, e_type = BRG_POS_INT32;
+    uint64_t* bad_start_row = nullptr;
+    uint64_t* bad_end_row = nullptr;
+};
+
+static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32_t* key, const void* start_v,
+                     const void* end_v, uint64_t n, int include_overlaps, int strict, int64_t* out_i64,
+                     uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist, KeyRuns runs = KeyRuns(), PosTypes pt = PosTypes()) {
+    if (pt.bad_start_row) *pt.bad_start_row = ~0ull;
+    if (pt.bad_end_row) *pt.bad_end_row = ~0ull;
     if (n == 0) return BRG_OK;
-    if (!start || !end) { set_error("probe: NULL column"); return BRG_ERR_INVALID; }
+    if (!start_v || !end_v) { set_error("probe: NULL column"); return BRG_ERR_INVALID; }
+    if (pt.s_type < BRG_POS_INT32 || pt.s_type > BRG_POS_UINT64 || pt.e_type < BRG_POS_INT32 || pt.e_type > BRG_POS_UINT64) {
+        set_error("probe: unknown position column type");
+        return BRG_ERR_INVALID;
+    }
+    const char* start = static_cast<const char*>(start_v);
+    const char* end = static_cast<const char*>(end_v);
+    const uint64_t ws = pos_width(pt.s_type), we = pos_width(pt.e_type);
+    const bool narrow_s = pt.s_type != BRG_POS_INT32, narrow_e = pt.e_type != BRG_POS_INT32;
     const bool by_runs = runs.run_key != nullptr;
     if (by_runs) {
         if (!runs.run_end || runs.n_runs == 0 || runs.n_runs > 0xFFFFFFFFull || runs.run_end[runs.n_runs - 1] != n) {
@@ -800,9 +867,15 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
     const bool dev_key = key != nullptr || by_runs;
     // chunk rows are a multiple of 32 so that validity bitmap words never straddle chunks
     const uint64_t C = std::min<uint64_t>((ctx->chunk_rows + 31) & ~31ull, (n + 31) & ~31ull);
+    if (narrow_s || narrow_e) {
+        if ((rc = l->bad_rows.ensure(16))) return rc;
+        BRG_CUDA(cudaMemsetAsync(l->bad_rows.p, 0xFF, 16, l->k));
+    }
     for (int b = 0; b < Lane::NBUF; b++) {
         if (dev_key && (rc = l->in_key[b].ensure(C * 4))) return rc;
         if ((rc = l->in_s[b].ensure(C * 4)) || (rc = l->in_e[b].ensure(C * 4))) return rc;
+        if (narrow_s && (rc = l->raw_s[b].ensure(C * ws))) return rc;
+        if (narrow_e && (rc = l->raw_e[b].ensure(C * we))) return rc;
         if (op == OP_NEAREST1) {
             if ((rc = l->out0[b].ensure(C * 4)) || (rc = l->out1[b].ensure(C / 8 + 4))) return rc;
             if (out_dist && (rc = l->out2[b].ensure(C * 8))) return rc;
@@ -817,8 +890,8 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
         // inputs of buffer b may be overwritten once the kernel that read them has finished
         BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
         if (key && !by_runs) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
-        BRG_CUDA(cudaMemcpyAsync(l->in_s[b].p, start + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
-        BRG_CUDA(cudaMemcpyAsync(l->in_e[b].p, end + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
+        BRG_CUDA(cudaMemcpyAsync(narrow_s ? l->raw_s[b].p : l->in_s[b].p, start + done * ws, m * ws, cudaMemcpyHostToDevice, l->h2d));
+        BRG_CUDA(cudaMemcpyAsync(narrow_e ? l->raw_e[b].p : l->in_e[b].p, end + done * we, m * we, cudaMemcpyHostToDevice, l->h2d));
         BRG_CUDA(cudaEventRecord(l->ev_in[b], l->h2d));
         // kernel: after its inputs landed and after the previous results of buffer b left the device
         BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_in[b], 0));
@@ -830,6 +903,8 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
                                                                               (uint32_t)runs.n_runs, done, m, l->in_key[b].as<uint32_t>());
             g_launches.fetch_add(1);
         }
+        if (narrow_s && (rc = launch_narrow(l->raw_s[b].p, pt.s_type, m, done, l->in_s[b].as<int32_t>(), l->bad_rows.as<unsigned long long>(), l->k))) { cudaDeviceSynchronize(); return rc; }
+        if (narrow_e && (rc = launch_narrow(l->raw_e[b].p, pt.e_type, m, done, l->in_e[b].as<int32_t>(), l->bad_rows.as<unsigned long long>() + 1, l->k))) { cudaDeviceSynchronize(); return rc; }
         if (op == OP_COUNT)
             rc = launch_count(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
         else if (op == OP_COVERAGE)
@@ -849,9 +924,25 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
         }
         BRG_CUDA(cudaEventRecord(l->ev_out[b], l->d2h));
     }
+    uint64_t bad[2] = {~0ull, ~0ull};
+    if (narrow_s || narrow_e) BRG_CUDA(cudaMemcpyAsync(bad, l->bad_rows.p, 16, cudaMemcpyDeviceToHost, l->k));
     BRG_CUDA(cudaStreamSynchronize(l->d2h));
     BRG_CUDA(cudaStreamSynchronize(l->k));
     BRG_CUDA(cudaStreamSynchronize(l->h2d));
+    if (bad[0] != ~0ull || bad[1] != ~0ull) {  // array_utils.rs:94-98 (the start column is resolved first)
+        if (pt.bad_start_row) *pt.bad_start_row = bad[0];
+        if (pt.bad_end_row) *pt.bad_end_row = bad[1];
+        const bool in_start = bad[0] != ~0ull;
+        const uint64_t row = in_start ? bad[0] : bad[1];
+        const int t = in_start ? pt.s_type : pt.e_type;
+        const char* col = in_start ? start : end;
+        std::string v;
+        if (t == BRG_POS_INT64) v = std::to_string(reinterpret_cast<const int64_t*>(col)[row]);
+        else if (t == BRG_POS_UINT32) v = std::to_string(reinterpret_cast<const uint32_t*>(col)[row]);
+        else v = std::to_string(reinterpret_cast<const uint64_t*>(col)[row]);
+        set_error("coordinate value " + v + " at row " + std::to_string(row) + " overflows i32 (max 2147483647)");
+        return BRG_ERR_OVERFLOW;
+    }
     return BRG_OK;
 }
 
@@ -888,6 +979,43 @@ extern "C" BRG_API int brg_nearest_k1_runs(brg_ctx* ctx, const brg_index* ix, co
     if (n && (!out_left || !out_bits || !run_key)) { set_error("brg_nearest_k1_runs: NULL argument"); return BRG_ERR_INVALID; }
     KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
     return run_fixed(ctx, ix, OP_NEAREST1, nullptr, start, end, n, include_overlaps, strict, nullptr, out_left, out_bits, out_dist, kr);
+}
+// Arrow ingest entry points: the position value buffers arrive in their native Arrow width
+static PosTypes pos_types(int s_type, int e_type, uint64_t* bad_rows) {
+    PosTypes pt;
+    pt.s_type = s_type; pt.e_type = e_type;
+    if (bad_rows) { pt.bad_start_row = bad_rows; pt.bad_end_row = bad_rows + 1; }
+    return pt;
+}
+extern "C" BRG_API int brg_count_overlaps_arrow(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                        uint64_t n_runs, const void* start, int start_type, const void* end, int end_type,
+                                        uint64_t n, int strict, int64_t* out, uint64_t* bad_rows) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COUNT | BRG_WANT_NEAREST, "brg_count_overlaps_arrow");
+    if (rc) return rc;
+    if (n && (!out || !run_key)) { set_error("brg_count_overlaps_arrow: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_COUNT, nullptr, start, end, n, 0, strict, out, nullptr, nullptr, nullptr, kr, pos_types(start_type, end_type, bad_rows));
+}
+extern "C" BRG_API int brg_coverage_arrow(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                  uint64_t n_runs, const void* start, int start_type, const void* end, int end_type, uint64_t n,
+                                  int strict, int64_t* out, uint64_t* bad_rows) {
+    int rc = check_probe(ctx, ix, BRG_WANT_COVERAGE, "brg_coverage_arrow");
+    if (rc) return rc;
+    if (n && (!out || !run_key)) { set_error("brg_coverage_arrow: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_COVERAGE, nullptr, start, end, n, 0, strict, out, nullptr, nullptr, nullptr, kr, pos_types(start_type, end_type, bad_rows));
+}
+extern "C" BRG_API int brg_nearest_k1_arrow(brg_ctx* ctx, const brg_index* ix, const uint32_t* run_key, const uint64_t* run_end,
+                                    uint64_t n_runs, const void* start, int start_type, const void* end, int end_type, uint64_t n,
+                                    int include_overlaps, int strict, uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist,
+                                    uint64_t* bad_rows) {
+    int rc = check_probe(ctx, ix, BRG_WANT_NEAREST, "brg_nearest_k1_arrow");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("right row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (n && (!out_left || !out_bits || !run_key)) { set_error("brg_nearest_k1_arrow: NULL argument"); return BRG_ERR_INVALID; }
+    KeyRuns kr; kr.run_key = run_key; kr.run_end = run_end; kr.n_runs = n_runs;
+    return run_fixed(ctx, ix, OP_NEAREST1, nullptr, start, end, n, include_overlaps, strict, nullptr, out_left, out_bits, out_dist, kr,
+                     pos_types(start_type, end_type, bad_rows));
 }
 extern "C" BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
                             const int32_t* end, uint64_t n, int strict, int64_t* out) {

@@ -391,6 +391,44 @@ static Err resolve_positions(const Batch& b, const std::string& name, const char
     return kOk;
 }
 
+// Arrow ingest: the value buffer of a position column as it is, for the *_arrow entry points that narrow
+// and check on the device.  Same type / NULL errors as PosArray::resolve (array_utils.rs:73-98); the bytes of the column's
+// rows are appended to `raw` so that coalesced batches form one buffer.
+static Err position_bytes(const Batch& b, const std::string& name, const char* label, std::vector<uint8_t>* raw, int* pos_type) {
+    const Column* c = b.find(name);
+    if (!c) return plan(std::string(label) + " column '" + name + "' not found in batch with columns: " + b.names());
+    const std::string& f = c->f.format;
+    if (f != "i" && f != "l" && f != "I" && f != "L")
+        return notimpl("unsupported data type " + type_name(f) + " for " + label + " column '" + name +
+                       "'; expected Int32, Int64, UInt32, or UInt64");
+    if (c->null_count > 0)
+        return exec("coordinate column contains null values; nearest requires non-null coordinates");  // array_utils.rs:80-85
+    *pos_type = f == "i" ? BRG_POS_INT32 : f == "l" ? BRG_POS_INT64 : f == "I" ? BRG_POS_UINT32 : BRG_POS_UINT64;
+    const size_t w = (f == "l" || f == "L") ? 8 : 4;
+    const uint8_t* src = (const uint8_t*)c->buffers[1] + (size_t)c->offset * w;
+    if (c->length) raw->insert(raw->end(), src, src + (size_t)c->length * w);
+    return kOk;
+}
+// the reference resolves batch by batch, start column first: of the first offending rows the device reports for a coalesced
+// group, the one in the earlier batch wins (start on a tie) and is reported with its batch-local row index
+static Err ingest_overflow(const uint64_t bad[2], const std::vector<uint64_t>& batch_first_row, const std::vector<uint8_t>& sraw,
+                           int s_type, const std::vector<uint8_t>& eraw, int e_type) {
+    auto batch_of = [&](uint64_t row) {
+        size_t bi = std::upper_bound(batch_first_row.begin(), batch_first_row.end(), row) - batch_first_row.begin();
+        return bi - 1;
+    };
+    const bool has_s = bad[0] != ~0ull, has_e = bad[1] != ~0ull;
+    const bool use_s = has_s && (!has_e || batch_of(bad[0]) <= batch_of(bad[1]));
+    const uint64_t row = use_s ? bad[0] : bad[1];
+    const int t = use_s ? s_type : e_type;
+    const uint8_t* col = use_s ? sraw.data() : eraw.data();
+    std::string v;
+    if (t == BRG_POS_INT64) v = std::to_string(reinterpret_cast<const int64_t*>(col)[row]);
+    else if (t == BRG_POS_UINT32) v = std::to_string(reinterpret_cast<const uint32_t*>(col)[row]);
+    else v = std::to_string(reinterpret_cast<const uint64_t*>(col)[row]);
+    return exec("coordinate value " + v + " at row " + std::to_string(row - batch_first_row[batch_of(row)]) + " overflows i32 (max 2147483647)");
+}
+
 // PosArray::resolve_i64 (array_utils.rs:137-171): Int32 / Int64 / UInt32 widen, UInt64 is checked against i64::MAX
 static Err resolve_positions_i64(const Batch& b, const std::string& name, const char* label, std::vector<int64_t>* out) {
     const Column* c = b.find(name);
@@ -1062,26 +1100,33 @@ static Err run_count(brgh_session* s, const char* left, const char* right, const
     // probe batches are coalesced up to coalesce_rows per device round trip; the output keeps the input batching
     size_t b0 = 0;
     while (b0 < rt->batches.size()) {
-        std::vector<int32_t> st, en;
+        // the position value buffers go to the device in their Arrow width (Int32 / Int64 / UInt32 / UInt64) and are narrowed
+        // there (brg_*_arrow): no per-row host loop
+        std::vector<uint8_t> sraw, eraw;
+        int s_type = BRG_POS_INT32, e_type = BRG_POS_INT32;
         std::vector<uint32_t> run_key;
-        std::vector<uint64_t> run_end;
+        std::vector<uint64_t> run_end, batch_first_row;
         size_t b1 = b0;
         uint64_t rows = 0;
         while (b1 < rt->batches.size() && (b1 == b0 || rows + (uint64_t)rt->batches[b1].rows <= s->coalesce_rows)) {
             const Batch& b = rt->batches[b1];
             ContigArray ca;
             BRGH_TRY(contig_array(b, ua.right.contig, &ca));
-            BRGH_TRY(resolve_positions(b, ua.right.start, "start", &st));
-            BRGH_TRY(resolve_positions(b, ua.right.end, "end", &en));
+            BRGH_TRY(position_bytes(b, ua.right.start, "start", &sraw, &s_type));
+            BRGH_TRY(position_bytes(b, ua.right.end, "end", &eraw, &e_type));
             probe_key_runs(ca, b.rows, dict, false, rows, &run_key, &run_end);
+            batch_first_row.push_back(rows);
             rows += (uint64_t)b.rows;
             b1++;
         }
         std::vector<int64_t> out(rows);
         if (rows) {
-            auto f = coverage ? brg_coverage_runs : brg_count_overlaps_runs;
-            BRGH_TRY(from_abi(f(s->ctx, ig.ix, run_key.data(), run_end.data(), run_key.size(), st.data(), en.data(), rows,
-                                ua.strict ? 1 : 0, out.data())));
+            auto f = coverage ? brg_coverage_arrow : brg_count_overlaps_arrow;
+            uint64_t bad[2];
+            const int rc = f(s->ctx, ig.ix, run_key.data(), run_end.data(), run_key.size(), sraw.data(), s_type, eraw.data(), e_type, rows,
+                             ua.strict ? 1 : 0, out.data(), bad);
+            if (rc == BRG_ERR_OVERFLOW && (bad[0] != ~0ull || bad[1] != ~0ull)) return ingest_overflow(bad, batch_first_row, sraw, s_type, eraw, e_type);
+            BRGH_TRY(from_abi(rc));
         }
         uint64_t pos = 0;
         for (size_t bi = b0; bi < b1; bi++) {
@@ -1111,9 +1156,16 @@ static Err run_nearest(brgh_session* s, const char* left, const char* right, int
     for (auto& b : rt->batches) {
         ContigArray ca;
         std::vector<int32_t> st, en;
+        std::vector<uint8_t> sraw, eraw;  // k == 1: value buffers in their Arrow width, narrowed on the device
+        int s_type = BRG_POS_INT32, e_type = BRG_POS_INT32;
         BRGH_TRY(contig_array(b, ua.right.contig, &ca));
-        BRGH_TRY(resolve_positions(b, ua.right.start, "start", &st));
-        BRGH_TRY(resolve_positions(b, ua.right.end, "end", &en));
+        if (k == 1) {
+            BRGH_TRY(position_bytes(b, ua.right.start, "start", &sraw, &s_type));
+            BRGH_TRY(position_bytes(b, ua.right.end, "end", &eraw, &e_type));
+        } else {
+            BRGH_TRY(resolve_positions(b, ua.right.start, "start", &st));
+            BRGH_TRY(resolve_positions(b, ua.right.end, "end", &en));
+        }
         std::vector<uint32_t> run_key;
         std::vector<uint64_t> run_end;
         probe_key_runs(ca, b.rows, dict, true, 0, &run_key, &run_end);
@@ -1126,10 +1178,15 @@ static Err run_nearest(brgh_session* s, const char* left, const char* right, int
             left_idx.resize(n);
             bits.assign(((n + 31) / 32) * 4, 0);
             if (compute_distance) dist.resize(n);
-            if (n)
-                BRGH_TRY(from_abi(brg_nearest_k1_runs(s->ctx, ig.ix, run_key.data(), run_end.data(), run_key.size(), st.data(),
-                                                      en.data(), n, include_overlaps, ua.strict, left_idx.data(), bits.data(),
-                                                      compute_distance ? dist.data() : nullptr)));
+            if (n) {
+                uint64_t bad[2];
+                const int rc = brg_nearest_k1_arrow(s->ctx, ig.ix, run_key.data(), run_end.data(), run_key.size(), sraw.data(), s_type,
+                                                    eraw.data(), e_type, n, include_overlaps, ua.strict, left_idx.data(), bits.data(),
+                                                    compute_distance ? dist.data() : nullptr, bad);
+                if (rc == BRG_ERR_OVERFLOW && (bad[0] != ~0ull || bad[1] != ~0ull))
+                    return ingest_overflow(bad, std::vector<uint64_t>{0}, sraw, s_type, eraw, e_type);
+                BRGH_TRY(from_abi(rc));
+            }
             right_idx.resize(n);
             for (uint64_t i = 0; i < n; i++) right_idx[i] = (uint32_t)i;
             m = n;

@@ -204,6 +204,29 @@ class Index:
                                                 A.np_ptr(start), A.np_ptr(end), len(start), int(strict), A.np_ptr(out)))
         return out
 
+    def probe_arrow(self, op, run_key, run_end, start, end, strict=False, include_overlaps=True, compute_distance=True):
+        """Arrow ingest (brg_*_arrow): start / end in their native width (int32 / int64 / uint32 / uint64), narrowed and
+        checked on the device.  op: 'count' | 'coverage' | 'nearest'."""
+        start, st = A.as_pos(start)
+        end, et = A.as_pos(end)
+        run_key = np.ascontiguousarray(run_key, np.uint32)
+        run_end = np.ascontiguousarray(run_end, np.uint64)
+        n = len(start)
+        L = A.lib()
+        if op in ("count", "coverage"):
+            out = np.empty(n, np.int64)
+            f = L.brg_count_overlaps_arrow if op == "count" else L.brg_coverage_arrow
+            A.check(f(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key), A.np_ptr(start), st, A.np_ptr(end), et, n,
+                      int(strict), A.np_ptr(out), None))
+            return out
+        left = np.empty(n, np.uint32)
+        bits = np.zeros(((n + 31) // 32) * 4, np.uint8)
+        dist = np.empty(n, np.int64) if compute_distance else None
+        A.check(L.brg_nearest_k1_arrow(self.ctx._h, self._h, A.np_ptr(run_key), A.np_ptr(run_end), len(run_key), A.np_ptr(start), st,
+                                       A.np_ptr(end), et, n, int(include_overlaps), int(strict), A.np_ptr(left), A.np_ptr(bits),
+                                       A.np_ptr(dist), None))
+        return left, A.unpack_bits(bits, n), dist
+
     def coverage_runs(self, run_key, run_end, start, end, strict=False, out=None):
         start, end = A.as_i32(start), A.as_i32(end)
         run_key = np.ascontiguousarray(run_key, np.uint32)

@@ -125,6 +125,25 @@ BRG_API int brg_nearest_k1_runs(brg_ctx* ctx, const brg_index* idx, const uint32
                         uint64_t n_runs, const int32_t* start, const int32_t* end, uint64_t n, int include_overlaps,
                         int strict, uint32_t* out_left_idx, uint8_t* out_valid_bits, int64_t* out_distance);
 
+/* ---- Arrow ingest (replaces the host copies of PosArray::resolve, array_utils.rs:73-131).  The start /
+ *      end VALUE BUFFERS of the probe batch are passed in their native Arrow width and cross PCIe as they are; the checked
+ *      narrowing to i32 (i32::try_from per row) runs on the device in front of the probe kernel.  A value that does not fit
+ *      fails the call with BRG_ERR_OVERFLOW and the reference's text "coordinate value {v} at row {i} overflows i32 (max
+ *      2147483647)" (start column first, array_utils.rs:94-98); when `bad_rows` is not NULL it receives the first offending
+ *      row of the start column and of the end column (UINT64_MAX = none) so that a caller that coalesced several record
+ *      batches can report the batch-local row.  Keys travel as runs (see brg_count_overlaps_runs). */
+enum { BRG_POS_INT32 = 0, BRG_POS_INT64 = 1, BRG_POS_UINT32 = 2, BRG_POS_UINT64 = 3 };
+BRG_API int brg_count_overlaps_arrow(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                             uint64_t n_runs, const void* start, int start_type, const void* end, int end_type, uint64_t n,
+                             int strict, int64_t* out_count, uint64_t* bad_rows /* [2] or NULL */);
+BRG_API int brg_coverage_arrow(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                       uint64_t n_runs, const void* start, int start_type, const void* end, int end_type, uint64_t n,
+                       int strict, int64_t* out_coverage, uint64_t* bad_rows /* [2] or NULL */);
+BRG_API int brg_nearest_k1_arrow(brg_ctx* ctx, const brg_index* idx, const uint32_t* run_key, const uint64_t* run_end,
+                         uint64_t n_runs, const void* start, int start_type, const void* end, int end_type, uint64_t n,
+                         int include_overlaps, int strict, uint32_t* out_left_idx, uint8_t* out_valid_bits,
+                         int64_t* out_distance, uint64_t* bad_rows /* [2] or NULL */);
+
 /* ---- coverage (replaces get_coverage + get_stream's row loop, interval_tree.rs:145-152, 155-221) ------ */
 BRG_API int brg_coverage(brg_ctx* ctx, const brg_index* idx, const uint32_t* key_id, const int32_t* start,
                  const int32_t* end, uint64_t n, int strict, int64_t* out_coverage);

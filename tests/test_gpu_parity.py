@@ -149,6 +149,47 @@ def test_gpu_key_runs_entry_points(ctx):
     gi.close()
 
 
+@pytest.mark.parametrize("dtypes", [(np.int64, np.int64), (np.uint32, np.uint64), (np.int32, np.int64), (np.uint64, np.int32)],
+                         ids=lambda d: f"{np.dtype(d[0]).name}-{np.dtype(d[1]).name}")
+def test_gpu_arrow_ingest_native_width_columns(ctx, dtypes):
+    """SURVEY 8f rank 4: position columns cross PCIe in their Arrow width; PosArray::resolve (array_utils.rs:73-131) runs on
+    the device.  Same answers as the i32 entry points; values that do not fit fail with the reference's text and first row."""
+    import bio_ranges_b200 as brg
+
+    rng = np.random.default_rng(77)
+    nk = 5
+    bk, bs, be = _rand(rng, 20_000, nk, 0, 2_000_000, 900)
+    pk, ps, pe = _sorted_probes(rng, 70_001, nk, 2_000_000, 1, 400, absent_runs=True)  # odd length: vector body + scalar tail
+    rk, rend = brg._cabi.key_runs(pk)
+    gi = ctx.build(bk, bs, be, nk)
+    s_t, e_t = ps.astype(dtypes[0]), pe.astype(dtypes[1])
+    for strict in (False, True):
+        assert (gi.probe_arrow("count", rk, rend, s_t, e_t, strict=strict) == gi.count_overlaps(pk, ps, pe, strict=strict)).all()
+        assert (gi.probe_arrow("coverage", rk, rend, s_t, e_t, strict=strict) == gi.coverage(pk, ps, pe, strict=strict)).all()
+        a = gi.probe_arrow("nearest", rk, rend, s_t, e_t, strict=strict)
+        b = gi.nearest_k1(pk, ps, pe, strict=strict)
+        assert all((x == y).all() for x, y in zip(a, b))
+    # overflow: first offending row of the start column wins over the end column (array_utils.rs:94-98)
+    big = 2**31
+    wide = [i for i, d in enumerate(dtypes) if np.dtype(d) != np.int32]
+    cols = [s_t.copy(), e_t.copy()]
+    rows = {0: (60_001, 12_345), 1: (70_000, 999)}  # (a row in the scalar tail / last vector, an earlier row)
+    for c in wide:
+        for r in rows[c]:
+            cols[c][r] = big + c
+    first_col = wide[0]
+    with pytest.raises(brg.BioRangesError) as ei:
+        gi.probe_arrow("count", rk, rend, cols[0], cols[1])
+    assert ei.value.status == 4  # BRG_ERR_OVERFLOW
+    assert f"coordinate value {big + first_col} at row {min(rows[first_col])} overflows i32 (max 2147483647)" in str(ei.value)
+    if np.dtype(dtypes[0]) == np.int64:  # negative values below i32::MIN are caught as well
+        s_neg = s_t.copy()
+        s_neg[7] = -(2**31) - 1
+        with pytest.raises(brg.BioRangesError, match=rf"coordinate value {-(2**31) - 1} at row 7 overflows i32"):
+            gi.probe_arrow("coverage", rk, rend, s_neg, e_t)
+    gi.close()
+
+
 def test_gpu_edge_cases(ctx):
     rng = np.random.default_rng(77)
     # empty build side, keys without rows, empty probe side

@@ -302,3 +302,33 @@ def test_join_int32_cast_error(ctx):
     with pytest.raises(BioRangesError) as ei:  # the table functions use PosArray::resolve's text (array_utils.rs:94-98)
         ctx.count_overlaps("l", "r")
     assert ei.value.status == EXECUTION and f"coordinate value {big} at row 0 overflows i32 (max 2147483647)" in str(ei.value)
+
+
+# ---- Arrow ingest through the table functions: Int64 / UInt32 / UInt64 position columns are narrowed on the device -------------
+def test_udtf_native_width_position_columns(ctx):
+    from bio_ranges_b200 import BioRangesError
+    from bio_ranges_b200.session import EXECUTION
+
+    big = 2**31 + 5
+    left = _tbl([("chr1", 100, 200), ("chr1", 150, 400), ("chr2", 10, 20)])
+    ctx.register_table("l", left)
+    want_i32 = None
+    for ts, te in [(pa.int32(), pa.int32()), (pa.int64(), pa.int64()), (pa.uint32(), pa.uint64())]:
+        r1 = pa.record_batch({"contig": ["chr1", "chr1"], "pos_start": pa.array([120, 500], ts), "pos_end": pa.array([160, 600], te)})
+        r2 = pa.record_batch({"contig": ["chr2", "chr3"], "pos_start": pa.array([15, 1], ts), "pos_end": pa.array([30, 2], te)})
+        ctx.register_table("r", pa.Table.from_batches([r1, r2]))
+        got = (pa.Table.from_batches(ctx.count_overlaps("l", "r")).column("count").to_pylist(),
+               pa.Table.from_batches(ctx.coverage("l", "r")).column("coverage").to_pylist(),
+               pa.Table.from_batches(ctx.nearest("l", "r")).column("distance").to_pylist())
+        if want_i32 is None:
+            want_i32 = got
+            assert got[0] == [2, 0, 1, 0]
+        assert got == want_i32
+    # the offending row is reported batch-local, in the first batch that holds one (the reference resolves batch by batch)
+    r1 = pa.record_batch({"contig": ["chr1", "chr1"], "pos_start": pa.array([120, 500], pa.int64()), "pos_end": pa.array([160, 600], pa.int64())})
+    r2 = pa.record_batch({"contig": ["chr2", "chr3"], "pos_start": pa.array([15, big], pa.int64()), "pos_end": pa.array([big + 1, 2], pa.int64())})
+    ctx.register_table("r", pa.Table.from_batches([r1, r2]), max_chunksize=2)  # two probe batches
+    for fn in (ctx.count_overlaps, ctx.coverage, ctx.nearest):
+        with pytest.raises(BioRangesError) as ei:
+            fn("l", "r")
+        assert ei.value.status == EXECUTION and f"coordinate value {big} at row 1 overflows i32 (max 2147483647)" in str(ei.value)
