@@ -883,10 +883,15 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
             if ((rc = l->out0[b].ensure(C * 8))) return rc;
         }
     }
+    // chunk schedule: full chunks of C rows.  (Tapering the ends -- C/8, C/4, C/2 ... -- to shorten the first H2D and the last
+    // D2H copy, which nothing overlaps, was measured and is slower: 24.2 ms vs 22.4 ms per 125M probes; so are smaller chunks
+    // throughout, profiles/r1_e2e_chunk_sweep.txt: the per-chunk cost outweighs the shorter pipeline fill.)
+    std::vector<uint64_t> sizes;
+    for (uint64_t left = n; left; left -= std::min(C, left)) sizes.push_back(std::min(C, left));
     uint64_t done = 0;
-    for (uint64_t j = 0; done < n; j++, done += C) {
+    for (uint64_t j = 0; j < sizes.size(); done += sizes[j], j++) {
         const int b = (int)(j % Lane::NBUF);
-        const uint64_t m = std::min<uint64_t>(C, n - done);
+        const uint64_t m = sizes[j];
         // inputs of buffer b may be overwritten once the kernel that read them has finished
         BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
         if (key && !by_runs) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));

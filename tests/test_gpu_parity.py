@@ -190,6 +190,32 @@ def test_gpu_arrow_ingest_native_width_columns(ctx, dtypes):
     gi.close()
 
 
+def test_gpu_host_buffer_chunk_schedule(monkeypatch):
+    """host-buffer entry points stream the probe table through double-buffered staging chunks: with a small chunk size the
+    schedule has several full chunks and an odd tail"""
+    import bio_ranges_b200 as brg
+
+    monkeypatch.setenv("BRG_CHUNK_ROWS", "262144")
+    c2 = brg.Context(0)
+    rng = np.random.default_rng(5)
+    nk = 4
+    bk, bs, be = _rand(rng, 50_000, nk, 0, 5_000_000, 800)
+    n = 262144 * 3 + 262144 // 2 + 77
+    pk, ps, pe = _sorted_probes(rng, n, nk, 5_000_000, 1, 300, absent_runs=True)
+    rk, rend = brg._cabi.key_runs(pk)
+    gi = c2.build(bk, bs, be, nk)
+    oi = O.OracleIndex(bk, bs, be, nk)
+    assert (gi.count_overlaps(pk, ps, pe) == oi.count_overlaps(pk, ps, pe)).all()
+    assert (gi.count_overlaps_runs(rk, rend, ps, pe) == oi.count_overlaps(pk, ps, pe)).all()
+    assert (gi.coverage_runs(rk, rend, ps, pe) == oi.coverage(pk, ps, pe)).all()
+    left, valid, dist = gi.nearest_k1_runs(rk, rend, ps, pe)
+    ol, ov, od = oi.nearest_k1(pk, ps, pe)
+    assert (valid == ov).all() and (left[valid] == ol[ov]).all() and (dist[valid] == od[ov]).all()
+    assert (gi.probe_arrow("count", rk, rend, ps.astype(np.int64), pe.astype(np.uint32)) == oi.count_overlaps(pk, ps, pe)).all()
+    gi.close()
+    c2.close()
+
+
 def test_gpu_edge_cases(ctx):
     rng = np.random.default_rng(77)
     # empty build side, keys without rows, empty probe side
