@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
         }
         if (ok) {
             uint32_t tot = 0;
-            ulonglong2* out = reinterpret_cast<ulonglong2*>(row_rng + t.row0);
 #pragma unroll
             for (int j = 0; j < PV; j++) {
                 // start <= end on the build side (checked at build time): a row that ends before qs also starts before qe
@@ -145,10 +144,10 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
                 if (t.qe[j] < t.qs[j]) c = (i0[j] < n_le[j]) ? walk_count(ix, i0[j], n_le[j], t.qs[j]) : 0u;  // unguarded predicate
                 tot += c;
             }
+            long long rng[PV];
 #pragma unroll
-            for (int j = 0; j < PV; j += 2)
-                __stcs(out + j / 2, make_ulonglong2((uint64_t)i0[j] | ((uint64_t)n_le[j] << 32),
-                                                    (uint64_t)i0[j + 1] | ((uint64_t)n_le[j + 1] << 32)));
+            for (int j = 0; j < PV; j++) rng[j] = (long long)((uint64_t)i0[j] | ((uint64_t)n_le[j] << 32));
+            store_chunk_i64(aux0, reinterpret_cast<int64_t*>(row_rng) + (t.row0 - (threadIdx.x & 31) * PV), rng);  // (aux0 + aux1)
             tot = __reduce_add_sync(0xFFFFFFFFu, tot);
             if ((threadIdx.x & 31) == 0) chunk_tot[t.chunk] = tot;
             fails = 0;

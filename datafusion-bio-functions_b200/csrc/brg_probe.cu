@@ -22,6 +22,10 @@
 namespace brg {
 
 constexpr int PB_THREADS = 256;
+#ifndef BRG_COUNT_THREADS
+#define BRG_COUNT_THREADS 320  // threads per CTA of the tiled count kernel: 96 registers, no spills, 20 warps per SM (0.549 -> 0.532 ms;
+                               // 352 / 384 threads spill: 0.61 / 0.58 ms).  env BRG_COUNT_THREADS overrides (debugging switch)
+#endif
 #ifndef BRG_CC_CTAS
 #define BRG_CC_CTAS 2  // resident CTAs per SM of the count / coverage tiled kernels: 128 registers per thread, no spills
                        // (3 CTAs = 80 registers spilled in the hot loop: 0.73 ms vs 0.59 ms per 125M probes on B200)
@@ -84,15 +88,16 @@ __device__ __forceinline__ void store8_i64(int64_t* out, const long long (&v)[PV
     for (int j = 0; j < PV / 2; j++) __stcs(o + j, make_longlong2(v[2 * j], v[2 * j + 1]));
 }
 
-__global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
-                                                                    const int32_t* __restrict__ start,
-                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                    int strict, int64_t* __restrict__ out, TodoList todo) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, BRG_CC_CTAS) count_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                 const int32_t* __restrict__ start,
+                                                                 const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                 int strict, int64_t* __restrict__ out, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
-    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
-    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    ProbePipe pipe(ring, key, start, end, n_rows);
+    WarpRing* rings = reinterpret_cast<WarpRing*>(smem_raw);  // one per warp of the CTA
+    uint32_t* aux0 = rings[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = rings[threadIdx.x >> 5].aux[1];
+    ProbePipe pipe(rings, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cs, ce;
     cs.reset();
@@ -126,6 +131,12 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) count_kernel_tiled(In
 #pragma unroll
             for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
                 cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
+            if (t.full) {
+                uint32_t c32[PV];
+#pragma unroll
+                for (int j = 0; j < PV; j++) c32[j] = (uint32_t)cnt[j];  // 0 <= count <= build rows < 2^32
+                store_chunk_i64_from32(aux0, out + (t.row0 - (threadIdx.x & 31) * PV), c32, false);
+            } else
             if (t.active) store8_i64(out + t.row0, cnt);
             fails = 0;
         } else {
@@ -260,10 +271,17 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled
             }
         }
         if (ok) {
-            long long cov[PV];
+            uint32_t c32[PV];
 #pragma unroll
-            for (int j = 0; j < PV; j++) cov[j] = t.active ? (long long)coverage_from_range<false>(ix, lo[j], hi[j], t.qs[j], t.qe[j]) : 0ll;
-            if (t.active) store8_i64(out + t.row0, cov);
+            for (int j = 0; j < PV; j++) c32[j] = t.active ? (uint32_t)coverage_from_range<false>(ix, lo[j], hi[j], t.qs[j], t.qe[j]) : 0u;
+            if (t.full) {
+                store_chunk_i64_from32(aux0, out + (t.row0 - (threadIdx.x & 31) * PV), c32, true);  // i32 accumulator, widened (interval_tree.rs:207)
+            } else if (t.active) {
+                long long cov[PV];
+#pragma unroll
+                for (int j = 0; j < PV; j++) cov[j] = (long long)(int32_t)c32[j];
+                store8_i64(out + t.row0, cov);
+            }
             fails = 0;
         } else {
             cl.valid = false;
@@ -467,11 +485,10 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                 const int32_t rs = strict ? wsub(t.qs[j], 1) : t.qs[j], re = strict ? wadd(t.qe[j], 1) : t.qe[j];
                 dd[j] = found ? cand_distance(rs, re, b.s, b.e) : 0ll;
             }
-            uint4* lp = reinterpret_cast<uint4*>(left_idx + t.row0);
-            __stcs(lp, make_uint4(pos[0], pos[1], pos[2], pos[3]));
-            __stcs(lp + 1, make_uint4(pos[4], pos[5], pos[6], pos[7]));
+            const uint64_t chunk_row0 = t.row0 - (threadIdx.x & 31) * PV;
+            store_chunk_u32(aux0, left_idx + chunk_row0, pos);
             valid_bytes[t.row0 >> 3] = (uint8_t)bits;  // Arrow validity bitmap, LSB first: byte r/8 holds rows r..r+7
-            if (dist) store8_i64(dist + t.row0, dd);
+            if (dist) store_chunk_i64(aux0, dist + chunk_row0, dd);  // (aux0 and aux1 are contiguous: 512 words)
             fails = 0;
         } else {
             cs.valid = false;
@@ -711,11 +728,24 @@ int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, con
     uint64_t done = 0;
     if (tiled_enabled("count", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
-        int rc = tiled_config((const void*)count_kernel_tiled);
-        if (rc) return rc;
+        static const int ct = [] { const char* v = getenv("BRG_COUNT_THREADS"); return v ? atoi(v) : BRG_COUNT_THREADS; }();
+        int rc = 0;
         TodoList todo;
         if ((rc = todo_alloc(done, &todo, st))) return rc;
-        count_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out, todo);
+#define BRG_COUNT_LAUNCH(T)                                                                                                        \
+    {                                                                                                                              \
+        const int smem = (int)sizeof(WarpRing) * ((T) / 32);                                                                       \
+        BRG_CUDA(cudaFuncSetAttribute((const void*)count_kernel_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     \
+        const uint64_t chunks = (done + TP_WTILE - 1) / TP_WTILE, per_cta = (T) / 32;                                              \
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + per_cta - 1) / per_cta, (uint64_t)kSMs * BRG_CC_CTAS)); \
+        count_kernel_tiled<T><<<grid, (T), smem, st>>>(ix, key, s, e, done, strict, out, todo);                                    \
+    }
+        if (ct == 288) BRG_COUNT_LAUNCH(288)
+        else if (ct == 320) BRG_COUNT_LAUNCH(320)
+        else if (ct == 352) BRG_COUNT_LAUNCH(352)
+        else if (ct == 384) BRG_COUNT_LAUNCH(384)
+        else BRG_COUNT_LAUNCH(256)
+#undef BRG_COUNT_LAUNCH
         BRG_LAUNCH_CHECK();
         count_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
         BRG_LAUNCH_CHECK();

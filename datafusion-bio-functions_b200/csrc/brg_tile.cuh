@@ -504,6 +504,52 @@ __device__ __forceinline__ bool warp_ranks_le_end(WarpCursor& cur, const DirView
     }
     return true;
 }
+// Transposed chunk stores (full 256-row chunks).  A lane owns 8 consecutive rows, so stored directly its outputs are 32 or
+// 64 contiguous bytes and every store instruction of the warp touches 32 half-written sectors.  Staged through the warp's
+// (now idle) histogram scratch, every store instruction writes 512 contiguous bytes: count 0.574 -> 0.549 ms per 125M probes.
+// x: 256 words (32-bit values) / 512 words (64-bit values) of per-warp shared memory; out: the chunk's first output row.
+__device__ __forceinline__ void store_chunk_i64_from32(uint32_t* x, int64_t* out, const uint32_t (&v)[PV], bool sign_extend) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    uint4* x4 = reinterpret_cast<uint4*>(x) + 2 * lane;
+    x4[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    x4[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    __syncwarp();
+    longlong2* o2 = reinterpret_cast<longlong2*>(out) + lane;
+    const uint2* x2 = reinterpret_cast<const uint2*>(x) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2 w = x2[k * 32];
+        __stcs(o2 + k * 32, sign_extend ? make_longlong2((long long)(int32_t)w.x, (long long)(int32_t)w.y)
+                                        : make_longlong2((long long)w.x, (long long)w.y));
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void store_chunk_i64(uint32_t* x, int64_t* out, const long long (&v)[PV]) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    longlong2* xl = reinterpret_cast<longlong2*>(x);
+#pragma unroll
+    for (int j = 0; j < PV / 2; j++) xl[lane * (PV / 2) + j] = make_longlong2(v[2 * j], v[2 * j + 1]);
+    __syncwarp();
+    longlong2* o2 = reinterpret_cast<longlong2*>(out) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; k++) __stcs(o2 + k * 32, xl[k * 32 + lane]);
+    __syncwarp();
+}
+__device__ __forceinline__ void store_chunk_u32(uint32_t* x, uint32_t* out, const uint32_t (&v)[PV]) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    uint4* x4 = reinterpret_cast<uint4*>(x);
+    x4[2 * lane] = make_uint4(v[0], v[1], v[2], v[3]);
+    x4[2 * lane + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+    __syncwarp();
+    uint4* o4 = reinterpret_cast<uint4*>(out) + lane;
+    __stcs(o4, x4[lane]);
+    __stcs(o4 + 32, x4[32 + lane]);
+    __syncwarp();
+}
+
 #endif
 
 }  // namespace brg
