@@ -22,6 +22,9 @@
 namespace brg {
 
 constexpr int PB_THREADS = 256;
+#ifndef BRG_COVERAGE_THREADS
+#define BRG_COVERAGE_THREADS 320  // as BRG_COUNT_THREADS: 96 registers, no spills; 0.521 -> 0.491 ms per 100M probes
+#endif
 #ifndef BRG_COUNT_THREADS
 #define BRG_COUNT_THREADS 320  // threads per CTA of the tiled count kernel: 96 registers, no spills, 20 warps per SM (0.549 -> 0.532 ms;
                                // 352 / 384 threads spill: 0.61 / 0.58 ms).  env BRG_COUNT_THREADS overrides (debugging switch)
@@ -234,15 +237,16 @@ __device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint
     return (lo < hi) ? acc : 0;
 }
 
-__global__ void __launch_bounds__(TP_THREADS, BRG_CC_CTAS) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
-                                                                       const int32_t* __restrict__ start,
-                                                                       const int32_t* __restrict__ end, uint64_t n_rows,
-                                                                       int strict, int64_t* __restrict__ out, TodoList todo) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, BRG_CC_CTAS) coverage_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+                                                                    const int32_t* __restrict__ start,
+                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
+                                                                    int strict, int64_t* __restrict__ out, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
-    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
-    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    ProbePipe pipe(ring, key, start, end, n_rows);
+    WarpRing* rings = reinterpret_cast<WarpRing*>(smem_raw);  // one per warp of the CTA
+    uint32_t* aux0 = rings[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = rings[threadIdx.x >> 5].aux[1];
+    ProbePipe pipe(rings, key, start, end, n_rows);
     ProbeTile t;
     WarpCursor cl, cf;
     cl.reset();
@@ -485,10 +489,13 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                 const int32_t rs = strict ? wsub(t.qs[j], 1) : t.qs[j], re = strict ? wadd(t.qe[j], 1) : t.qe[j];
                 dd[j] = found ? cand_distance(rs, re, b.s, b.e) : 0ll;
             }
-            const uint64_t chunk_row0 = t.row0 - (threadIdx.x & 31) * PV;
-            store_chunk_u32(aux0, left_idx + chunk_row0, pos);
+            // (transposing these stores through shared memory, as count / coverage do, changes nothing here: 0.767 vs 0.772 ms --
+            // the kernel is bound by its ~1900 warp instructions per chunk, not by the store path)
+            uint4* lp = reinterpret_cast<uint4*>(left_idx + t.row0);
+            __stcs(lp, make_uint4(pos[0], pos[1], pos[2], pos[3]));
+            __stcs(lp + 1, make_uint4(pos[4], pos[5], pos[6], pos[7]));
             valid_bytes[t.row0 >> 3] = (uint8_t)bits;  // Arrow validity bitmap, LSB first: byte r/8 holds rows r..r+7
-            if (dist) store_chunk_i64(aux0, dist + chunk_row0, dd);  // (aux0 and aux1 are contiguous: 512 words)
+            if (dist) store8_i64(dist + t.row0, dd);
             fails = 0;
         } else {
             cs.valid = false;
@@ -764,11 +771,22 @@ int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, 
     uint64_t done = 0;
     if (tiled_enabled("coverage", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
-        int rc = tiled_config((const void*)coverage_kernel_tiled);
-        if (rc) return rc;
+        static const int ct = [] { const char* v = getenv("BRG_COVERAGE_THREADS"); return v ? atoi(v) : BRG_COVERAGE_THREADS; }();
+        int rc = 0;
         TodoList todo;
         if ((rc = todo_alloc(done, &todo, st))) return rc;
-        coverage_kernel_tiled<<<tiled_grid(done), TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, done, strict, out, todo);
+#define BRG_COV_LAUNCH(T)                                                                                                          \
+    {                                                                                                                              \
+        const int smem = (int)sizeof(WarpRing) * ((T) / 32);                                                                       \
+        BRG_CUDA(cudaFuncSetAttribute((const void*)coverage_kernel_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        const uint64_t chunks = (done + TP_WTILE - 1) / TP_WTILE, per_cta = (T) / 32;                                              \
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + per_cta - 1) / per_cta, (uint64_t)kSMs * BRG_CC_CTAS)); \
+        coverage_kernel_tiled<T><<<grid, (T), smem, st>>>(ix, key, s, e, done, strict, out, todo);                                 \
+    }
+        if (ct == 320) BRG_COV_LAUNCH(320)
+        else if (ct == 288) BRG_COV_LAUNCH(288)
+        else BRG_COV_LAUNCH(256)
+#undef BRG_COV_LAUNCH
         BRG_LAUNCH_CHECK();
         coverage_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
         BRG_LAUNCH_CHECK();
