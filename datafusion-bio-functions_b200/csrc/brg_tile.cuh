@@ -29,7 +29,7 @@ constexpr int PV = 8;                       // consecutive probe rows per thread
 constexpr int TP_WTILE = 32 * PV;           // 256 consecutive rows per warp chunk
 constexpr int TP_TILE = TP_THREADS * PV;    // rows in flight per CTA step
 constexpr int TP_STAGES = 2;
-constexpr int TP_WCAP = 256;                // words of per-array scratch (histogram bins / window copy of the fallback)
+constexpr int TP_WCAP = 288;                // words of per-array scratch (256 histogram bins, padded / window copy of the fallback)
 #ifndef BRG_NWIN
 #define BRG_NWIN 3
 #endif
@@ -256,6 +256,13 @@ __device__ __forceinline__ bool warp_uniform_key(const uint32_t (&key)[PV], bool
     return a == o && o < n_keys;  // (no active lane: a = ~0, o = 0 -> false)
 }
 
+// Histogram bins live at word i + 4 * (i / 32): 16 pad bytes after every 128.  A lane zeroes and reads back its 8 bins with
+// two 128-bit accesses; unpadded, lanes L and L + 4 of a quarter warp hit the same banks (every such access takes two
+// wavefronts) -- and the tiled kernels are bound by the shared-memory pipe (ncu: l1tex data-pipe wavefronts at 86 % of peak,
+// profiles/r1_count_v14_ncu.txt), not by DRAM or issue slots.
+__device__ __forceinline__ uint32_t hist_slot(uint32_t bin) { return bin + ((bin >> 5) << 2); }
+__device__ __forceinline__ uint4* hist_lane_bins(uint32_t* aux, int lane) { return reinterpret_cast<uint4*>(aux) + 2 * lane + (lane >> 2); }
+
 // ---- warp cursor over one sorted array ---------------------------------------------------------------------------
 // Invariant while valid: every element of key `key`'s segment before `pos` is <= bound (LT: < bound), hence `pos` is a
 // legal window start for any tile whose smallest query is >= bound.
@@ -321,7 +328,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
             }
         }
         // ---- inverse search ---------------------------------------------------------------------------------------
-        uint4* a4 = reinterpret_cast<uint4*>(aux) + 2 * lane;
+        uint4* a4 = hist_lane_bins(aux, lane);
         a4[0] = make_uint4(0, 0, 0, 0);
         a4[1] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -346,7 +353,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
                     pos += (LT ? (qv <= v) : (qv < v)) ? step : 0u;
                 }
                 // (the 8 steps cover Q[0..254]; an in-window element never lies above Q[255] = mx, so pos <= 255 is exact)
-                if (in) atomicAdd(&aux[pos], 1u);
+                if (in) atomicAdd(&aux[hist_slot(pos)], 1u);
             }
         }
         __syncwarp();
@@ -429,8 +436,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
     const bool in1 = lo1 + lane < k1.seg_end && (LT1 ? v1 < mx1 : v1 <= mx1);
     const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
     if (m0 == 0xFFFFFFFFu || m1 == 0xFFFFFFFFu) return false;  // a window continues past this round
-    uint4* a0 = reinterpret_cast<uint4*>(aux0) + 2 * lane;
-    uint4* a1 = reinterpret_cast<uint4*>(aux1) + 2 * lane;
+    uint4* a0 = hist_lane_bins(aux0, lane);
+    uint4* a1 = hist_lane_bins(aux1, lane);
     a0[0] = make_uint4(0, 0, 0, 0); a0[1] = make_uint4(0, 0, 0, 0);
     a1[0] = make_uint4(0, 0, 0, 0); a1[1] = make_uint4(0, 0, 0, 0);
     __syncwarp();
@@ -442,8 +449,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
             p0 += (LT0 ? (x0 <= v0) : (x0 < v0)) ? step : 0u;
             p1 += (LT1 ? (x1 <= v1) : (x1 < v1)) ? step : 0u;
         }
-        if (in0) atomicAdd(&aux0[p0], 1u);
-        if (in1) atomicAdd(&aux1[p1], 1u);
+        if (in0) atomicAdd(&aux0[hist_slot(p0)], 1u);
+        if (in1) atomicAdd(&aux1[hist_slot(p1)], 1u);
     }
     __syncwarp();
     c0.pos = lo0 + __popc(m0); c0.bound = mx0;
@@ -507,19 +514,20 @@ __device__ __forceinline__ bool warp_ranks_le_end(WarpCursor& cur, const DirView
 // Transposed chunk stores (full 256-row chunks).  A lane owns 8 consecutive rows, so stored directly its outputs are 32 or
 // 64 contiguous bytes and every store instruction of the warp touches 32 half-written sectors.  Staged through the warp's
 // (now idle) histogram scratch, every store instruction writes 512 contiguous bytes: count 0.574 -> 0.549 ms per 125M probes.
-// x: 256 words (32-bit values) / 512 words (64-bit values) of per-warp shared memory; out: the chunk's first output row.
+// The staging area uses the padded layout of the histograms (16-byte unit u lives at u + u / 8): conflict-free both ways.
+// x: one aux buffer (32-bit values) / two consecutive ones (64-bit values); out: the chunk's first output row.
+__device__ __forceinline__ uint32_t pad_unit(uint32_t u) { return u + (u >> 3); }
 __device__ __forceinline__ void store_chunk_i64_from32(uint32_t* x, int64_t* out, const uint32_t (&v)[PV], bool sign_extend) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    uint4* x4 = reinterpret_cast<uint4*>(x) + 2 * lane;
+    uint4* x4 = hist_lane_bins(x, lane);
     x4[0] = make_uint4(v[0], v[1], v[2], v[3]);
     x4[1] = make_uint4(v[4], v[5], v[6], v[7]);
     __syncwarp();
     longlong2* o2 = reinterpret_cast<longlong2*>(out) + lane;
-    const uint2* x2 = reinterpret_cast<const uint2*>(x) + lane;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint2 w = x2[k * 32];
+        const uint2 w = *reinterpret_cast<const uint2*>(x + hist_slot(2u * (k * 32 + lane)));
         __stcs(o2 + k * 32, sign_extend ? make_longlong2((long long)(int32_t)w.x, (long long)(int32_t)w.y)
                                         : make_longlong2((long long)w.x, (long long)w.y));
     }
@@ -530,26 +538,25 @@ __device__ __forceinline__ void store_chunk_i64(uint32_t* x, int64_t* out, const
     __syncwarp();
     longlong2* xl = reinterpret_cast<longlong2*>(x);
 #pragma unroll
-    for (int j = 0; j < PV / 2; j++) xl[lane * (PV / 2) + j] = make_longlong2(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < PV / 2; j++) xl[pad_unit(lane * (PV / 2) + j)] = make_longlong2(v[2 * j], v[2 * j + 1]);
     __syncwarp();
     longlong2* o2 = reinterpret_cast<longlong2*>(out) + lane;
 #pragma unroll
-    for (int k = 0; k < 4; k++) __stcs(o2 + k * 32, xl[k * 32 + lane]);
+    for (int k = 0; k < 4; k++) __stcs(o2 + k * 32, xl[pad_unit(k * 32 + lane)]);
     __syncwarp();
 }
 __device__ __forceinline__ void store_chunk_u32(uint32_t* x, uint32_t* out, const uint32_t (&v)[PV]) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     uint4* x4 = reinterpret_cast<uint4*>(x);
-    x4[2 * lane] = make_uint4(v[0], v[1], v[2], v[3]);
-    x4[2 * lane + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+    x4[pad_unit(2 * lane)] = make_uint4(v[0], v[1], v[2], v[3]);
+    x4[pad_unit(2 * lane + 1)] = make_uint4(v[4], v[5], v[6], v[7]);
     __syncwarp();
     uint4* o4 = reinterpret_cast<uint4*>(out) + lane;
-    __stcs(o4, x4[lane]);
-    __stcs(o4 + 32, x4[32 + lane]);
+    __stcs(o4, x4[pad_unit(lane)]);
+    __stcs(o4 + 32, x4[pad_unit(32 + lane)]);
     __syncwarp();
 }
-
 #endif
 
 }  // namespace brg
