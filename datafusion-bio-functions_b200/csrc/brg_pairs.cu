@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
     uint32_t kd_key = 0xFFFFFFFFu;
     uint32_t fails = 0;
     while (pipe.next(t)) {
+        pad_tile(t);
         uint32_t kuni;
         bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
         uint32_t n_le[PV], i0[PV], ended[PV];

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(THREADS, BRG_CC_CTAS) count_kernel_tiled(Index
     uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
+        pad_tile(t);
         uint32_t kuni;
         bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
         uint32_t started[PV], ended[PV];
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(THREADS, BRG_CC_CTAS) coverage_kernel_tiled(In
     uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
+        pad_tile(t);
         uint32_t kuni;
         bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
         uint32_t lo[PV], hi[PV];
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
     uint32_t fails = 0;  // consecutive deferred chunks
     while (pipe.next(t)) {
         if (strict) strict_adjust(t);
+        pad_tile(t);
         uint32_t kuni;
         bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
         uint32_t n_le[PV], i_pme[PV], l_idx[PV];

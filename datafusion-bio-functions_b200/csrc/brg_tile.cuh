@@ -93,8 +93,8 @@ __device__ __forceinline__ void todo_push(const TodoList& td, uint64_t chunk) {
 // TMA bulk copies that lane 0 issues, a private mbarrier per stage, private window buffers.  Warps never wait for
 // each other (no __syncthreads in the main loop).
 struct __align__(128) WarpRing {
-    int32_t start[TP_STAGES][TP_WTILE];
-    int32_t end[TP_STAGES][TP_WTILE];
+    int32_t start[TP_STAGES][TP_WCAP];  // 256 rows land here linearly (TMA); pad_tile() rewrites them in the padded layout
+    int32_t end[TP_STAGES][TP_WCAP];
     uint32_t key[TP_STAGES][TP_WTILE];
     uint32_t aux[TP_NWIN][TP_WCAP];  // per array: histogram of the inverse search / window copy of the fallback
     uint64_t full[TP_STAGES];
@@ -228,18 +228,11 @@ struct ProbePipe {
     }
 };
 
-// strict filter: probe start+1 / end-1 (interval_tree.rs:253-256, nearest.rs:341-344); the shared copy of the columns is
-// kept in step with the registers because the inverse search reads the queries from shared memory
+// strict filter: probe start+1 / end-1 (interval_tree.rs:253-256, nearest.rs:341-344); registers only -- pad_tile() below
+// brings the shared copy of the columns, which the inverse search reads, in step
 __device__ __forceinline__ void strict_adjust(ProbeTile& t) {
 #pragma unroll
     for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
-    if (t.active) {
-        int4* ps = reinterpret_cast<int4*>(t.s_qs + (threadIdx.x & 31) * PV);
-        int4* pe = reinterpret_cast<int4*>(t.s_qe + (threadIdx.x & 31) * PV);
-        ps[0] = make_int4(t.qs[0], t.qs[1], t.qs[2], t.qs[3]); ps[1] = make_int4(t.qs[4], t.qs[5], t.qs[6], t.qs[7]);
-        pe[0] = make_int4(t.qe[0], t.qe[1], t.qe[2], t.qe[3]); pe[1] = make_int4(t.qe[4], t.qe[5], t.qe[6], t.qe[7]);
-    }
-    __syncwarp();
 }
 
 // All PV keys of every lane of the warp equal one valid key?  (AND == OR over all 256 keys.)  Inactive lanes pass
@@ -262,6 +255,38 @@ __device__ __forceinline__ bool warp_uniform_key(const uint32_t (&key)[PV], bool
 // profiles/r1_count_v14_ncu.txt), not by DRAM or issue slots.
 __device__ __forceinline__ uint32_t hist_slot(uint32_t bin) { return bin + ((bin >> 5) << 2); }
 __device__ __forceinline__ uint4* hist_lane_bins(uint32_t* aux, int lane) { return reinterpret_cast<uint4*>(aux) + 2 * lane + (lane >> 2); }
+
+// Rewrites the chunk's start / end columns in shared memory (in place, from the registers) in the padded layout of hist_slot:
+// word i at i + 4 * (i / 32).  The binary searches of the inverse search probe Q[pos + step - 1] with pos a multiple of
+// 2 * step: on a linear layout the probes of one step fall into 1, 1, 1, 1, 2, 4, 8, 16 banks (up to 8 wavefronts per
+// load); padded, a step's probes spread over 8 to 32 banks.  Two conflict-free 128-bit stores per column and lane.
+// Call once per chunk after next() (and after strict_adjust); Q below always means this layout.
+__device__ __forceinline__ void pad_tile(ProbeTile& t) {
+    __syncwarp();  // every lane holds its rows in registers
+    if (t.active) {
+        const int lane = threadIdx.x & 31;
+        uint4* ps = hist_lane_bins(reinterpret_cast<uint32_t*>(t.s_qs), lane);
+        uint4* pe = hist_lane_bins(reinterpret_cast<uint32_t*>(t.s_qe), lane);
+        ps[0] = make_uint4(t.qs[0], t.qs[1], t.qs[2], t.qs[3]); ps[1] = make_uint4(t.qs[4], t.qs[5], t.qs[6], t.qs[7]);
+        pe[0] = make_uint4(t.qe[0], t.qe[1], t.qe[2], t.qe[3]); pe[1] = make_uint4(t.qe[4], t.qe[5], t.qe[6], t.qe[7]);
+    }
+    __syncwarp();
+}
+// One step of a binary search over the 256 padded queries, in padded coordinates: `pos` is the padded slot of a multiple of
+// 2 * STEP, the probe is linear element pos + STEP - 1, the advance is STEP elements.
+template <uint32_t STEP> struct PadStep {
+    static constexpr uint32_t probe = STEP >= 32 ? STEP + 4 * (STEP / 32) - 5 : STEP - 1;  // (the element before a block boundary)
+    static constexpr uint32_t advance = STEP >= 32 ? STEP + 4 * (STEP / 32) : STEP;
+};
+// padded insertion slot of v among the chunk's queries:  LT = false: #(Q < v),  LT = true: #(Q <= v)   (0 .. 255, padded)
+template <bool LT>
+__device__ __forceinline__ uint32_t padded_insertion_slot(const int32_t* Q, int32_t v) {
+    uint32_t pos = 0;
+#define BRG_PAD_STEP(S) { const int32_t qv = Q[pos + PadStep<S>::probe]; pos += (LT ? (qv <= v) : (qv < v)) ? PadStep<S>::advance : 0u; }
+    BRG_PAD_STEP(128) BRG_PAD_STEP(64) BRG_PAD_STEP(32) BRG_PAD_STEP(16) BRG_PAD_STEP(8) BRG_PAD_STEP(4) BRG_PAD_STEP(2) BRG_PAD_STEP(1)
+#undef BRG_PAD_STEP
+    return pos;
+}
 
 // ---- warp cursor over one sorted array ---------------------------------------------------------------------------
 // Invariant while valid: every element of key `key`'s segment before `pos` is <= bound (LT: < bound), hence `pos` is a
@@ -346,14 +371,9 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
             open = (m == 0xFFFFFFFFu);
             if (m) {
                 // insertion point of v among the 256 sorted queries:  LE: #(Q < v)   LT: #(Q <= v)
-                uint32_t pos = 0;
-#pragma unroll
-                for (uint32_t step = 128; step; step >>= 1) {
-                    const int32_t qv = Q[pos + step - 1];
-                    pos += (LT ? (qv <= v) : (qv < v)) ? step : 0u;
-                }
                 // (the 8 steps cover Q[0..254]; an in-window element never lies above Q[255] = mx, so pos <= 255 is exact)
-                if (in) atomicAdd(&aux[hist_slot(pos)], 1u);
+                const uint32_t slot = padded_insertion_slot<LT>(Q, v);
+                if (in) atomicAdd(&aux[slot], 1u);
             }
         }
         __syncwarp();
@@ -442,15 +462,17 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
     a1[0] = make_uint4(0, 0, 0, 0); a1[1] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     if (m0 | m1) {
-        uint32_t p0 = 0, p1 = 0;
-#pragma unroll
-        for (uint32_t step = 128; step; step >>= 1) {
-            const int32_t x0 = Q0[p0 + step - 1], x1 = Q1[p1 + step - 1];
-            p0 += (LT0 ? (x0 <= v0) : (x0 < v0)) ? step : 0u;
-            p1 += (LT1 ? (x1 <= v1) : (x1 < v1)) ? step : 0u;
-        }
-        if (in0) atomicAdd(&aux0[hist_slot(p0)], 1u);
-        if (in1) atomicAdd(&aux1[hist_slot(p1)], 1u);
+        uint32_t p0 = 0, p1 = 0;  // padded slots
+#define BRG_PAD_STEP2(S)                                                                              \
+    {                                                                                                 \
+        const int32_t x0 = Q0[p0 + PadStep<S>::probe], x1 = Q1[p1 + PadStep<S>::probe];               \
+        p0 += (LT0 ? (x0 <= v0) : (x0 < v0)) ? PadStep<S>::advance : 0u;                              \
+        p1 += (LT1 ? (x1 <= v1) : (x1 < v1)) ? PadStep<S>::advance : 0u;                              \
+    }
+        BRG_PAD_STEP2(128) BRG_PAD_STEP2(64) BRG_PAD_STEP2(32) BRG_PAD_STEP2(16) BRG_PAD_STEP2(8) BRG_PAD_STEP2(4) BRG_PAD_STEP2(2) BRG_PAD_STEP2(1)
+#undef BRG_PAD_STEP2
+        if (in0) atomicAdd(&aux0[p0], 1u);
+        if (in1) atomicAdd(&aux1[p1], 1u);
     }
     __syncwarp();
     c0.pos = lo0 + __popc(m0); c0.bound = mx0;
