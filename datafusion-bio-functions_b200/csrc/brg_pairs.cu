@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
     while (pipe.next(t)) {
         pad_tile(t);
         uint32_t kuni;
-        bool ok = warp_uniform_key(t.key, t.active, ix.n_keys, &kuni);
+        bool ok = warp_uniform_key(t, ix.n_keys, &kuni);
         uint32_t n_le[PV], i0[PV], ended[PV];
         if (ok) {
             if (kuni != kd_key) {

@@ -106,7 +106,7 @@ struct __align__(128) ProbeRing {
 
 struct ProbeTile {
     int32_t qs[PV], qe[PV];
-    uint32_t key[PV];
+    uint32_t key_and, key_or;  // AND / OR over some of the chunk's keys (all of them once reduced over the warp)
     uint64_t row0;   // global row of this thread's first probe
     uint64_t chunk;  // index of this 256-row chunk
     bool active;     // thread owns rows in this chunk
@@ -184,19 +184,23 @@ struct ProbePipe {
             tile.qs[4] = b.x; tile.qs[5] = b.y; tile.qs[6] = b.z; tile.qs[7] = b.w;
             tile.qe[0] = c4.x; tile.qe[1] = c4.y; tile.qe[2] = c4.z; tile.qe[3] = c4.w;
             tile.qe[4] = d.x; tile.qe[5] = d.y; tile.qe[6] = d.z; tile.qe[7] = d.w;
-            if (key) {
-                const uint4* pk = reinterpret_cast<const uint4*>(&ring->key[s][my]);
-                uint4 k0 = pk[0], k1 = pk[1];
-                tile.key[0] = k0.x; tile.key[1] = k0.y; tile.key[2] = k0.z; tile.key[3] = k0.w;
-                tile.key[4] = k1.x; tile.key[5] = k1.y; tile.key[6] = k1.z; tile.key[7] = k1.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < PV; j++) tile.key[j] = 0u;
-            }
         } else {
 #pragma unroll
-            for (int j = 0; j < PV; j++) { tile.qs[j] = 0; tile.qe[j] = 0; tile.key[j] = 0xFFFFFFFFu; }
+            for (int j = 0; j < PV; j++) { tile.qs[j] = 0; tile.qe[j] = 0; }
         }
+        // The keys are only checked for uniformity, so which lane looks at which rows does not matter: lane L reads the 16-byte
+        // units L and L + 32 (conflict-free; the 8 consecutive rows it owns would cost two wavefronts per load).
+        uint32_t ka = 0xFFFFFFFFu, ko = 0u;
+        if (key) {
+            const uint4* pk = reinterpret_cast<const uint4*>(ring->key[s]);
+            const uint32_t lane = threadIdx.x & 31;
+            if (4u * lane < rows) { const uint4 k0 = pk[lane]; ka &= k0.x & k0.y & k0.z & k0.w; ko |= k0.x | k0.y | k0.z | k0.w; }
+            if (128u + 4u * lane < rows) { const uint4 k1 = pk[32 + lane]; ka &= k1.x & k1.y & k1.z & k1.w; ko |= k1.x | k1.y | k1.z | k1.w; }
+        } else if (tile.active) {
+            ka = 0u;  // no key column: every row has key 0
+        }
+        tile.key_and = ka;
+        tile.key_or = ko;
         tile.full = rows == (uint32_t)TP_WTILE;
         tile.s_qs = ring->start[s];
         tile.s_qe = ring->end[s];
@@ -235,18 +239,12 @@ __device__ __forceinline__ void strict_adjust(ProbeTile& t) {
     for (int j = 0; j < PV; j++) { t.qs[j] = wadd(t.qs[j], 1); t.qe[j] = wsub(t.qe[j], 1); }
 }
 
-// All PV keys of every lane of the warp equal one valid key?  (AND == OR over all 256 keys.)  Inactive lanes pass
-// their own neutral values via `active`.
-__device__ __forceinline__ bool warp_uniform_key(const uint32_t (&key)[PV], bool active, uint32_t n_keys, uint32_t* kout) {
-    uint32_t a = 0xFFFFFFFFu, o = 0u;
-    if (active) {
-#pragma unroll
-        for (int j = 0; j < PV; j++) { a &= key[j]; o |= key[j]; }
-    }
-    a = __reduce_and_sync(0xFFFFFFFFu, a);
-    o = __reduce_or_sync(0xFFFFFFFFu, o);
+// All keys of the chunk equal one valid key?  (AND == OR over all of them; rows past the end contribute neutral values.)
+__device__ __forceinline__ bool warp_uniform_key(const ProbeTile& t, uint32_t n_keys, uint32_t* kout) {
+    const uint32_t a = __reduce_and_sync(0xFFFFFFFFu, t.key_and);
+    const uint32_t o = __reduce_or_sync(0xFFFFFFFFu, t.key_or);
     *kout = o;
-    return a == o && o < n_keys;  // (no active lane: a = ~0, o = 0 -> false)
+    return a == o && o < n_keys;  // (no rows: a = ~0, o = 0 -> false)
 }
 
 // Histogram bins live at word i + 4 * (i / 32): 16 pad bytes after every 128.  A lane zeroes and reads back its 8 bins with
@@ -255,6 +253,26 @@ __device__ __forceinline__ bool warp_uniform_key(const uint32_t (&key)[PV], bool
 // profiles/r1_count_v14_ncu.txt), not by DRAM or issue slots.
 __device__ __forceinline__ uint32_t hist_slot(uint32_t bin) { return bin + ((bin >> 5) << 2); }
 __device__ __forceinline__ uint4* hist_lane_bins(uint32_t* aux, int lane) { return reinterpret_cast<uint4*>(aux) + 2 * lane + (lane >> 2); }
+
+// The histogram of an inverse search has one BYTE per padded query slot (288 bytes): a window holds at most TP_WMAX = 128
+// elements, so no bin overflows and the packed prefix sums below stay below 256.  Against 32-bit bins: zeroing is one
+// 128-bit store by 18 lanes (3 wavefronts instead of 8), a lane reads its 8 bins with two 32-bit loads (4 instead of 8), and
+// the serial part of the prefix sum is two multiplications.
+__device__ __forceinline__ void hist8_zero(uint32_t* aux, int lane) {
+    if (lane < 18) reinterpret_cast<uint4*>(aux)[lane] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void hist8_add(uint32_t* aux, uint32_t padded_slot) {
+    atomicAdd(&aux[padded_slot >> 2], 1u << ((padded_slot & 3u) << 3));
+}
+// inclusive prefix sums (within the lane) of the lane's 8 bins, and their total
+__device__ __forceinline__ void hist8_lane_prefix(const uint32_t* aux, int lane, uint32_t (&c)[PV], uint32_t* total) {
+    const uint32_t w = 2 * lane + (lane >> 2);  // the lane's 8 bins start at padded slot 8 * lane + 4 * (lane / 4)
+    const uint32_t p0 = aux[w] * 0x01010101u;
+    const uint32_t p1 = (aux[w + 1] + (p0 >> 24)) * 0x01010101u;  // (the first half's total rides in byte 0: it enters every prefix)
+    c[0] = p0 & 0xFFu; c[1] = (p0 >> 8) & 0xFFu; c[2] = (p0 >> 16) & 0xFFu; c[3] = p0 >> 24;
+    c[4] = p1 & 0xFFu; c[5] = (p1 >> 8) & 0xFFu; c[6] = (p1 >> 16) & 0xFFu; c[7] = p1 >> 24;
+    *total = c[7];
+}
 
 // Rewrites the chunk's start / end columns in shared memory (in place, from the registers) in the padded layout of hist_slot:
 // word i at i + 4 * (i / 32).  The binary searches of the inverse search probe Q[pos + step - 1] with pos a multiple of
@@ -353,9 +371,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
             }
         }
         // ---- inverse search ---------------------------------------------------------------------------------------
-        uint4* a4 = hist_lane_bins(aux, lane);
-        a4[0] = make_uint4(0, 0, 0, 0);
-        a4[1] = make_uint4(0, 0, 0, 0);
+        hist8_zero(aux, lane);
         __syncwarp();
         uint32_t wn = 0;
         bool open = true;
@@ -373,18 +389,15 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
                 // insertion point of v among the 256 sorted queries:  LE: #(Q < v)   LT: #(Q <= v)
                 // (the 8 steps cover Q[0..254]; an in-window element never lies above Q[255] = mx, so pos <= 255 is exact)
                 const uint32_t slot = padded_insertion_slot<LT>(Q, v);
-                if (in) atomicAdd(&aux[slot], 1u);
+                if (in) hist8_add(aux, slot);
             }
         }
         __syncwarp();
         if (!open) {
             cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
             cur.pre = (cur.pos + lane < k.seg_end) ? __ldg(d.A + cur.pos + lane) : INT32_MAX;
-            const uint4 h0 = a4[0], h1 = a4[1];
-            uint32_t c[PV] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-            for (int j = 1; j < PV; j++) c[j] += c[j - 1];
-            uint32_t incl = c[PV - 1];
+            uint32_t c[PV], incl;
+            hist8_lane_prefix(aux, lane, c, &incl);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -456,10 +469,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
     const bool in1 = lo1 + lane < k1.seg_end && (LT1 ? v1 < mx1 : v1 <= mx1);
     const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
     if (m0 == 0xFFFFFFFFu || m1 == 0xFFFFFFFFu) return false;  // a window continues past this round
-    uint4* a0 = hist_lane_bins(aux0, lane);
-    uint4* a1 = hist_lane_bins(aux1, lane);
-    a0[0] = make_uint4(0, 0, 0, 0); a0[1] = make_uint4(0, 0, 0, 0);
-    a1[0] = make_uint4(0, 0, 0, 0); a1[1] = make_uint4(0, 0, 0, 0);
+    hist8_zero(aux0, lane);
+    hist8_zero(aux1, lane);
     __syncwarp();
     if (m0 | m1) {
         uint32_t p0 = 0, p1 = 0;  // padded slots
@@ -471,20 +482,17 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
     }
         BRG_PAD_STEP2(128) BRG_PAD_STEP2(64) BRG_PAD_STEP2(32) BRG_PAD_STEP2(16) BRG_PAD_STEP2(8) BRG_PAD_STEP2(4) BRG_PAD_STEP2(2) BRG_PAD_STEP2(1)
 #undef BRG_PAD_STEP2
-        if (in0) atomicAdd(&aux0[p0], 1u);
-        if (in1) atomicAdd(&aux1[p1], 1u);
+        if (in0) hist8_add(aux0, p0);
+        if (in1) hist8_add(aux1, p1);
     }
     __syncwarp();
     c0.pos = lo0 + __popc(m0); c0.bound = mx0;
     c1.pos = lo1 + __popc(m1); c1.bound = mx1;
     c0.pre = (c0.pos + lane < k0.seg_end) ? __ldg(d0.A + c0.pos + lane) : INT32_MAX;
     c1.pre = (c1.pos + lane < k1.seg_end) ? __ldg(d1.A + c1.pos + lane) : INT32_MAX;
-    const uint4 h00 = a0[0], h01 = a0[1], h10 = a1[0], h11 = a1[1];
-    uint32_t e0[PV] = {h00.x, h00.y, h00.z, h00.w, h01.x, h01.y, h01.z, h01.w};
-    uint32_t e1[PV] = {h10.x, h10.y, h10.z, h10.w, h11.x, h11.y, h11.z, h11.w};
-#pragma unroll
-    for (int j = 1; j < PV; j++) { e0[j] += e0[j - 1]; e1[j] += e1[j - 1]; }
-    uint32_t i0 = e0[PV - 1], i1 = e1[PV - 1];
+    uint32_t e0[PV], e1[PV], i0, i1;
+    hist8_lane_prefix(aux0, lane, e0, &i0);
+    hist8_lane_prefix(aux1, lane, e1, &i1);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), y1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
