@@ -222,9 +222,12 @@ constexpr int PF_WARPS = PF_THREADS / 32;
 #define BRG_PF_CTAS 4
 #endif
 constexpr int PF_U = BRG_PF_U;  // slot steps in flight per iteration of the emit loop
-constexpr int PF_CAP = 2560;  // candidate slots a warp flattens at a time (bytes of the slot -> row map)
+constexpr int PF_CAP = 2304;  // candidate slots a warp flattens at a time (bytes of the slot -> row map); sized so that 4 CTAs fit an SM
+// row r lives at slot r + r / 8: a lane writes the records of its 8 consecutive rows, and unpadded the 32 lanes of one such
+// store instruction (128 bytes apart) would all hit the same banks -- 32 wavefronts per store, 250 conflict wavefronts per chunk
+__device__ __forceinline__ uint32_t flat_row_slot(uint32_t r) { return r + (r >> 3); }
 struct __align__(16) FlatWarp {
-    uint4 row[TP_WTILE + 1];    // per row {P = exclusive prefix of the candidate counts, i0, qs, -}; row[256].x = total
+    uint4 row[TP_WTILE + TP_WTILE / 8 + 2];  // per row {P = exclusive prefix of the candidate counts, i0, qs, -}; row 256: .x = total
     uint8_t rowof[PF_CAP];
 };
 
@@ -280,8 +283,8 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
         for (int j = 1; j < PV; j++) pj[j] = pj[j - 1] + cand[j - 1];
         __syncwarp();  // the previous chunk's readers are done with the shared arrays
 #pragma unroll
-        for (int j = 0; j < PV; j++) sm.row[lane * PV + j] = make_uint4(pj[j], i0[j], (uint32_t)qs[j], 0u);
-        if (lane == 31) sm.row[TP_WTILE] = make_uint4(incl, 0u, 0u, 0u);
+        for (int j = 0; j < PV; j++) sm.row[lane * (PV + 1) + j] = make_uint4(pj[j], i0[j], (uint32_t)qs[j], 0u);  // = flat_row_slot(lane * PV + j)
+        if (lane == 31) sm.row[flat_row_slot(TP_WTILE)] = make_uint4(incl, 0u, 0u, 0u);
         __syncwarp();
         uint32_t* gb = build_idx + base;
         uint32_t* gp = probe_idx + base;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
         uint32_t run = 0;  // pairs of this chunk written so far (warp-uniform)
         uint32_t ra = 0;   // rows [0, ra) are done (warp-uniform)
         while (ra < (uint32_t)TP_WTILE) {
-            const uint32_t Pa = sm.row[ra].x;
+            const uint32_t Pa = sm.row[flat_row_slot(ra)].x;
             // rows [ra, rb) whose candidates fit the slot map together (their prefix is monotone)
             uint32_t fit = 0;
 #pragma unroll
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
             fit = __reduce_add_sync(0xFFFFFFFFu, fit);
             if (fit == 0) {
                 // one row alone exceeds the map: the warp sweeps its range 32 candidates at a time
-                const uint32_t rI0 = sm.row[ra].y, rN = sm.row[ra + 1].x - Pa;
-                const int32_t rQ = (int32_t)sm.row[ra].z;
+                const uint32_t rI0 = sm.row[flat_row_slot(ra)].y, rN = sm.row[flat_row_slot(ra + 1)].x - Pa;
+                const int32_t rQ = (int32_t)sm.row[flat_row_slot(ra)].z;
                 for (uint32_t sb = 0; sb < rN; sb += 32) {
                     const uint32_t s = sb + lane;
                     const bool m = s < rN && __ldg(ix.s_end + rI0 + s) >= rQ;
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
                 continue;
             }
             const uint32_t rb = ra + fit;
-            const uint32_t n_slots = sm.row[rb].x - Pa;
+            const uint32_t n_slots = sm.row[flat_row_slot(rb)].x - Pa;
             if (n_slots) {
                 // ---- slot -> row map: zero, one byte per non-empty row at its first slot, packed prefix-max ---------
                 const uint32_t n_words = (n_slots + 3) >> 2;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
                         const uint32_t s = sb + u * 32 + lane;
                         const bool v = s < n_slots;
                         rr[u] = v ? sm.rowof[s] : ra;
-                        const uint4 rw = sm.row[rr[u]];
+                        const uint4 rw = sm.row[flat_row_slot(rr[u])];
                         const uint32_t i = rw.y + (s + Pa - rw.x);
                         mt[u] = v && __ldg(ix.s_end + i) >= (int32_t)rw.z;
                         pos[u] = v ? __ldg(ix.s_pos + i) : 0u;

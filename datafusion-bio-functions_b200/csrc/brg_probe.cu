@@ -22,6 +22,9 @@
 namespace brg {
 
 constexpr int PB_THREADS = 256;
+#ifndef BRG_NEAREST_THREADS
+#define BRG_NEAREST_THREADS 256
+#endif
 #ifndef BRG_COVERAGE_THREADS
 #define BRG_COVERAGE_THREADS 320  // as BRG_COUNT_THREADS: 96 registers, no spills; 0.521 -> 0.491 ms per 100M probes
 #endif
@@ -434,7 +437,8 @@ __device__ __forceinline__ bool nearest_from_ranks(const IndexView& ix, uint32_t
     return ov || (include_overlaps != 2 && (has_left || has_right));  // 2 = overlaps only
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) nearest_k1_kernel_tiled(IndexView ix, const uint32_t* __restrict__ key,
                                                                          const int32_t* __restrict__ start,
                                                                          const int32_t* __restrict__ end, uint64_t n_rows,
                                                                          int include_overlaps, int strict,
@@ -442,11 +446,11 @@ __global__ void __launch_bounds__(TP_THREADS, 2) nearest_k1_kernel_tiled(IndexVi
                                                                          uint8_t* __restrict__ valid_bytes,
                                                                          int64_t* __restrict__ dist, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
-    uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
-    uint32_t* aux1 = ring->w[threadIdx.x >> 5].aux[1];
-    uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
-    ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256 here: every chunk is full
+    WarpRing* rings = reinterpret_cast<WarpRing*>(smem_raw);  // one per warp of the CTA
+    uint32_t* aux0 = rings[threadIdx.x >> 5].aux[0];
+    uint32_t* aux1 = rings[threadIdx.x >> 5].aux[1];
+    uint32_t* aux2 = rings[threadIdx.x >> 5].aux[2];
+    ProbePipe pipe(rings, key, start, end, n_rows);  // n_rows is a multiple of 256 here: every chunk is full
     ProbeTile t;
     WarpCursor cs, cp, ce;
     cs.reset();
@@ -812,12 +816,23 @@ int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s
     if (tiled_enabled("nearest", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(left_idx) && aligned16(dist) &&
         n >= TP_WTILE) {
         done = (n / TP_WTILE) * TP_WTILE;  // whole chunks only: validity words never straddle the two kernels
-        int rc = tiled_config((const void*)nearest_k1_kernel_tiled);
-        if (rc) return rc;
+        static const int ct = [] { const char* v = getenv("BRG_NEAREST_THREADS"); return v ? atoi(v) : BRG_NEAREST_THREADS; }();
+        int rc = 0;
         TodoList todo;
         if ((rc = todo_alloc(done, &todo, st))) return rc;
-        nearest_k1_kernel_tiled<<<tiled_grid(done, 2), TP_THREADS, sizeof(ProbeRing), st>>>(
-            ix, key, s, e, done, include_overlaps, strict, left_idx, reinterpret_cast<uint8_t*>(valid_bits), dist, todo);
+#define BRG_NEAR_LAUNCH(T)                                                                                                         \
+    {                                                                                                                              \
+        const int smem = (int)sizeof(WarpRing) * ((T) / 32);                                                                       \
+        BRG_CUDA(cudaFuncSetAttribute((const void*)nearest_k1_kernel_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        const uint64_t chunks = (done + TP_WTILE - 1) / TP_WTILE, per_cta = (T) / 32;                                              \
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + per_cta - 1) / per_cta, (uint64_t)kSMs * 2)); \
+        nearest_k1_kernel_tiled<T><<<grid, (T), smem, st>>>(ix, key, s, e, done, include_overlaps, strict, left_idx,               \
+                                                            reinterpret_cast<uint8_t*>(valid_bits), dist, todo);                   \
+    }
+        if (ct == 320) BRG_NEAR_LAUNCH(320)
+        else if (ct == 288) BRG_NEAR_LAUNCH(288)
+        else BRG_NEAR_LAUNCH(256)
+#undef BRG_NEAR_LAUNCH
         BRG_LAUNCH_CHECK();
         nearest_k1_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, include_overlaps, strict, left_idx,
                                                                      valid_bits, dist, todo);
