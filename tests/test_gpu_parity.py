@@ -125,6 +125,29 @@ def test_gpu_sorted_probe_regimes(ctx, regime):
     _compare_all(ctx, bk, bs, be, pk, ps, pe, nk, ks=(3,))
 
 
+@pytest.mark.parametrize("pile", [1, 31, 32, 33, 96, 126, 127, 128, 129, 200])
+def test_gpu_window_piles_in_one_histogram_bin(ctx, pile):
+    """inverse search edge: `pile` build elements share one insertion point among a chunk's 256 sorted queries (the histogram
+    bins are bytes; a window holds at most 127 elements before the chunk is handed to the per-row kernel), in the first,
+    a middle and the last bin, for the start-, end- and prefix-max-keyed searches"""
+    rng = np.random.default_rng(pile)
+    n_rows = 256 * 6
+    for where in (0, 100, 255):
+        # sorted probes, fixed length (ends monotone too); the pile sits between row `where - 1` and row `where` of chunk 2
+        ps = np.arange(n_rows, dtype=np.int64) * 1000 + 10_000
+        pe = ps + 200
+        gap_lo = ps[512 + where] - 700 if where else ps[511] + 300
+        bs_pile = gap_lo + rng.integers(0, 50, pile)            # starts piled into one gap between consecutive probes
+        be_pile = bs_pile + rng.integers(0, 40, pile)
+        bs_far = rng.integers(0, int(ps[-1]) + 5000, 300)       # a sparse background
+        be_far = bs_far + rng.integers(0, 3000, 300)
+        bs = np.concatenate([bs_pile, bs_far]).astype(np.int32)
+        be = np.concatenate([be_pile, be_far]).astype(np.int32)
+        bk = np.zeros(len(bs), np.uint32)
+        pk = np.zeros(n_rows, np.uint32)
+        _compare_all(ctx, bk, bs, be, pk, ps.astype(np.int32), pe.astype(np.int32), 1, ks=(2,))
+
+
 def test_gpu_key_runs_entry_points(ctx):
     """run-length key column (what the host's contig-cache loop yields) == per-row key column"""
     import bio_ranges_b200 as brg
