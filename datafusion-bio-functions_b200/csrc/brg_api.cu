@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <vector>
 
 #include "../../include/bioranges.h"
@@ -33,6 +34,34 @@ struct DevBuf {
         if (b == 0) return 0;
         cudaError_t e = cudaMalloc(&p, b);
         if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaMalloc(") + std::to_string(b) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+        bytes = b;
+        return 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Temporaries of the build / sort + sweep pipelines: stream-ordered allocations from the device's default pool, whose release
+// threshold is "keep" (brg_ctx_create), so after the first call an allocation is a pointer bump instead of a cudaMalloc +
+// cudaFree pair (each of which costs 0.1 - 0.3 ms and synchronises the device; ~25 of them per build).
+// A ScratchScope names the stream the buffers of the enclosing function live on.
+static thread_local cudaStream_t tls_scratch_stream = nullptr;
+struct ScratchScope {
+    cudaStream_t prev;
+    explicit ScratchScope(cudaStream_t st) : prev(tls_scratch_stream) { tls_scratch_stream = st; }
+    ~ScratchScope() { tls_scratch_stream = prev; }
+};
+struct ScratchBuf {
+    void* p = nullptr;
+    uint64_t bytes = 0;
+    cudaStream_t st = nullptr;
+    ~ScratchBuf() { if (p) cudaFreeAsync(p, st); }
+    int ensure(uint64_t b) {
+        if (b <= bytes) return 0;
+        if (p) { cudaFreeAsync(p, st); p = nullptr; bytes = 0; }
+        if (b == 0) return 0;
+        st = tls_scratch_stream;
+        cudaError_t e = cudaMallocAsync(&p, b, st);
+        if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaMallocAsync(") + std::to_string(b) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
         bytes = b;
         return 0;
     }
@@ -362,7 +391,7 @@ static void pinned_put(brg_ctx* c, PinnedBlock b) {
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
 
 struct DirBuild {
-    DevBuf kd;         // KeyDir[n_keys]
+    ScratchBuf kd;         // KeyDir[n_keys]
     uint32_t shift = 0;
     uint32_t entries = 0;
 };
@@ -408,6 +437,18 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     BRG_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->build_stream;
     want &= BRG_WANT_ALL;
+    ScratchScope scratch_scope(st);
+    // BRG_BUILD_TRACE=1: wall-clock time of the build stages on stderr (each mark synchronises the stream)
+    static const bool trace = getenv("BRG_BUILD_TRACE") != nullptr;
+    static const bool trace_sync = trace && getenv("BRG_BUILD_TRACE")[0] != '2';  // 2: host-side timestamps only
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        if (trace_sync) cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[brg_build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     const bool full = (want & (BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0;
     const bool need_soa = (want & BRG_WANT_PAIRS) != 0;     // s_end / s_pos as plain arrays (pair walk)
     const bool need_rec = (want & BRG_WANT_NEAREST) != 0;   // s_rec / e_rec
@@ -417,7 +458,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
 
     // ---- temporaries: two ping-pong row sets (key,start,end,pos) + scan/histogram scratch -----------
     const uint64_t nn = std::max<uint64_t>(n, 1);
-    DevBuf setA[4], setB[4], hist, scan, small;
+    ScratchBuf setA[4], setB[4], hist, scan, small;
     int rc;
     for (int i = 0; i < 4; i++) {
         if ((rc = setA[i].ensure(nn * 4))) return rc;
@@ -429,6 +470,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     unsigned long long* d_bins = small.as<unsigned long long>();           // 32 x u64
     uint32_t* d_scalar = reinterpret_cast<uint32_t*>(small.as<char>() + 512);  // misc u32 results
 
+    mark("alloc temporaries");
     uint32_t* a[4] = {setA[0].as<uint32_t>(), setA[1].as<uint32_t>(), setA[2].as<uint32_t>(), setA[3].as<uint32_t>()};
     uint32_t* b[4] = {setB[0].as<uint32_t>(), setB[1].as<uint32_t>(), setB[2].as<uint32_t>(), setB[3].as<uint32_t>()};
     if (n) {
@@ -450,9 +492,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     if (rc) return rc;
     uint32_t** S = res == 0 ? a : b;   // sorted rows
     uint32_t** T = res == 0 ? b : a;   // free set
+    mark("S-order sort");
 
     // segment offsets per key; rows with key >= n_keys form the ignored tail
-    DevBuf off, m_off;
+    ScratchBuf off, m_off;
     if ((rc = off.ensure(((uint64_t)n_keys + 2) * 4))) return rc;
     if ((rc = segment_offsets(S[0], n, n_keys, off.as<uint32_t>(), st))) return rc;
     uint32_t n_valid = 0;
@@ -470,14 +513,14 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     }
 
     // prefix_max_end over the S-order (per key)
-    DevBuf pme;
+    ScratchBuf pme;
     if (need_pme) {
         if ((rc = pme.ensure(nn * 4))) return rc;
         if ((rc = segmented_running_max(S[0], (const int32_t*)S[2], pme.as<int32_t>(), n_valid, scan.as<int32_t>(), st))) return rc;
     }
 
     // merged intervals (coverage)
-    DevBuf m_first, m_last, m_key, m_pre, m_rec;
+    ScratchBuf m_first, m_last, m_key, m_pre, m_rec;
     uint32_t n_merged = 0;
     if (need_cov) {
         if ((rc = m_first.ensure(nn * 4)) || (rc = m_last.ensure(nn * 4)) || (rc = m_key.ensure(nn * 4)) ||
@@ -499,8 +542,9 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
             return rc;
     }
 
+    mark("pme / merge");
     // keep the S-order columns: they are consumed by the E-order sort below
-    DevBuf s_start, s_end, s_pos, s_rec, e_rec;
+    ScratchBuf s_start, s_end, s_pos, s_rec, e_rec;
     if ((rc = s_start.ensure(nn * 4))) return rc;
     BRG_CUDA(cudaMemcpyAsync(s_start.p, S[1], (uint64_t)n_valid * 4, cudaMemcpyDeviceToDevice, st));
     if (need_soa) {
@@ -531,6 +575,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
             return rc;
     }
 
+    mark("E-order sort");
     // ---- rank directories ----------------------------------------------------------------------------------
     DirBuild db[5];
     const bool need_dir[5] = {(want & (BRG_WANT_COUNT | BRG_WANT_NEAREST | BRG_WANT_PAIRS)) != 0, need_e,
@@ -545,9 +590,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         if ((rc = dir_plan(dirA[i], dirOff[i], n_keys, dirN[i], &db[i], d_bins, d_scalar, st))) return rc;
     }
 
+    mark("directory plans");
     // ---- compact rank index of s_start / e_end: the L2-resident structure of the per-row count kernels -------
     const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0;
-    DevBuf boff_d, cS[2], cB[2];
+    ScratchBuf boff_d, cS[2], cB[2];
     DirBuild cdb[2];
     uint32_t n_blocks = 0;
     if (need_ci) {
@@ -571,6 +617,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         BRG_CUDA(cudaStreamSynchronize(st));  // h_boff is read by the copy above
     }
 
+    mark("compact rank index");
     // ---- lay out and fill the slab -------------------------------------------------------------------------
     IndexHeader h{};
     h.magic = kMagic; h.version = 3;
@@ -649,7 +696,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     }
     if (need_ci)
         for (int a = 0; a < 2; a++) {
-            DevBuf dtmp;  // plain table first, then packed into the slab
+            ScratchBuf dtmp;  // plain table first, then packed into the slab
             if ((rc = dtmp.ensure(((uint64_t)cdb[a].entries + 1) * 4))) { cudaFree(slab); return rc; }
             rc = dir_fill(cS[a].as<int32_t>(), cdb[a].kd.as<KeyDir>(), n_keys, cdb[a].shift, dtmp.as<uint32_t>(), cdb[a].entries, st);
             if (!rc) rc = ci_pack_table(dtmp.as<uint32_t>(), cdb[a].entries, (uint32_t*)(base + h.cdir[a].off_D), st);
@@ -660,6 +707,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { cudaFree(slab); set_error(std::string("build sync: ") + cudaGetErrorString(e)); return BRG_ERR_CUDA; }
     }
+    mark("slab fill");
     brg_index* ix = new brg_index();
     ix->ctx = ctx; ix->h = h; ix->slab = slab; ix->view = make_view(h, slab);
     *out = ix;
@@ -672,12 +720,13 @@ extern "C" BRG_API int brg_build(brg_ctx* ctx, const uint32_t* key, const int32_
     *out = nullptr;
     if (n > 0 && (!start || !end)) { set_error("brg_build: NULL column"); return BRG_ERR_INVALID; }
     BRG_CUDA(cudaSetDevice(ctx->device));
-    DevBuf dk, ds, de;
+    cudaStream_t st = ctx->build_stream;
+    ScratchScope scratch_scope(st);
+    ScratchBuf dk, ds, de;
     int rc;
     const uint64_t bytes = std::max<uint64_t>(n, 1) * 4;
     if ((rc = ds.ensure(bytes)) || (rc = de.ensure(bytes))) return rc;
     if (key && (rc = dk.ensure(bytes))) return rc;
-    cudaStream_t st = ctx->build_stream;
     if (n) {
         if (key) BRG_CUDA(cudaMemcpyAsync(dk.p, key, n * 4, cudaMemcpyHostToDevice, st));
         BRG_CUDA(cudaMemcpyAsync(ds.p, start, n * 4, cudaMemcpyHostToDevice, st));
@@ -1244,7 +1293,8 @@ extern "C" BRG_API int brg_sort_rows(brg_ctx* ctx, const uint32_t* key, const in
     if (n == 0) return BRG_OK;
     BRG_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->build_stream;
-    DevBuf in[3], setA[4], setB[4], hist, scan;
+    ScratchScope scratch_scope(st);
+    ScratchBuf in[3], setA[4], setB[4], hist, scan;
     int rc;
     for (int i = 0; i < 3; i++) if ((rc = in[i].ensure(n * 4))) return rc;
     for (int i = 0; i < 4; i++) if ((rc = setA[i].ensure(n * 4)) || (rc = setB[i].ensure(n * 4))) return rc;
@@ -1346,7 +1396,8 @@ extern "C" BRG_API int brg_cluster(brg_ctx* ctx, const uint32_t* key, const int3
 // complement with the merged intervals (m of them, key order) on the device: count -> scan -> emit over the views
 static int complement_views(brg_ctx* ctx, const uint32_t* m_key, const int32_t* m_first, const int32_t* m_last, uint64_t m,
                             uint32_t n_keys, const ViewArgs& va, uint32_t* scan_scratch, cudaStream_t st) {
-    DevBuf v_key, v_start, v_end, m_off, g_tmp, G, plan, counts, offsets, scan64, o_view, o_start, o_end;
+    ScratchScope scratch_scope(st);
+    ScratchBuf v_key, v_start, v_end, m_off, g_tmp, G, plan, counts, offsets, scan64, o_view, o_start, o_end;
     int rc;
     const uint64_t nv = va.n;
     if ((rc = v_key.ensure(nv * 4)) || (rc = v_start.ensure(nv * 8)) || (rc = v_end.ensure(nv * 8)) ||
@@ -1395,16 +1446,17 @@ static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* star
     brg_merged* r = new brg_merged();
     r->ctx = ctx;
     cudaStream_t st = ctx->build_stream;
+    ScratchScope scratch_scope(st);
     if (n == 0) {
         *out = r;
         if (!views) return BRG_OK;
-        DevBuf scan0;  // no input rows: no merged intervals, every view is answered from its own bounds
+        ScratchBuf scan0;  // no input rows: no merged intervals, every view is answered from its own bounds
         int rc0 = scan0.ensure(64);
         if (!rc0) rc0 = complement_views(ctx, nullptr, nullptr, nullptr, 0, n_keys, *views, scan0.as<uint32_t>(), st);
         if (rc0) cudaStreamSynchronize(st);
         return rc0;
     }
-    DevBuf in[3], setA[4], setB[4], hist, scan, small, pme, flags, midx, m_key, m_first, m_last, m_row0, m_count;
+    ScratchBuf in[3], setA[4], setB[4], hist, scan, small, pme, flags, midx, m_key, m_first, m_last, m_row0, m_count;
     int rc;
     auto fail = [&](int code) { cudaStreamSynchronize(st); brg_merged_release(r); return code; };
     for (int i = 0; i < 3; i++) if ((rc = in[i].ensure(n * 4))) return fail(rc);
@@ -1462,7 +1514,7 @@ static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* star
         // one result row per input row, in (key, start, end, row) order:
         //   key -> original row id, start / end -> extent of the row's run, count -> run id (global, key order)
         // flags / midx stay as they are; the run heads move out of the way first (m_count, m_row0, pme as outputs)
-        DevBuf c_start, c_end;
+        ScratchBuf c_start, c_end;
         if ((rc = c_start.ensure(n * 4)) || (rc = c_end.ensure(n * 4))) return fail(rc);
         if ((rc = cluster_rows(flags.as<uint32_t>(), midx.as<uint32_t>(), m_first.as<int32_t>(), m_last.as<int32_t>(), n,
                                m_count.as<uint32_t>(), c_start.as<int32_t>(), c_end.as<int32_t>(), st)))
