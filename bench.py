@@ -257,6 +257,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    near_cores = 0
+    if world > 1:  # (N = 1 keeps every host core for the CPU arm)
+        from bio_ranges_b200.sharding import bind_near_gpu
+
+        near_cores = bind_near_gpu(local_rank)
+        config["host_affinity"] = f"each rank bound to the {near_cores} cores next to its GPU (NVML)" if near_cores else "unbound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     import bio_ranges_b200 as brg

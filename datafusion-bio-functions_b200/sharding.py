@@ -28,6 +28,30 @@ def shard_range(n_rows, rank, world):
     return shard_bounds(n_rows, world)[rank]
 
 
+def bind_near_gpu(local_rank):
+    """One process per GPU: restrict this process to the CPU cores next to its GPU (NVML's ideal affinity), so that the pinned
+    staging buffers it allocates afterwards are first-touched on the GPU's NUMA node.  With several ranks streaming probe
+    tables over PCIe at once, buffers that all sit on one node cap the end-to-end rate of the whole box.  Returns the
+    number of cores the process is bound to, or 0 when NVML is not usable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local_rank)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return 0
+
+
 def replicate_index(ctx, index, dist, rank, world, device, src=0):
     """Every rank returns an index equal to rank `src`'s.  `index` is only read on rank `src`."""
     import torch
