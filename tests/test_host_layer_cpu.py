@@ -82,6 +82,26 @@ def test_udtf_argument_grammar_errors():
     ctx.close()
 
 
+def test_sweep_function_argument_errors():
+    """merge / cluster / complement argument grammar (table_function.rs:236-241, 472-520, 615-767): raised before any device work"""
+    ctx = S.create_bio_session()
+    ctx.register_table("a", _tbl([("chr1", 1, 5)]))
+    st, msg = _err(ctx.merge, "a", min_dist=-1)
+    assert st == S.PLAN and "merge() min_dist must be >= 0, got -1" in msg
+    st, msg = _err(ctx.cluster, "a", "x", "y")
+    assert st == S.PLAN and "cluster() expects 0 or 3 column name arguments (got 2)" in msg
+    st, msg = _err(ctx.complement, "a", "views", "c")
+    assert st == S.PLAN and "complement() unexpected number of arguments (2 extra args after table name)" in msg
+    assert "Usage: complement('table' [, 'view_table'] [, col1, col2, col3 [, vcol1, vcol2, vcol3]] [, 'strict'|'weak'])" in msg
+    st, msg = _err(ctx.complement, "a", "views", "c", "s", "e", "strict", "x", "y", "z", "w")
+    assert st == S.PLAN and "9 extra args" in msg  # (a trailing 'strict' is only recognised in last position)
+    st, msg = _err(ctx.complement, "nope")
+    assert st == S.PLAN and "table 'nope' not found" in msg
+    st, msg = _err(ctx.complement, "a", "no_view")
+    assert st == S.PLAN and "table 'no_view' not found" in msg
+    ctx.close()
+
+
 def test_resolve_positions_like_posarray_resolve():
     """array_utils.rs:73-131"""
     b = pa.record_batch({"i32": pa.array([1, -5, 2**31 - 1], pa.int32()), "i64": pa.array([1, 2, 3], pa.int64()),
