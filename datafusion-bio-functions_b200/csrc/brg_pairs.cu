@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
     uint32_t* aux2 = ring->w[threadIdx.x >> 5].aux[2];
     ProbePipe pipe(ring, key, start, end, n_rows);  // n_rows is a multiple of 256: every chunk is full
     ProbeTile t;
-    WarpCursor cs, cp, ce;
+    WarpCursorFar cs, cp, ce;  // all three are served by single searches
     cs.reset(); cp.reset(); ce.reset();
     KeyDir ks, kp, ke;
     uint32_t kd_key = 0xFFFFFFFFu;

@@ -312,15 +312,27 @@ __device__ __forceinline__ uint32_t padded_insertion_slot(const int32_t* Q, int3
 // ---- warp cursor over one sorted array ---------------------------------------------------------------------------
 // Invariant while valid: every element of key `key`'s segment before `pos` is <= bound (LT: < bound), hence `pos` is a
 // legal window start for any tile whose smallest query is >= bound.
-struct WarpCursor {
+template <bool FAR>
+struct WarpCursorT {
+    static constexpr bool kFar = FAR;
     uint32_t pos;
     int32_t bound;
     uint32_t key;
     bool valid;
     bool wide;    // the last failure was a window wider than TP_WMAX: a property of the region, not of one chunk
     int32_t pre;  // prefetched A[pos + lane] (or +inf past the segment): the first 32 window candidates of the next chunk
-    __device__ __forceinline__ void reset() { valid = false; wide = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; pre = INT32_MAX; }
+    int32_t far;  // FAR only: prefetched A[pos + TP_WMAX - 1] (or +inf): decides "window too wide" without a dependent load
+    __device__ __forceinline__ void reset() { valid = false; wide = false; pos = 0; bound = 0; key = 0xFFFFFFFFu; pre = INT32_MAX; far = INT32_MAX; }
+    // (after pos changed) loads what the next chunk's search looks at first
+    __device__ __forceinline__ void prefetch(const int32_t* A, uint32_t seg_end, int lane) {
+        pre = (pos + lane < seg_end) ? __ldg(A + pos + lane) : INT32_MAX;
+        if (FAR) far = (pos + (uint32_t)TP_WMAX - 1 < seg_end) ? __ldg(A + pos + (uint32_t)TP_WMAX - 1) : INT32_MAX;
+    }
 };
+// The far prefetch pays where cursors are served by the single search (nearest: 0.767 -> 0.700 ms); kernels whose cursors
+// go through the interleaved dual search, which never looks at the far element, lose 1-2 % (and registers) to it.
+using WarpCursor = WarpCursorT<false>;
+using WarpCursorFar = WarpCursorT<true>;
 
 // are the chunk's 256 query values non-decreasing in row order?  (only full chunks qualify)
 __device__ __forceinline__ bool chunk_mono(const int32_t (&q)[PV], bool full) {
@@ -338,8 +350,8 @@ __device__ __forceinline__ bool chunk_mono(const int32_t (&q)[PV], bool full) {
 // unspecified ranks.  Returns false when the chunk's window does not fit the shared buffers (the caller defers the chunk
 // to the per-row kernel).  mono = chunk_mono(q).  Q = the chunk's 256 query values in shared memory (same values as q,
 // row-major), only read when mono.  aux = this warp's 256-word scratch for this array.
-template <bool LT>
-__device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+template <bool LT, typename CUR>
+__device__ __forceinline__ bool warp_window_ranks(CUR& cur, const DirView& d, const KeyDir& k, uint32_t kid,
                                                   const int32_t (&q)[PV], bool active, bool mono, const int32_t* Q,
                                                   uint32_t* aux, uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
@@ -369,7 +381,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
         {
             const uint32_t far = lo + (uint32_t)TP_WMAX - 1;
             if (far < k.seg_end) {
-                const int32_t vf = __ldg(d.A + far);
+                const int32_t vf = (CUR::kFar && reuse) ? cur.far : __ldg(d.A + far);  // (reuse: loaded while the previous chunk was being finished)
                 if (LT ? vf < mx : vf <= mx) { cur.valid = false; cur.wide = true; return false; }
             }
         }
@@ -398,7 +410,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
         __syncwarp();
         if (!open) {
             cur.pos = lo + wn; cur.bound = mx; cur.key = kid; cur.valid = true;
-            cur.pre = (cur.pos + lane < k.seg_end) ? __ldg(d.A + cur.pos + lane) : INT32_MAX;
+            cur.prefetch(d.A, k.seg_end, lane);
             uint32_t c[PV], incl;
             hist8_lane_prefix(aux, lane, c, &incl);
 #pragma unroll
@@ -418,7 +430,7 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
         const uint32_t hi = LT ? rank_lt_kd(d, k, mx) : rank_le_kd(d, k, mx);
         const uint32_t wn = hi - lo;
         cur.pos = hi; cur.bound = mx; cur.key = kid; cur.valid = true;
-        cur.pre = (hi + lane < k.seg_end) ? __ldg(d.A + hi + lane) : INT32_MAX;
+        cur.prefetch(d.A, k.seg_end, lane);
         if (wn == 0) {
 #pragma unroll
             for (int j = 0; j < PV; j++) r[j] = lo;
@@ -455,9 +467,9 @@ __device__ __forceinline__ bool warp_window_ranks(WarpCursor& cur, const DirView
 // of the two arrays interleaved doubles the instruction-level parallelism of the warp.  Returns false WITHOUT touching
 // cursors or results when the case does not apply (a cursor that cannot be reused, a window wider than one round); the caller
 // then runs the two searches one after the other.  Preconditions: full chunk, q0 and q1 non-decreasing.
-template <bool LT0, bool LT1>
-__device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView& d0, const KeyDir& k0, const int32_t (&q0)[PV],
-                                                   const int32_t* Q0, uint32_t* aux0, uint32_t (&r0)[PV], WarpCursor& c1,
+template <bool LT0, bool LT1, typename CUR0, typename CUR1>
+__device__ __forceinline__ bool warp_window_ranks2(CUR0& c0, const DirView& d0, const KeyDir& k0, const int32_t (&q0)[PV],
+                                                   const int32_t* Q0, uint32_t* aux0, uint32_t (&r0)[PV], CUR1& c1,
                                                    const DirView& d1, const KeyDir& k1, const int32_t (&q1)[PV],
                                                    const int32_t* Q1, uint32_t* aux1, uint32_t (&r1)[PV], uint32_t kid) {
     const int lane = threadIdx.x & 31;
@@ -491,8 +503,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
     __syncwarp();
     c0.pos = lo0 + __popc(m0); c0.bound = mx0;
     c1.pos = lo1 + __popc(m1); c1.bound = mx1;
-    c0.pre = (c0.pos + lane < k0.seg_end) ? __ldg(d0.A + c0.pos + lane) : INT32_MAX;
-    c1.pre = (c1.pos + lane < k1.seg_end) ? __ldg(d1.A + c1.pos + lane) : INT32_MAX;
+    c0.prefetch(d0.A, k0.seg_end, lane);
+    c1.prefetch(d1.A, k1.seg_end, lane);
     uint32_t e0[PV], e1[PV], i0, i1;
     hist8_lane_prefix(aux0, lane, e0, &i0);
     hist8_lane_prefix(aux1, lane, e1, &i1);
@@ -514,7 +526,8 @@ __device__ __forceinline__ bool warp_window_ranks2(WarpCursor& c0, const DirView
 //                   in (qs, qe] -- their number is the number of build values inside the probe interval.  Rows that need
 //                   more than TP_SCAN_MAX steps, and degenerate rows (qe < qs), ask the rank directory.
 // Same contract as warp_window_ranks.
-__device__ __forceinline__ bool warp_ranks_le_end(WarpCursor& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+template <typename CUR>
+__device__ __forceinline__ bool warp_ranks_le_end(CUR& cur, const DirView& d, const KeyDir& k, uint32_t kid,
                                                   const int32_t (&qs)[PV], const int32_t (&qe)[PV], bool active, bool mono_s,
                                                   bool mono_e, const int32_t* Qs, const int32_t* Qe, uint32_t* aux,
                                                   uint32_t (&r)[PV]) {
