@@ -272,6 +272,8 @@ __device__ __forceinline__ uint32_t rank_lt_kd(const DirView& d, const KeyDir& k
 }
 
 // seg_begin(A) + #(A <= q) within a key, through the compact index; k = the key's constants (shared or global memory)
+// (the delta blocks are loaded with ld.global.cg: every lane reads a different one, an L1 line allocation per lane buys nothing
+//  -- shuffled 125M-probe count 3.35 -> 3.26 ms; the packed table keeps ld.global.nc, its hot entries do hit in L1)
 __device__ __forceinline__ uint32_t rank_le_compact(const CompactView& c, const CompactKey& k, int32_t q) {
     if (k.nb == 0 || q < k.lo) return k.eb;
     // J = last block whose first element is <= q
@@ -280,7 +282,7 @@ __device__ __forceinline__ uint32_t rank_le_compact(const CompactView& c, const 
     uint4 w;
     if (bin >= k.nb) {
         J = k.blk_end - 1;
-        w = __ldg(c.blocks + J);
+        w = __ldcg(c.blocks + J);
     } else {
         const uint32_t e = __ldg(c.d.D + k.base + bin);
         const uint32_t j0 = e >> 2;
@@ -290,12 +292,12 @@ __device__ __forceinline__ uint32_t rank_le_compact(const CompactView& c, const 
         if (cnt) {
             if (cnt == 3u) cnt = (__ldg(c.d.D + k.base + bin + 1) >> 2) - j0;  // saturated: the real count
             for (uint32_t j = j0; j < j0 + cnt; j++) {  // block starts inside the bin: one, seldom more
-                const uint4 t = __ldg(c.blocks + j);
+                const uint4 t = __ldcg(c.blocks + j);
                 if ((int32_t)t.x > q) break;
                 J = j; w = t; found = true;
             }
         }
-        if (!found) w = __ldg(c.blocks + J);
+        if (!found) w = __ldcg(c.blocks + J);
     }
     const uint32_t e0 = k.eb + (J - k.blk_begin) * CI_BLOCK;
     if ((w.y & 0xFFFFu) == 0xFFFFu) {  // wide block: search the elements themselves
