@@ -579,6 +579,19 @@ __device__ __forceinline__ void store_chunk_i64_from32(uint32_t* x, int64_t* out
     }
     __syncwarp();
 }
+// the second half of store_chunk_i64_from32: the 256 32-bit values are already staged (value of row r at word hist_slot(r))
+__device__ __forceinline__ void store_chunk_i64_staged32(uint32_t* x, int64_t* out, bool sign_extend) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    longlong2* o2 = reinterpret_cast<longlong2*>(out) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2 w = *reinterpret_cast<const uint2*>(x + hist_slot(2u * (k * 32 + lane)));
+        __stcs(o2 + k * 32, sign_extend ? make_longlong2((long long)(int32_t)w.x, (long long)(int32_t)w.y)
+                                        : make_longlong2((long long)w.x, (long long)w.y));
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void store_chunk_i64(uint32_t* x, int64_t* out, const long long (&v)[PV]) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
