@@ -17,7 +17,13 @@ namespace brg {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+#ifndef BRG_RS_ITEMS
+#define BRG_RS_ITEMS 16
+#endif
+#ifndef BRG_RS_MINB
+#define BRG_RS_MINB 3  // resident CTAs per SM of the scatter kernel: 80 registers; it is latency-bound (ncu: issue slots 9 % busy at 2 CTAs)
+#endif
+constexpr int RS_ITEMS = BRG_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 rows per CTA
 constexpr int RS_MAX_ARR = 4;
 
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     hist[(uint64_t)t * n_tiles + blockIdx.x] = h[t];  // digit-major table
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(SortArrays arr, uint64_t n, SortPass pass,
+__global__ void __launch_bounds__(RS_THREADS, BRG_RS_MINB) radix_scatter_kernel(SortArrays arr, uint64_t n, SortPass pass,
                                                                    uint32_t n_tiles,
                                                                    const uint32_t* __restrict__ hist_scanned) {
     __shared__ uint32_t wc[RS_WARPS][256];  // per-warp digit counters -> per-warp exclusive offsets
