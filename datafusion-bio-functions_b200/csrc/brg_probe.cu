@@ -138,17 +138,20 @@ __global__ void __launch_bounds__(THREADS, BRG_CC_CTAS) count_kernel_tiled(Index
             }
         }
         if (ok) {
-            long long cnt[PV];
+            // end < start -> 0 (interval_tree.rs:42-44); otherwise (started - ended_before) as i64 (:46-48), which is negative
+            // when build rows with start > end make more ends than starts precede the probe.  With fewer than 2^31 build rows
+            // the difference is exact as a signed 32-bit value, which is what the transposed store widens.
+            uint32_t c32[PV];
 #pragma unroll
-            for (int j = 0; j < PV; j++)  // end < start -> 0 (interval_tree.rs:42-44)
-                cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
-            if (t.full) {
-                uint32_t c32[PV];
+            for (int j = 0; j < PV; j++) c32[j] = (t.qe[j] < t.qs[j]) ? 0u : started[j] - ended[j];
+            if (t.full && ix.n < 0x80000000u) {
+                store_chunk_i64_from32(aux0, out + (t.row0 - (threadIdx.x & 31) * PV), c32, true);
+            } else if (t.active) {
+                long long cnt[PV];
 #pragma unroll
-                for (int j = 0; j < PV; j++) c32[j] = (uint32_t)cnt[j];  // 0 <= count <= build rows < 2^32
-                store_chunk_i64_from32(aux0, out + (t.row0 - (threadIdx.x & 31) * PV), c32, false);
-            } else
-            if (t.active) store8_i64(out + t.row0, cnt);
+                for (int j = 0; j < PV; j++) cnt[j] = (t.qe[j] < t.qs[j]) ? 0ll : (long long)started[j] - (long long)ended[j];
+                store8_i64(out + t.row0, cnt);
+            }
             fails = 0;
         } else {
             // mixed keys (contig boundary, unsorted input), keys absent from the build side, or a window wider than the

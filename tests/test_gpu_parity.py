@@ -148,6 +148,31 @@ def test_gpu_window_piles_in_one_histogram_bin(ctx, pile):
         _compare_all(ctx, bk, bs, be, pk, ps.astype(np.int32), pe.astype(np.int32), 1, ks=(2,))
 
 
+def test_gpu_count_with_inverted_build_rows(ctx):
+    """build rows with start > end: `(started - ended_before) as i64` (interval_tree.rs:46-48) goes negative where more ends
+    than starts precede the probe; sorted probes (the tiled kernel's transposed 32-bit staging) and shuffled ones (per row)"""
+    rng = np.random.default_rng(99)
+    nk, nb, npb = 3, 20_000, 60_000
+    bk, bs, be = _rand(rng, nb, nk, 0, 1_000_000, 400)
+    inv = rng.random(nb) < 0.3
+    bs2, be2 = np.where(inv, be + 5000, bs).astype(np.int32), np.where(inv, bs, be).astype(np.int32)  # start > end on 30 % of the rows
+    pk, ps, pe = _sorted_probes(rng, npb, nk, 1_000_000, 1, 300)
+    gi = ctx.build(bk, bs2, be2, nk, brg_want_count())
+    oi = O.OracleIndex(bk, bs2, be2, nk)
+    want = oi.count_overlaps(pk, ps, pe)
+    assert (want < 0).any() and (want > 0).any()
+    assert (gi.count_overlaps(pk, ps, pe) == want).all()
+    perm = rng.permutation(npb)
+    assert (gi.count_overlaps(pk[perm], ps[perm], pe[perm]) == want[perm]).all()
+    gi.close()
+
+
+def brg_want_count():
+    import bio_ranges_b200 as brg
+
+    return brg.WANT_COUNT
+
+
 def test_gpu_key_runs_entry_points(ctx):
     """run-length key column (what the host's contig-cache loop yields) == per-row key column"""
     import bio_ranges_b200 as brg
