@@ -47,14 +47,24 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     h[t] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
+    // all loads first (the kernel was bound by the latency of load -> match.any -> atomic chains, ncu: issue slots 11 % busy)
+    uint32_t d[RS_ITEMS];
+#pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
-        uint64_t i = base + (uint64_t)j * RS_THREADS + t;
-        bool valid = i < n;
-        uint32_t d = valid ? digit_of(__ldg(src + i), pass) : 0x100u;
-        // warp-level histogram: one shared atomic per distinct digit in the warp
-        uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        if (valid && (__ffs(peers) - 1) == (t & 31)) atomicAdd(&h[d], __popc(peers));
+        const uint64_t i = base + (uint64_t)j * RS_THREADS + t;
+        d[j] = i < n ? digit_of(__ldg(src + i), pass) : 0x100u;
+    }
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        // a warp whose 32 digits agree (the high bytes of sorted or clustered coordinates) adds once; otherwise one shared
+        // atomic per lane: random digits rarely collide, and match.any costs more than the few serialised collisions
+        int all_same;
+        __match_all_sync(0xFFFFFFFFu, d[j], &all_same);
+        if (all_same) {
+            if ((t & 31) == 0 && d[j] < 256u) atomicAdd(&h[d[j]], 32u);
+        } else if (d[j] < 256u) {
+            atomicAdd(&h[d[j]], 1u);
+        }
     }
     __syncthreads();
     hist[(uint64_t)t * n_tiles + blockIdx.x] = h[t];  // digit-major table
