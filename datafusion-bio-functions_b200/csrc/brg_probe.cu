@@ -22,6 +22,9 @@
 namespace brg {
 
 constexpr int PB_THREADS = 256;
+#ifndef BRG_NEAREST_PREFETCH
+#define BRG_NEAREST_PREFETCH 1
+#endif
 #ifndef BRG_NEAREST_THREADS
 #define BRG_NEAREST_THREADS 256
 #endif
@@ -529,6 +532,16 @@ __global__ void __launch_bounds__(THREADS, 2) nearest_k1_kernel_tiled(IndexView 
             }
         }
         if (ok) {
+#if BRG_NEAREST_PREFETCH
+            // The candidate records of the NEXT chunk sit where this chunk's windows ended (the cursors): s_rec / e_rec are
+            // 160 MB for 5M build rows, more than the L2 keeps next to the probe stream, so the first touch of each record
+            // would wait for DRAM in the middle of the next chunk's epilogue.
+            {
+                const uint32_t lane_ = threadIdx.x & 31, last_ = ks.seg_end ? ks.seg_end - 1 : 0u;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.s_rec + min(cs.pos + lane_, last_)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.e_rec + min(ce.pos + lane_, last_)));
+            }
+#endif
             uint32_t pos[PV];
             long long dd[PV];
             uint32_t bits = 0;
