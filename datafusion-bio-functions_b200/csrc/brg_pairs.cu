@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
 
 constexpr int PF_THREADS = 256;
 constexpr int PF_WARPS = PF_THREADS / 32;
+#ifndef BRG_PF_PREFETCH
+#define BRG_PF_PREFETCH 1
+#endif
 #ifndef BRG_PF_U
 #define BRG_PF_U 4
 #endif
@@ -271,6 +274,20 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
         uint32_t lane_tot = 0;
 #pragma unroll
         for (int j = 0; j < PV; j++) { cand[j] = cand[j] > i0[j] ? cand[j] - i0[j] : 0u; lane_tot += cand[j]; }
+#if BRG_PF_PREFETCH
+        {   // the build rows the chunk is going to gather: prefetched now, needed after the slot map is built
+            uint32_t wlo = 0xFFFFFFFFu, whi = 0u;
+#pragma unroll
+            for (int j = 0; j < PV; j++)
+                if (cand[j]) { wlo = min(wlo, i0[j]); whi = max(whi, i0[j] + cand[j]); }
+            wlo = __reduce_min_sync(0xFFFFFFFFu, wlo);
+            whi = __reduce_max_sync(0xFFFFFFFFu, whi);
+            for (uint32_t e = (wlo & ~31u) + lane * 32u; e < whi; e += 32u * 32u) {  // one 128-byte line per lane and step
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.s_end + e));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.s_pos + e));
+            }
+        }
+#endif
         uint32_t incl = lane_tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
