@@ -505,7 +505,14 @@ static ChunkPlan plan_chunks(const IndexView& ix, const uint32_t* key, const int
     p.n_chunks = (n + TP_WTILE - 1) / TP_WTILE;
     p.full_rows = (n / TP_WTILE) * TP_WTILE;
     p.tail_chunk = (n % TP_WTILE) ? (uint32_t)(p.n_chunks - 1) : 0xFFFFFFFFu;
-    p.tiled = pairs_tiled_enabled() && p.full_rows > 0 && aligned16p(key) && aligned16p(s) && aligned16p(e) &&
+    // A build side with at least as many rows as the probe table puts more than TP_WMAX elements under most chunks (unless the
+    // probe table covers only a slice of the build side's coordinate range, which the row counts cannot tell): the tiled
+    // kernel would look at each warp's first chunk, find its window too wide and hand everything over (19 us per 10M rows
+    // with the to-do list).  Such calls go to the one-row-per-thread kernel directly; both paths are exact, this only picks
+    // the likely faster one.  (Not applied to count / coverage / nearest: their host-buffer entry points probe in 8M-row
+    // slices of a sorted table, where a 10M-row build side is sparse.)
+    const bool dense = (uint64_t)ix.n >= n;
+    p.tiled = pairs_tiled_enabled() && !dense && p.full_rows > 0 && aligned16p(key) && aligned16p(s) && aligned16p(e) &&
               (ix.flags & BRG_IDX_INVERTED) == 0;
     return p;
 }
