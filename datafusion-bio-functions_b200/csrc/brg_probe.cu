@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(THREADS, 2) nearest_k1_kernel_tiled(IndexView 
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
-            // the two start-keyed searches interleaved when both windows are short, else one after the other
+            // the two start-keyed searches interleaved when both windows are short, else one after the other (forward searches
+            // for these two as well lose: 0.60 vs 0.567 ms -- for sorted queries the inverse search is the cheaper one)
             const bool dual = mono_s && warp_window_ranks2<true, true>(cp, ix.d_pme, kp, t.qs, t.s_qs, aux1, i_pme, ce, ix.d_eend, ke,
                                                                        t.qs, t.s_qs, aux2, l_idx, kuni);
             ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);

@@ -529,23 +529,18 @@ __device__ __forceinline__ bool warp_window_ranks2(CUR0& c0, const DirView& d0, 
 // elements inside its probe: 0.86 ms per 125M probes of 100-200 bp and 1.58 ms at 1-3000 bp, against 0.47 ms for fixed
 // lengths; the forward search: 0.65 and 0.69 ms, nearest 0.685 -> 0.568 ms.)  Degenerate rows (qe < qs) ask the directory.
 // Same contract as warp_window_ranks.
-template <typename CUR>
-__device__ __forceinline__ bool warp_ranks_le_end(CUR& cur, const DirView& d, const KeyDir& k, uint32_t kid,
-                                                  const int32_t (&qs)[PV], const int32_t (&qe)[PV], bool active, bool mono_s,
-                                                  bool mono_e, const int32_t* Qs, const int32_t* Qe, uint32_t* aux,
-                                                  uint32_t (&r)[PV]) {
-    if (mono_e || !mono_s) return warp_window_ranks<false>(cur, d, k, kid, qe, active, mono_e, Qe, aux, r);
+// The forward search itself: r[j] = global index of the first element of the key's segment that is > q[j] (LT: >= q[j]).
+// mn / mx = smallest / largest START of the (start-sorted, full) chunk: they steer the cursor; mxq = largest query, >= mx.
+template <bool LT, typename CUR>
+__device__ __forceinline__ bool warp_forward_ranks(CUR& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+                                                   const int32_t (&q)[PV], int32_t mn, int32_t mx, int32_t mxq, uint32_t* aux,
+                                                   uint32_t (&r)[PV]) {
     const int lane = threadIdx.x & 31;
-    const int32_t mn = __shfl_sync(0xFFFFFFFFu, qs[0], 0), mx = __shfl_sync(0xFFFFFFFFu, qs[PV - 1], 31);
-    int32_t mxe = qe[0];
-#pragma unroll
-    for (int j = 1; j < PV; j++) mxe = max(mxe, qe[j]);
-    mxe = max(__reduce_max_sync(0xFFFFFFFFu, mxe), mx);  // (a degenerate last row: the cursor still has to pass the starts)
     const bool reuse = cur.valid && cur.key == kid && mn >= cur.bound;
-    const uint32_t lo = reuse ? cur.pos : rank_le_kd(d, k, mn);
+    const uint32_t lo = reuse ? cur.pos : (LT ? rank_lt_kd(d, k, mn) : rank_le_kd(d, k, mn));
     int32_t* w = reinterpret_cast<int32_t*>(aux);
     __syncwarp();
-    uint32_t wn_e = 0, wn_s = 0, staged = 0;
+    uint32_t wn_q = 0, wn_c = 0, staged = 0;
     bool open = true;
 #pragma unroll 1
     for (; open && staged < (uint32_t)TP_WTILE; staged += 32) {
@@ -555,36 +550,56 @@ __device__ __forceinline__ bool warp_ranks_le_end(CUR& cur, const DirView& d, co
         else v = idx < k.seg_end ? __ldg(d.A + idx) : INT32_MAX;
         w[staged + lane] = v;
         const bool have = idx < k.seg_end;
-        const uint32_t me = __ballot_sync(0xFFFFFFFFu, have && v <= mxe);
-        wn_e += __popc(me);
-        wn_s += __popc(__ballot_sync(0xFFFFFFFFu, have && v <= mx));
-        open = (me == 0xFFFFFFFFu);
+        const uint32_t mq = __ballot_sync(0xFFFFFFFFu, have && (LT ? v < mxq : v <= mxq));
+        wn_q += __popc(mq);
+        wn_c += __popc(__ballot_sync(0xFFFFFFFFu, have && (LT ? v < mx : v <= mx)));
+        open = (mq == 0xFFFFFFFFu);
     }
     __syncwarp();
     if (open) {  // more than 256 build values under one chunk: not this kernel's case
         cur.valid = false; cur.wide = true;
         return false;
     }
-    cur.pos = lo + wn_s; cur.bound = mx; cur.key = kid; cur.valid = true;
+    cur.pos = lo + wn_c; cur.bound = mx; cur.key = kid; cur.valid = true;
     cur.prefetch(d.A, k.seg_end, lane);
     uint32_t pos[PV];
 #pragma unroll
     for (int j = 0; j < PV; j++) pos[j] = 0;
-    uint32_t len = wn_e;  // branchless upper bound with a warp-uniform trip count; the 8 rows of a lane advance in lock step
+    uint32_t len = wn_q;  // branchless bound search with a warp-uniform trip count; the 8 rows of a lane advance in lock step
 #pragma unroll 1
     while (len > 1) {
         const uint32_t half = len >> 1;
 #pragma unroll
-        for (int j = 0; j < PV; j++) pos[j] += (w[pos[j] + half - 1] <= qe[j]) ? half : 0u;
+        for (int j = 0; j < PV; j++) {
+            const int32_t v = w[pos[j] + half - 1];
+            pos[j] += (LT ? v < q[j] : v <= q[j]) ? half : 0u;
+        }
         len -= half;
     }
 #pragma unroll
     for (int j = 0; j < PV; j++) {
-        if (wn_e) pos[j] += (w[pos[j]] <= qe[j]) ? 1u : 0u;
+        if (wn_q) { const int32_t v = w[pos[j]]; pos[j] += (LT ? v < q[j] : v <= q[j]) ? 1u : 0u; }
         r[j] = lo + pos[j];
-        if (qe[j] < qs[j]) r[j] = rank_le_kd(d, k, qe[j]);  // degenerate row: its end may lie in front of the window
     }
     __syncwarp();
+    return true;
+}
+
+template <typename CUR>
+__device__ __forceinline__ bool warp_ranks_le_end(CUR& cur, const DirView& d, const KeyDir& k, uint32_t kid,
+                                                  const int32_t (&qs)[PV], const int32_t (&qe)[PV], bool active, bool mono_s,
+                                                  bool mono_e, const int32_t* Qs, const int32_t* Qe, uint32_t* aux,
+                                                  uint32_t (&r)[PV]) {
+    if (mono_e || !mono_s) return warp_window_ranks<false>(cur, d, k, kid, qe, active, mono_e, Qe, aux, r);
+    const int32_t mn = __shfl_sync(0xFFFFFFFFu, qs[0], 0), mx = __shfl_sync(0xFFFFFFFFu, qs[PV - 1], 31);
+    int32_t mxe = qe[0];
+#pragma unroll
+    for (int j = 1; j < PV; j++) mxe = max(mxe, qe[j]);
+    mxe = max(__reduce_max_sync(0xFFFFFFFFu, mxe), mx);  // (a degenerate last row: the cursor still has to pass the starts)
+    if (!warp_forward_ranks<false>(cur, d, k, kid, qe, mn, mx, mxe, aux, r)) return false;
+#pragma unroll
+    for (int j = 0; j < PV; j++)
+        if (qe[j] < qs[j]) r[j] = rank_le_kd(d, k, qe[j]);  // degenerate row: its end may lie in front of the window
     return true;
 }
 // Transposed chunk stores (full 256-row chunks).  A lane owns 8 consecutive rows, so stored directly its outputs are 32 or
