@@ -132,9 +132,14 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
                 ke = load_keydir(ix.d_eend.kd, kuni);
             }
             const bool mono_s = chunk_mono(t.qs, t.full), mono_e = chunk_mono(t.qe, t.full);
+            // the two start-keyed searches interleaved when both windows are short (as in the nearest kernel), else one by one
+            const bool dual = mono_s && warp_window_ranks2<true, true>(cp, ix.d_pme, kp, t.qs, t.s_qs, aux1, i0, ce, ix.d_eend, ke, t.qs,
+                                                                       t.s_qs, aux2, ended, kuni);
             ok = warp_ranks_le_end(cs, ix.d_sstart, ks, kuni, t.qs, t.qe, t.active, mono_s, mono_e, t.s_qs, t.s_qe, aux0, n_le);
-            ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i0);
-            ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, ended);
+            if (!dual) {
+                ok = ok && warp_window_ranks<true>(cp, ix.d_pme, kp, kuni, t.qs, t.active, mono_s, t.s_qs, aux1, i0);
+                ok = ok && warp_window_ranks<true>(ce, ix.d_eend, ke, kuni, t.qs, t.active, mono_s, t.s_qs, aux2, ended);
+            }
         }
         if (ok) {
             uint32_t tot = 0;
