@@ -1,6 +1,6 @@
 #!/bin/bash
 # headline kernel time as a function of the CTA size of count_kernel_tiled (2 CTAs per SM; registers per thread follow)
-for t in 256 288 320 352 384; do
+for t in 256 320; do
   BRG_COUNT_THREADS=$t python bench.py --steps 10 --warmup 3 --no-cpu --no-extras 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
