@@ -50,6 +50,13 @@ struct ScratchScope {
     explicit ScratchScope(cudaStream_t st) : prev(tls_scratch_stream) { tls_scratch_stream = st; }
     ~ScratchScope() { tls_scratch_stream = prev; }
 };
+// The pool keeps what it is given back (that is what makes the second build fast), so the scratch of one very large build
+// would stay reserved for good: every build starts by returning everything above 4 GB that earlier calls left unused.
+static void trim_scratch_pool(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 4ull << 30);
+    cudaGetLastError();
+}
 struct ScratchBuf {
     void* p = nullptr;
     uint64_t bytes = 0;
@@ -438,6 +445,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->build_stream;
     want &= BRG_WANT_ALL;
     ScratchScope scratch_scope(st);
+    trim_scratch_pool(ctx->device);
     // BRG_BUILD_TRACE=1: wall-clock time of the build stages on stderr (each mark synchronises the stream)
     static const bool trace = getenv("BRG_BUILD_TRACE") != nullptr;
     static const bool trace_sync = trace && getenv("BRG_BUILD_TRACE")[0] != '2';  // 2: host-side timestamps only
