@@ -179,12 +179,42 @@ __global__ void __launch_bounds__(SC_THREADS) tile_scan_kernel(Load ld, Store st
     }
 }
 
+// Short inputs (the n / 256 chunk totals of the pair join, per-key tables): one CTA, one launch instead of three.  Every thread
+// owns a contiguous slice, reduces it, the CTA scans the 1024 slice totals, every thread re-reads its slice and writes.
+constexpr uint64_t SC_SMALL_MAX = 4096;  // (at 39063 elements the single CTA takes 30 us against 12 us for the three launches)
+template <typename T, typename Op, typename Load, typename Store, bool INCLUSIVE>
+__global__ void __launch_bounds__(1024) small_scan_kernel(Load ld, Store stf, uint64_t n, T* total_out) {
+    __shared__ T sm[32];
+    __shared__ T inc_sm[1024];
+    Op op;
+    const uint64_t per = (n + 1023) / 1024;
+    const uint64_t b = min(n, (uint64_t)threadIdx.x * per), e = min(n, b + per);
+    T acc = Op::identity();
+    for (uint64_t i = b; i < e; i++) acc = op(acc, ld(i));
+    T tot;
+    const T inc = block_inclusive_scan<T, Op, 1024>(acc, op, sm, &tot);
+    inc_sm[threadIdx.x] = inc;
+    __syncthreads();
+    T run = threadIdx.x ? inc_sm[threadIdx.x - 1] : Op::identity();
+    for (uint64_t i = b; i < e; i++) {
+        const T x = ld(i);
+        if (INCLUSIVE) { run = op(run, x); stf(i, run); }
+        else { stf(i, run); run = op(run, x); }
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = tot;
+}
+
 template <typename T, typename Op, typename Load, typename Store, bool INCLUSIVE>
 static int run_scan(Load ld, Store stf, uint64_t n, T* scratch, T* total_out, cudaStream_t st) {
     if (n == 0) {
         if (total_out) {
             BRG_CUDA(cudaMemsetAsync(total_out, 0, sizeof(T), st));
         }
+        return 0;
+    }
+    if (n <= SC_SMALL_MAX) {
+        small_scan_kernel<T, Op, Load, Store, INCLUSIVE><<<1, 1024, 0, st>>>(ld, stf, n, total_out);
+        BRG_LAUNCH_CHECK();
         return 0;
     }
     const uint64_t nb = (n + SC_TILE - 1) / SC_TILE;
