@@ -18,6 +18,11 @@
 // the chunk, a partial chunk, a window wider than TP_WMAX (a build side about as dense as the probe side) -- makes the
 // warp defer the chunk (or, for a wide window, its whole remaining range) to a one-row-per-thread kernel through a
 // to-do list, so results are exact for any input.
+//
+// Shared-memory layout: these kernels are bound by the shared-memory pipe, so everything a lane touches with 128-bit
+// accesses or that a binary search probes (query columns, histograms, output staging) lives at word i + 4 * (i / 32)
+// (hist_slot / pad_tile / PadStep below): conflict-free for both access patterns.  Histograms have one byte per bin.
+// Unsorted ends (variable-length probes) are ranked by a forward search over the staged window (warp_forward_ranks).
 #pragma once
 #include "brg_internal.cuh"
 
