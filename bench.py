@@ -405,9 +405,13 @@ def main():
         h2d, d2h, e_units = n * (8 if use_runs else 12), n * 12 + n // 8, n
     else:
         use_runs = False
-        estep = lambda: ix.overlap_pairs(npk, nps, npe)
+        estep = lambda: ix.overlap_pairs(npk, nps, npe, copy=False)  # results stay in the library's pinned buffers (zero-copy views)
         h2d, d2h, e_units = n * 12, units_per_step * 8, units_per_step
-    estep()
+    # warm-up: two results alive at once, as in the timed loop below (`r` still holds step k - 1 while step k runs), so that
+    # the library's pinned result pool holds both sets before the clock starts
+    w0 = estep()
+    w1 = estep()
+    del w0, w1
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()

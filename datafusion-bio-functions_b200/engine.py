@@ -305,11 +305,22 @@ class Index:
             A.lib().brg_rows_release(r)
         return out
 
-    def overlap_pairs(self, key, start, end, mode=A.PAIRS_INNER, max_rows=0, return_consumed=False):
+    def overlap_pairs(self, key, start, end, mode=A.PAIRS_INNER, max_rows=0, return_consumed=False, copy=True):
+        """copy=False: the index arrays are views of the library's pinned result buffers (what a Rust host wraps with
+        Buffer::from_custom_allocation); the buffers go back to the library when the last view is garbage-collected"""
         key, start, end = self._cols(key, start, end)
         r, consumed = C.c_void_p(), C.c_uint64()
         A.check(A.lib().brg_overlap_pairs(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start),
                                           int(mode), int(max_rows), C.byref(r), C.byref(consumed)))
+        if not copy:
+            owner = _RowsOwner(r)
+            L = A.lib()
+            m = L.brg_rows_len(r)
+            b = owner.view(L.brg_rows_build_idx(r), m, np.uint32) if mode == A.PAIRS_INNER else None
+            p = owner.view(L.brg_rows_probe_idx(r), m, np.uint32)
+            if mode != A.PAIRS_INNER:
+                return (p, consumed.value) if return_consumed else p
+            return (b, p, consumed.value) if return_consumed else (b, p)
         try:
             L = A.lib()
             m = L.brg_rows_len(r)
@@ -375,6 +386,28 @@ class Index:
         st = torch.cuda.current_stream().cuda_stream
         A.check(A.lib().brg_pairs_fill_dev(self.ctx._h, self._h, _tptr(start), start.numel(), _tptr(chunk_base),
                                            _tptr(row_ranges), _tptr(build_idx), _tptr(probe_idx), st))
+
+
+class _RowsOwner:
+    """keeps a brg_rows result alive while numpy views of its pinned buffers exist"""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def view(self, ptr, n, dtype):
+        if n == 0 or not ptr:
+            return np.empty(0, dtype)
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        buf._brg_owner = self  # array.base -> buf -> owner
+        return np.frombuffer(buf, dtype=dtype, count=n)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                A.lib().brg_rows_release(self._h)
+            except Exception:
+                pass
+            self._h = None
 
 
 _default = {}

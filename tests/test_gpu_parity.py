@@ -173,6 +173,30 @@ def brg_want_count():
     return brg.WANT_COUNT
 
 
+def test_gpu_pairs_zero_copy_views(ctx):
+    """overlap_pairs(copy=False): numpy views of the library's pinned result buffers, released with the last view"""
+    import gc
+
+    rng = np.random.default_rng(3)
+    bk, bs, be = _rand(rng, 5000, 2, 0, 200_000, 500)
+    pk, ps, pe = _rand(rng, 20_000, 2, 0, 200_000, 300)
+    gi = ctx.build(bk, bs, be, 2)
+    b0, p0 = gi.overlap_pairs(pk, ps, pe)
+    b1, p1 = gi.overlap_pairs(pk, ps, pe, copy=False)
+    assert (b0 == b1).all() and (p0 == p1).all() and not b1.flags.owndata
+    keep = p1[10:20].copy()
+    tail = b1[-5:]  # a slice keeps the buffers alive after the parents are gone
+    del b1, p1
+    gc.collect()
+    assert (tail == b0[-5:]).all() and (keep == p0[10:20]).all()
+    del tail
+    gc.collect()
+    for _ in range(3):  # buffers return to the pool and are handed out again
+        b2, p2 = gi.overlap_pairs(pk, ps, pe, copy=False)
+        assert (b2 == b0).all() and (p2 == p0).all()
+    gi.close()
+
+
 def test_gpu_key_runs_entry_points(ctx):
     """run-length key column (what the host's contig-cache loop yields) == per-row key column"""
     import bio_ranges_b200 as brg
