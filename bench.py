@@ -10,9 +10,14 @@ with an NCCL broadcast, probe rows are sharded by contiguous row range, no colle
 
 One JSON line on rank 0:
   value     probes/s, whole job, inputs resident in HBM, K timed steps bracketed by barrier + synchronize, max over ranks
-  e2e       same metric through the host-buffer C-ABI call (brg_count_overlaps) with pinned HOST buffers: H2D + kernels +
-            D2H inside the timed region
-  roofline  dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  e2e       same metric through the host-buffer C-ABI call (brg_count_overlaps: per-row key id column, start, end in PINNED
+            host buffers -> int64 counts in a pinned host buffer); H2D + the library's per-chunk key-run scan + kernels + D2H
+            inside the timed region.  e2e_pageable: the same call on ordinary heap buffers (what arrow-rs allocates)
+  roofline  dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json); roofline_with_build = index build + one
+            probe step (SURVEY 8d's build-amortised figure)
+  parity    EVERY rank compares ALL rows of its device-resident output and of its end-to-end output with the oracle
+            (pairs: per-probe counts + an order-independent checksum of the pair set); min over ranks
+  extras    the other section-8 workloads (coverage, nearest, pairs; sorted and shuffled), each with its own parity, at every N
   cpu_baseline  the oracle port (reference algorithm restated in C + OpenMP) on a bounded sample, rank 0, N=1
 """
 import argparse
@@ -39,6 +44,9 @@ WORKLOADS = {
     "coverage": (100_000_000, 1_000_000, "coverage 100M reads (150 bp) x 1M exon-like targets, 24 contigs (configs[2])"),
     "nearest": (50_000_000, 5_000_000, "nearest k=1 50M queries x 5M sparse targets, 24 contigs (configs[3])"),
 }
+KERNELS = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
+           "pairs": "pairs_join_kernel"}
+API = {"count": "brg_count_overlaps", "coverage": "brg_coverage", "nearest": "brg_nearest_k1", "pairs": "brg_overlap_pairs"}
 
 
 def hbm_peak():
@@ -48,13 +56,13 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, workload, args):
+def ncu_traffic(kernel, workload, order, scale):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this same workload (profiles/traffic.json); None when the run differs from it."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if not os.path.exists(p) or args.scale != 1.0:
+    if not os.path.exists(p) or scale != 1.0:
         return None
-    rec = json.load(open(p)).get(f"{workload}:{args.order}")
+    rec = json.load(open(p)).get(f"{workload}:{order}")
     return rec["dram_bytes_per_launch"] if rec and rec.get("kernel") == kernel else None
 
 
@@ -198,11 +206,308 @@ def cpu_run(name, b, p, sample_rows, steps, warmup):
     units = len(ps)
     if name == "pairs":
         units = int(res.sum())
-    return units / dt, cores, f"first {len(ps)} probe rows of the workload, {steps} timed passes, index build {t_build:.2f}s excluded", dt
+    return units / dt, cores, (f"first {len(ps)} probe rows of the workload (coordinate-sorted: mostly the first contigs), {steps} timed "
+                               f"passes, index build {t_build:.2f}s excluded; C port of the reference algorithm, not the Rust crate"), dt
 
 
 def to_np(t):
     return t.cpu().numpy()
+
+
+def split_affinity(local_rank, world):
+    """N processes on one box: give each rank its own slice of the cores this job may use (the NVML "ideal" affinity of every
+    GPU of a single-NUMA-node box is ALL cores, which leaves every rank's host threads on the same cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per < 1:
+            return len(cores)
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return 0
+
+
+class Harness:
+    """process-wide state shared by the headline and the extras"""
+
+    def __init__(self, torch, dist, brg, rank, local_rank, world, device, args):
+        self.torch, self.dist, self.brg = torch, dist, brg
+        self.rank, self.local_rank, self.world, self.device, self.args = rank, local_rank, world, device, args
+        self.ctx = brg.Context(local_rank)
+        self.lib = brg._cabi.lib()
+        self.peak, self.peak_src = hbm_peak()
+        self._oracle_cache = {}
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, v, op):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return float(t.item())
+
+    def oracle_threads(self):
+        from oracle import oracle as O
+
+        return max(1, O.max_threads())
+
+    def oracle_index(self, name, b):
+        """the checker's index over the build side of workload `name` (one per workload and process)"""
+        from oracle import oracle as O
+
+        if name not in self._oracle_cache:
+            self._oracle_cache.clear()  # one at a time: 10M-row indexes are not small
+            self._oracle_cache[name] = O.OracleIndex(to_np(b[0]).astype(np.uint32), to_np(b[1]), to_np(b[2]), len(HG38))
+        return self._oracle_cache[name]
+
+
+def check_fixed(h, name, oi, pnp, got):
+    """ALL rows of a fixed-size result against the oracle; got = numpy arrays as the C ABI returns them"""
+    thr = h.oracle_threads()
+    npk, nps, npe = pnp
+    if name == "count":
+        return bool((got[0] == oi.count_overlaps(npk, nps, npe, threads=thr)).all())
+    if name == "coverage":
+        return bool((got[0] == oi.coverage(npk, nps, npe, threads=thr)).all())
+    left, bits, dist_ = got
+    ol, ov, od = oi.nearest_k1(npk, nps, npe, threads=thr)
+    valid = np.unpackbits(bits.view(np.uint8), bitorder="little")[: len(nps)].astype(bool)
+    return bool((valid == ov).all() and (left.view(np.uint32)[ov] == ol[ov]).all() and (dist_[ov] == od[ov]).all())
+
+
+def check_pairs(h, oi, pnp, bi, pi):
+    """per-probe counts + the order-independent checksum (sum h, sum h^2, xor h) of the whole pair set"""
+    from oracle import oracle as O
+
+    npk, nps, npe = pnp
+    want, cnt = oi.overlap_checksum(npk, nps, npe, row_base=0, threads=h.oracle_threads(), counts=True)
+    bi, pi = np.asarray(bi).view(np.uint32), np.asarray(pi).view(np.uint32)
+    if len(bi) != want[3]:
+        return False
+    got_cnt = np.bincount(pi, minlength=len(nps)).astype(np.uint64)
+    return bool((got_cnt == cnt).all() and O.pair_checksum(bi, pi) == want)
+
+
+def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, want_build_fig=False, sampler=None):
+    """one workload on this rank's shard: build + replicate, device-resident timed steps, end-to-end steps, parity"""
+    torch, dist, brg = h.torch, h.dist, h.brg
+    rank, world, device, args = h.rank, h.world, h.device, h.args
+    b, p = make_workload(torch, name, device, rank, world, order, args.scale)
+    want = {"count": brg.WANT_COUNT, "pairs": brg.WANT_PAIRS, "coverage": brg.WANT_COVERAGE, "nearest": brg.WANT_NEAREST}[name]
+    nb = b[1].numel()
+    res = {"workload": WORKLOADS[name][2], "probe_order": order}
+
+    # ---- build on rank 0, replicate the index slab (it carries its own header) with ONE NCCL broadcast ----------------------
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ix = None
+    if rank == 0:
+        ix = h.ctx.build_dev(*b, len(HG38), want)
+        torch.cuda.synchronize()
+    build_first_s = time.perf_counter() - t0
+    build = {"seconds_rank0_first_call": build_first_s}
+    if world > 1:
+        from bio_ranges_b200.sharding import replicate_index
+
+        times = []
+        for rep in range(2):  # first call: NCCL channel set-up + cudaMalloc of the replica slab; second call: the transfer itself
+            h.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            rep_ix = replicate_index(h.ctx, ix if rank == 0 else None, dist, rank, world, device)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append((h.reduce(e0.elapsed_time(e1), "max"), h.reduce((time.perf_counter() - t0) * 1e3, "max")))
+            if rep == 0 and rank != 0:
+                rep_ix.close()
+        ix = rep_ix
+        build["broadcast_ms_first_call"] = {"device": times[0][0], "wall": times[0][1]}
+        build["broadcast_ms"] = {"device": times[1][0], "wall": times[1][1]}
+        build["broadcast_gbs"] = ix.device_bytes / (times[1][0] * 1e-3) / 1e9
+    build["index_bytes"] = ix.device_bytes
+    pk, ps, pe = p
+    n = ps.numel()
+
+    # ---- device-resident step ------------------------------------------------------------------------------
+    total = None
+    if name in ("count", "coverage"):
+        out = torch.empty(n, dtype=torch.int64, device=device)
+        fn = (ix.count_overlaps_dev if name == "count" else ix.coverage_dev)
+        step = lambda: fn(pk, ps, pe, out)
+        units_per_step = n
+        alg_bytes = n * 20 + nb * 8
+        outs = (out,)
+    elif name == "nearest":
+        left = torch.empty(n, dtype=torch.int32, device=device)
+        bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device=device)
+        dd = torch.empty(n, dtype=torch.int64, device=device)
+        step = lambda: ix.nearest_k1_dev(pk, ps, pe, left, bits, dd)
+        units_per_step = n
+        alg_bytes = n * 28 + n // 8 + nb * 12
+        outs = (left, bits, dd)
+    else:
+        offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
+        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
+        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
+        torch.cuda.synchronize()
+        total = int(offsets[-1].item())
+        bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+        pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+
+        def step():  # count -> scan -> emit
+            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
+            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
+
+        units_per_step = total
+        alg_bytes = n * 12 + total * 8 + nb * 12
+        outs = (bi, pi)
+    for _ in range(warmup):
+        step()
+    h.barrier()
+    if sampler is not None and rank == 0:
+        sampler.start()
+    l0 = h.lib.brg_kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    h.barrier()
+    ev[0].record()
+    for i in range(steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    h.barrier()
+    total_ms = h.reduce(ev[0].elapsed_time(ev[-1]), "max")
+    launches = h.lib.brg_kernel_launches() - l0
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    ms_per_step = total_ms / steps
+    res["value"] = h.reduce(units_per_step, "sum") / (ms_per_step * 1e-3)
+    res["unit"] = "pairs/s" if name == "pairs" else "probes/s"
+    res["ms_per_step"] = ms_per_step
+    res["gpu_launches"] = int(launches)
+    kern_ms = float(np.mean(per_step_ms))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": h.peak, "unit": "GB/s", "frac": achieved / h.peak,
+                       "traffic": ncu_traffic(KERNELS[name], name, order, args.scale), "peak_source": h.peak_src, "kernel": KERNELS[name],
+                       "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
+    if name == "pairs":
+        res["pairs_per_probe"] = total / n
+
+    # ---- parity of the DEVICE-RESIDENT result that produced `value`: all rows, this rank ----------------------------------
+    parity = {}
+    oi = None
+    pnp = None
+    if not args.no_parity:
+        oi = h.oracle_index(name, b)
+        pnp = (to_np(pk).astype(np.uint32), to_np(ps), to_np(pe))
+        if name == "pairs":
+            ok = check_pairs(h, oi, pnp, to_np(bi[:total]), to_np(pi[:total]))
+        else:
+            ok = check_fixed(h, name, oi, pnp, tuple(to_np(o) for o in outs))
+        parity["device_resident"] = bool(h.reduce(1.0 if ok else 0.0, "min") == 1.0)
+
+    # ---- index build amortised into one probe step (SURVEY 8d): a second build with the scratch pool warm ------------------
+    if want_build_fig and rank == 0:
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        ix2 = h.ctx.build_dev(*b, len(HG38), want)
+        e1.record()
+        step()
+        e2.record()
+        torch.cuda.synchronize()
+        ix2.close()
+        bms, sms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        build["ms_warm"] = bms
+        res["roofline_with_build"] = {"build_ms": bms, "step_ms": sms, "frac": alg_bytes / ((bms + sms) * 1e-3) / 1e9 / h.peak,
+                                      "value": units_per_step / ((bms + sms) * 1e-3), "unit": res["unit"],
+                                      "what": "one index build (device-resident build columns, scratch pool warm) + one probe step"}
+    res["build"] = build
+    del outs
+    if name == "pairs":
+        del bi, pi, offsets, ranges
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the host-buffer C-ABI call: host inputs -> H2D -> kernels -> D2H ---------------------------------
+    if want_e2e:
+        def pinned(t):
+            x = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+            x.copy_(t)
+            return x
+
+        h_pk, h_ps, h_pe = pinned(pk), pinned(ps), pinned(pe)
+        npk, nps, npe = h_pk.numpy().view(np.uint32), h_ps.numpy(), h_pe.numpy()
+        e2e_steps = max(3, min(steps, 5))
+
+        def make_step(k_, s_, e_, pin):
+            alloc = (lambda m, dt: torch.empty(m, dtype=dt).pin_memory().numpy()) if pin else (lambda m, dt: torch.empty(m, dtype=dt).numpy())
+            if name in ("count", "coverage"):
+                ho = alloc(n, torch.int64)
+                hfn = ix.count_overlaps if name == "count" else ix.coverage
+                return (lambda: hfn(k_, s_, e_, out=ho)), (lambda r: (ho,)), n * 12, n * 8
+            if name == "nearest":
+                o3 = (alloc(n, torch.int32).view(np.uint32), alloc(((n + 31) // 32) * 4, torch.uint8), alloc(n, torch.int64))
+                return (lambda: ix.nearest_k1_into(k_, s_, e_, o3)), (lambda r: o3), n * 12, n * 12 + n // 8
+            # pairs: results stay in the library's pinned buffers (zero-copy views)
+            return (lambda: ix.overlap_pairs(k_, s_, e_, copy=False)), (lambda r: r), n * 12, units_per_step * 8
+
+        def time_e2e(estep):
+            # warm-up: two results alive at once, as in the timed loop (`r` still holds step k - 1 while step k runs), so that
+            # the library's pinned result pool and staging ring hold everything before the clock starts
+            w0 = estep()
+            w1 = estep()
+            del w0, w1
+            h.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(e2e_steps):
+                r = estep()
+            e1.record()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            return h.reduce(max(e0.elapsed_time(e1), wall_ms), "max") / e2e_steps, r
+
+        estep, result_of, h2d, d2h = make_step(npk, nps, npe, True)
+        e2e_ms, r = time_e2e(estep)
+        e_units = units_per_step
+        res["e2e"] = {"value": h.reduce(e_units, "sum") / (e2e_ms * 1e-3), "unit": res["unit"], "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                      "api": API[name] + " (pinned host buffers; per-row key id column in, the library scans it for runs chunk by chunk"
+                                         " inside the timed region and sends runs where a chunk has <= 1024 of them)",
+                      "h2d_bytes_note": "counted as the caller's columns (12 B/row); with key runs 8 B/row cross PCIe"}
+        if not args.no_parity:
+            got = result_of(r)
+            ok = check_pairs(h, oi, pnp, got[0], got[1]) if name == "pairs" else check_fixed(h, name, oi, pnp, got)
+            parity["e2e"] = bool(h.reduce(1.0 if ok else 0.0, "min") == 1.0)
+        del r
+        if want_pageable:
+            # ordinary heap memory, as arrow-rs allocates it: the library stages it through its pinned ring with host threads
+            gk, gs, ge = npk.copy(), nps.copy(), npe.copy()
+            estep2, result_of2, _, _ = make_step(gk, gs, ge, False)
+            pg_ms, r2 = time_e2e(estep2)
+            res["e2e_pageable"] = {"value": h.reduce(e_units, "sum") / (pg_ms * 1e-3), "unit": res["unit"], "ms_per_step": pg_ms,
+                                   "what": "same call, pageable (heap) input and output buffers: copied through the library's pinned "
+                                           "staging ring by its host threads (BRG_HOST_THREADS)"}
+            if not args.no_parity:
+                got = result_of2(r2)
+                ok = check_pairs(h, oi, pnp, got[0], got[1]) if name == "pairs" else check_fixed(h, name, oi, pnp, got)
+                parity["e2e_pageable"] = bool(h.reduce(1.0 if ok else 0.0, "min") == 1.0)
+            del r2, gk, gs, ge
+        res["_host_cols"] = (npk, nps, npe)
+    if parity:
+        res["parity"] = parity
+        res["parity_all"] = all(parity.values())
+        if not res["parity_all"]:
+            raise SystemExit(f"bench result of {name}:{order} differs from the oracle ({parity}): refusing to report a number")
+    res["_build_cols"] = b
+    ix.close()
+    return res
 
 
 def main():
@@ -218,6 +523,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32_000_000)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison (profiling runs only)")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident steps only (profiling runs only)")
+    ap.add_argument("--affinity", default=os.environ.get("BRG_BENCH_AFFINITY", "split"), choices=["split", "nvml", "none"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -257,220 +565,79 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
-    near_cores = 0
-    if world > 1:  # (N = 1 keeps every host core for the CPU arm)
-        from bio_ranges_b200.sharding import bind_near_gpu
+    if world > 1 and args.affinity != "none":  # (N = 1 keeps every host core for the CPU arm)
+        if args.affinity == "nvml":
+            from bio_ranges_b200.sharding import bind_near_gpu
 
-        near_cores = bind_near_gpu(local_rank)
-        config["host_affinity"] = f"each rank bound to the {near_cores} cores next to its GPU (NVML)" if near_cores else "unbound"
+            cores = bind_near_gpu(local_rank)
+            config["host_affinity"] = f"each rank bound to the {cores} cores NVML names for its GPU" if cores else "unbound"
+        else:
+            cores = split_affinity(local_rank, world)
+            config["host_affinity"] = f"each rank bound to its own {cores} of the job's cores" if cores else "unbound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     import bio_ranges_b200 as brg
 
-    ctx = brg.Context(local_rank)
-    lib = brg._cabi.lib()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    b, p = make_workload(torch, name, device, rank, world, args.order, args.scale)
-    want = {"count": brg.WANT_COUNT, "pairs": brg.WANT_PAIRS, "coverage": brg.WANT_COVERAGE, "nearest": brg.WANT_NEAREST}[name]
-
-    # ---- build on rank 0, replicate with an NCCL broadcast of the index slab --------------------------------
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    if rank == 0:
-        ix = ctx.build_dev(*b, len(HG38), want)
-        torch.cuda.synchronize()
-    build_s = time.perf_counter() - t0
-    bcast_ms = 0.0
-    if world > 1:
-        from bio_ranges_b200.sharding import replicate_index
-
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ix = replicate_index(ctx, ix if rank == 0 else None, dist, rank, world, device)  # header + one slab broadcast
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = max_over_ranks(e0.elapsed_time(e1))
-    pk, ps, pe = p
-    n = ps.numel()
-
-    # ---- device-resident step ------------------------------------------------------------------------------
-    if name in ("count", "coverage"):
-        out = torch.empty(n, dtype=torch.int64, device=device)
-        fn = (ix.count_overlaps_dev if name == "count" else ix.coverage_dev)
-        step = lambda: fn(pk, ps, pe, out)
-        units_per_step = n
-        alg_bytes = n * 20 + int(WORKLOADS[name][1] * args.scale) * 8
-        launches_per_step = 1
-    elif name == "nearest":
-        left = torch.empty(n, dtype=torch.int32, device=device)
-        bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=device)
-        dd = torch.empty(n, dtype=torch.int64, device=device)
-        step = lambda: ix.nearest_k1_dev(pk, ps, pe, left, bits, dd)
-        units_per_step = n
-        alg_bytes = n * 28 + n // 8 + int(WORKLOADS[name][1] * args.scale) * 12
-        launches_per_step = 1
-    else:
-        offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
-        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
-        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
-        torch.cuda.synchronize()
-        total = int(offsets[-1].item())
-        bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
-        pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
-
-        def step():  # count -> scan -> emit
-            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
-            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
-
-        units_per_step = total
-        alg_bytes = n * 12 + total * 8 + int(WORKLOADS[name][1] * args.scale) * 12
-        launches_per_step = 7
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    h = Harness(torch, dist, brg, rank, local_rank, world, device, args)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = lib.brg_kernel_launches()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    barrier()
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
-    launches = lib.brg_kernel_launches() - l0
-    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    ms_per_step = total_ms / args.steps
-    value = sum_over_ranks(units_per_step) / (ms_per_step * 1e-3)
-    peak, peak_src = hbm_peak()
-    kern_ms = float(np.mean(per_step_ms))
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    kernel_name = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
-                   "pairs": "pairs_ranges_kernel_tiled+scan+pairs_emit_kernel_flat"}[name]
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(kernel_name, name, args), "peak_source": peak_src, "kernel": kernel_name,
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
-
-    # ---- end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H ----------
-    e2e = None
-    h_pk = torch.empty(n, dtype=torch.int32).pin_memory(); h_pk.copy_(pk)
-    h_ps = torch.empty(n, dtype=torch.int32).pin_memory(); h_ps.copy_(ps)
-    h_pe = torch.empty(n, dtype=torch.int32).pin_memory(); h_pe.copy_(pe)
-    npk, nps, npe = h_pk.numpy().view(np.uint32), h_ps.numpy(), h_pe.numpy()
-    e2e_steps = max(3, min(args.steps, 5))
-    # The contig column travels in run-length form (brg_*_runs): the host's contig-cache loop (interval_tree.rs:258-265)
-    # yields runs on a coordinate-sorted table; a shuffled table has no runs to speak of and sends the id column.
-    run_key, run_end = brg._cabi.key_runs(npk)
-    use_runs = len(run_key) <= max(1024, n // 4096)
-    if name in ("count", "coverage"):
-        h_out = torch.empty(n, dtype=torch.int64).pin_memory()
-        if use_runs:
-            hfn = ix.count_overlaps_runs if name == "count" else ix.coverage_runs
-            estep = lambda: hfn(run_key, run_end, nps, npe, out=h_out.numpy())
-        else:
-            hfn = ix.count_overlaps if name == "count" else ix.coverage
-            estep = lambda: hfn(npk, nps, npe, out=h_out.numpy())
-        h2d, d2h, e_units = n * (8 if use_runs else 12), n * 8, n
-    elif name == "nearest":
-        if not use_runs:  # the id column form has no caller-buffer variant in the python wrapper: send one run per row change
-            use_runs = True
-        h_left = torch.empty(n, dtype=torch.int32).pin_memory()
-        h_bits = torch.zeros(((n + 31) // 32) * 4, dtype=torch.uint8).pin_memory()
-        h_dist = torch.empty(n, dtype=torch.int64).pin_memory()
-        nout = (h_left.numpy().view(np.uint32), h_bits.numpy(), h_dist.numpy())
-        estep = lambda: ix.nearest_k1_runs(run_key, run_end, nps, npe, out=nout)
-        h2d, d2h, e_units = n * (8 if use_runs else 12), n * 12 + n // 8, n
-    else:
-        use_runs = False
-        estep = lambda: ix.overlap_pairs(npk, nps, npe, copy=False)  # results stay in the library's pinned buffers (zero-copy views)
-        h2d, d2h, e_units = n * 12, units_per_step * 8, units_per_step
-    # warm-up: two results alive at once, as in the timed loop below (`r` still holds step k - 1 while step k runs), so that
-    # the library's pinned result pool holds both sets before the clock starts
-    w0 = estep()
-    w1 = estep()
-    del w0, w1
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        r = estep()
-    e1.record()
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / e2e_steps
-    # the sampler (100 ms period) ran through both timed regions: the device-resident steps and the end-to-end steps
+    head = run_workload(h, name, args.order, args.steps, args.warmup, want_e2e=not args.no_e2e, want_pageable=True, want_build_fig=True,
+                        sampler=sampler)
+    # the sampler (20 ms period) ran through both timed regions: the device-resident steps and the end-to-end steps
     clocks = sampler.stop() if rank == 0 else None
-    e2e = {"value": sum_over_ranks(e_units) / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms, "api": {"count": "brg_count_overlaps", "coverage": "brg_coverage", "nearest": "brg_nearest_k1",
-                                          "pairs": "brg_overlap_pairs"}[name] + ("_runs (host buffers, pinned; contig column as key runs)"
-                                                                                if use_runs else " (host buffers, pinned)")}
-    # parity spot check of the timed result against the oracle (rank 0, small sample) -- the checker, not the product
-    parity = None
-    if rank == 0 and name in ("count", "coverage") and not args.no_cpu:
-        from oracle import oracle as O
-
-        m = min(200_000, n)
-        sel = slice(0, m)
-        oi = O.OracleIndex(to_np(b[0]).astype(np.uint32), to_np(b[1]), to_np(b[2]), len(HG38))
-        got = h_out.numpy()[sel]
-        wantv = (oi.count_overlaps if name == "count" else oi.coverage)(npk[sel], nps[sel], npe[sel], threads=O.max_threads())
-        parity = bool((got == wantv).all())
-        if not parity:
-            raise SystemExit("bench result differs from the oracle: refusing to report a number")
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1) ----------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        sample = min(args.cpu_sample, n)
+    if rank == 0 and world == 1 and not args.no_cpu and "_host_cols" in head:
+        npk, nps, npe = head["_host_cols"]
+        sample = min(args.cpu_sample, len(nps))
+        b = head["_build_cols"]
         bnp = (to_np(b[0]).astype(np.uint32), to_np(b[1]), to_np(b[2]))
         pnp = (npk[:sample], nps[:sample], npe[:sample])
         v, cores, desc, _ = cpu_run(name, bnp, pnp, sample, 2, 1)
         cpu = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": desc}
+    head.pop("_host_cols", None)
+    head.pop("_build_cols", None)
+    h._oracle_cache.clear()
 
-    # ---- other section-8 workloads, device-resident, short (N=1 only; reported as extras) ------------------------
+    # ---- the other section-8 workloads: every rank runs its shard, each with its own parity (reported as extras) -----------
     extras = {}
-    if rank == 0 and world == 1 and not args.no_extras and name == "count":
-        del h_pk, h_ps, h_pe, h_out
+    if not args.no_extras and name == "count":
         alt = "shuffled" if args.order == "sorted" else "sorted"
-        try:
-            extras[f"count_{alt}"] = quick_device_run(torch, brg, ctx, "count", alt, args.scale, device, peak, 5)
-            for other in ("coverage", "nearest", "pairs"):
-                extras[other] = quick_device_run(torch, brg, ctx, other, args.order, args.scale, device, peak, 5)
-            extras["merge"] = quick_merge_run(torch, ctx, args.scale, device)
-        except Exception as ex:  # extras never invalidate the headline
-            extras["error"] = repr(ex)
+        plan = [("count", alt, False), ("coverage", args.order, True), ("nearest", args.order, True), ("pairs", args.order, True)]
+        if world == 1:
+            plan += [("coverage", alt, False), ("nearest", alt, False), ("pairs", alt, False)]
+        for wname, worder, we2e in plan:
+            key = wname if worder == args.order else f"{wname}_{worder}"
+            try:
+                r = run_workload(h, wname, worder, 5, 3, want_e2e=we2e and not args.no_e2e)
+                r.pop("_host_cols", None)
+                r.pop("_build_cols", None)
+                r["roofline_frac"] = r["roofline"]["frac"]
+                extras[key] = r
+            except SystemExit:
+                raise
+            except Exception as ex:  # an extra that cannot run never invalidates the headline
+                extras[key] = {"error": repr(ex)}
+            h._oracle_cache.clear()
+            torch.cuda.empty_cache()
+        if world == 1 and rank == 0:
+            try:
+                extras["merge"] = quick_merge_run(torch, h.ctx, args.scale, device)
+                extras["nearest_k5"] = quick_nearest_k_run(torch, h, 5)
+            except Exception as ex:
+                extras["error"] = repr(ex)
 
     if rank == 0:
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "build": {"seconds_rank0": build_s, "index_bytes": ix.device_bytes,
-                                                                      "broadcast_ms": bcast_ms},
-                "parity_vs_oracle_sample": parity, "extras": extras}
+        parity_all = bool(head.get("parity_all", False)) and all(v.get("parity_all", True) for v in extras.values() if isinstance(v, dict))
+        line = {"metric": metric, "value": head["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": head.get("e2e"), "e2e_pageable": head.get("e2e_pageable"),
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "roofline_with_build": head.get("roofline_with_build"),
+                "cpu_baseline": cpu, "build": head["build"],
+                "parity": None if args.no_parity else {"all_ranks_all_rows": parity_all, "headline": head.get("parity"),
+                                                       "how": "every rank: all rows of the device-resident output and of the end-to-end "
+                                                              "output vs the oracle; min over ranks"},
+                "parity_vs_oracle_sample": None if args.no_parity else parity_all, "extras": extras}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -492,52 +659,21 @@ def quick_merge_run(torch, ctx, scale, device):
             "value": n / dt, "unit": "intervals/s", "ms_per_step": dt * 1e3, "merged_rows": int(len(out[0]))}
 
 
-def quick_device_run(torch, brg, ctx, name, order, scale, device, peak, steps):
-    b, p = make_workload(torch, name, device, 0, 1, order, scale)
-    want = {"count": brg.WANT_COUNT, "pairs": brg.WANT_PAIRS, "coverage": brg.WANT_COVERAGE, "nearest": brg.WANT_NEAREST}[name]
-    ix = ctx.build_dev(*b, len(HG38), want)
-    pk, ps, pe = p
-    n = ps.numel()
-    nb = b[1].numel()
-    if name in ("count", "coverage"):
-        out = torch.empty(n, dtype=torch.int64, device=device)
-        fn = ix.count_overlaps_dev if name == "count" else ix.coverage_dev
-        step = lambda: fn(pk, ps, pe, out)
-        units, alg = n, n * 20 + nb * 8
-    elif name == "nearest":
-        left = torch.empty(n, dtype=torch.int32, device=device)
-        bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=device)
-        dd = torch.empty(n, dtype=torch.int64, device=device)
-        step = lambda: ix.nearest_k1_dev(pk, ps, pe, left, bits, dd)
-        units, alg = n, n * 28 + n // 8 + nb * 12
-    else:
-        offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
-        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
-        ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
-        torch.cuda.synchronize()
-        total = int(offsets[-1].item())
-        bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
-        pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
-
-        def step():  # count -> scan -> emit
-            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
-            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
-
-        units, alg = total, n * 12 + total * 8 + nb * 12
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+def quick_nearest_k_run(torch, h, k):
+    """nearest with k > 1 (nearest_index.rs:103-190) through brg_nearest: 5M queries x 5M sparse targets, host buffers"""
+    b, p = make_workload(torch, "nearest", h.device, 0, 1, "sorted", h.args.scale * 0.1)
+    b = gen_intervals(torch, max(1024, int(5_000_000 * h.args.scale)), 42, 50, 500, h.device)
+    ix = h.ctx.build_dev(*b, len(HG38), h.brg.WANT_NEAREST)
+    npk, nps, npe = to_np(p[0]).astype(np.uint32), to_np(p[1]), to_np(p[2])
+    ix.nearest_k(npk, nps, npe, k)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        out = ix.nearest_k(npk, nps, npe, k)
+    dt = (time.perf_counter() - t0) / reps
     ix.close()
-    return {"workload": WORKLOADS[name][2], "probe_order": order, "value": units / (ms * 1e-3), "unit": "pairs/s" if name == "pairs" else "probes/s",
-            "ms_per_step": ms, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
-            **({"pairs_per_probe": units / n} if name == "pairs" else {})}
+    return {"workload": f"nearest k={k}: {len(nps)} sorted queries x {b[1].numel()} sparse targets (host buffers, count -> scan -> emit, "
+                        "one row per thread)", "value": len(nps) / dt, "unit": "probes/s", "ms_per_step": dt * 1e3, "rows_out": int(len(out[0]))}
 
 
 if __name__ == "__main__":

@@ -17,7 +17,8 @@ PAIRS_INNER, PAIRS_SEMI, PAIRS_ANTI = 0, 1, 2
 ABI_SYMBOLS = [
     "brg_last_error", "brg_version", "brg_ctx_create", "brg_ctx_destroy", "brg_ctx_device", "brg_ctx_sm_count",
     "brg_pinned_alloc", "brg_pinned_free", "brg_build", "brg_build_dev", "brg_index_destroy", "brg_index_rows",
-    "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_count_overlaps",
+    "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_index_slab_alloc",
+    "brg_index_slab_free", "brg_index_attach", "brg_index_replicate", "brg_count_overlaps",
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
     "brg_count_overlaps_arrow", "brg_coverage_arrow", "brg_nearest_k1_arrow",
@@ -80,6 +81,11 @@ def lib():
         f.restype = u64
     L.brg_index_export.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
     L.brg_index_import.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.brg_index_slab_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.brg_index_slab_free.argtypes = [vp, vp]
+    L.brg_index_slab_free.restype = None
+    L.brg_index_attach.argtypes = [vp, vp, u64, vp, C.POINTER(vp)]
+    L.brg_index_replicate.argtypes = [vp, C.POINTER(vp), i32, C.POINTER(vp)]
     L.brg_count_overlaps.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
     L.brg_coverage.argtypes = [vp, vp, vp, vp, vp, u64, i32, vp]
     L.brg_count_overlaps_runs.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, i32, vp]

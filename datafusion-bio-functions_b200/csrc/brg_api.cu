@@ -2,6 +2,7 @@
 // context / stream lanes, index build pipeline (K1 sort -> K2 scans -> rank directories -> one HBM slab),
 // chunked host<->device pipelines for the probe entry points, variable-length results in pooled pinned memory.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -9,6 +10,9 @@
 #include <cstring>
 #include <mutex>
 #include <chrono>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "../../include/bioranges.h"
@@ -77,6 +81,87 @@ struct ScratchBuf {
 
 struct PinnedBlock { void* p; uint64_t bytes; };
 
+// page-locked host buffer owned by a lane (the staging ring of pageable caller buffers, key runs)
+struct HostBuf {
+    void* p = nullptr;
+    uint64_t bytes = 0;
+    ~HostBuf() { if (p) cudaFreeHost(p); }
+    int ensure(uint64_t b) {
+        if (b <= bytes) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaHostAlloc(") + std::to_string(b) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+        bytes = b;
+        return 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Host worker threads of a context: the copies between pageable caller buffers and the pinned staging ring, and the scan of
+// a probe key column for runs.  parallel_for(n, fn) runs fn(0..n-1) on the workers plus the calling thread and returns when
+// all are done; one caller at a time (callers serialise on `call_mu`).
+class HostPool {
+public:
+    explicit HostPool(int n_threads) {
+        for (int i = 0; i < n_threads; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int width() const { return (int)workers_.size() + 1; }
+    void parallel_for(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        std::lock_guard<std::mutex> call(call_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; next_ = 0; total_ = n; pending_ = n; gen_++;
+        }
+        cv_.notify_all();
+        run_some();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void run_some() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= total_) return;
+                i = next_++;
+                f = fn_;
+            }
+            (*f)(i);
+            bool last;
+            { std::lock_guard<std::mutex> lk(mu_); last = --pending_ == 0; }
+            if (last) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            run_some();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int next_ = 0, total_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 struct Lane {
     cudaStream_t h2d = nullptr, k = nullptr, d2h = nullptr;
     static constexpr int NBUF = 2;
@@ -84,6 +169,9 @@ struct Lane {
     cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
     DevBuf scratch_a, scratch_b, scratch_c, scratch_d;  // counts / offsets / scan scratch / flags
     DevBuf raw_s[NBUF], raw_e[NBUF], bad_rows;          // Arrow ingest: position columns in their native width; first bad rows
+    // pinned staging ring for pageable caller buffers (filled / drained by the context's host pool) and per-chunk key runs
+    HostBuf stage_key[NBUF], stage_s[NBUF], stage_e[NBUF], stage_o0[NBUF], stage_o1[NBUF], stage_o2[NBUF], stage_runs[NBUF];
+    DevBuf runs_key[NBUF], runs_end[NBUF];
     bool busy = false;
 };
 
@@ -100,7 +188,22 @@ struct brg_ctx {
     std::vector<Lane*> lanes;
     std::vector<PinnedBlock> pinned_free;
     uint64_t chunk_rows = 8ull << 20;
+    // Variable-length results (brg_rows, brg_merged, brg_gaps) hand out pinned blocks of this context's pool and may outlive
+    // brg_ctx_destroy (a garbage-collected host language releases them late): every result holds a reference; the struct is
+    // freed by whoever drops the last one, and after `dead` blocks go straight back to the driver.
+    std::atomic<int> refs{1};
+    std::atomic<bool> dead{false};
+    std::unique_ptr<HostPool> pool;  // created on first use
+    int host_threads = 0;
 };
+static void ctx_unref(brg_ctx* c) {
+    if (c && c->refs.fetch_sub(1) == 1) delete c;
+}
+static HostPool* host_pool(brg_ctx* c) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->pool) c->pool.reset(new HostPool(std::max(0, c->host_threads - 1)));
+    return c->pool.get();
+}
 
 // serialisable description of the slab
 struct DirDesc { uint64_t off_kd, off_D; uint32_t shift, entries; };
@@ -117,7 +220,10 @@ struct IndexHeader {
     uint32_t n_blocks, pad_;
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
+static const uint32_t kVersion = 4;
 static const uint64_t kNone = ~0ull;
+static const uint64_t kSlabHeaderBytes = 4096;  // reserved at the front of every slab for the IndexHeader
+static_assert(sizeof(IndexHeader) <= kSlabHeaderBytes, "IndexHeader must fit the reserved slab prefix");
 
 struct brg_index {
     brg_ctx* ctx = nullptr;
@@ -280,21 +386,38 @@ extern "C" BRG_API int brg_ctx_create(int device_id, brg_ctx** out) {
                   "; libbioranges is built for sm_100a only");
         return BRG_ERR_CUDA;
     }
-    brg_ctx* c = new brg_ctx();
+    std::unique_ptr<brg_ctx> c(new brg_ctx());  // (freed on every early return below)
     c->device = device_id;
     c->sms = prop.multiProcessorCount;
     BRG_CUDA(cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking));
+    auto fail = [&](cudaError_t err, const char* what) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(err));
+        cudaStreamDestroy(c->build_stream);
+        return BRG_ERR_CUDA;
+    };
     {   // stream-ordered scratch (cudaMallocAsync) must not go back to the OS between calls
         cudaMemPool_t pool;
-        BRG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_id));
+        cudaError_t pe = cudaDeviceGetDefaultMemPool(&pool, device_id);
+        if (pe != cudaSuccess) return fail(pe, "cudaDeviceGetDefaultMemPool");
         uint64_t keep = ~0ull;
-        BRG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pe = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (pe != cudaSuccess) return fail(pe, "cudaMemPoolSetAttribute");
     }
     if (const char* env = getenv("BRG_CHUNK_ROWS")) {
         uint64_t v = strtoull(env, nullptr, 10);
         if (v >= 1024) c->chunk_rows = v;
     }
-    *out = c;
+    {   // host worker threads (staging of pageable buffers, key-run scans): BRG_HOST_THREADS, default min(8, cores of the process)
+        int t = 0;
+        if (const char* env = getenv("BRG_HOST_THREADS")) t = atoi(env);
+        if (t <= 0) {
+            cpu_set_t set;
+            int cores = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            t = std::max(1, std::min(8, cores));
+        }
+        c->host_threads = std::min(t, 64);
+    }
+    *out = c.release();
     return BRG_OK;
 }
 
@@ -314,10 +437,17 @@ extern "C" BRG_API void brg_ctx_destroy(brg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (Lane* l : c->lanes) lane_free(l);
-    for (auto& b : c->pinned_free) cudaFreeHost(b.p);
-    if (c->build_stream) cudaStreamDestroy(c->build_stream);
-    delete c;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->dead.store(true);
+        for (Lane* l : c->lanes) lane_free(l);
+        c->lanes.clear();
+        for (auto& b : c->pinned_free) cudaFreeHost(b.p);
+        c->pinned_free.clear();
+        c->pool.reset();
+    }
+    if (c->build_stream) { cudaStreamDestroy(c->build_stream); c->build_stream = nullptr; }
+    ctx_unref(c);  // results still alive keep the (now empty) struct until they are released
 }
 extern "C" BRG_API int brg_ctx_device(const brg_ctx* c) { return c ? c->device : -1; }
 extern "C" BRG_API int brg_ctx_sm_count(const brg_ctx* c) { return c ? c->sms : 0; }
@@ -388,7 +518,7 @@ static int pinned_get(brg_ctx* c, uint64_t bytes, PinnedBlock* out) {
 static void pinned_put(brg_ctx* c, PinnedBlock b) {
     if (!b.p) return;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (c->pinned_free.size() >= 16) { cudaFreeHost(b.p); return; }
+    if (c->dead.load() || c->pinned_free.size() >= 16) { cudaFreeHost(b.p); return; }  // (dead: the context was destroyed first)
     c->pinned_free.push_back(b);
 }
 
@@ -628,9 +758,9 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     mark("compact rank index");
     // ---- lay out and fill the slab -------------------------------------------------------------------------
     IndexHeader h{};
-    h.magic = kMagic; h.version = 3;
+    h.magic = kMagic; h.version = kVersion;
     h.n_keys = n_keys; h.n = n_valid; h.n_merged = n_merged; h.flags = want | idx_props;
-    uint64_t cur = 0;
+    uint64_t cur = kSlabHeaderBytes;  // the slab starts with a copy of its own header: one buffer describes and replicates itself
     auto place = [&](bool on, uint64_t bytes) -> uint64_t {
         if (!on) return kNone;
         uint64_t o = cur;
@@ -696,6 +826,8 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
             chk(copy_in(h.off_cB[a], cB[a].p, (uint64_t)n_blocks * 16));
             chk(copy_in(h.cdir[a].off_kd, cdb[a].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
         }
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(base, 0, kSlabHeaderBytes, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st);  // (synchronised below, before h dies)
     if (ce != cudaSuccess) { cudaFree(slab); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
     for (int i = 0; i < 5; i++) {
         if (!need_dir[i]) continue;
@@ -774,7 +906,7 @@ extern "C" BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64
     if (header_len != sizeof(IndexHeader)) { set_error("brg_index_import: header size mismatch"); return BRG_ERR_INVALID; }
     IndexHeader h;
     memcpy(&h, header, sizeof(h));
-    if (h.magic != kMagic || h.version != 3) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
+    if (h.magic != kMagic || h.version != kVersion) { set_error("brg_index_import: bad magic/version"); return BRG_ERR_INVALID; }
     BRG_CUDA(cudaSetDevice(ctx->device));
     void* slab = nullptr;
     cudaError_t e = cudaMalloc(&slab, h.slab_bytes);
@@ -784,6 +916,94 @@ extern "C" BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64
     *out = ix;
     if (d_slab) *d_slab = slab;
     if (slab_bytes) *slab_bytes = h.slab_bytes;
+    return BRG_OK;
+}
+
+// One-collective replication (one process per GPU): the slab carries its header, so a receiver needs only the byte count up
+// front: brg_index_slab_alloc -> receive the bytes (ncclBroadcast / cudaMemcpyPeer) -> brg_index_attach.
+extern "C" BRG_API int brg_index_slab_alloc(brg_ctx* ctx, uint64_t slab_bytes, void** d_slab) {
+    if (!ctx || !d_slab || slab_bytes < kSlabHeaderBytes) { set_error("brg_index_slab_alloc: bad argument"); return BRG_ERR_INVALID; }
+    *d_slab = nullptr;
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(d_slab, slab_bytes);
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(index slab): ") + cudaGetErrorString(e)); cudaGetLastError(); *d_slab = nullptr; return BRG_ERR_OOM; }
+    return BRG_OK;
+}
+extern "C" BRG_API void brg_index_slab_free(brg_ctx* ctx, void* d_slab) {
+    if (!d_slab) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(d_slab);
+}
+extern "C" BRG_API int brg_index_attach(brg_ctx* ctx, void* d_slab, uint64_t slab_bytes, void* stream, brg_index** out) {
+    if (!ctx || !d_slab || !out) { set_error("brg_index_attach: NULL argument"); return BRG_ERR_INVALID; }
+    *out = nullptr;
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    IndexHeader h;
+    cudaStream_t st = (cudaStream_t)stream;
+    BRG_CUDA(cudaMemcpyAsync(&h, d_slab, sizeof(h), cudaMemcpyDeviceToHost, st));  // ordered after the receive on `stream`
+    BRG_CUDA(cudaStreamSynchronize(st));
+    if (h.magic != kMagic || h.version != kVersion || h.slab_bytes != slab_bytes) { set_error("brg_index_attach: the buffer does not hold an index slab of this size"); return BRG_ERR_INVALID; }
+    brg_index* ix = new brg_index();
+    ix->ctx = ctx; ix->h = h; ix->slab = d_slab; ix->view = make_view(h, d_slab);
+    *out = ix;
+    return BRG_OK;
+}
+
+// Replication inside ONE process (the Rust ExecutionPlan maps partitions to GPUs, interval_join.rs:442-550; the build side is
+// shared by all partitions, joins/utils.rs:73-107): out[i] = a replica of `src` on the device of dst[i].  The slab travels
+// device to device (NVLink peer copies where the topology has them) in a doubling tree: every GPU that already holds the
+// slab feeds one that does not, so N replicas take ceil(log2(N + 1)) copy rounds instead of N copies out of one GPU.
+extern "C" BRG_API int brg_index_replicate(const brg_index* src, brg_ctx* const* dst, int n_dst, brg_index** out) {
+    if (!src || !src->ctx || (n_dst > 0 && (!dst || !out))) { set_error("brg_index_replicate: NULL argument"); return BRG_ERR_INVALID; }
+    for (int i = 0; i < n_dst; i++) out[i] = nullptr;
+    for (int i = 0; i < n_dst; i++)
+        if (!dst[i]) { set_error("brg_index_replicate: NULL destination context"); return BRG_ERR_INVALID; }
+    const uint64_t bytes = src->h.slab_bytes;
+    std::vector<void*> slab((size_t)n_dst, nullptr);
+    std::vector<cudaEvent_t> ready((size_t)n_dst + 1, nullptr);  // [0] = source, [i + 1] = replica i holds the bytes
+    auto cleanup = [&](bool failed) {
+        for (auto e : ready) if (e) cudaEventDestroy(e);
+        if (failed) for (int i = 0; i < n_dst; i++) { if (slab[i]) { cudaSetDevice(dst[i]->device); cudaFree(slab[i]); } if (out[i]) { delete out[i]; out[i] = nullptr; } }
+    };
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n_dst && e == cudaSuccess; i++) {
+        e = cudaSetDevice(dst[i]->device);
+        if (e == cudaSuccess) e = cudaMalloc(&slab[i], bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[i + 1], cudaEventDisableTiming);
+        if (e == cudaSuccess && dst[i]->device != src->ctx->device) {  // direct peer access where available (an error here only means "not needed / not possible")
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dst[i]->device, src->ctx->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(src->ctx->device, 0);
+            cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaSetDevice(src->ctx->device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ready[0], src->ctx->build_stream);
+    // holder h (0 = the source, i + 1 = replica i) feeds replica t in the round in which the number of holders doubles
+    for (int have = 1; have < n_dst + 1 && e == cudaSuccess; have *= 2) {
+        for (int hsrc = 0; hsrc < have && hsrc + have < n_dst + 1 && e == cudaSuccess; hsrc++) {
+            const int t = hsrc + have - 1;  // replica index
+            const brg_ctx* from = hsrc == 0 ? src->ctx : dst[hsrc - 1];
+            const void* from_p = hsrc == 0 ? src->slab : slab[hsrc - 1];
+            e = cudaSetDevice(dst[t]->device);
+            cudaStream_t st = dst[t]->build_stream;
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ready[hsrc], 0);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(slab[t], dst[t]->device, from_p, from->device, bytes, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ready[t + 1], st);
+        }
+    }
+    for (int i = 0; i < n_dst && e == cudaSuccess; i++) {
+        e = cudaSetDevice(dst[i]->device);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dst[i]->build_stream);
+    }
+    if (e != cudaSuccess) { set_error(std::string("brg_index_replicate: ") + cudaGetErrorString(e)); cudaGetLastError(); cleanup(true); return BRG_ERR_CUDA; }
+    for (int i = 0; i < n_dst; i++) {
+        brg_index* ix = new brg_index();
+        ix->ctx = dst[i]; ix->h = src->h; ix->slab = slab[i]; ix->view = make_view(src->h, slab[i]);
+        out[i] = ix;
+    }
+    cleanup(false);
+    cudaSetDevice(src->ctx->device);
     return BRG_OK;
 }
 
@@ -889,6 +1109,60 @@ struct PosTypes {  // Arrow ingest: native width of the start / end value buffer
     uint64_t* bad_end_row = nullptr;
 };
 
+// ---- pageable caller buffers ---------------------------------------------------------------------------------------
+// cudaMemcpyAsync on pageable memory is staged by the driver on the calling thread: nothing overlaps and the copy runs at
+// a fraction of the PCIe rate.  The Arrow buffers DataFusion hands over are ordinary heap memory, so run_fixed detects them
+// and moves them through the lane's PINNED staging ring itself: the context's host threads copy chunk j + 1 in (and chunk
+// j - 1 out) while chunk j is on the wire / in the kernel.
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static void pool_memcpy(HostPool* pool, void* dst, const void* src, uint64_t bytes) {
+    const uint64_t slice = 4ull << 20;
+    const int parts = (int)std::min<uint64_t>((bytes + slice - 1) / slice, (uint64_t)pool->width() * 4);
+    if (parts <= 1) { memcpy(dst, src, bytes); return; }
+    const uint64_t per = ((bytes + parts - 1) / parts + 63) & ~63ull;
+    pool->parallel_for(parts, [&](int i) {
+        const uint64_t b = (uint64_t)i * per;
+        if (b < bytes) memcpy((char*)dst + b, (const char*)src + b, std::min(per, bytes - b));
+    });
+}
+// Runs of equal ids in key[0, m): at most `cap` of them are written as (id, end row relative to the chunk start + row0);
+// returns the number of runs, or 0 when there are more than cap (the caller then sends the column itself).  This is the
+// contig-cache loop of the reference's row loops (interval_tree.rs:258-265) done once per staging chunk: on a coordinate-
+// sorted table a chunk holds a handful of runs, and 8 + 4 bytes per run cross PCIe instead of 4 bytes per row.
+static uint32_t detect_key_runs(HostPool* pool, const uint32_t* key, uint64_t m, uint64_t row0, uint32_t cap, uint32_t* run_key,
+                                uint64_t* run_end) {
+    if (m == 0) return 0;
+    const int parts = (int)std::min<uint64_t>((m + (1u << 20) - 1) >> 20, (uint64_t)pool->width() * 4);
+    const uint64_t per = (m + parts - 1) / parts;
+    std::vector<std::vector<uint64_t>> cuts((size_t)parts);  // rows i (relative) with key[i] != key[i - 1]
+    std::atomic<uint32_t> total{0};
+    pool->parallel_for(parts, [&](int t) {
+        const uint64_t b = std::max<uint64_t>((uint64_t)t * per, 1), e = std::min(m, ((uint64_t)t + 1) * per);
+        std::vector<uint64_t>& c = cuts[(size_t)t];
+        for (uint64_t blk = b; blk < e && total.load(std::memory_order_relaxed) <= cap; blk += 4096) {
+            const uint64_t be = std::min(e, blk + 4096);
+            uint32_t acc = 0;
+            for (uint64_t i = blk; i < be; i++) acc |= key[i] ^ key[i - 1];  // (vectorises; almost every block has no boundary)
+            if (!acc) continue;
+            for (uint64_t i = blk; i < be; i++)
+                if (key[i] != key[i - 1]) { c.push_back(i); total.fetch_add(1, std::memory_order_relaxed); }
+        }
+    });
+    if (total.load() + 1 > cap) return 0;
+    uint32_t r = 0;
+    uint64_t begin = 0;
+    for (auto& c : cuts)
+        for (uint64_t cut : c) { run_key[r] = key[begin]; run_end[r] = row0 + cut; r++; begin = cut; }
+    run_key[r] = key[begin]; run_end[r] = row0 + m; r++;
+    return r;
+}
+constexpr uint32_t kMaxChunkRuns = 1024;
+
 static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32_t* key, const void* start_v,
                      const void* end_v, uint64_t n, int include_overlaps, int strict, int64_t* out_i64,
                      uint32_t* out_left, uint8_t* out_bits, int64_t* out_dist, KeyRuns runs = KeyRuns(), PosTypes pt = PosTypes()) {
@@ -916,96 +1190,173 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
     int rc;
     if ((rc = g.acquire())) return rc;
     Lane* l = g.l;
-    if (by_runs) {  // the runs travel once (a few bytes per contig); the per-row key column is expanded on the device
-        if ((rc = l->scratch_a.ensure(runs.n_runs * 4)) || (rc = l->scratch_b.ensure(runs.n_runs * 8))) return rc;
-        BRG_CUDA(cudaMemcpyAsync(l->scratch_a.p, runs.run_key, runs.n_runs * 4, cudaMemcpyHostToDevice, l->k));
-        BRG_CUDA(cudaMemcpyAsync(l->scratch_b.p, runs.run_end, runs.n_runs * 8, cudaMemcpyHostToDevice, l->k));
-    }
-    const bool dev_key = key != nullptr || by_runs;
-    // chunk rows are a multiple of 32 so that validity bitmap words never straddle chunks
-    const uint64_t C = std::min<uint64_t>((ctx->chunk_rows + 31) & ~31ull, (n + 31) & ~31ull);
-    if (narrow_s || narrow_e) {
-        if ((rc = l->bad_rows.ensure(16))) return rc;
-        BRG_CUDA(cudaMemsetAsync(l->bad_rows.p, 0xFF, 16, l->k));
-    }
-    for (int b = 0; b < Lane::NBUF; b++) {
-        if (dev_key && (rc = l->in_key[b].ensure(C * 4))) return rc;
-        if ((rc = l->in_s[b].ensure(C * 4)) || (rc = l->in_e[b].ensure(C * 4))) return rc;
-        if (narrow_s && (rc = l->raw_s[b].ensure(C * ws))) return rc;
-        if (narrow_e && (rc = l->raw_e[b].ensure(C * we))) return rc;
-        if (op == OP_NEAREST1) {
-            if ((rc = l->out0[b].ensure(C * 4)) || (rc = l->out1[b].ensure(C / 8 + 4))) return rc;
-            if (out_dist && (rc = l->out2[b].ensure(C * 8))) return rc;
-        } else {
-            if ((rc = l->out0[b].ensure(C * 8))) return rc;
+    // which caller buffers are pageable (BRG_STAGE=0 leaves them to the driver: the measured alternative)
+    static const bool stage_on = !(getenv("BRG_STAGE") && getenv("BRG_STAGE")[0] == '0');
+    static const bool runs_on = !(getenv("BRG_CHUNK_RUNS") && getenv("BRG_CHUNK_RUNS")[0] == '0');
+    const bool pg_s = stage_on && is_pageable(start), pg_e = stage_on && is_pageable(end);
+    const bool pg_o0 = stage_on && is_pageable(op == OP_NEAREST1 ? (const void*)out_left : (const void*)out_i64);
+    const bool pg_o1 = stage_on && op == OP_NEAREST1 && is_pageable(out_bits);
+    const bool pg_o2 = stage_on && op == OP_NEAREST1 && out_dist && is_pageable(out_dist);
+    const bool pg_key = stage_on && key && !by_runs && is_pageable(key);
+    const bool staged_out = pg_o0 || pg_o1 || pg_o2;
+    const bool chunk_runs = runs_on && key && !by_runs;  // look for runs in every chunk of a per-row key column
+    HostPool* pool = (pg_s || pg_e || pg_key || staged_out || chunk_runs) ? host_pool(ctx) : nullptr;
+
+    // everything below is asynchronous on the lane's three streams: a failure must drain them before the lane (and the
+    // caller's buffers) are released
+    auto body = [&]() -> int {
+        int rc;
+        if (by_runs) {  // the runs travel once (a few bytes per contig); the per-row key column is expanded on the device
+            if ((rc = l->scratch_a.ensure(runs.n_runs * 4)) || (rc = l->scratch_b.ensure(runs.n_runs * 8))) return rc;
+            BRG_CUDA(cudaMemcpyAsync(l->scratch_a.p, runs.run_key, runs.n_runs * 4, cudaMemcpyHostToDevice, l->k));
+            BRG_CUDA(cudaMemcpyAsync(l->scratch_b.p, runs.run_end, runs.n_runs * 8, cudaMemcpyHostToDevice, l->k));
         }
-    }
-    // chunk schedule: full chunks of C rows.  (Tapering the ends -- C/8, C/4, C/2 ... -- to shorten the first H2D and the last
-    // D2H copy, which nothing overlaps, was measured and is slower: 24.2 ms vs 22.4 ms per 125M probes; so are smaller chunks
-    // throughout, profiles/r1_e2e_chunk_sweep.txt: the per-chunk cost outweighs the shorter pipeline fill.)
-    std::vector<uint64_t> sizes;
-    for (uint64_t left = n; left; left -= std::min(C, left)) sizes.push_back(std::min(C, left));
-    uint64_t done = 0;
-    for (uint64_t j = 0; j < sizes.size(); done += sizes[j], j++) {
-        const int b = (int)(j % Lane::NBUF);
-        const uint64_t m = sizes[j];
-        // inputs of buffer b may be overwritten once the kernel that read them has finished
-        BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
-        if (key && !by_runs) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, key + done, m * 4, cudaMemcpyHostToDevice, l->h2d));
-        BRG_CUDA(cudaMemcpyAsync(narrow_s ? l->raw_s[b].p : l->in_s[b].p, start + done * ws, m * ws, cudaMemcpyHostToDevice, l->h2d));
-        BRG_CUDA(cudaMemcpyAsync(narrow_e ? l->raw_e[b].p : l->in_e[b].p, end + done * we, m * we, cudaMemcpyHostToDevice, l->h2d));
-        BRG_CUDA(cudaEventRecord(l->ev_in[b], l->h2d));
-        // kernel: after its inputs landed and after the previous results of buffer b left the device
-        BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_in[b], 0));
-        BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_out[b], 0));
-        const uint32_t* dk = dev_key ? l->in_key[b].as<uint32_t>() : nullptr;
-        if (by_runs) {  // (the k stream already waited for the previous kernel that read this buffer)
-            expand_runs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->k>>>(l->scratch_a.as<uint32_t>(),
-                                                                              l->scratch_b.as<unsigned long long>(),
-                                                                              (uint32_t)runs.n_runs, done, m, l->in_key[b].as<uint32_t>());
-            g_launches.fetch_add(1);
+        const bool dev_key = key != nullptr || by_runs;
+        // chunk rows are a multiple of 32 so that validity bitmap words never straddle chunks
+        const uint64_t C = std::min<uint64_t>((ctx->chunk_rows + 31) & ~31ull, (n + 31) & ~31ull);
+        if (narrow_s || narrow_e) {
+            if ((rc = l->bad_rows.ensure(16))) return rc;
+            BRG_CUDA(cudaMemsetAsync(l->bad_rows.p, 0xFF, 16, l->k));
         }
-        if (narrow_s && (rc = launch_narrow(l->raw_s[b].p, pt.s_type, m, done, l->in_s[b].as<int32_t>(), l->bad_rows.as<unsigned long long>(), l->k))) { cudaDeviceSynchronize(); return rc; }
-        if (narrow_e && (rc = launch_narrow(l->raw_e[b].p, pt.e_type, m, done, l->in_e[b].as<int32_t>(), l->bad_rows.as<unsigned long long>() + 1, l->k))) { cudaDeviceSynchronize(); return rc; }
-        if (op == OP_COUNT)
-            rc = launch_count(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
-        else if (op == OP_COVERAGE)
-            rc = launch_coverage(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
-        else
-            rc = launch_nearest_k1(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, include_overlaps, strict,
-                                   l->out0[b].as<uint32_t>(), l->out1[b].as<uint32_t>(), out_dist ? l->out2[b].as<int64_t>() : nullptr, l->k);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
-        BRG_CUDA(cudaEventRecord(l->ev_k[b], l->k));
-        BRG_CUDA(cudaStreamWaitEvent(l->d2h, l->ev_k[b], 0));
-        if (op == OP_NEAREST1) {
-            BRG_CUDA(cudaMemcpyAsync(out_left + done, l->out0[b].p, m * 4, cudaMemcpyDeviceToHost, l->d2h));
-            BRG_CUDA(cudaMemcpyAsync(out_bits + done / 8, l->out1[b].p, ((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, l->d2h));
-            if (out_dist) BRG_CUDA(cudaMemcpyAsync(out_dist + done, l->out2[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
-        } else {
-            BRG_CUDA(cudaMemcpyAsync(out_i64 + done, l->out0[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+        for (int b = 0; b < Lane::NBUF; b++) {
+            if (dev_key && (rc = l->in_key[b].ensure(C * 4))) return rc;
+            if ((rc = l->in_s[b].ensure(C * 4)) || (rc = l->in_e[b].ensure(C * 4))) return rc;
+            if (narrow_s && (rc = l->raw_s[b].ensure(C * ws))) return rc;
+            if (narrow_e && (rc = l->raw_e[b].ensure(C * we))) return rc;
+            if (op == OP_NEAREST1) {
+                if ((rc = l->out0[b].ensure(C * 4)) || (rc = l->out1[b].ensure(C / 8 + 4))) return rc;
+                if (out_dist && (rc = l->out2[b].ensure(C * 8))) return rc;
+            } else {
+                if ((rc = l->out0[b].ensure(C * 8))) return rc;
+            }
+            if (pg_s && (rc = l->stage_s[b].ensure(C * ws))) return rc;
+            if (pg_e && (rc = l->stage_e[b].ensure(C * we))) return rc;
+            if (pg_key && (rc = l->stage_key[b].ensure(C * 4))) return rc;
+            if (pg_o0 && (rc = l->stage_o0[b].ensure(C * 8))) return rc;
+            if (pg_o1 && (rc = l->stage_o1[b].ensure(C / 8 + 4))) return rc;
+            if (pg_o2 && (rc = l->stage_o2[b].ensure(C * 8))) return rc;
+            if (chunk_runs && ((rc = l->stage_runs[b].ensure((uint64_t)kMaxChunkRuns * 12)) || (rc = l->runs_key[b].ensure((uint64_t)kMaxChunkRuns * 4)) ||
+                               (rc = l->runs_end[b].ensure((uint64_t)kMaxChunkRuns * 8))))
+                return rc;
         }
-        BRG_CUDA(cudaEventRecord(l->ev_out[b], l->d2h));
+        // chunk schedule: full chunks of C rows.  (Tapering the ends -- C/8, C/4, C/2 ... -- to shorten the first H2D and the
+        // last D2H copy, which nothing overlaps, was measured and is slower: 24.2 ms vs 22.4 ms per 125M probes; so are smaller
+        // chunks throughout, profiles/r1_e2e_chunk_sweep.txt: the per-chunk cost outweighs the shorter pipeline fill.)
+        std::vector<uint64_t> sizes, offs;
+        for (uint64_t left = n, at = 0; left;) { const uint64_t m = std::min(C, left); sizes.push_back(m); offs.push_back(at); at += m; left -= m; }
+        // drains chunk j's staged results into the caller's (pageable) output buffers
+        auto drain = [&](uint64_t j) -> int {
+            const int b = (int)(j % Lane::NBUF);
+            const uint64_t m = sizes[j], done = offs[j];
+            BRG_CUDA(cudaEventSynchronize(l->ev_out[b]));
+            if (op == OP_NEAREST1) {
+                if (pg_o0) pool_memcpy(pool, out_left + done, l->stage_o0[b].p, m * 4);
+                if (pg_o1) pool_memcpy(pool, out_bits + done / 8, l->stage_o1[b].p, ((m + 31) / 32) * 4);
+                if (pg_o2) pool_memcpy(pool, out_dist + done, l->stage_o2[b].p, m * 8);
+            } else if (pg_o0) {
+                pool_memcpy(pool, out_i64 + done, l->stage_o0[b].p, m * 8);
+            }
+            return 0;
+        };
+        for (uint64_t j = 0; j < sizes.size(); j++) {
+            const int b = (int)(j % Lane::NBUF);
+            const uint64_t m = sizes[j], done = offs[j];
+            // ---- host side of the input: staging copies and the key-run scan (they overlap the chunks already enqueued) ----
+            if ((pg_s || pg_e || pg_key || chunk_runs) && j >= (uint64_t)Lane::NBUF)
+                BRG_CUDA(cudaEventSynchronize(l->ev_in[b]));  // the H2D copies that read this staging buffer are done
+            uint32_t n_chunk_runs = 0;
+            if (chunk_runs) {
+                uint32_t* rk = l->stage_runs[b].as<uint32_t>();
+                uint64_t* re = reinterpret_cast<uint64_t*>(l->stage_runs[b].as<char>() + (uint64_t)kMaxChunkRuns * 4);
+                n_chunk_runs = detect_key_runs(pool, key + done, m, 0, kMaxChunkRuns, rk, re);
+            }
+            const bool send_key = key && !by_runs && n_chunk_runs == 0;
+            const void* src_s = start + done * ws;
+            const void* src_e = end + done * we;
+            const void* src_k = key ? (const void*)(key + done) : nullptr;
+            if (pg_s) { pool_memcpy(pool, l->stage_s[b].p, src_s, m * ws); src_s = l->stage_s[b].p; }
+            if (pg_e) { pool_memcpy(pool, l->stage_e[b].p, src_e, m * we); src_e = l->stage_e[b].p; }
+            if (pg_key && send_key) { pool_memcpy(pool, l->stage_key[b].p, src_k, m * 4); src_k = l->stage_key[b].p; }
+            // ---- device side -----------------------------------------------------------------------------------------------
+            // inputs of buffer b may be overwritten once the kernel that read them has finished
+            BRG_CUDA(cudaStreamWaitEvent(l->h2d, l->ev_k[b], 0));
+            if (send_key) BRG_CUDA(cudaMemcpyAsync(l->in_key[b].p, src_k, m * 4, cudaMemcpyHostToDevice, l->h2d));
+            if (n_chunk_runs) {
+                BRG_CUDA(cudaMemcpyAsync(l->runs_key[b].p, l->stage_runs[b].p, (uint64_t)n_chunk_runs * 4, cudaMemcpyHostToDevice, l->h2d));
+                BRG_CUDA(cudaMemcpyAsync(l->runs_end[b].p, l->stage_runs[b].as<char>() + (uint64_t)kMaxChunkRuns * 4, (uint64_t)n_chunk_runs * 8,
+                                         cudaMemcpyHostToDevice, l->h2d));
+            }
+            BRG_CUDA(cudaMemcpyAsync(narrow_s ? l->raw_s[b].p : l->in_s[b].p, src_s, m * ws, cudaMemcpyHostToDevice, l->h2d));
+            BRG_CUDA(cudaMemcpyAsync(narrow_e ? l->raw_e[b].p : l->in_e[b].p, src_e, m * we, cudaMemcpyHostToDevice, l->h2d));
+            BRG_CUDA(cudaEventRecord(l->ev_in[b], l->h2d));
+            // kernel: after its inputs landed and after the previous results of buffer b left the device
+            BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_in[b], 0));
+            BRG_CUDA(cudaStreamWaitEvent(l->k, l->ev_out[b], 0));
+            const uint32_t* dk = dev_key ? l->in_key[b].as<uint32_t>() : nullptr;
+            if (by_runs) {  // (the k stream already waited for the previous kernel that read this buffer)
+                expand_runs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->k>>>(l->scratch_a.as<uint32_t>(),
+                                                                                  l->scratch_b.as<unsigned long long>(),
+                                                                                  (uint32_t)runs.n_runs, done, m, l->in_key[b].as<uint32_t>());
+                g_launches.fetch_add(1);
+            } else if (n_chunk_runs) {
+                expand_runs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->k>>>(l->runs_key[b].as<uint32_t>(),
+                                                                                  l->runs_end[b].as<unsigned long long>(), n_chunk_runs, 0, m,
+                                                                                  l->in_key[b].as<uint32_t>());
+                g_launches.fetch_add(1);
+            }
+            if (narrow_s && (rc = launch_narrow(l->raw_s[b].p, pt.s_type, m, done, l->in_s[b].as<int32_t>(), l->bad_rows.as<unsigned long long>(), l->k))) return rc;
+            if (narrow_e && (rc = launch_narrow(l->raw_e[b].p, pt.e_type, m, done, l->in_e[b].as<int32_t>(), l->bad_rows.as<unsigned long long>() + 1, l->k))) return rc;
+            if (op == OP_COUNT)
+                rc = launch_count(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
+            else if (op == OP_COVERAGE)
+                rc = launch_coverage(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, strict, l->out0[b].as<int64_t>(), l->k);
+            else
+                rc = launch_nearest_k1(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, include_overlaps, strict,
+                                       l->out0[b].as<uint32_t>(), l->out1[b].as<uint32_t>(), out_dist ? l->out2[b].as<int64_t>() : nullptr, l->k);
+            if (rc) return rc;
+            BRG_CUDA(cudaEventRecord(l->ev_k[b], l->k));
+            BRG_CUDA(cudaStreamWaitEvent(l->d2h, l->ev_k[b], 0));
+            if (op == OP_NEAREST1) {
+                BRG_CUDA(cudaMemcpyAsync(pg_o0 ? l->stage_o0[b].p : (void*)(out_left + done), l->out0[b].p, m * 4, cudaMemcpyDeviceToHost, l->d2h));
+                BRG_CUDA(cudaMemcpyAsync(pg_o1 ? l->stage_o1[b].p : (void*)(out_bits + done / 8), l->out1[b].p, ((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, l->d2h));
+                if (out_dist) BRG_CUDA(cudaMemcpyAsync(pg_o2 ? l->stage_o2[b].p : (void*)(out_dist + done), l->out2[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+            } else {
+                BRG_CUDA(cudaMemcpyAsync(pg_o0 ? l->stage_o0[b].p : (void*)(out_i64 + done), l->out0[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+            }
+            BRG_CUDA(cudaEventRecord(l->ev_out[b], l->d2h));
+            // ---- host side of the output: the previous chunk's results leave the staging ring while this one is in flight ----
+            if (staged_out && j >= 1 && (rc = drain(j - 1))) return rc;
+        }
+        if (staged_out && (rc = drain(sizes.size() - 1))) return rc;
+        uint64_t bad[2] = {~0ull, ~0ull};
+        if (narrow_s || narrow_e) BRG_CUDA(cudaMemcpyAsync(bad, l->bad_rows.p, 16, cudaMemcpyDeviceToHost, l->k));
+        BRG_CUDA(cudaStreamSynchronize(l->d2h));
+        BRG_CUDA(cudaStreamSynchronize(l->k));
+        BRG_CUDA(cudaStreamSynchronize(l->h2d));
+        if (bad[0] != ~0ull || bad[1] != ~0ull) {  // array_utils.rs:94-98 (the start column is resolved first)
+            if (pt.bad_start_row) *pt.bad_start_row = bad[0];
+            if (pt.bad_end_row) *pt.bad_end_row = bad[1];
+            const bool in_start = bad[0] != ~0ull;
+            const uint64_t row = in_start ? bad[0] : bad[1];
+            const int t = in_start ? pt.s_type : pt.e_type;
+            const char* col = in_start ? start : end;
+            std::string v;
+            if (t == BRG_POS_INT64) v = std::to_string(reinterpret_cast<const int64_t*>(col)[row]);
+            else if (t == BRG_POS_UINT32) v = std::to_string(reinterpret_cast<const uint32_t*>(col)[row]);
+            else v = std::to_string(reinterpret_cast<const uint64_t*>(col)[row]);
+            set_error("coordinate value " + v + " at row " + std::to_string(row) + " overflows i32 (max 2147483647)");
+            return BRG_ERR_OVERFLOW;
+        }
+        return BRG_OK;
+    };
+    rc = body();
+    if (rc) {  // in-flight copies / kernels still use the lane's and the caller's buffers: drain before anyone reuses them
+        const std::string msg = brg_last_error();
+        cudaStreamSynchronize(l->h2d); cudaStreamSynchronize(l->k); cudaStreamSynchronize(l->d2h);
+        cudaGetLastError();
+        set_error(msg);
     }
-    uint64_t bad[2] = {~0ull, ~0ull};
-    if (narrow_s || narrow_e) BRG_CUDA(cudaMemcpyAsync(bad, l->bad_rows.p, 16, cudaMemcpyDeviceToHost, l->k));
-    BRG_CUDA(cudaStreamSynchronize(l->d2h));
-    BRG_CUDA(cudaStreamSynchronize(l->k));
-    BRG_CUDA(cudaStreamSynchronize(l->h2d));
-    if (bad[0] != ~0ull || bad[1] != ~0ull) {  // array_utils.rs:94-98 (the start column is resolved first)
-        if (pt.bad_start_row) *pt.bad_start_row = bad[0];
-        if (pt.bad_end_row) *pt.bad_end_row = bad[1];
-        const bool in_start = bad[0] != ~0ull;
-        const uint64_t row = in_start ? bad[0] : bad[1];
-        const int t = in_start ? pt.s_type : pt.e_type;
-        const char* col = in_start ? start : end;
-        std::string v;
-        if (t == BRG_POS_INT64) v = std::to_string(reinterpret_cast<const int64_t*>(col)[row]);
-        else if (t == BRG_POS_UINT32) v = std::to_string(reinterpret_cast<const uint32_t*>(col)[row]);
-        else v = std::to_string(reinterpret_cast<const uint64_t*>(col)[row]);
-        set_error("coordinate value " + v + " at row " + std::to_string(row) + " overflows i32 (max 2147483647)");
-        return BRG_ERR_OVERFLOW;
-    }
-    return BRG_OK;
+    return rc;
 }
 
 extern "C" BRG_API int brg_count_overlaps(brg_ctx* ctx, const brg_index* ix, const uint32_t* key, const int32_t* start,
@@ -1116,6 +1467,7 @@ extern "C" BRG_API void brg_rows_release(brg_rows* r) {
     pinned_put(r->ctx, r->blk_ps); pinned_put(r->ctx, r->blk_pe);
     pinned_put(r->ctx, r->blk_build); pinned_put(r->ctx, r->blk_probe);
     pinned_put(r->ctx, r->blk_bits); pinned_put(r->ctx, r->blk_dist);
+    ctx_unref(r->ctx);
     delete r;
 }
 
@@ -1146,10 +1498,11 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     BRG_CUDA(cudaSetDevice(ctx->device));
     brg_rows* r = new brg_rows();
     r->ctx = ctx;
+    ctx->refs.fetch_add(1);
     if (consumed) *consumed = n;
     if (n == 0) { *out = r; return BRG_OK; }
     LaneGuard g(ctx);
-    if ((rc = g.acquire())) { delete r; return rc; }
+    if ((rc = g.acquire())) { brg_rows_release(r); return rc; }
     Lane* l = g.l;
     cudaStream_t st = l->k;
     auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };
@@ -1249,9 +1602,10 @@ extern "C" BRG_API int brg_subtract(brg_ctx* ctx, const brg_index* ix, const uin
     BRG_CUDA(cudaSetDevice(ctx->device));
     brg_rows* r = new brg_rows();
     r->ctx = ctx;
+    ctx->refs.fetch_add(1);
     if (n == 0) { *out = r; return BRG_OK; }
     LaneGuard g(ctx);
-    if ((rc = g.acquire())) { delete r; return rc; }
+    if ((rc = g.acquire())) { brg_rows_release(r); return rc; }
     Lane* l = g.l;
     cudaStream_t st = l->k;
     auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };
@@ -1348,6 +1702,7 @@ extern "C" BRG_API const uint32_t* brg_merged_count(const brg_merged* m) { retur
 extern "C" BRG_API void brg_merged_release(brg_merged* m) {
     if (!m) return;
     pinned_put(m->ctx, m->key); pinned_put(m->ctx, m->start); pinned_put(m->ctx, m->end); pinned_put(m->ctx, m->count);
+    ctx_unref(m->ctx);
     delete m;
 }
 
@@ -1363,6 +1718,7 @@ extern "C" BRG_API const int64_t* brg_gaps_end(const brg_gaps* g) { return g ? (
 extern "C" BRG_API void brg_gaps_release(brg_gaps* g) {
     if (!g) return;
     pinned_put(g->ctx, g->view); pinned_put(g->ctx, g->start); pinned_put(g->ctx, g->end);
+    ctx_unref(g->ctx);
     delete g;
 }
 struct ViewArgs {  // complement: the view rows and where the gaps go
@@ -1384,6 +1740,7 @@ extern "C" BRG_API int brg_complement(brg_ctx* ctx, const uint32_t* key, const i
     if (n_views >= 0xFFFFFFFFull) { set_error("brg_complement: view row count exceeds UInt32 capacity"); return BRG_ERR_OVERFLOW; }
     brg_gaps* g = new brg_gaps();
     g->ctx = ctx;
+    ctx->refs.fetch_add(1);
     if (n_views == 0) { *out = g; return BRG_OK; }
     ViewArgs va{view_key, view_start, view_end, n_views, g};
     brg_merged* unused = nullptr;
@@ -1453,6 +1810,7 @@ static int merge_pipeline(brg_ctx* ctx, const uint32_t* key, const int32_t* star
     BRG_CUDA(cudaSetDevice(ctx->device));
     brg_merged* r = new brg_merged();
     r->ctx = ctx;
+    ctx->refs.fetch_add(1);
     cudaStream_t st = ctx->build_stream;
     ScratchScope scratch_scope(st);
     if (n == 0) {
@@ -1563,9 +1921,10 @@ extern "C" BRG_API int brg_nearest(brg_ctx* ctx, const brg_index* ix, const uint
     BRG_CUDA(cudaSetDevice(ctx->device));
     brg_rows* r = new brg_rows();
     r->ctx = ctx;
+    ctx->refs.fetch_add(1);
     if (n == 0) { *out = r; return BRG_OK; }
     LaneGuard g(ctx);
-    if ((rc = g.acquire())) { delete r; return rc; }
+    if ((rc = g.acquire())) { brg_rows_release(r); return rc; }
     Lane* l = g.l;
     cudaStream_t st = l->k;
     auto fail = [&](int code) { cudaStreamSynchronize(st); brg_rows_release(r); return code; };

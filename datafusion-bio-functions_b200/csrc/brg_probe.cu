@@ -618,6 +618,13 @@ __device__ __forceinline__ uint32_t nearest_k_walk(const IndexView& ix, uint32_t
         }
         n_out++;
     };
+    if (k == 1) {
+        // nearest_k(k == 1) delegates to nearest_one (nearest_index.rs:110-115), whose overlap step is skipped for a degenerate
+        // probe (end < start after the strict adjustment, :222-225) -- the walk below would report a spanning interval instead
+        Cand b{0, 0, 0};
+        if (nearest_one(ix, c, qs, qe, include_overlaps ? 1 : 0, &b)) emit(b);
+        return n_out;
+    }
     KeyDir ks = load_keydir(ix.d_sstart.kd, c);
     if (ks.seg_begin == ks.seg_end || k == 0) return 0;
     const uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);

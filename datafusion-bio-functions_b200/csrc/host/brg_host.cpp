@@ -1290,9 +1290,14 @@ static Err run_join(brgh_session* s, const Table& lt, const Table& rt, const cha
     brg_ctx* ctx;
     BRGH_TRY(session_ctx(s, &ctx));
     IndexGuard ig;
-    BRGH_TRY(from_abi(brg_build(ctx, key.data(), bst.data(), ben.data(), key.size(), std::max<uint32_t>(1, (uint32_t)dict.ids.size()),
-                                nearest_mode ? BRG_WANT_NEAREST : BRG_WANT_PAIRS, &ig.ix)));
     const int mode = join_type == BRGH_JOIN_RIGHT_SEMI ? BRG_PAIRS_SEMI : (join_type == BRGH_JOIN_RIGHT_ANTI ? BRG_PAIRS_ANTI : BRG_PAIRS_INNER);
+    // Existence joins ask IntervalJoinAlgorithm::get whether ANY interval is visited (interval_join.rs:1433-1463): under
+    // CoitreesCountOverlaps that is the plain tree query (:854-863) -> the pair structures; under CoitreesNearest it is
+    // nearest_one(start, end, true) (:864-870) -> every probe row of a key with a non-empty index "matches".
+    const bool exist_by_nearest = mode != BRG_PAIRS_INNER && s->algorithm == CoitreesNearest;
+    const bool want_nearest = (nearest_mode && mode == BRG_PAIRS_INNER) || exist_by_nearest;
+    BRGH_TRY(from_abi(brg_build(ctx, key.data(), bst.data(), ben.data(), key.size(), std::max<uint32_t>(1, (uint32_t)dict.ids.size()),
+                                want_nearest ? BRG_WANT_NEAREST : BRG_WANT_PAIRS, &ig.ix)));
     const uint64_t cap = s->low_memory ? max_output_batch_size() : 0;
     // ---- probe side, batch by batch (interval_join.rs:1418-1676) ----------------------------------------------------------
     for (auto& b : rt.batches) {
@@ -1326,6 +1331,22 @@ static Err run_join(brgh_session* s, const Table& lt, const Table& rt, const cha
             ob.rows = (int64_t)n;
             if (emit_left) BRGH_TRY(take_table(lt, li.data(), nulls ? bits.data() : nullptr, (int64_t)n, left_prefix, -1, &ob.cols));
             if (emit_right) BRGH_TRY(take_table(rb, ri.data(), nullptr, (int64_t)n, right_prefix, -1, &ob.cols));
+            res->batches.push_back(std::move(ob));
+            continue;
+        }
+        if (exist_by_nearest) {
+            std::vector<uint32_t> li(n);
+            std::vector<uint8_t> bits(((n + 31) / 32) * 4, 0);
+            if (n) BRGH_TRY(from_abi(brg_nearest_k1(ctx, ig.ix, pk.data(), pst.data(), pen.data(), n, 1, 0, li.data(), bits.data(), nullptr)));
+            std::vector<uint32_t> pi;
+            for (uint64_t i = 0; i < n; i++) {
+                const bool has_match = (bits[i >> 3] >> (i & 7)) & 1;
+                if (has_match == (mode == BRG_PAIRS_SEMI)) pi.push_back((uint32_t)i);  // should_emit_probe_row
+            }
+            if (pi.empty()) continue;  // (the reference emits no batch for a probe batch without surviving rows)
+            Batch ob;
+            ob.rows = (int64_t)pi.size();
+            BRGH_TRY(take_table(rb, pi.data(), nullptr, ob.rows, right_prefix, -1, &ob.cols));
             res->batches.push_back(std::move(ob));
             continue;
         }

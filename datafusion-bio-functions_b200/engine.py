@@ -121,6 +121,31 @@ class Context:
         return ix, _wrap_device(slab.value, nbytes.value, self.device)
 
 
+    def slab_alloc(self, nbytes):
+        """an empty device buffer for a replica slab, as a torch uint8 tensor (receive the slab into it, then attach_slab)"""
+        p = C.c_void_p()
+        A.check(A.lib().brg_index_slab_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value, _wrap_device(p.value, int(nbytes), self.device)
+
+    def attach_slab(self, ptr, nbytes, stream=None):
+        """Index over a received slab (it carries its own header); takes ownership of the buffer"""
+        h = C.c_void_p()
+        rc = A.lib().brg_index_attach(self._h, C.c_void_p(ptr), int(nbytes), stream, C.byref(h))
+        if rc != 0:
+            A.lib().brg_index_slab_free(self._h, C.c_void_p(ptr))
+            A.check(rc)
+        return Index(self, h)
+
+
+def replicate(index, contexts):
+    """replicas of `index` on the devices of `contexts`, all inside this process (brg_index_replicate)"""
+    n = len(contexts)
+    dst = (C.c_void_p * n)(*[c._h for c in contexts])
+    out = (C.c_void_p * n)()
+    A.check(A.lib().brg_index_replicate(index._h, dst, n, out))
+    return [Index(c, C.c_void_p(h)) for c, h in zip(contexts, out)]
+
+
 def _tptr(t):
     if t is None:
         return None
@@ -273,6 +298,15 @@ class Index:
         A.check(A.lib().brg_nearest_k1(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), n,
                                        int(include_overlaps), int(strict), A.np_ptr(left), A.np_ptr(bits), A.np_ptr(dist)))
         return left, A.unpack_bits(bits, n), dist
+
+    def nearest_k1_into(self, key, start, end, out, include_overlaps=True, strict=False):
+        """brg_nearest_k1 into caller buffers out = (left_idx u32[n], valid_bits u8[4*ceil(n/32)], distance i64[n] or None);
+        the packed Arrow validity bitmap is returned as is"""
+        key, start, end = self._cols(key, start, end)
+        left, bits, dist = out
+        A.check(A.lib().brg_nearest_k1(self.ctx._h, self._h, A.np_ptr(key), A.np_ptr(start), A.np_ptr(end), len(start),
+                                       int(include_overlaps), int(strict), A.np_ptr(left), A.np_ptr(bits), A.np_ptr(dist)))
+        return out
 
     def nearest_k(self, key, start, end, k, include_overlaps=True, strict=False, compute_distance=True):
         key, start, end = self._cols(key, start, end)

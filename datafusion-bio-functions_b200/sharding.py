@@ -1,15 +1,15 @@
 """Multi-GPU plumbing of the hot path: one process per GPU, `torch.distributed` for the rendezvous.
 
 The path shards with no data-path collective (mirrors PartitionMode::CollectLeft, interval_join.rs:396-399,466-480):
-  * the build-side index is built on rank 0 and REPLICATED: its POD header travels as a byte tensor, its single device
-    slab with one broadcast (NCCL over NVLink on GPUs);
+  * the build-side index is built on rank 0 and REPLICATED: its single device slab, which starts with its own POD header,
+    travels with one broadcast (NCCL over NVLink on GPUs) after an 8-byte size broadcast;
   * probe rows are split into contiguous row ranges, rank g gets rows [g*n/N, (g+1)*n/N);
   * every rank produces the results of its own range; concatenating the per-rank results in rank order reproduces the
     single-GPU row order (pairs: probe_idx is rebased by the shard's first row).
 
-Nothing here touches CUDA directly: the index object only has to offer export() -> (header bytes, slab tensor) and the
-context import_index(header bytes) -> (index, empty slab tensor), so the same code runs over gloo with CPU tensors in
-the world_size-2 tests.
+Nothing here touches CUDA directly: the index object only has to offer device_bytes and export() -> (header bytes, slab
+tensor), the context slab_alloc(nbytes) / attach_slab(ptr, nbytes, stream) (or attach_tensor(slab) for the CPU stand-in of
+the world_size-2 gloo tests), so the same code runs over gloo with CPU tensors.
 """
 import numpy as np
 
@@ -53,25 +53,30 @@ def bind_near_gpu(local_rank):
 
 
 def replicate_index(ctx, index, dist, rank, world, device, src=0):
-    """Every rank returns an index equal to rank `src`'s.  `index` is only read on rank `src`."""
+    """Every rank returns an index equal to rank `src`'s.  `index` is only read on rank `src`.
+
+    The slab carries its own header (brg_index_attach reads it back on the receiver), so the data path is ONE broadcast of
+    one buffer; the only thing a receiver needs first is the byte count (an 8-byte broadcast)."""
     import torch
 
     if world == 1:
         return index
+    size = torch.tensor([index.device_bytes if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(size, src)
+    nbytes = int(size.item())
     if rank == src:
-        header, slab = index.export()
-        hdr = torch.tensor(list(header), dtype=torch.uint8, device=device)
-        hlen = torch.tensor([hdr.numel()], dtype=torch.int64, device=device)
-    else:
-        hlen = torch.zeros(1, dtype=torch.int64, device=device)
-    dist.broadcast(hlen, src)
-    if rank != src:
-        hdr = torch.empty(int(hlen.item()), dtype=torch.uint8, device=device)
-    dist.broadcast(hdr, src)
-    if rank != src:
-        index, slab = ctx.import_index(bytes(hdr.cpu().numpy().tobytes()))
+        _, slab = index.export()
+        dist.broadcast(slab, src)
+        return index
+    if hasattr(ctx, "slab_alloc"):
+        ptr, slab = ctx.slab_alloc(nbytes)
+        dist.broadcast(slab, src)
+        st = torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() and str(device).startswith("cuda") else None
+        return ctx.attach_slab(ptr, nbytes, st)
+    # CPU stand-in of the gloo tests: same protocol, the slab's first bytes are the header
+    slab = torch.empty(nbytes, dtype=torch.uint8, device=device)
     dist.broadcast(slab, src)
-    return index
+    return ctx.attach_tensor(slab)
 
 
 def gather_rows_in_order(local, dist, rank, world, device="cpu"):

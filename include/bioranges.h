@@ -17,7 +17,14 @@
  *    NULL when there is a single key (all rows key 0).
  *  - "host" entry points take caller-owned host buffers (Arrow value buffers; pinned or pageable) and
  *    include the host<->device copies; "_dev" entry points take device pointers, enqueue on the given
- *    cudaStream_t (passed as void*) and do not synchronise.
+ *    cudaStream_t (passed as void*) and do not synchronise.  Pageable host buffers (ordinary heap memory, what
+ *    arrow-rs allocates) are detected and moved through a pinned staging ring by the context's host threads
+ *    (BRG_HOST_THREADS, default min(8, cores)), so the PCIe copies stay asynchronous; buffers from brg_pinned_alloc
+ *    or cudaHostRegister are used in place.  A per-row probe key column is scanned for runs chunk by chunk
+ *    (the reference's contig-cache loop, interval_tree.rs:258-265): a coordinate-sorted table sends a few runs per
+ *    8M-row chunk instead of 4 bytes per row.
+ *  - results that the library owns (brg_rows, brg_merged, brg_gaps) may be released after brg_ctx_destroy of the
+ *    context that produced them; an index must be destroyed before its context.
  *  - brg_index is immutable after build and may be probed concurrently from many threads
  *    (the reference shares it as Arc across partitions: joins/utils.rs:73-107).
  *  - There is no CPU fallback: every entry point fails with BRG_ERR_CUDA when no sm_100 device is usable.
@@ -102,6 +109,20 @@ BRG_API int brg_index_export(const brg_index* idx, void* header_buf, uint64_t he
                      void** d_slab, uint64_t* slab_bytes);
 BRG_API int brg_index_import(brg_ctx* ctx, const void* header, uint64_t header_len, brg_index** out, void** d_slab,
                      uint64_t* slab_bytes);
+
+/* The slab starts with a copy of its own header, so a replica needs nothing but the slab bytes.  One process per GPU:
+ * broadcast brg_index_device_bytes (8 bytes), then every other rank does brg_index_slab_alloc, receives the slab with ONE
+ * ncclBroadcast into it and calls brg_index_attach (which reads the header back from the front of the slab, after the work
+ * queued on `stream`, and takes ownership of the buffer; on failure the caller frees it with brg_index_slab_free). */
+BRG_API int brg_index_slab_alloc(brg_ctx* ctx, uint64_t slab_bytes, void** d_slab);
+BRG_API void brg_index_slab_free(brg_ctx* ctx, void* d_slab);
+BRG_API int brg_index_attach(brg_ctx* ctx, void* d_slab, uint64_t slab_bytes, void* stream, brg_index** out);
+/* One process driving several GPUs (a DataFusion ExecutionPlan whose execute(partition) maps partitions to devices,
+ * interval_join.rs:442-550, with the build side shared by all partitions, joins/utils.rs:73-107): out[i] receives a replica
+ * of `src` on the device of dst[i] (one brg_ctx per GPU).  The slab is copied device to device -- NVLink peer copies where
+ * the topology has them -- in a doubling tree.  Replicas are independent indexes: destroy each with brg_index_destroy.
+ * dst[i] may be on the source's own device (a plain device copy). */
+BRG_API int brg_index_replicate(const brg_index* src, brg_ctx* const* dst, int n_dst, brg_index** out);
 
 /* ---- count_overlaps (replaces CountOverlapIndex::query_count + get_count_stream's row loop,
  *      interval_tree.rs:41-49, 224-280).  strict => probe start+1 / end-1 (interval_tree.rs:253-256). ---- */

@@ -444,6 +444,35 @@ void brgo_overlap_counts(const brgo_index *ix, const uint32_t *key, const int32_
     }
 }
 
+/* Order-independent checksum of the pair set (the scheme of the reference's large-table test, TEST:4289-4404: row hashes
+ * combined by wrapping sum, wrapping sum of squares and XOR, so that any emission order gives the same triple).
+ * h(build_row, probe_row) is brgo_pair_hash below; probe rows are numbered row_base + i.  out_counts may be NULL.
+ * sums[0] = sum h, sums[1] = sum h*h (both mod 2^64), sums[2] = XOR h, sums[3] = number of pairs. */
+static inline uint64_t brgo_pair_hash(uint32_t b, uint64_t p) {
+    uint64_t h = (uint64_t)b * 0x9E3779B97F4A7C15ull + p * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    return h;
+}
+typedef struct { uint64_t s1, s2, x, n, p; } csum_t;
+static void csum_visit(const rec_t *node, void *ud) {
+    csum_t *c = ud;
+    const uint64_t h = brgo_pair_hash(node->pos, c->p);
+    c->s1 += h; c->s2 += h * h; c->x ^= h; c->n++;
+}
+void brgo_overlap_checksum(const brgo_index *ix, const uint32_t *key, const int32_t *start, const int32_t *end, uint64_t n,
+                           uint64_t row_base, uint64_t *out_counts, uint64_t *sums, int threads) {
+    uint64_t S1 = 0, S2 = 0, X = 0, N = 0;
+#pragma omp parallel for schedule(static, 8192) num_threads(threads > 0 ? threads : 1) reduction(+ : S1, S2, N) reduction(^ : X)
+    for (uint64_t i = 0; i < n; i++) {
+        const key_index_t *k = lookup(ix, key, i);
+        csum_t c = {0, 0, 0, 0, row_base + i};
+        if (k) tree_query(k->by_start, k->tree_max, 0, (int64_t)k->n, start[i], end[i], csum_visit, &c);
+        if (out_counts) out_counts[i] = c.n;
+        S1 += c.s1; S2 += c.s2; X ^= c.x; N += c.n;
+    }
+    sums[0] = S1; sums[1] = S2; sums[2] = X; sums[3] = N;
+}
+
 /* IT:52-73 exposed for the unit-test literals (IT:291-353): input need not be sorted */
 uint64_t brgo_merge_intervals(const int32_t *first, const int32_t *last, uint64_t n,
                               int32_t *out_first, int32_t *out_last) {

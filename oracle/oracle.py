@@ -50,6 +50,7 @@ def lib():
         L.brgo_overlap_pairs.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.brgo_overlap_counts.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, _u64p, C.c_int]
+        L.brgo_overlap_checksum.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint64, C.c_void_p, _u64p, C.c_int]
         L.brgo_merge_intervals.restype = C.c_uint64
         L.brgo_merge_intervals.argtypes = [_i32p, _i32p, C.c_uint64, _i32p, _i32p]
         L.brgo_free.argtypes = [C.c_void_p]
@@ -143,6 +144,40 @@ class OracleIndex:
         out = np.empty(len(start), np.uint64)
         lib().brgo_overlap_counts(self._h, kp, start, end, len(start), out, threads)
         return out
+
+
+    def overlap_checksum(self, key, start, end, row_base=0, threads=1, counts=False):
+        """order-independent checksum of the pair set: (sum h, sum h^2, xor h, n_pairs) as python ints, h = pair_hash(build_row,
+        row_base + probe_row); with counts=True also the per-probe match counts"""
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        sums = np.zeros(4, np.uint64)
+        cnt = np.empty(len(start), np.uint64) if counts else None
+        lib().brgo_overlap_checksum(self._h, kp, start, end, len(start), int(row_base), cnt.ctypes.data if counts else None, sums, threads)
+        t = tuple(int(x) for x in sums)
+        return (t, cnt) if counts else t
+
+
+def pair_hash(build_idx, probe_idx):
+    """numpy twin of brgo_pair_hash (uint64 arithmetic wraps)"""
+    b = np.asarray(build_idx).astype(np.uint64)
+    p = np.asarray(probe_idx).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = b * np.uint64(0x9E3779B97F4A7C15) + p * np.uint64(0xC2B2AE3D27D4EB4F) + np.uint64(0x165667B19E3779F9)
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+    return h
+
+
+def pair_checksum(build_idx, probe_idx):
+    """(sum h, sum h^2, xor h, n) of a pair list, any order -- compare with OracleIndex.overlap_checksum"""
+    h = pair_hash(build_idx, probe_idx)
+    with np.errstate(over="ignore"):
+        s1 = int(h.sum(dtype=np.uint64))
+        s2 = int((h * h).sum(dtype=np.uint64))
+    x = int(np.bitwise_xor.reduce(h)) if len(h) else 0
+    return s1, s2, x, len(h)
 
 
 def merge_intervals(first, last):

@@ -288,6 +288,72 @@ def test_gpu_host_buffer_chunk_schedule(monkeypatch):
     c2.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+@pytest.mark.parametrize("order", ["sorted", "shuffled"])
+def test_gpu_host_buffers_pageable_and_pinned(monkeypatch, pinned, order):
+    """host-buffer entry points with ordinary heap arrays (moved through the pinned staging ring by the host threads) and with
+    page-locked arrays (used in place); a per-row key column is sent as per-chunk runs when the table is sorted and as the
+    column itself when a chunk holds more than 1024 runs"""
+    import torch
+
+    import bio_ranges_b200 as brg
+
+    monkeypatch.setenv("BRG_CHUNK_ROWS", "131072")
+    monkeypatch.setenv("BRG_HOST_THREADS", "4")
+    c2 = brg.Context(0)
+    rng = np.random.default_rng(9)
+    nk = 6
+    bk, bs, be = _rand(rng, 80_000, nk, 0, 8_000_000, 900)
+    n = 131072 * 4 + 4321
+    pk, ps, pe = _sorted_probes(rng, n, nk, 8_000_000, 1, 400, absent_runs=True)
+    if order == "shuffled":
+        o = rng.permutation(n)
+        pk, ps, pe = pk[o], ps[o], pe[o]
+
+    def host(a):
+        if not pinned:
+            return np.ascontiguousarray(a)
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.int32 if a.dtype == np.uint32 else a.dtype)).pin_memory()
+        return t.numpy().view(a.dtype)
+
+    pk_h, ps_h, pe_h = host(pk), host(ps), host(pe)
+    gi = c2.build(bk, bs, be, nk)
+    oi = O.OracleIndex(bk, bs, be, nk)
+    out = host(np.zeros(n, np.int64))
+    got = gi.count_overlaps(pk_h, ps_h, pe_h, out=out)
+    assert got is out and (out == oi.count_overlaps(pk, ps, pe)).all()
+    assert (gi.coverage(pk_h, ps_h, pe_h, strict=True, out=out) == oi.coverage(pk, ps, pe, strict=True)).all()
+    left, valid, dist = gi.nearest_k1(pk_h, ps_h, pe_h)
+    ol, ov, od = oi.nearest_k1(pk, ps, pe)
+    assert (valid == ov).all() and (left[valid] == ol[ov]).all() and (dist[valid] == od[ov]).all()
+    assert (gi.probe_arrow("count", *brg._cabi.key_runs(pk), host(ps.astype(np.int64)), host(pe.astype(np.uint64))) == oi.count_overlaps(pk, ps, pe)).all()
+    gi.close()
+    c2.close()
+
+
+def test_gpu_nearest_k1_through_the_k_walker(ctx):
+    """brg_nearest(k = 1) must behave as nearest_one (nearest_index.rs:110-115): a strict probe 1-2 bp wide is degenerate
+    (qs + 1 > qe - 1), skips the overlap step (:222-225) and falls to the neighbour search"""
+    rng = np.random.default_rng(21)
+    nk = 3
+    bk, bs, be = _rand(rng, 4000, nk, 0, 100_000, 300)
+    pk = rng.integers(0, nk, 30_000).astype(np.uint32)
+    ps = rng.integers(0, 100_000, 30_000).astype(np.int32)
+    pe = (ps + rng.integers(0, 3, 30_000)).astype(np.int32)  # widths 0, 1, 2
+    gi = ctx.build(bk, bs, be, nk)
+    oi = O.OracleIndex(bk, bs, be, nk)
+    for strict in (True, False):
+        for inc in (True, False):
+            g = gi.nearest_k(pk, ps, pe, 1, include_overlaps=inc, strict=strict)
+            o = oi.nearest_k(pk, ps, pe, 1, include_overlaps=inc, strict=strict)
+            assert len(g[0]) == len(o[0])
+            for a, b in zip(g, o):
+                assert (a == b).all()
+            l1, v1, d1 = gi.nearest_k1(pk, ps, pe, include_overlaps=inc, strict=strict)
+            assert (v1 == g[1]).all() and (l1[v1] == g[0][v1]).all() and (d1[v1] == g[3][v1]).all()
+    gi.close()
+
+
 def test_gpu_edge_cases(ctx):
     rng = np.random.default_rng(77)
     # empty build side, keys without rows, empty probe side

@@ -33,6 +33,11 @@ def _rows(batches, cols=None):
     return sorted(zip(*[t.column(c).to_pylist() for c in cols]), key=repr)
 
 
+def _tab(batches, like):
+    """table of the batches; an operator that emitted no batch at all yields the empty table"""
+    return pa.Table.from_batches(batches) if batches else like.slice(0, 0)
+
+
 def init_tables(ctx, **kw):  # testing/data/interval/{reads,targets}.csv
     ctx.register_table("reads", _tbl(INTERVAL_READS, **kw))
     ctx.register_table("targets", _tbl(INTERVAL_TARGETS, **kw))
@@ -284,6 +289,35 @@ def test_join_semi_anti_and_low_memory(ctx, monkeypatch):
     out = ctx.interval_join("a", "b", on, cols, cols)
     assert len(out) > 3 and max(x.num_rows for x in out) <= max(500, max(len(m) for m in match))
     assert sorted(zip(*[pa.Table.from_batches(out).column(i).to_pylist() for i in range(6)])) == want
+
+
+# ---- existence joins under the one-row-per-probe algorithms (interval_join.rs:849-870, 1433-1463): CoitreesCountOverlaps asks
+#      the plain tree query, CoitreesNearest asks nearest_one(start, end, true) -- any probe row whose key has build rows matches
+@pytest.mark.parametrize("alg", ["CoitreesCountOverlaps", "CoitreesNearest"])
+def test_join_semi_anti_under_one_row_algorithms(ctx, alg):
+    from bio_ranges_b200.session import JOIN_RIGHT_ANTI, JOIN_RIGHT_SEMI
+
+    a = pa.table({"contig": ["chr1", "chr1", "chr2"], "pos_start": pa.array([10, 100, 5], pa.int64()), "pos_end": pa.array([20, 110, 9], pa.int64())})
+    b = pa.table({"contig": ["chr1", "chr1", "chr2", "chr3", "chr1"], "pos_start": pa.array([15, 50, 100, 1, 200], pa.int64()),
+                  "pos_end": pa.array([16, 60, 120, 2, 300], pa.int64())})
+    ctx.register_table("a", a)
+    ctx.register_table("b", b, max_chunksize=2)
+    ctx.set("bio.interval_join_algorithm", alg)
+    al, bl = list(zip(*[a.column(i).to_pylist() for i in range(3)])), list(zip(*[b.column(i).to_pylist() for i in range(3)]))
+    if alg == "CoitreesNearest":  # nearest_one(.., true) is Some for every probe row of a key that has an index
+        has = [any(x[0] == y[0] for x in al) for y in bl]
+    else:
+        has = [any(x[0] == y[0] and x[1] <= y[2] and x[2] >= y[1] for x in al) for y in bl]
+    on, cols = [("contig", "contig")], ("pos_start", "pos_end")
+    semi = _tab(ctx.interval_join("a", "b", on, cols, cols, join_type=JOIN_RIGHT_SEMI), b)
+    anti = _tab(ctx.interval_join("a", "b", on, cols, cols, join_type=JOIN_RIGHT_ANTI), b)
+    assert list(zip(*[semi.column(i).to_pylist() for i in range(3)])) == [y for y, m in zip(bl, has) if m]
+    assert list(zip(*[anti.column(i).to_pylist() for i in range(3)])) == [y for y, m in zip(bl, has) if not m]
+    # overlap(.., 'left') = RIGHT SEMI JOIN with the right table built, the left one probed (overlap.rs:205-226)
+    ctx.register_table("reads", b)
+    ctx.register_table("targets", a)
+    d = _tab(ctx.overlap("reads", "targets", "left"), b)
+    assert list(zip(*[d.column(i).to_pylist() for i in range(3)])) == [y for y, m in zip(bl, has) if m]
 
 
 # ---- interval_join.rs:1963-2002: a coordinate that does not fit Int32 fails the join with arrow's cast error -------------------------------

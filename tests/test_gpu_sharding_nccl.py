@@ -1,4 +1,4 @@
-"""The multi-GPU path on real GPUs (needs >= 2; skipped otherwise): rank 0 builds, the index slab is replicated with an NCCL
+"""The multi-GPU path on real GPUs (needs >= 2; skipped otherwise; uses every GPU of the box): rank 0 builds, the index slab is replicated with an NCCL
 broadcast, every rank probes its contiguous row range, the in-order gather equals the oracle.  The gloo twin of this test
 (tests/test_sharding_gloo.py) covers the same plumbing on the CPU box."""
 import os
@@ -74,7 +74,7 @@ def test_nccl_replicated_index_and_sharded_probes_equal_oracle():
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    world = 2
+    world = min(torch.cuda.device_count(), 8)  # every GPU of the lease: 2 on a two-GPU box, 8 on the full node
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     procs = [ctxm.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]

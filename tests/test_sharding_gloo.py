@@ -27,8 +27,9 @@ def test_shard_bounds_cover_rows_in_order():
 
 
 class _CpuIndex:
-    """export()/probe protocol of engine.Index over the oracle: header = pickled build columns length, slab = the
-    build columns as one byte tensor.  Only the replication + sharding logic is under test here."""
+    """device_bytes / export() / probe protocol of engine.Index over the oracle.  Like the real slab, the byte tensor starts
+    with its own header (row count, key count) followed by the build columns.  Only the replication + sharding logic is under
+    test here."""
 
     def __init__(self, key, start, end, n_keys):
         from oracle import oracle as O
@@ -38,12 +39,16 @@ class _CpuIndex:
         self.n_keys = n_keys
         self.o = O.OracleIndex(*self.cols, n_keys)
 
+    @property
+    def device_bytes(self):
+        return 16 + 12 * len(self.cols[0])
+
     def export(self):
         import torch
 
         n = len(self.cols[0])
         header = np.array([n, self.n_keys], np.uint64).tobytes()
-        slab = torch.from_numpy(np.concatenate([c.view(np.uint8) for c in self.cols]).copy())
+        slab = torch.from_numpy(np.concatenate([np.frombuffer(header, np.uint8)] + [c.view(np.uint8) for c in self.cols]).copy())
         return header, slab
 
     def __getattr__(self, name):
@@ -51,32 +56,12 @@ class _CpuIndex:
 
 
 class _CpuCtx:
-    def import_index(self, header):
-        import torch
-
-        n, n_keys = (int(x) for x in np.frombuffer(header, np.uint64))
-        slab = torch.zeros(n * 12, dtype=torch.uint8)
-        return _Pending(slab, n, n_keys), slab
-
-
-class _Pending:
-    """replica whose slab is filled by the broadcast; materialised on first use"""
-
-    def __init__(self, slab, n, n_keys):
-        self.slab, self.n, self.n_keys, self._ix = slab, n, n_keys, None
-
-    def _get(self):
-        if self._ix is None:
-            raw = self.slab.numpy()
-            n = self.n
-            k = raw[: 4 * n].view(np.uint32)
-            s = raw[4 * n: 8 * n].view(np.int32)
-            e = raw[8 * n: 12 * n].view(np.int32)
-            self._ix = _CpuIndex(k, s, e, self.n_keys)
-        return self._ix
-
-    def __getattr__(self, name):
-        return getattr(self._get(), name)
+    def attach_tensor(self, slab):
+        raw = slab.numpy()
+        n, n_keys = (int(x) for x in raw[:16].view(np.uint64))
+        assert len(raw) == 16 + 12 * n
+        body = raw[16:]
+        return _CpuIndex(body[: 4 * n].view(np.uint32), body[4 * n: 8 * n].view(np.int32), body[8 * n: 12 * n].view(np.int32), n_keys)
 
 
 def _data():
