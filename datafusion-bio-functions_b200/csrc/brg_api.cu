@@ -218,9 +218,11 @@ struct IndexHeader {
     uint64_t off_cS[2], off_cB[2];
     DirDesc cdir[2];
     uint32_t n_blocks, pad_;
+    // count bins (32-byte records; cbdir.off_kd = per-key constants, cbdir.off_D = the records, cbdir.entries = record count)
+    DirDesc cbdir;
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
-static const uint32_t kVersion = 4;
+static const uint32_t kVersion = 5;
 static const uint64_t kNone = ~0ull;
 static const uint64_t kSlabHeaderBytes = 4096;  // reserved at the front of every slab for the IndexHeader
 static_assert(sizeof(IndexHeader) <= kSlabHeaderBytes, "IndexHeader must fit the reserved slab prefix");
@@ -261,6 +263,9 @@ static IndexView make_view(const IndexHeader& h, void* slab) {
         cv[a]->d.A = (const int32_t*)P(h.off_cS[a]);
         cv[a]->d.shift = h.cdir[a].shift;
     }
+    v.cb_rec = (const uint4*)P(h.cbdir.off_D);
+    v.cb_kd = (const KeyDir*)P(h.cbdir.off_kd);
+    v.cb_shift = h.cbdir.shift;
     return v;
 }
 
@@ -730,7 +735,35 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
 
     mark("directory plans");
     // ---- compact rank index of s_start / e_end: the L2-resident structure of the per-row count kernels -------
-    const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0;
+    // ---- count bins: the structure the per-row count kernels search (unsorted probe tables) ------------------------------
+    // At most kCbTarget elements of each array per bin on average.  Offsets inside a bin are u16, so bins are at most 65536
+    // wide: a build side too sparse for that (more than 2 records per row) keeps the compact rank index below instead.
+    static const uint32_t kCbTarget = [] { const char* v = getenv("BRG_CB_TARGET"); const int t = v ? atoi(v) : 2; return (uint32_t)(t > 0 ? t : 0); }();
+    ScratchBuf cb_kd;
+    uint32_t cb_shift = 0, cb_entries = 0;
+    bool need_cb = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && kCbTarget > 0;
+    if (need_cb) {
+        if ((rc = cb_kd.ensure((uint64_t)std::max(1u, n_keys) * sizeof(KeyDir)))) return rc;
+        if ((rc = cb_key_ranges(s_start.as<int32_t>(), (const int32_t*)E[2], off.as<uint32_t>(), n_keys, cb_kd.as<KeyDir>(), d_bins, st))) return rc;
+        unsigned long long bins[32];
+        BRG_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof(bins), cudaMemcpyDeviceToHost, st));
+        BRG_CUDA(cudaStreamSynchronize(st));
+        // widest bins that still hold at most kCbTarget elements of each array on average (so between target / 2 and target)
+        const uint64_t at_least = std::max<uint64_t>((uint64_t)n_valid / kCbTarget, 1);
+        uint32_t shift = 0;
+        for (uint32_t sft = 16; sft > 0; sft--)
+            if (bins[sft] >= at_least) { shift = sft; break; }
+        if (bins[shift] > 2ull * n_valid + 2ull * n_keys + (1ull << 16)) {  // (a build side too sparse for 65536-wide bins)
+            need_cb = false;
+        } else {
+            cb_shift = shift;
+            if ((rc = dir_assign_bases(cb_kd.as<KeyDir>(), n_keys, shift, d_scalar, st))) return rc;
+            BRG_CUDA(cudaMemcpyAsync(&cb_entries, d_scalar, 4, cudaMemcpyDeviceToHost, st));
+            BRG_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    mark("count bins plan");
+    const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && !need_cb;
     ScratchBuf boff_d, cS[2], cB[2];
     DirBuild cdb[2];
     uint32_t n_blocks = 0;
@@ -794,6 +827,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         h.cdir[a].shift = cdb[a].shift;
         h.cdir[a].entries = cdb[a].entries;
     }
+    h.cbdir.off_kd = place(need_cb, (uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+    h.cbdir.off_D = place(need_cb, (uint64_t)cb_entries * 32);
+    h.cbdir.shift = cb_shift;
+    h.cbdir.entries = cb_entries;
     h.slab_bytes = std::max<uint64_t>(cur, 256);
 
     void* slab = nullptr;
@@ -826,12 +863,17 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
             chk(copy_in(h.off_cB[a], cB[a].p, (uint64_t)n_blocks * 16));
             chk(copy_in(h.cdir[a].off_kd, cdb[a].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
         }
+    if (need_cb) chk(copy_in(h.cbdir.off_kd, cb_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
     if (ce == cudaSuccess) ce = cudaMemsetAsync(base, 0, kSlabHeaderBytes, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st);  // (synchronised below, before h dies)
     if (ce != cudaSuccess) { cudaFree(slab); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
     for (int i = 0; i < 5; i++) {
         if (!need_dir[i]) continue;
         rc = dir_fill(dirA[i], db[i].kd.as<KeyDir>(), n_keys, db[i].shift, (uint32_t*)(base + h.dir[i].off_D), db[i].entries, st);
+        if (rc) { cudaFree(slab); return rc; }
+    }
+    if (need_cb) {
+        rc = cb_fill(s_start.as<int32_t>(), (const int32_t*)E[2], cb_kd.as<KeyDir>(), n_keys, cb_shift, (uint4*)(base + h.cbdir.off_D), cb_entries, st);
         if (rc) { cudaFree(slab); return rc; }
     }
     if (need_ci)
@@ -1049,16 +1091,19 @@ extern "C" BRG_API int brg_pairs_count_dev(brg_ctx* ctx, const brg_index* ix, co
     int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_count");
     if (rc) return rc;
     if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
-    LaneGuard g(ctx);
-    if ((rc = g.acquire())) return rc;
-    if ((rc = pairs_scratch(g.l, n))) return rc;
+    // temporaries are stream-ordered allocations on the caller's stream: nothing to synchronise, as for every _dev entry point
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_pairs_count(ix->view, k, s, e, n, g.l->scratch_a.as<uint32_t>(), st))) return rc;
-    rc = exclusive_scan_u32_to_u64(g.l->scratch_a.as<uint32_t>(), d_offsets, n, g.l->scratch_c.as<uint64_t>(), st);
-    if (rc) return rc;
-    // the lane's scratch is reused by the next call on this lane: make sure this one is done with it
-    BRG_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    uint32_t* counts = nullptr;
+    uint64_t* scratch = nullptr;
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    BRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&counts), std::max<uint64_t>(n, 1) * 4, st));
+    cudaError_t e2 = cudaMallocAsync(reinterpret_cast<void**>(&scratch), (scan_scratch_words(std::max<uint64_t>(n, 1)) + 16) * 4, st);
+    if (e2 != cudaSuccess) { cudaFreeAsync(counts, st); set_error(std::string("cudaMallocAsync: ") + cudaGetErrorString(e2)); return BRG_ERR_OOM; }
+    rc = launch_pairs_count(ix->view, k, s, e, n, counts, st);
+    if (!rc) rc = exclusive_scan_u32_to_u64(counts, d_offsets, n, scratch, st);
+    cudaFreeAsync(counts, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 extern "C" BRG_API int brg_pairs_emit_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s,
                                   const int32_t* e, uint64_t n, const uint64_t* d_offsets, uint32_t* d_build_idx,

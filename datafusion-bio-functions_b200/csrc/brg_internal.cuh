@@ -114,8 +114,32 @@ struct IndexView {
     const int4* e_rec;
     const int4* m_rec;
     DirView d_sstart, d_eend, d_pme, d_mfirst, d_mlast;
-    CompactView c_sstart, c_eend;  // per-row path of count_overlaps
+    CompactView c_sstart, c_eend;  // per-row path of count_overlaps (superseded by the count bins when those are present)
+    // Count bins: ONE 32-byte record per coordinate bin answers both rank queries of a count_overlaps row (see CountBin)
+    const uint4* cb_rec;   // 2 x uint4 per bin; nullptr = absent
+    const KeyDir* cb_kd;   // per key: lo, nb, base (first record), seg_begin / seg_end (shared by s_start and e_end)
+    uint32_t cb_shift;     // bin width 2^cb_shift (<= 65536: in-bin offsets are u16)
 };
+
+// ------------------------------------------------------------------------------------------------
+// Count bins: the search structure of count_overlaps for UNSORTED probe tables.  A shuffled probe row costs one fully
+// divergent load instruction per structure it touches, and the L1 pipeline pays those per lane: the per-row kernels run at
+// about 32 cycles per divergent load instruction and warp whatever its width (measured: 5-6 of them per row through the
+// compact rank index = 3.2 ms per 125M rows, whether the index has 1M or 10M rows; ncu: long_scoreboard 53 warps per issue,
+// lg_throttle 8 -- the load/store queue is the bound, not DRAM, not L2 capacity, not issue slots).  So the bins fold everything
+// a row needs into ONE 32-byte record = one sector = two 128-bit loads:
+//   bin = (coordinate - key.lo) >> shift, about 2 starts + 2 ends per bin
+//   record = { cs : global index of the first start >= the bin's first coordinate                          (u32)
+//              depth : cs - (index of the first end >= the bin's first coordinate) = intervals open there   (u16)
+//              ns, ne : starts / ends inside the bin                                                        (u8, u8)
+//              12 x u16 : in-bin offsets of the ns starts, then of the ne ends, both ascending }
+//   ne == 0xFF marks a record that does not fit (more than 12 elements, depth >= 65535): the row searches the plain arrays.
+//   It has to be rare -- one overflowing lane sends its whole warp through the slow path -- hence the narrow bins.
+//   #(starts <= qe) = cs(bin(qe)) + #(start offsets <= qe's offset);   #(ends < qs) likewise from bin(qs - 1).
+// A 150 bp read has both coordinates in one bin most of the time: 2 divergent loads per row instead of 5-6.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CB_SLOTS = 12;
+constexpr uint32_t CB_OVERFLOW = 0xFFu;
 
 // ------------------------------------------------------------------------------------------------
 // launchers (each returns a brg_status; all work is enqueued on `st`)
@@ -138,6 +162,7 @@ uint64_t scan_scratch_words(uint64_t n);
 int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch, cudaStream_t st);
 int exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* scratch,
                               cudaStream_t st);
+int exclusive_scan_u64(const uint64_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* scratch, cudaStream_t st);
 int segmented_running_max(const uint32_t* key, const int32_t* val, int32_t* out, uint64_t n, int32_t* scratch,
                           cudaStream_t st);
 // merge_intervals on the S-order arrays: writes m_first/m_last/(m_key) and *d_n_merged
@@ -172,6 +197,11 @@ int ci_build(const int32_t* A, const uint32_t* off, const uint32_t* boff, uint32
 int ci_patch_keydir(KeyDir* kd, const uint32_t* off, uint32_t n_keys, cudaStream_t st);
 // P[i] = D[i] << 2 | min(D[i + 1] - D[i], 3)
 int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaStream_t st);
+// count bins: per-key value range over BOTH arrays (kd.nb = provisional range), then one thread per record
+int cb_key_ranges(const int32_t* s_start, const int32_t* e_end, const uint32_t* off, uint32_t n_keys, KeyDir* kd,
+                  unsigned long long* d_bins_by_shift, cudaStream_t st);
+int cb_fill(const int32_t* s_start, const int32_t* e_end, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint4* rec,
+            uint32_t total_entries, cudaStream_t st);
 // rank directory
 int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
                    cudaStream_t st);
@@ -325,6 +355,33 @@ __device__ __forceinline__ CompactKey load_compact_key(const CompactView& c, uin
     k.blk_end = (uint32_t)b.x; k.eb = (uint32_t)b.y; k.ee = (uint32_t)b.z; k.pad = 0;
     return k;
 }
+
+// One count bin record (32 bytes = one sector), loaded once and used for both rank queries of a row.
+struct CountBinRec { uint32_t w[8]; };
+__device__ __forceinline__ CountBinRec load_count_bin(const IndexView& ix, uint32_t rec) {
+    const uint4* r = ix.cb_rec + 2ull * rec;
+    const uint4 a = __ldg(r), b = __ldg(r + 1);
+    CountBinRec x;
+    x.w[0] = a.x; x.w[1] = a.y; x.w[2] = a.z; x.w[3] = a.w; x.w[4] = b.x; x.w[5] = b.y; x.w[6] = b.z; x.w[7] = b.w;
+    return x;
+}
+__device__ __forceinline__ bool count_bin_overflowed(const CountBinRec& x) { return (x.w[1] >> 24) == CB_OVERFLOW; }
+// #(elements of the bin <= off) among the starts (ENDS = false) or the ends (true) of a record that did not overflow
+template <bool ENDS>
+__device__ __forceinline__ uint32_t count_bin_slots(const CountBinRec& x, uint32_t off) {
+    const uint32_t ns = (x.w[1] >> 16) & 0xFFu, ne = x.w[1] >> 24;
+    const uint32_t first = ENDS ? ns : 0u, last = ENDS ? ns + ne : ns;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < CB_SLOTS; i++) {
+        const uint32_t v = (x.w[2 + (i >> 1)] >> ((i & 1u) * 16u)) & 0xFFFFu;
+        c += (i >= first && i < last && v <= off) ? 1u : 0u;
+    }
+    return c;
+}
+// global index of the first start / end >= the bin's first coordinate
+__device__ __forceinline__ uint32_t count_bin_cs(const CountBinRec& x) { return x.w[0]; }
+__device__ __forceinline__ uint32_t count_bin_ce(const CountBinRec& x) { return x.w[0] - (x.w[1] & 0xFFFFu); }
 
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
                                                                            const int32_t* __restrict__ start,
                                                                            const int32_t* __restrict__ end, uint64_t n_rows,
                                                                            uint64_t* __restrict__ row_rng,
-                                                                           uint32_t* __restrict__ chunk_tot, TodoList todo) {
+                                                                           uint64_t* __restrict__ chunk_tot, TodoList todo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ProbeRing* ring = reinterpret_cast<ProbeRing*>(smem_raw);
     uint32_t* aux0 = ring->w[threadIdx.x >> 5].aux[0];
@@ -142,20 +142,24 @@ __global__ void __launch_bounds__(TP_THREADS, BRG_PR_CTAS) pairs_ranges_kernel_t
             }
         }
         if (ok) {
-            uint32_t tot = 0;
+            // (a row matches < 2^32 build rows, but the 256 rows of a chunk together may not fit 32 bits -- a huge pile of duplicate
+            //  build rows under wide probes: the halves of the counts are summed separately and recombined as u64)
+            uint32_t tot_lo = 0, tot_hi = 0;
 #pragma unroll
             for (int j = 0; j < PV; j++) {
                 // start <= end on the build side (checked at build time): a row that ends before qs also starts before qe
                 uint32_t c = n_le[j] - ended[j];
                 if (t.qe[j] < t.qs[j]) c = (i0[j] < n_le[j]) ? walk_count(ix, i0[j], n_le[j], t.qs[j]) : 0u;  // unguarded predicate
-                tot += c;
+                tot_lo += c & 0xFFFFu;
+                tot_hi += c >> 16;
             }
             long long rng[PV];
 #pragma unroll
             for (int j = 0; j < PV; j++) rng[j] = (long long)((uint64_t)i0[j] | ((uint64_t)n_le[j] << 32));
             store_chunk_i64(aux0, reinterpret_cast<int64_t*>(row_rng) + (t.row0 - (threadIdx.x & 31) * PV), rng);  // (aux0 + aux1)
-            tot = __reduce_add_sync(0xFFFFFFFFu, tot);
-            if ((threadIdx.x & 31) == 0) chunk_tot[t.chunk] = tot;
+            tot_lo = __reduce_add_sync(0xFFFFFFFFu, tot_lo);
+            tot_hi = __reduce_add_sync(0xFFFFFFFFu, tot_hi);
+            if ((threadIdx.x & 31) == 0) chunk_tot[t.chunk] = (uint64_t)tot_lo + ((uint64_t)tot_hi << 16);
             fails = 0;
         } else {
             cs.valid = false; cp.valid = false; ce.valid = false;
@@ -172,9 +176,9 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
                                                                      const int32_t* __restrict__ start,
                                                                      const int32_t* __restrict__ end, uint64_t n_rows,
                                                                      uint64_t* __restrict__ row_rng,
-                                                                     uint32_t* __restrict__ chunk_tot, TodoList todo,
+                                                                     uint64_t* __restrict__ chunk_tot, TodoList todo,
                                                                      uint32_t all_chunks, uint32_t tail_chunk) {
-    __shared__ uint32_t wsum[TP_WTILE / 32];
+    __shared__ uint64_t wsum[TP_WTILE / 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_list = todo.count ? *todo.count : all_chunks;
     const uint32_t n_items = n_list + (tail_chunk != 0xFFFFFFFFu ? 1u : 0u);
@@ -205,11 +209,11 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
             }
             row_rng[i] = (uint64_t)i0 | ((uint64_t)i1 << 32);
         }
-        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        if (lane == 0) wsum[warp] = cnt;
+        const uint32_t c_lo = __reduce_add_sync(0xFFFFFFFFu, cnt & 0xFFFFu), c_hi = __reduce_add_sync(0xFFFFFFFFu, cnt >> 16);
+        if (lane == 0) wsum[warp] = (uint64_t)c_lo + ((uint64_t)c_hi << 16);  // (u64: see pairs_ranges_kernel_tiled)
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t total = 0;
+            uint64_t total = 0;
 #pragma unroll
             for (int w = 0; w < TP_WTILE / 32; w++) total += wsum[w];
             chunk_tot[chunk] = total;
@@ -287,6 +291,9 @@ __global__ void __launch_bounds__(PF_THREADS, BRG_PF_CTAS) pairs_emit_kernel_fla
                 if (cand[j]) { wlo = min(wlo, i0[j]); whi = max(whi, i0[j] + cand[j]); }
             wlo = __reduce_min_sync(0xFFFFFFFFu, wlo);
             whi = __reduce_max_sync(0xFFFFFFFFu, whi);
+            // (only a compact window: the rows of an unsorted probe table point all over the build side, and walking from the
+            //  smallest to the largest candidate would sweep the whole array per chunk -- 108 ms per 10M shuffled probes)
+            if (whi > wlo && whi - wlo > 4u * (uint32_t)PF_CAP) whi = wlo;
             for (uint32_t e = (wlo & ~31u) + lane * 32u; e < whi; e += 32u * 32u) {  // one 128-byte line per lane and step
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.s_end + e));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.s_pos + e));
@@ -536,31 +543,35 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
                                uint64_t* chunk_base, uint64_t* row_rng, cudaStream_t st) {
     const ChunkPlan p = plan_chunks(ix, key, s, e, n);
     if (p.n_chunks == 0) { BRG_CUDA(cudaMemsetAsync(chunk_base, 0, sizeof(uint64_t), st)); return 0; }
-    uint32_t* tot = nullptr;
+    // per-call temporaries from the stream-ordered pool; one exit frees them whatever happened in between
+    uint64_t* tot = nullptr;
     uint64_t* scratch = nullptr;
-    BRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tot), p.n_chunks * sizeof(uint32_t), st));
-    BRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (scan_scratch_words(p.n_chunks) + 16) * 4, st));
-    int rc = 0;
-    if (p.tiled) {
-        TodoList todo;
-        if ((rc = todo_list_alloc(p.n_chunks, &todo, st))) return rc;
-        BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_ranges_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
-        const uint64_t tiles = p.full_rows / TP_TILE + 1;
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * BRG_PR_CTAS));
-        pairs_ranges_kernel_tiled<<<grid, TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, p.full_rows, row_rng, tot, todo);
-        BRG_LAUNCH_CHECK();
-        pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, todo, 0u, p.tail_chunk);
-        BRG_LAUNCH_CHECK();
-        BRG_CUDA(cudaFreeAsync(todo.count, st));
-    } else {
-        pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, TodoList{nullptr, nullptr},
-                                                                               (uint32_t)p.n_chunks, 0xFFFFFFFFu);
-        BRG_LAUNCH_CHECK();
-    }
-    if ((rc = exclusive_scan_u32_to_u64(tot, chunk_base, p.n_chunks, scratch, st))) return rc;
-    BRG_CUDA(cudaFreeAsync(tot, st));
-    BRG_CUDA(cudaFreeAsync(scratch, st));
-    return 0;
+    TodoList todo{nullptr, nullptr};
+    auto body = [&]() -> int {
+        int rc = 0;
+        BRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tot), p.n_chunks * sizeof(uint64_t), st));
+        BRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (scan_scratch_words(p.n_chunks) + 16) * 4, st));
+        if (p.tiled) {
+            if ((rc = todo_list_alloc(p.n_chunks, &todo, st))) return rc;
+            BRG_CUDA(cudaFuncSetAttribute((const void*)pairs_ranges_kernel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
+            const uint64_t tiles = p.full_rows / TP_TILE + 1;
+            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)kSMs * BRG_PR_CTAS));
+            pairs_ranges_kernel_tiled<<<grid, TP_THREADS, sizeof(ProbeRing), st>>>(ix, key, s, e, p.full_rows, row_rng, tot, todo);
+            BRG_LAUNCH_CHECK();
+            pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, todo, 0u, p.tail_chunk);
+            BRG_LAUNCH_CHECK();
+        } else {
+            pairs_ranges_todo_kernel<<<chunk_todo_grid(p.n_chunks), TP_WTILE, 0, st>>>(ix, key, s, e, n, row_rng, tot, TodoList{nullptr, nullptr},
+                                                                                   (uint32_t)p.n_chunks, 0xFFFFFFFFu);
+            BRG_LAUNCH_CHECK();
+        }
+        return exclusive_scan_u64(tot, chunk_base, p.n_chunks, scratch, st);
+    };
+    const int rc = body();
+    if (todo.count) cudaFreeAsync(todo.count, st);
+    if (tot) cudaFreeAsync(tot, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const uint64_t* chunk_base, const uint64_t* row_rng,

@@ -53,6 +53,31 @@ __device__ __forceinline__ uint32_t load_key(const uint32_t* key, uint64_t i) { 
 // skeys = the compact index' per-key constants in shared memory ([0] starts, [n_keys] ends), or nullptr.
 constexpr uint32_t CI_SMEM_KEYS = 256;  // keys whose constants the per-row kernels keep in shared memory (2 x 8 KB)
 __device__ __forceinline__ int64_t count_one_row(const IndexView& ix, const CompactKey* skeys, uint32_t c, int32_t qs, int32_t qe) {
+    if (ix.cb_rec) {  // count bins: one 32-byte record answers both rank queries when the row lies inside one bin (the usual case)
+        const KeyDir k = skeys ? reinterpret_cast<const KeyDir*>(skeys)[c] : load_keydir(ix.cb_kd, c);
+        if (k.nb == 0) return 0;
+        // #(starts <= qe): bin be;  #(ends < qs) = #(ends <= qs - 1): bin bs   (outside [lo, lo + nb * width): the segment bounds)
+        const bool e_in = qe >= k.lo, s_in = qs > k.lo;  // (qs - 1 >= lo)
+        const uint32_t de = (uint32_t)qe - (uint32_t)k.lo, ds = (uint32_t)qs - 1u - (uint32_t)k.lo;
+        const uint32_t be = de >> ix.cb_shift, bs = ds >> ix.cb_shift;
+        const bool need_e = e_in && be < k.nb, need_s = s_in && bs < k.nb;
+        uint32_t started = e_in ? k.seg_end : k.seg_begin, ended = s_in ? k.seg_end : k.seg_begin;
+        const uint32_t msk = (1u << ix.cb_shift) - 1u;
+        CountBinRec r;
+        bool have = false;
+        if (need_e) {
+            r = load_count_bin(ix, k.base + be);
+            have = true;
+            if (count_bin_overflowed(r)) started = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
+            else started = count_bin_cs(r) + count_bin_slots<false>(r, de & msk);
+        }
+        if (need_s) {
+            if (!(have && bs == be)) r = load_count_bin(ix, k.base + bs);
+            if (count_bin_overflowed(r)) ended = rank_lt_kd(ix.d_eend, load_keydir(ix.d_eend.kd, c), qs);
+            else ended = count_bin_ce(r) + count_bin_slots<true>(r, ds & msk);
+        }
+        return (int64_t)started - (int64_t)ended;
+    }
     if (ix.c_sstart.blocks) {
         if (skeys)
             return (int64_t)rank_le_compact(ix.c_sstart, skeys[c], qe) - (int64_t)rank_lt_compact(ix.c_eend, skeys[ix.n_keys + c], qs);
@@ -65,6 +90,15 @@ __device__ __forceinline__ int64_t count_one_row(const IndexView& ix, const Comp
 }
 // copies the compact index' per-key constants to shared memory (all threads of the CTA; returns nullptr when they do not fit)
 __device__ __forceinline__ const CompactKey* stage_compact_keys(const IndexView& ix, CompactKey* smem) {
+    if (ix.cb_rec) {  // count bins: one 32-byte KeyDir per key
+        if (ix.n_keys > 2 * CI_SMEM_KEYS) return nullptr;
+        const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(ix.cb_kd);
+        uint32_t* s = reinterpret_cast<uint32_t*>(smem);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = __ldg(g + i);
+        __syncthreads();
+        return smem;
+    }
     if (!ix.c_sstart.blocks || ix.n_keys > CI_SMEM_KEYS) return nullptr;
     const uint32_t words = ix.n_keys * (uint32_t)(sizeof(CompactKey) / 4);
     const uint32_t* g0 = reinterpret_cast<const uint32_t*>(ix.c_sstart.d.kd);

@@ -84,6 +84,10 @@ struct LoadU32as64 {
     const uint32_t* in;
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)in[i]; }
 };
+struct LoadU64 {
+    const uint64_t* in;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return in[i]; }
+};
 struct LoadSegMax {
     const uint32_t* key;
     const int32_t* val;
@@ -245,6 +249,10 @@ int exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, uint64_t n, uin
     // out[n] receives the grand total
     return run_scan<uint64_t, SumOp<uint64_t>, LoadU32as64, StoreU64, false>(LoadU32as64{in}, StoreU64{out}, n, scratch,
                                                                            out + n, st);
+}
+int exclusive_scan_u64(const uint64_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, cudaStream_t st) {
+    // out[n] receives the grand total (chunk totals of the pair join: 256 rows of < 2^32 matches each)
+    return run_scan<uint64_t, SumOp<uint64_t>, LoadU64, StoreU64, false>(LoadU64{in}, StoreU64{out}, n, scratch, out + n, st);
 }
 int segmented_running_max(const uint32_t* key, const int32_t* val, int32_t* out, uint64_t n, int32_t* scratch,
                           cudaStream_t st) {
@@ -503,6 +511,89 @@ int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaSt
 int ci_patch_keydir(KeyDir* kd, const uint32_t* off, uint32_t n_keys, cudaStream_t st) {
     if (n_keys == 0) return 0;
     ci_patch_keydir_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(kd, off, n_keys);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// count bins (see CountBin in brg_internal.cuh)
+// ---------------------------------------------------------------------------------------------------
+__global__ void cb_key_ranges_kernel(const int32_t* __restrict__ S, const int32_t* __restrict__ E, const uint32_t* __restrict__ off,
+                                     uint32_t n_keys, KeyDir* __restrict__ kd, unsigned long long* __restrict__ bins_by_shift) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_keys) return;
+    uint32_t b = off[c], e = off[c + 1];
+    KeyDir k;
+    k.seg_begin = b; k.seg_end = e; k.base = 0; k.pad[0] = k.pad[1] = k.pad[2] = 0;
+    if (b == e) {
+        k.lo = 0; k.nb = 0;
+    } else {
+        // (starts <= ends row by row unless the table holds inverted rows: take both arrays into account either way)
+        const int32_t lo = min(S[b], E[b]), hi = max(S[e - 1], E[e - 1]);
+        const uint32_t range = (uint32_t)hi - (uint32_t)lo;
+        k.lo = lo;
+        k.nb = range;  // provisional: the range; dir_assign_bases turns it into a bin count
+        for (int s = 0; s < 32; s++) atomicAdd(&bins_by_shift[s], (unsigned long long)(range >> s) + 1ull);
+    }
+    kd[c] = k;
+}
+int cb_key_ranges(const int32_t* s_start, const int32_t* e_end, const uint32_t* off, uint32_t n_keys, KeyDir* kd,
+                  unsigned long long* d_bins, cudaStream_t st) {
+    BRG_CUDA(cudaMemsetAsync(d_bins, 0, 32 * sizeof(unsigned long long), st));
+    if (n_keys == 0) return 0;
+    cb_key_ranges_kernel<<<(n_keys + 255) / 256, 256, 0, st>>>(s_start, e_end, off, n_keys, kd, d_bins);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+__device__ __forceinline__ uint32_t cb_lower_bound(const int32_t* __restrict__ A, uint32_t a, uint32_t b, int64_t thr) {
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if ((int64_t)A[mid] < thr) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+// one thread per record
+__global__ void cb_fill_kernel(const int32_t* __restrict__ S, const int32_t* __restrict__ E, const KeyDir* __restrict__ kd,
+                               uint32_t n_keys, uint32_t shift, uint4* __restrict__ rec, uint32_t total) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    uint32_t lo = 0, hi = n_keys;  // last key with base <= g that owns records
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (kd[mid].base <= g) lo = mid; else hi = mid;
+    }
+    uint32_t c = lo;
+    while (kd[c].nb == 0 || g - kd[c].base > kd[c].nb) {  // keys without records share the base of their successor
+        if (c == 0) return;
+        c--;
+    }
+    const KeyDir k = kd[c];
+    const uint32_t j = g - k.base;
+    uint32_t w[8] = {k.seg_end, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (j < k.nb) {
+        const int64_t thr = (int64_t)k.lo + ((int64_t)j << shift), nxt = thr + (1ll << shift);
+        const uint32_t cs = cb_lower_bound(S, k.seg_begin, k.seg_end, thr), cs1 = cb_lower_bound(S, cs, k.seg_end, nxt);
+        const uint32_t ce = cb_lower_bound(E, k.seg_begin, k.seg_end, thr), ce1 = cb_lower_bound(E, ce, k.seg_end, nxt);
+        const uint32_t ns = cs1 - cs, ne = ce1 - ce;
+        w[0] = cs;
+        // depth = cs - ce: intervals that start before the bin and have not ended (negative only with inverted rows: overflow)
+        if (ns + ne > CB_SLOTS || ce > cs || cs - ce >= 0xFFFFu) {
+            w[1] = CB_OVERFLOW << 24;
+        } else {
+            w[1] = (cs - ce) | (ns << 16) | (ne << 24);
+            for (uint32_t i = 0; i < ns + ne; i++) {
+                const int64_t v = (int64_t)(i < ns ? S[cs + i] : E[ce + (i - ns)]) - thr;  // 0 .. 2^shift - 1
+                w[2 + (i >> 1)] |= ((uint32_t)v & 0xFFFFu) << ((i & 1u) * 16u);
+            }
+        }
+    }
+    rec[2ull * g] = make_uint4(w[0], w[1], w[2], w[3]);
+    rec[2ull * g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+int cb_fill(const int32_t* s_start, const int32_t* e_end, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint4* rec,
+            uint32_t total, cudaStream_t st) {
+    if (total == 0 || n_keys == 0) return 0;
+    cb_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(s_start, e_end, kd, n_keys, shift, rec, total);
     BRG_LAUNCH_CHECK();
     return 0;
 }

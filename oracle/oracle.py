@@ -84,8 +84,11 @@ class OracleIndex:
         self._h = lib().brgo_build(kp, start, end, len(start), n_keys)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().brgo_index_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals are already gone at interpreter shutdown)
+            try:
+                _lib.brgo_index_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def count_overlaps(self, key, start, end, strict=False, threads=1):
