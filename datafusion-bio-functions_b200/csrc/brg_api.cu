@@ -231,6 +231,7 @@ struct brg_index {
     brg_ctx* ctx = nullptr;
     IndexHeader h{};
     void* slab = nullptr;
+    bool pooled = false;  // slab came from the stream-ordered pool (brg_build): a second build reuses it without a cudaMalloc
     IndexView view{};
 };
 
@@ -624,16 +625,25 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     int key_passes = 0;
     for (uint64_t v = n_keys; v > 0; v >>= 8) key_passes++;
 
+    // A count-only build keeps nothing but the two sorted value arrays (CountOverlapIndex discards the pairing,
+    // interval_tree.rs:26-38): each sort then moves (key, value) -- two word arrays instead of four.
+    const bool two_col = want == BRG_WANT_COUNT;
+    ScratchBuf e_key, e_val, e_key2, e_val2;  // two_col: the (key, end) rows of the E-order sort and their ping-pong set
+    if (two_col && n) {
+        if ((rc = e_key.ensure(nn * 4)) || (rc = e_val.ensure(nn * 4)) || (rc = e_key2.ensure(nn * 4)) || (rc = e_val2.ensure(nn * 4))) return rc;
+        BRG_CUDA(cudaMemcpyAsync(e_key.p, a[0], n * 4, cudaMemcpyDeviceToDevice, st));
+        BRG_CUDA(cudaMemcpyAsync(e_val.p, a[2], n * 4, cudaMemcpyDeviceToDevice, st));
+    }
     // ---- S-order: (key, start, end, pos) -----------------------------------------------------------------
     std::vector<SortPass> passes;
     if (full) for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
     for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
     for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
     int res = 0;
-    rc = radix_sort_rows(a, b, 4, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4,
+    rc = radix_sort_rows(a, b, two_col ? 2 : 4, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4,
                          scan.as<uint32_t>(), st, &res);
     if (rc) return rc;
-    uint32_t** S = res == 0 ? a : b;   // sorted rows
+    uint32_t** S = res == 0 ? a : b;   // sorted rows  (two_col: only [0] key and [1] start are meaningful)
     uint32_t** T = res == 0 ? b : a;   // free set
     mark("S-order sort");
 
@@ -704,7 +714,22 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
 
     // ---- E-order: (key, end, start, pos): stable sort of the S-order rows by end, then key -----------------
     uint32_t** E = nullptr;
-    if (need_e) {
+    uint32_t* e2a[4] = {e_key.as<uint32_t>(), e_val.as<uint32_t>(), nullptr, nullptr};
+    uint32_t* e2b[4] = {e_key2.as<uint32_t>(), e_val2.as<uint32_t>(), nullptr, nullptr};
+    uint32_t* e2view[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (need_e && two_col) {
+        // (key, end) of the ORIGINAL rows, sorted on their own: rows with an invalid key sort last, the first n_valid are kept
+        passes.clear();
+        for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{1, sh, 1, 0xFFFFFFFFu});
+        for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
+        int res2 = 0;
+        rc = radix_sort_rows(e2a, e2b, 2, n, passes.data(), (int)passes.size(), hist.as<uint32_t>(), hist.bytes / 4,
+                             scan.as<uint32_t>(), st, &res2);
+        if (rc) return rc;
+        uint32_t** R = res2 == 0 ? e2a : e2b;
+        e2view[0] = R[0]; e2view[2] = R[1];  // E[2] = sorted ends, as in the four-column layout
+        E = e2view;
+    } else if (need_e) {
         passes.clear();
         for (int sh = 0; sh < 32; sh += 8) passes.push_back(SortPass{2, sh, 1, 0xFFFFFFFFu});
         for (int p = 0; p < key_passes; p++) passes.push_back(SortPass{0, 8 * p, 0, n_keys});
@@ -833,11 +858,14 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     h.cbdir.entries = cb_entries;
     h.slab_bytes = std::max<uint64_t>(cur, 256);
 
+    // The slab comes from the stream-ordered pool like the temporaries: cudaMalloc of a few hundred MB costs 1-3 ms (a third of
+    // a warm 10M-row build), a pool allocation that reuses the slab of an index destroyed earlier costs microseconds.
     void* slab = nullptr;
     {
-        cudaError_t e = cudaMalloc(&slab, h.slab_bytes);
-        if (e != cudaSuccess) { set_error(std::string("cudaMalloc(index slab ") + std::to_string(h.slab_bytes) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
+        cudaError_t e = cudaMallocAsync(&slab, h.slab_bytes, st);
+        if (e != cudaSuccess) { set_error(std::string("cudaMallocAsync(index slab ") + std::to_string(h.slab_bytes) + "): " + cudaGetErrorString(e)); cudaGetLastError(); return BRG_ERR_OOM; }
     }
+    auto slab_free = [&]() { cudaFreeAsync(slab, st); };
     char* base = reinterpret_cast<char*>(slab);
     auto copy_in = [&](uint64_t off_, const void* src, uint64_t bytes) -> cudaError_t {
         if (off_ == kNone || bytes == 0) return cudaSuccess;
@@ -866,32 +894,38 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     if (need_cb) chk(copy_in(h.cbdir.off_kd, cb_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
     if (ce == cudaSuccess) ce = cudaMemsetAsync(base, 0, kSlabHeaderBytes, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st);  // (synchronised below, before h dies)
-    if (ce != cudaSuccess) { cudaFree(slab); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
+    if (ce != cudaSuccess) { slab_free(); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
     for (int i = 0; i < 5; i++) {
         if (!need_dir[i]) continue;
         rc = dir_fill(dirA[i], db[i].kd.as<KeyDir>(), n_keys, db[i].shift, (uint32_t*)(base + h.dir[i].off_D), db[i].entries, st);
-        if (rc) { cudaFree(slab); return rc; }
+        if (rc) { slab_free(); return rc; }
     }
-    if (need_cb) {
-        rc = cb_fill(s_start.as<int32_t>(), (const int32_t*)E[2], cb_kd.as<KeyDir>(), n_keys, cb_shift, (uint4*)(base + h.cbdir.off_D), cb_entries, st);
-        if (rc) { cudaFree(slab); return rc; }
+    if (need_cb) {  // (after the rank directories of s_start and e_end: the record bounds are looked up through them)
+        ScratchBuf cs_tmp, ce_tmp;
+        if ((rc = cs_tmp.ensure(((uint64_t)cb_entries + 1) * 4)) || (rc = ce_tmp.ensure(((uint64_t)cb_entries + 1) * 4))) { slab_free(); return rc; }
+        DirView ds, de;
+        ds.kd = db[0].kd.as<KeyDir>(); ds.D = (const uint32_t*)(base + h.dir[0].off_D); ds.A = s_start.as<int32_t>(); ds.shift = db[0].shift;
+        de.kd = db[1].kd.as<KeyDir>(); de.D = (const uint32_t*)(base + h.dir[1].off_D); de.A = (const int32_t*)E[2]; de.shift = db[1].shift;
+        rc = cb_fill(ds, de, cb_kd.as<KeyDir>(), n_keys, cb_shift, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(), (uint4*)(base + h.cbdir.off_D),
+                     cb_entries, st);
+        if (rc) { slab_free(); return rc; }
     }
     if (need_ci)
         for (int a = 0; a < 2; a++) {
             ScratchBuf dtmp;  // plain table first, then packed into the slab
-            if ((rc = dtmp.ensure(((uint64_t)cdb[a].entries + 1) * 4))) { cudaFree(slab); return rc; }
+            if ((rc = dtmp.ensure(((uint64_t)cdb[a].entries + 1) * 4))) { slab_free(); return rc; }
             rc = dir_fill(cS[a].as<int32_t>(), cdb[a].kd.as<KeyDir>(), n_keys, cdb[a].shift, dtmp.as<uint32_t>(), cdb[a].entries, st);
             if (!rc) rc = ci_pack_table(dtmp.as<uint32_t>(), cdb[a].entries, (uint32_t*)(base + h.cdir[a].off_D), st);
             if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("compact table: sync failed"); rc = BRG_ERR_CUDA; }
-            if (rc) { cudaFree(slab); return rc; }
+            if (rc) { slab_free(); return rc; }
         }
     {
         cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { cudaFree(slab); set_error(std::string("build sync: ") + cudaGetErrorString(e)); return BRG_ERR_CUDA; }
+        if (e != cudaSuccess) { slab_free(); set_error(std::string("build sync: ") + cudaGetErrorString(e)); return BRG_ERR_CUDA; }
     }
     mark("slab fill");
     brg_index* ix = new brg_index();
-    ix->ctx = ctx; ix->h = h; ix->slab = slab; ix->view = make_view(h, slab);
+    ix->ctx = ctx; ix->h = h; ix->slab = slab; ix->pooled = true; ix->view = make_view(h, slab);
     *out = ix;
     return BRG_OK;
 }
@@ -922,7 +956,14 @@ extern "C" BRG_API int brg_build(brg_ctx* ctx, const uint32_t* key, const int32_
 extern "C" BRG_API void brg_index_destroy(brg_index* ix) {
     if (!ix) return;
     if (ix->ctx) cudaSetDevice(ix->ctx->device);
-    if (ix->slab) cudaFree(ix->slab);
+    if (ix->slab) {
+        if (ix->pooled && ix->ctx && !ix->ctx->dead.load() && ix->ctx->build_stream) {
+            cudaDeviceSynchronize();  // (what cudaFree does implicitly: probes still in flight on other streams finish first)
+            cudaFreeAsync(ix->slab, ix->ctx->build_stream);
+        } else {
+            cudaFree(ix->slab);  // (also valid for pool memory)
+        }
+    }
     delete ix;
 }
 extern "C" BRG_API uint64_t brg_index_rows(const brg_index* ix) { return ix ? ix->h.n : 0; }

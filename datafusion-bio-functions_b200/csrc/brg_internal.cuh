@@ -200,8 +200,8 @@ int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaSt
 // count bins: per-key value range over BOTH arrays (kd.nb = provisional range), then one thread per record
 int cb_key_ranges(const int32_t* s_start, const int32_t* e_end, const uint32_t* off, uint32_t n_keys, KeyDir* kd,
                   unsigned long long* d_bins_by_shift, cudaStream_t st);
-int cb_fill(const int32_t* s_start, const int32_t* e_end, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint4* rec,
-            uint32_t total_entries, cudaStream_t st);
+int cb_fill(const DirView& d_sstart, const DirView& d_eend, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* cs_tmp,
+            uint32_t* ce_tmp /* total_entries + 1 words each */, uint4* rec, uint32_t total_entries, cudaStream_t st);
 // rank directory
 int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
                    cudaStream_t st);
