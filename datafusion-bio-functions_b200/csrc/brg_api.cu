@@ -353,6 +353,11 @@ static int launch_narrow(const void* src, int pos_type, uint64_t m, uint64_t row
     BRG_LAUNCH_CHECK();
     return 0;
 }
+// experiment switch BRG_NARROW_OUT=1: counts / coverage cross PCIe as 32-bit values and are widened by the host threads
+__global__ void narrow_i64_kernel(const long long* __restrict__ in, uint64_t m, int32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = (int32_t)in[i];
+}
 static inline uint64_t pos_width(int t) { return (t == BRG_POS_INT64 || t == BRG_POS_UINT64) ? 8 : 4; }
 // largest m in [1, n] with offsets[m] <= max_rows (at least one probe row is always consumed)
 __global__ void find_cut_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t max_rows, uint64_t* out) {
@@ -1008,14 +1013,17 @@ extern "C" BRG_API int brg_index_slab_alloc(brg_ctx* ctx, uint64_t slab_bytes, v
     if (!ctx || !d_slab || slab_bytes < kSlabHeaderBytes) { set_error("brg_index_slab_alloc: bad argument"); return BRG_ERR_INVALID; }
     *d_slab = nullptr;
     BRG_CUDA(cudaSetDevice(ctx->device));
-    cudaError_t e = cudaMalloc(d_slab, slab_bytes);
-    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(index slab): ") + cudaGetErrorString(e)); cudaGetLastError(); *d_slab = nullptr; return BRG_ERR_OOM; }
+    // from the stream-ordered pool, like the slab of a build: a replica that replaces an earlier one of the same size costs
+    // microseconds instead of a cudaMalloc of a few hundred MB (2-3 ms, more than the NVLink transfer itself)
+    cudaError_t e = cudaMallocAsync(d_slab, slab_bytes, ctx->build_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->build_stream);  // usable on any stream from here on
+    if (e != cudaSuccess) { set_error(std::string("cudaMallocAsync(index slab): ") + cudaGetErrorString(e)); cudaGetLastError(); *d_slab = nullptr; return BRG_ERR_OOM; }
     return BRG_OK;
 }
 extern "C" BRG_API void brg_index_slab_free(brg_ctx* ctx, void* d_slab) {
     if (!d_slab) return;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(d_slab);
+    cudaFree(d_slab);  // (valid for pool memory as well)
 }
 extern "C" BRG_API int brg_index_attach(brg_ctx* ctx, void* d_slab, uint64_t slab_bytes, void* stream, brg_index** out) {
     if (!ctx || !d_slab || !out) { set_error("brg_index_attach: NULL argument"); return BRG_ERR_INVALID; }
@@ -1027,7 +1035,7 @@ extern "C" BRG_API int brg_index_attach(brg_ctx* ctx, void* d_slab, uint64_t sla
     BRG_CUDA(cudaStreamSynchronize(st));
     if (h.magic != kMagic || h.version != kVersion || h.slab_bytes != slab_bytes) { set_error("brg_index_attach: the buffer does not hold an index slab of this size"); return BRG_ERR_INVALID; }
     brg_index* ix = new brg_index();
-    ix->ctx = ctx; ix->h = h; ix->slab = d_slab; ix->view = make_view(h, d_slab);
+    ix->ctx = ctx; ix->h = h; ix->slab = d_slab; ix->pooled = true; ix->view = make_view(h, d_slab);
     *out = ix;
     return BRG_OK;
 }
@@ -1284,9 +1292,21 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
     const bool pg_o1 = stage_on && op == OP_NEAREST1 && is_pageable(out_bits);
     const bool pg_o2 = stage_on && op == OP_NEAREST1 && out_dist && is_pageable(out_dist);
     const bool pg_key = stage_on && key && !by_runs && is_pageable(key);
-    const bool staged_out = pg_o0 || pg_o1 || pg_o2;
+    // BRG_NARROW_OUT=1 (experiment): Int64 count / coverage values fit 32 bits (< 2^31 build rows; the coverage accumulator is
+    // i32): send 4 bytes per row over PCIe and let the host threads widen them into the caller's Int64 buffer
+    static const bool narrow_env = getenv("BRG_NARROW_OUT") && getenv("BRG_NARROW_OUT")[0] == '1';
+    const bool narrow_out = narrow_env && op != OP_NEAREST1 && ix->h.n < 0x80000000u;
+    const bool staged_out = pg_o0 || pg_o1 || pg_o2 || narrow_out;
     const bool chunk_runs = runs_on && key && !by_runs;  // look for runs in every chunk of a per-row key column
     HostPool* pool = (pg_s || pg_e || pg_key || staged_out || chunk_runs) ? host_pool(ctx) : nullptr;
+    auto widen = [&](int64_t* dst, const int32_t* src, uint64_t m) {
+        const int parts = (int)std::min<uint64_t>((m + (1u << 20) - 1) >> 20, (uint64_t)pool->width() * 4);
+        const uint64_t per = (m + std::max(parts, 1) - 1) / std::max(parts, 1);
+        pool->parallel_for(std::max(parts, 1), [&](int t) {
+            const uint64_t b = (uint64_t)t * per, e = std::min(m, b + per);
+            for (uint64_t i = b; i < e; i++) dst[i] = (int64_t)src[i];
+        });
+    };
 
     // everything below is asynchronous on the lane's three streams: a failure must drain them before the lane (and the
     // caller's buffers) are released
@@ -1318,7 +1338,8 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
             if (pg_s && (rc = l->stage_s[b].ensure(C * ws))) return rc;
             if (pg_e && (rc = l->stage_e[b].ensure(C * we))) return rc;
             if (pg_key && (rc = l->stage_key[b].ensure(C * 4))) return rc;
-            if (pg_o0 && (rc = l->stage_o0[b].ensure(C * 8))) return rc;
+            if ((pg_o0 || narrow_out) && (rc = l->stage_o0[b].ensure(C * 8))) return rc;
+            if (narrow_out && (rc = l->out1[b].ensure(C * 4))) return rc;
             if (pg_o1 && (rc = l->stage_o1[b].ensure(C / 8 + 4))) return rc;
             if (pg_o2 && (rc = l->stage_o2[b].ensure(C * 8))) return rc;
             if (chunk_runs && ((rc = l->stage_runs[b].ensure((uint64_t)kMaxChunkRuns * 12)) || (rc = l->runs_key[b].ensure((uint64_t)kMaxChunkRuns * 4)) ||
@@ -1339,6 +1360,8 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
                 if (pg_o0) pool_memcpy(pool, out_left + done, l->stage_o0[b].p, m * 4);
                 if (pg_o1) pool_memcpy(pool, out_bits + done / 8, l->stage_o1[b].p, ((m + 31) / 32) * 4);
                 if (pg_o2) pool_memcpy(pool, out_dist + done, l->stage_o2[b].p, m * 8);
+            } else if (narrow_out) {
+                widen(out_i64 + done, l->stage_o0[b].as<int32_t>(), m);
             } else if (pg_o0) {
                 pool_memcpy(pool, out_i64 + done, l->stage_o0[b].p, m * 8);
             }
@@ -1400,12 +1423,18 @@ static int run_fixed(brg_ctx* ctx, const brg_index* ix, FixedOp op, const uint32
                 rc = launch_nearest_k1(ix->view, dk, l->in_s[b].as<int32_t>(), l->in_e[b].as<int32_t>(), m, include_overlaps, strict,
                                        l->out0[b].as<uint32_t>(), l->out1[b].as<uint32_t>(), out_dist ? l->out2[b].as<int64_t>() : nullptr, l->k);
             if (rc) return rc;
+            if (narrow_out) {
+                narrow_i64_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->k>>>(l->out0[b].as<long long>(), m, l->out1[b].as<int32_t>());
+                g_launches.fetch_add(1);
+            }
             BRG_CUDA(cudaEventRecord(l->ev_k[b], l->k));
             BRG_CUDA(cudaStreamWaitEvent(l->d2h, l->ev_k[b], 0));
             if (op == OP_NEAREST1) {
                 BRG_CUDA(cudaMemcpyAsync(pg_o0 ? l->stage_o0[b].p : (void*)(out_left + done), l->out0[b].p, m * 4, cudaMemcpyDeviceToHost, l->d2h));
                 BRG_CUDA(cudaMemcpyAsync(pg_o1 ? l->stage_o1[b].p : (void*)(out_bits + done / 8), l->out1[b].p, ((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, l->d2h));
                 if (out_dist) BRG_CUDA(cudaMemcpyAsync(pg_o2 ? l->stage_o2[b].p : (void*)(out_dist + done), l->out2[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
+            } else if (narrow_out) {
+                BRG_CUDA(cudaMemcpyAsync(l->stage_o0[b].p, l->out1[b].p, m * 4, cudaMemcpyDeviceToHost, l->d2h));
             } else {
                 BRG_CUDA(cudaMemcpyAsync(pg_o0 ? l->stage_o0[b].p : (void*)(out_i64 + done), l->out0[b].p, m * 8, cudaMemcpyDeviceToHost, l->d2h));
             }
