@@ -375,7 +375,7 @@ __device__ __forceinline__ uint32_t count_bin_slots(const CountBinRec& x, uint32
 #pragma unroll
     for (uint32_t i = 0; i < CB_SLOTS; i++) {
         const uint32_t v = (x.w[2 + (i >> 1)] >> ((i & 1u) * 16u)) & 0xFFFFu;
-        c += (i >= first && i < last && v <= off) ? 1u : 0u;
+        c += ((!ENDS || i >= first) && i < last && v <= off) ? 1u : 0u;
     }
     return c;
 }

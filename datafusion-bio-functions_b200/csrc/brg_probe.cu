@@ -793,12 +793,6 @@ __global__ void __launch_bounds__(PB_THREADS) subtract_kernel(IndexView ix, cons
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
-// persistent grid for the tiled kernels: 3 CTAs per SM (shared-memory bound), never more CTAs than tiles
-static inline unsigned tiled_grid(uint64_t rows, int per_sm = BRG_CC_CTAS) {
-    uint64_t tiles = (rows + TP_TILE - 1) / TP_TILE;
-    uint64_t cap = (uint64_t)kSMs * per_sm;
-    return (unsigned)std::max<uint64_t>(1, std::min(tiles, cap));
-}
 // to-do list of deferred chunks: stream-ordered allocation, so concurrent calls on different streams never share it
 static int todo_alloc(uint64_t rows, TodoList* td, cudaStream_t st) {
     const uint64_t chunks = (rows + TP_WTILE - 1) / TP_WTILE;
@@ -816,11 +810,6 @@ static int todo_free(const TodoList& td, cudaStream_t st) {
 static inline unsigned todo_grid(uint64_t rows) {
     uint64_t chunks = (rows + TP_WTILE - 1) / TP_WTILE;
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(chunks, (uint64_t)kSMs * 8));
-}
-static int tiled_config(const void* fn) {
-    // opt in to > 48 KB dynamic shared memory (once per kernel per process; cheap to repeat)
-    BRG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeRing)));
-    return 0;
 }
 // The TMA-tiled kernels are the default for all three probes (measured on B200, bench extras: count 0.64 ms tiled vs
 // 1.07 ms per-row; coverage 0.68 vs 0.69; nearest 0.72 vs 0.79).  BRG_TILED=<list> restricts the tiled path to the

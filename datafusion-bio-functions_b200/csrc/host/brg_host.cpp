@@ -1377,6 +1377,154 @@ static Err run_join(brgh_session* s, const Table& lt, const Table& rt, const cha
     return kOk;
 }
 
+// ---- the range-join filter parser (physical_planner/intervals.rs:30-218) -----------------------------------------------------
+// The reference walks DataFusion's JoinFilter: an AND of exactly two comparisons, each between an expression over ONE column of
+// the left input and an expression over ONE column of the right input.  It assigns the four bounds by the side of the operands
+// and the direction of the comparison, and rewrites a strict comparison by subtracting one from the END it involves
+// (`minus_one`, intervals.rs:63-65).  DataFusion itself is out of scope here, so the filter arrives as the SQL text of the ON
+// clause's residual; column references are `alias.column` (optionally quoted with " or `, optionally inside CAST(.. AS type) as
+// the reference's own OverlapProvider writes them, overlap.rs:171-181).
+struct FilterOperand {
+    int side = -1;  // 0 = left, 1 = right
+    std::string column;
+};
+struct FilterCmp {
+    FilterOperand a, b;
+    std::string op;
+};
+struct FilterLexer {
+    const std::string& s;
+    size_t i = 0;
+    explicit FilterLexer(const std::string& t) : s(t) {}
+    void ws() { while (i < s.size() && isspace((unsigned char)s[i])) i++; }
+    bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { i++; return true; } return false; }
+    bool eat_word(const char* w) {  // case-insensitive keyword followed by a non-identifier character
+        ws();
+        size_t n = strlen(w);
+        if (i + n > s.size()) return false;
+        for (size_t k = 0; k < n; k++) if (tolower((unsigned char)s[i + k]) != tolower((unsigned char)w[k])) return false;
+        if (i + n < s.size() && (isalnum((unsigned char)s[i + n]) || s[i + n] == '_')) return false;
+        i += n;
+        return true;
+    }
+    bool ident(std::string* out) {
+        ws();
+        out->clear();
+        if (i < s.size() && (s[i] == '"' || s[i] == '`')) {
+            const char q = s[i++];
+            while (i < s.size() && s[i] != q) out->push_back(s[i++]);
+            if (i >= s.size()) return false;
+            i++;
+            return true;
+        }
+        while (i < s.size() && (isalnum((unsigned char)s[i]) || s[i] == '_')) out->push_back(s[i++]);
+        return !out->empty();
+    }
+};
+// one side of a comparison: [CAST(] alias.column [AS type)] possibly parenthesised.  Anything that combines two columns (the
+// reference panics with "complex sub queries are not supported", intervals.rs:47-52) or no column at all is refused.
+static Err parse_filter_operand(FilterLexer& lx, const std::string& la, const std::string& ra, FilterOperand* out) {
+    if (lx.eat('(')) {
+        BRGH_TRY(parse_filter_operand(lx, la, ra, out));
+        lx.ws();
+        if (lx.i < lx.s.size() && strchr("+-*/", lx.s[lx.i])) return internal("complex sub queries are not supported " + lx.s);
+        if (!lx.eat(')')) return internal("filter expression: missing ')' in " + lx.s);
+        return kOk;
+    }
+    if (lx.eat_word("CAST")) {
+        if (!lx.eat('(')) return internal("filter expression: CAST without '(' in " + lx.s);
+        BRGH_TRY(parse_filter_operand(lx, la, ra, out));
+        if (!lx.eat_word("AS")) return internal("filter expression: CAST without AS in " + lx.s);
+        std::string ty;
+        if (!lx.ident(&ty)) return internal("filter expression: CAST without a type in " + lx.s);
+        if (!lx.eat(')')) return internal("filter expression: missing ')' after CAST in " + lx.s);
+        return kOk;
+    }
+    std::string alias, col;
+    if (!lx.ident(&alias) || !lx.eat('.') || !lx.ident(&col)) return internal("filter expression: expected alias.column in " + lx.s);
+    if (lower(alias) == lower(la)) out->side = 0;
+    else if (lower(alias) == lower(ra)) out->side = 1;
+    else return internal("filter expression: unknown table alias '" + alias + "'");
+    out->column = col;
+    return kOk;
+}
+static Err parse_filter_cmp(FilterLexer& lx, const std::string& la, const std::string& ra, FilterCmp* out) {
+    const bool paren = [&] { const size_t save = lx.i; if (lx.eat('(')) { FilterOperand probe; FilterLexer t(lx.s); t.i = lx.i; Err e = parse_filter_operand(t, la, ra, &probe);
+                                 t.ws(); if (!e.code && t.i < t.s.size() && strchr("<>=!", t.s[t.i])) return true; } lx.i = save; return false; }();
+    BRGH_TRY(parse_filter_operand(lx, la, ra, &out->a));
+    lx.ws();
+    out->op.clear();
+    while (lx.i < lx.s.size() && strchr("<>=!", lx.s[lx.i])) out->op.push_back(lx.s[lx.i++]);
+    if (out->op.empty()) {
+        if (lx.i < lx.s.size() && strchr("+-*/", lx.s[lx.i])) return internal("complex sub queries are not supported " + lx.s);
+        return internal("filter expression is not a BinaryExpr");
+    }
+    BRGH_TRY(parse_filter_operand(lx, la, ra, &out->b));
+    lx.ws();
+    if (lx.i < lx.s.size() && strchr("+-*/", lx.s[lx.i])) return internal("complex sub queries are not supported " + lx.s);
+    if (paren && !lx.eat(')')) return internal("filter expression: missing ')' in " + lx.s);
+    return kOk;
+}
+struct ColIntervalsOut {
+    std::string ls, le, rs, re;
+    bool have_ls = false, have_le = false, have_rs = false, have_re = false;
+    bool le_minus_one = false, re_minus_one = false;
+};
+// parse_condition (intervals.rs:67-124): which bound each operand is, by side and comparison direction
+static Err apply_filter_cmp(const FilterCmp& c, ColIntervalsOut* o) {
+    const bool is_lt = c.op == "<", is_lteq = c.op == "<=", is_gteq = c.op == ">=", is_gt = c.op == ">";
+    if (!(is_lt || is_lteq || is_gteq || is_gt)) return internal("Unsupported operator: " + c.op);
+    auto set = [&](bool* have, std::string* dst, const std::string& v, const char* what) -> Err {
+        if (*have) return internal(std::string(what) + " already set");
+        *have = true; *dst = v;
+        return kOk;
+    };
+    if (c.a.side == 1 && (is_lteq || is_lt)) {          // rs </<= le
+        if (c.b.side != 0) return internal("couldn't parse as rs </<= le");
+        BRGH_TRY(set(&o->have_rs, &o->rs, c.a.column, "rs"));
+        BRGH_TRY(set(&o->have_le, &o->le, c.b.column, "le"));
+        o->le_minus_one = is_lt;
+    } else if (c.a.side == 0 && (is_lteq || is_lt)) {   // ls </<= re
+        if (c.b.side != 1) return internal("couldn't parse as ls </<= re");
+        BRGH_TRY(set(&o->have_re, &o->re, c.b.column, "re"));
+        BRGH_TRY(set(&o->have_ls, &o->ls, c.a.column, "ls"));
+        o->re_minus_one = is_lt;
+    } else if (c.a.side == 1 && (is_gteq || is_gt)) {   // re >/>= ls
+        if (c.b.side != 0) return internal("couldn't parse as re >/>= ls");
+        BRGH_TRY(set(&o->have_re, &o->re, c.a.column, "re"));
+        BRGH_TRY(set(&o->have_ls, &o->ls, c.b.column, "ls"));
+        o->re_minus_one = is_gt;
+    } else if (c.a.side == 0 && (is_gteq || is_gt)) {   // le >/>= rs
+        if (c.b.side != 1) return internal("couldn't parse as le >/>= rs");
+        BRGH_TRY(set(&o->have_rs, &o->rs, c.b.column, "rs"));
+        BRGH_TRY(set(&o->have_le, &o->le, c.a.column, "le"));
+        o->le_minus_one = is_gt;
+    } else {
+        return internal("couldn't parse left side as neither 'rs </<=' nor 'ls </<=' nor 're >/>=' nor 'le >/>='");
+    }
+    return kOk;
+}
+// try_parse (intervals.rs:184-218)
+static Err parse_join_filter(const std::string& text, const std::string& la, const std::string& ra, ColIntervalsOut* out) {
+    FilterLexer lx(text);
+    FilterCmp c1, c2;
+    BRGH_TRY(parse_filter_cmp(lx, la, ra, &c1));
+    if (!lx.eat_word("AND")) {
+        lx.ws();
+        return internal(lx.i >= lx.s.size() ? "filter expression is not an AND" : "filter expression is not an AND");
+    }
+    BRGH_TRY(parse_filter_cmp(lx, la, ra, &c2));
+    lx.ws();
+    if (lx.i < lx.s.size()) return internal("left side of AND is not a BinaryExpr");  // (a third conjunct nests the AND)
+    BRGH_TRY(apply_filter_cmp(c1, out));
+    BRGH_TRY(apply_filter_cmp(c2, out));
+    if (!out->have_ls) return internal("left start bound not found");
+    if (!out->have_le) return internal("left end bound not found");
+    if (!out->have_rs) return internal("right start bound not found");
+    if (!out->have_re) return internal("right end bound not found");
+    return kOk;
+}
+
 }  // namespace
 
 // ============================================================================================================================
@@ -1541,6 +1689,33 @@ BRG_API int brgh_interval_join(brgh_session* s, const char* left, const char* ri
         e = run_join(s, *lt, *rt, on_left, on_right, n_on, left_start, left_end, right_start, right_end, lt_strict != 0, gt_strict != 0,
                      join_type, "", "", true, true, r);
     return run_to_result(e, r, out);
+}
+BRG_API int brgh_parse_join_filter(const char* filter, const char* left_alias, const char* right_alias, brgh_col_intervals* out) {
+    if (!filter || !left_alias || !right_alias || !out) return finish(internal("brgh_parse_join_filter: NULL argument"));
+    ColIntervalsOut o;
+    Err e = parse_join_filter(filter, left_alias, right_alias, &o);
+    if (e.code) return finish(e);
+    auto put = [&](char* dst, const std::string& v) -> bool {
+        if (v.size() + 1 > sizeof(out->left_start)) return false;
+        memcpy(dst, v.c_str(), v.size() + 1);
+        return true;
+    };
+    if (!put(out->left_start, o.ls) || !put(out->left_end, o.le) || !put(out->right_start, o.rs) || !put(out->right_end, o.re))
+        return finish(internal("brgh_parse_join_filter: column name too long"));
+    out->left_end_minus_one = o.le_minus_one ? 1 : 0;
+    out->right_end_minus_one = o.re_minus_one ? 1 : 0;
+    return 0;
+}
+BRG_API int brgh_interval_join_filter(brgh_session* s, const char* left, const char* right, const char* const* on_left,
+                                      const char* const* on_right, int n_on, const char* filter, const char* left_alias,
+                                      const char* right_alias, int join_type, brgh_result** out) {
+    if (!s || !left || !right || !filter || !out) return finish(internal("brgh_interval_join_filter: NULL argument"));
+    brgh_col_intervals ci;
+    const int rc = brgh_parse_join_filter(filter, left_alias ? left_alias : left, right_alias ? right_alias : right, &ci);
+    if (rc) return rc;
+    // `l.end > r.start` compares l.end - 1 (gt_strict), `l.start < r.end` compares r.end - 1 (lt_strict): intervals.rs:85-115
+    return brgh_interval_join(s, left, right, on_left, on_right, n_on, ci.left_start, ci.left_end, ci.right_start, ci.right_end,
+                              ci.right_end_minus_one, ci.left_end_minus_one, join_type, out);
 }
 BRG_API int brgh_explain_interval_join(const brgh_session* s, int join_type, char* buf, uint64_t cap) {
     if (!s || !buf || !cap) return finish(internal("brgh_explain_interval_join: NULL argument"));

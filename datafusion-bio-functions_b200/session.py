@@ -20,9 +20,15 @@ JOIN_INNER, JOIN_RIGHT_SEMI, JOIN_RIGHT_ANTI = 0, 1, 2
 HOST_SYMBOLS = [
     "brgh_create_bio_session", "brgh_session_destroy", "brgh_session_set", "brgh_session_get", "brgh_session_set_coalesce_rows",
     "brgh_register_batch", "brgh_deregister_table", "brgh_count_overlaps", "brgh_coverage", "brgh_nearest", "brgh_overlap",
-    "brgh_merge", "brgh_cluster", "brgh_subtract", "brgh_complement", "brgh_interval_join", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
+    "brgh_merge", "brgh_cluster", "brgh_subtract", "brgh_complement", "brgh_interval_join", "brgh_parse_join_filter", "brgh_interval_join_filter", "brgh_explain_interval_join", "brgh_result_num_batches", "brgh_result_num_rows", "brgh_result_export",
     "brgh_result_release", "brgh_resolve_positions", "brgh_take",
 ]
+
+class ColIntervals(C.Structure):
+    """brgh_col_intervals (include/bioranges_host.h)"""
+    _fields_ = [("left_start", C.c_char * 128), ("left_end", C.c_char * 128), ("right_start", C.c_char * 128),
+                ("right_end", C.c_char * 128), ("left_end_minus_one", C.c_int), ("right_end_minus_one", C.c_int)]
+
 
 _bound = False
 
@@ -52,6 +58,8 @@ def _lib():
     L.brgh_complement.argtypes = [vp, cp, strs, i32, C.POINTER(vp)]
     L.brgh_interval_join.argtypes = [vp, cp, cp, strs, strs, i32, cp, cp, cp, cp, i32, i32, i32, C.POINTER(vp)]
     L.brgh_explain_interval_join.argtypes = [vp, i32, cp, u64]
+    L.brgh_parse_join_filter.argtypes = [cp, cp, cp, C.POINTER(ColIntervals)]
+    L.brgh_interval_join_filter.argtypes = [vp, cp, cp, strs, strs, i32, cp, cp, cp, i32, C.POINTER(vp)]
     L.brgh_result_num_batches.argtypes = [vp]
     L.brgh_result_num_batches.restype = u64
     L.brgh_result_num_rows.argtypes = [vp]
@@ -200,10 +208,29 @@ class BioSession:
                                           right_cols[1].encode(), int(lt_strict), int(gt_strict), int(join_type), C.byref(res)))
         return self._collect(res)
 
+    def interval_join_filter(self, left, right, on, filter, left_alias=None, right_alias=None, join_type=JOIN_INNER):
+        """SELECT * FROM left <left_alias> JOIN right <right_alias> ON l.on = r.on AND <filter>: the range condition as text,
+        parsed the way the planner rule parses the JoinFilter (physical_planner/intervals.rs)"""
+        res = C.c_void_p()
+        ol, orr = [a for a, _ in on], [b for _, b in on]
+        A.check(_lib().brgh_interval_join_filter(self._h, left.encode(), right.encode(), _cstrs(ol), _cstrs(orr), len(on), filter.encode(),
+                                                 (left_alias or left).encode(), (right_alias or right).encode(), int(join_type), C.byref(res)))
+        return self._collect(res)
+
     def explain_interval_join(self, join_type=JOIN_INNER):
         buf = C.create_string_buffer(512)
         A.check(_lib().brgh_explain_interval_join(self._h, int(join_type), buf, 512))
         return buf.value.decode()
+
+
+def parse_join_filter(filter, left_alias, right_alias):
+    """the range-join filter parser alone (needs no GPU): -> dict(left_start, left_end, right_start, right_end,
+    left_end_minus_one, right_end_minus_one)"""
+    ci = ColIntervals()
+    A.check(_lib().brgh_parse_join_filter(filter.encode(), left_alias.encode(), right_alias.encode(), C.byref(ci)))
+    return {"left_start": ci.left_start.decode(), "left_end": ci.left_end.decode(), "right_start": ci.right_start.decode(),
+            "right_end": ci.right_end.decode(), "left_end_minus_one": bool(ci.left_end_minus_one),
+            "right_end_minus_one": bool(ci.right_end_minus_one)}
 
 
 def create_bio_session(device=0):

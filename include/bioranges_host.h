@@ -126,6 +126,23 @@ BRG_API int brgh_interval_join(brgh_session* s, const char* left, const char* ri
                        const char* const* on_right, int n_on, const char* left_start, const char* left_end,
                        const char* right_start, const char* right_end, int lt_strict, int gt_strict, int join_type,
                        brgh_result** out);
+/* The range-join filter parser (physical_planner/intervals.rs:30-218, tests :220-525).  `filter` is the residual of the ON
+ * clause as SQL text: the AND of exactly two comparisons (<, <=, >, >=), each between ONE column of the left input and ONE
+ * column of the right input, written `alias.column` (optionally quoted, parenthesised or inside CAST(.. AS type)).  The four
+ * bounds are assigned by side and direction as parse_condition does; a strict comparison subtracts one from the END it
+ * involves (`minus_one`): left_end_minus_one for `l.end > r.start` / `r.start < l.end`, right_end_minus_one for
+ * `l.start < r.end` / `r.end > l.start`.  Failures are Internal errors with the reference's texts ("filter expression is not
+ * an AND", "Unsupported operator: =", "rs already set", "left end bound not found", "complex sub queries are not supported"). */
+typedef struct {
+    char left_start[128], left_end[128], right_start[128], right_end[128];
+    int left_end_minus_one, right_end_minus_one;
+} brgh_col_intervals;
+BRG_API int brgh_parse_join_filter(const char* filter, const char* left_alias, const char* right_alias, brgh_col_intervals* out);
+/* brgh_interval_join with the range condition given as filter text (what the planner rule extracts from the join,
+ * physical_planner/mod.rs + intervals.rs): SELECT * FROM left <left_alias> JOIN right <right_alias> ON <on pairs> AND <filter> */
+BRG_API int brgh_interval_join_filter(brgh_session* s, const char* left, const char* right, const char* const* on_left,
+                              const char* const* on_right, int n_on, const char* filter, const char* left_alias,
+                              const char* right_alias, int join_type, brgh_result** out);
 /* text IntervalJoinExec prints in EXPLAIN for this session's algorithm: "IntervalJoinExec: mode=CollectLeft,
  * join_type=Inner, alg=Coitrees" style (interval_join.rs:353-362; the reference's tests assert on `alg=`) */
 BRG_API int brgh_explain_interval_join(const brgh_session* s, int join_type, char* buf, uint64_t cap);

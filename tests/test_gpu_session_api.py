@@ -87,6 +87,23 @@ def test_all_weak_and_strict_conditions(ctx):
             assert sorted(zip(t.column(bcols[0]).to_pylist(), t.column(bcols[1]).to_pylist())) == sorted(want)
 
 
+# ---- the same conditions as SQL text through the filter parser (physical_planner/intervals.rs) -------------------------------
+def test_range_join_from_filter_text(ctx):
+    b12 = [(11, 15), (10, 15), (10, 10), (9, 15), (5, 15), (4, 15), (4, 10), (6, 8), (4, 8), (4, 5), (5, 5), (4, 4)]
+    ctx.register_table("a", pa.table({"start": pa.array([5], pa.int32()), "end": pa.array([10], pa.int32())}))
+    ctx.register_table("b", pa.table({"start": pa.array([r[0] for r in b12], pa.int32()), "end": pa.array([r[1] for r in b12], pa.int32())}))
+    weak = [(10, 15), (10, 10), (9, 15), (5, 15), (4, 15), (4, 10), (6, 8), (4, 8), (5, 5), (4, 5)]
+    strict = [(9, 15), (5, 15), (4, 15), (4, 10), (6, 8), (4, 8)]
+    for cond, want in (("a.start <= b.end AND a.end >= b.start", weak), ("b.end >= a.start AND b.start <= a.end", weak),
+                       ("a.start < b.end AND a.end > b.start", strict), ("b.start < a.end AND b.end > a.start", strict)):
+        t = pa.Table.from_batches(ctx.interval_join_filter("a", "b", [], cond))
+        assert sorted(zip(t.column(2).to_pylist(), t.column(3).to_pylist())) == sorted(want)
+    from bio_ranges_b200 import BioRangesError
+
+    with pytest.raises(BioRangesError, match="filter expression is not an AND"):
+        ctx.interval_join_filter("a", "b", [], "a.start <= b.end OR a.end >= b.start")
+
+
 # ---- TEST:371-418 test_nearest: CoitreesNearest join, two-column key, strict ------------------------------------------------
 def test_join_coitrees_nearest_two_column_key(ctx):
     ctx.register_table("a", pa.table({"contig": ["a"], "strand": ["s"], "start": pa.array([5], pa.int32()), "end": pa.array([10], pa.int32())}))

@@ -150,3 +150,54 @@ def test_take_matches_arrow_compute():
         assert got2.column("s").equals(pc.take(src.column("s"), pa.array(ii, pa.uint32())))
     st, msg = _err(S.take, b, np.array([n], np.uint32))
     assert st == S.ARROW and "index out of bounds" in msg.lower()
+
+
+# ---- the range-join filter parser: physical_planner/intervals.rs:220-525, the reference's own test cases -----------------------
+# tables of the reference test: a(contig, l_start, l_end) is the SQL-left input, b(contig, name, r_end, r_start) the right one
+GTEQ_LTEQ = ["b.r_end >= a.l_start AND a.l_end >= b.r_start", "b.r_end >= a.l_start AND b.r_start <= a.l_end",
+             "a.l_start <= b.r_end AND a.l_end >= b.r_start", "a.l_start <= b.r_end AND b.r_start <= a.l_end",
+             "a.l_end >= b.r_start AND b.r_end >= a.l_start", "a.l_end >= b.r_start AND a.l_start <= b.r_end",
+             "b.r_start <= a.l_end AND b.r_end >= a.l_start", "b.r_start <= a.l_end AND a.l_start <= b.r_end"]
+GT_LT = ["b.r_end > a.l_start AND a.l_end > b.r_start", "b.r_end > a.l_start AND b.r_start < a.l_end",
+         "a.l_start < b.r_end AND a.l_end > b.r_start", "a.l_start < b.r_end AND b.r_start < a.l_end",
+         "a.l_end > b.r_start AND b.r_end > a.l_start", "a.l_end > b.r_start AND a.l_start < b.r_end",
+         "b.r_start < a.l_end AND b.r_end > a.l_start", "b.r_start < a.l_end AND a.l_start < b.r_end"]
+
+
+@pytest.mark.parametrize("cond", GTEQ_LTEQ)
+def test_join_filter_all_weak_orderings(cond):
+    """intervals.rs:246-338 test_all_comp_combinations_for_gteq_lteq"""
+    got = S.parse_join_filter(cond, "a", "b")
+    assert got == {"left_start": "l_start", "left_end": "l_end", "right_start": "r_start", "right_end": "r_end",
+                   "left_end_minus_one": False, "right_end_minus_one": False}
+
+
+@pytest.mark.parametrize("cond", GT_LT)
+def test_join_filter_all_strict_orderings(cond):
+    """intervals.rs:347-462 test_all_comp_combinations_for_gt_lt: both ends become `end - 1`"""
+    got = S.parse_join_filter(cond, "a", "b")
+    assert got == {"left_start": "l_start", "left_end": "l_end", "right_start": "r_start", "right_end": "r_end",
+                   "left_end_minus_one": True, "right_end_minus_one": True}
+
+
+def test_join_filter_mixed_strictness_or_and_complex():
+    # intervals.rs:464-490: only the strict comparison's END gets the minus one
+    got = S.parse_join_filter("b.r_start < a.l_end AND a.l_start <= b.r_end", "a", "b")
+    assert got["left_end_minus_one"] and not got["right_end_minus_one"]
+    got = S.parse_join_filter("b.r_start <= a.l_end AND a.l_start < b.r_end", "a", "b")
+    assert not got["left_end_minus_one"] and got["right_end_minus_one"]
+    # intervals.rs:340-342: OR is not a range join
+    st, msg = _err(S.parse_join_filter, "b.r_start <= a.l_end OR a.l_start <= b.r_end", "a", "b")
+    assert st == S.INTERNAL and "filter expression is not an AND" in msg
+    # intervals.rs:494-499: an operand over two columns ("complex sub queries are not supported": the reference panics)
+    st, msg = _err(S.parse_join_filter, "(b.r_end - a.l_start) >= a.l_start AND a.l_end >= b.r_start", "a", "b")
+    assert "complex sub queries are not supported" in msg
+    # parse_condition's other refusals, with the reference's texts
+    assert "Unsupported operator: =" in _err(S.parse_join_filter, "a.l_start = b.r_end AND a.l_end >= b.r_start", "a", "b")[1]
+    assert "couldn't parse as ls </<= re" in _err(S.parse_join_filter, "a.l_start <= a.l_end AND a.l_end >= b.r_start", "a", "b")[1]
+    assert "already set" in _err(S.parse_join_filter, "a.l_start <= b.r_end AND a.l_end <= b.r_start", "a", "b")[1]
+    # the form the reference's own OverlapProvider writes (overlap.rs:171-181): CASTs, quoted names, case-insensitive aliases
+    got = S.parse_join_filter("CAST(a.`pos_end` AS INTEGER) >= CAST(b.`pos_start` AS INTEGER) and CAST(A.\"pos_start\" AS INTEGER) <= CAST(B.pos_end AS INTEGER)", "a", "b")
+    assert got["left_start"] == "pos_start" and got["left_end"] == "pos_end" and got["right_start"] == "pos_start" and got["right_end"] == "pos_end"
+    got = S.parse_join_filter("(a.s <= b.e) AND (a.e > b.s)", "a", "b")
+    assert got == {"left_start": "s", "left_end": "e", "right_start": "s", "right_end": "e", "left_end_minus_one": True, "right_end_minus_one": False}
