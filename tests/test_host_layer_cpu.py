@@ -201,3 +201,19 @@ def test_join_filter_mixed_strictness_or_and_complex():
     assert got["left_start"] == "pos_start" and got["left_end"] == "pos_end" and got["right_start"] == "pos_start" and got["right_end"] == "pos_end"
     got = S.parse_join_filter("(a.s <= b.e) AND (a.e > b.s)", "a", "b")
     assert got == {"left_start": "s", "left_end": "e", "right_start": "s", "right_end": "e", "left_end_minus_one": True, "right_end_minus_one": False}
+
+
+def test_ingest_contig_runs_from_dictionary_column(tmp_path):
+    """ingest.py: a dictionary-encoded contig column becomes key runs without touching a string per row"""
+    import pyarrow.parquet as pq
+
+    from bio_ranges_b200 import ingest
+
+    names = ["chr1"] * 5 + ["chr2"] * 3 + ["chrUn"] * 2 + ["chr1"] * 1
+    t = pa.table({"contig": pa.array(names), "pos_start": pa.array(range(11), pa.int64()), "pos_end": pa.array(range(1, 12), pa.int64())})
+    pq.write_table(t, str(tmp_path / "t.parquet"))
+    (rb,) = list(ingest.iter_parquet(str(tmp_path / "t.parquet"), ("contig", "pos_start", "pos_end")))
+    assert pa.types.is_dictionary(rb.column(0).type)  # decoded from the dictionary pages, not re-encoded
+    rk, rend = ingest.contig_runs(rb.column(0), {"chr1": 0, "chr2": 1})
+    assert rk.tolist() == [0, 1, brg.KEY_ABSENT, 0] and rend.tolist() == [5, 8, 10, 11]
+    assert ingest._column_values(rb.column(1), "start").dtype == np.int64
