@@ -220,9 +220,10 @@ struct IndexHeader {
     uint32_t n_blocks, pad_;
     // count bins (32-byte records; cbdir.off_kd = per-key constants, cbdir.off_D = the records, cbdir.entries = record count)
     DirDesc cbdir;
+    DirDesc cvdir;  // coverage bins over (m_first, m_last), same layout
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
-static const uint32_t kVersion = 5;
+static const uint32_t kVersion = 6;
 static const uint64_t kNone = ~0ull;
 static const uint64_t kSlabHeaderBytes = 4096;  // reserved at the front of every slab for the IndexHeader
 static_assert(sizeof(IndexHeader) <= kSlabHeaderBytes, "IndexHeader must fit the reserved slab prefix");
@@ -264,9 +265,12 @@ static IndexView make_view(const IndexHeader& h, void* slab) {
         cv[a]->d.A = (const int32_t*)P(h.off_cS[a]);
         cv[a]->d.shift = h.cdir[a].shift;
     }
-    v.cb_rec = (const uint4*)P(h.cbdir.off_D);
-    v.cb_kd = (const KeyDir*)P(h.cbdir.off_kd);
-    v.cb_shift = h.cbdir.shift;
+    v.cb.rec = (const uint4*)P(h.cbdir.off_D);
+    v.cb.kd = (const KeyDir*)P(h.cbdir.off_kd);
+    v.cb.shift = h.cbdir.shift;
+    v.cvb.rec = (const uint4*)P(h.cvdir.off_D);
+    v.cvb.kd = (const KeyDir*)P(h.cvdir.off_kd);
+    v.cvb.shift = h.cvdir.shift;
     return v;
 }
 
@@ -769,29 +773,36 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     // At most kCbTarget elements of each array per bin on average.  Offsets inside a bin are u16, so bins are at most 65536
     // wide: a build side too sparse for that (more than 2 records per row) keeps the compact rank index below instead.
     static const uint32_t kCbTarget = [] { const char* v = getenv("BRG_CB_TARGET"); const int t = v ? atoi(v) : 2; return (uint32_t)(t > 0 ? t : 0); }();
-    ScratchBuf cb_kd;
-    uint32_t cb_shift = 0, cb_entries = 0;
-    bool need_cb = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && kCbTarget > 0;
-    if (need_cb) {
-        if ((rc = cb_kd.ensure((uint64_t)std::max(1u, n_keys) * sizeof(KeyDir)))) return rc;
-        if ((rc = cb_key_ranges(s_start.as<int32_t>(), (const int32_t*)E[2], off.as<uint32_t>(), n_keys, cb_kd.as<KeyDir>(), d_bins, st))) return rc;
+    // plan of one bins table over the array pair (A, B) that shares the key segments `seg`: per-key ranges, bin width, record count
+    auto plan_bins = [&](const int32_t* A, const int32_t* B, const uint32_t* seg, uint64_t n_elems, ScratchBuf* kd, uint32_t* shift_out,
+                         uint32_t* entries_out, bool* ok) -> int {
+        int rc;
+        *ok = false;
+        if ((rc = kd->ensure((uint64_t)std::max(1u, n_keys) * sizeof(KeyDir)))) return rc;
+        if ((rc = cb_key_ranges(A, B, seg, n_keys, kd->as<KeyDir>(), d_bins, st))) return rc;
         unsigned long long bins[32];
         BRG_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof(bins), cudaMemcpyDeviceToHost, st));
         BRG_CUDA(cudaStreamSynchronize(st));
         // widest bins that still hold at most kCbTarget elements of each array on average (so between target / 2 and target)
-        const uint64_t at_least = std::max<uint64_t>((uint64_t)n_valid / kCbTarget, 1);
+        const uint64_t at_least = std::max<uint64_t>(n_elems / kCbTarget, 1);
         uint32_t shift = 0;
         for (uint32_t sft = 16; sft > 0; sft--)
             if (bins[sft] >= at_least) { shift = sft; break; }
-        if (bins[shift] > 2ull * n_valid + 2ull * n_keys + (1ull << 16)) {  // (a build side too sparse for 65536-wide bins)
-            need_cb = false;
-        } else {
-            cb_shift = shift;
-            if ((rc = dir_assign_bases(cb_kd.as<KeyDir>(), n_keys, shift, d_scalar, st))) return rc;
-            BRG_CUDA(cudaMemcpyAsync(&cb_entries, d_scalar, 4, cudaMemcpyDeviceToHost, st));
-            BRG_CUDA(cudaStreamSynchronize(st));
-        }
-    }
+        if (bins[shift] > 2ull * n_elems + 2ull * n_keys + (1ull << 16)) return 0;  // (too sparse for 65536-wide bins)
+        *shift_out = shift;
+        if ((rc = dir_assign_bases(kd->as<KeyDir>(), n_keys, shift, d_scalar, st))) return rc;
+        BRG_CUDA(cudaMemcpyAsync(entries_out, d_scalar, 4, cudaMemcpyDeviceToHost, st));
+        BRG_CUDA(cudaStreamSynchronize(st));
+        *ok = true;
+        return 0;
+    };
+    ScratchBuf cb_kd, cv_kd;
+    uint32_t cb_shift = 0, cb_entries = 0, cv_shift = 0, cv_entries = 0;
+    bool need_cb = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && kCbTarget > 0;
+    if (need_cb && (rc = plan_bins(s_start.as<int32_t>(), (const int32_t*)E[2], off.as<uint32_t>(), n_valid, &cb_kd, &cb_shift, &cb_entries, &need_cb))) return rc;
+    // coverage: the same bins over the merged intervals' (first, last) -- the per-row coverage kernels (unsorted probe tables)
+    bool need_cvb = need_cov && n_merged > 0 && kCbTarget > 0;
+    if (need_cvb && (rc = plan_bins(m_first.as<int32_t>(), m_last.as<int32_t>(), m_off.as<uint32_t>(), n_merged, &cv_kd, &cv_shift, &cv_entries, &need_cvb))) return rc;
     mark("count bins plan");
     const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && !need_cb;
     ScratchBuf boff_d, cS[2], cB[2];
@@ -861,6 +872,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     h.cbdir.off_D = place(need_cb, (uint64_t)cb_entries * 32);
     h.cbdir.shift = cb_shift;
     h.cbdir.entries = cb_entries;
+    h.cvdir.off_kd = place(need_cvb, (uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+    h.cvdir.off_D = place(need_cvb, (uint64_t)cv_entries * 32);
+    h.cvdir.shift = cv_shift;
+    h.cvdir.entries = cv_entries;
     h.slab_bytes = std::max<uint64_t>(cur, 256);
 
     // The slab comes from the stream-ordered pool like the temporaries: cudaMalloc of a few hundred MB costs 1-3 ms (a third of
@@ -897,6 +912,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
             chk(copy_in(h.cdir[a].off_kd, cdb[a].kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
         }
     if (need_cb) chk(copy_in(h.cbdir.off_kd, cb_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
+    if (need_cvb) chk(copy_in(h.cvdir.off_kd, cv_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
     if (ce == cudaSuccess) ce = cudaMemsetAsync(base, 0, kSlabHeaderBytes, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st);  // (synchronised below, before h dies)
     if (ce != cudaSuccess) { slab_free(); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
@@ -913,6 +929,16 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         de.kd = db[1].kd.as<KeyDir>(); de.D = (const uint32_t*)(base + h.dir[1].off_D); de.A = (const int32_t*)E[2]; de.shift = db[1].shift;
         rc = cb_fill(ds, de, cb_kd.as<KeyDir>(), n_keys, cb_shift, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(), (uint4*)(base + h.cbdir.off_D),
                      cb_entries, st);
+        if (rc) { slab_free(); return rc; }
+    }
+    if (need_cvb) {
+        ScratchBuf cs_tmp, ce_tmp;
+        if ((rc = cs_tmp.ensure(((uint64_t)cv_entries + 1) * 4)) || (rc = ce_tmp.ensure(((uint64_t)cv_entries + 1) * 4))) { slab_free(); return rc; }
+        DirView df, dl;
+        df.kd = db[3].kd.as<KeyDir>(); df.D = (const uint32_t*)(base + h.dir[3].off_D); df.A = m_first.as<int32_t>(); df.shift = db[3].shift;
+        dl.kd = db[4].kd.as<KeyDir>(); dl.D = (const uint32_t*)(base + h.dir[4].off_D); dl.A = m_last.as<int32_t>(); dl.shift = db[4].shift;
+        rc = cb_fill(df, dl, cv_kd.as<KeyDir>(), n_keys, cv_shift, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(), (uint4*)(base + h.cvdir.off_D),
+                     cv_entries, st);
         if (rc) { slab_free(); return rc; }
     }
     if (need_ci)

@@ -89,6 +89,13 @@ struct CompactKey {       // per-key constants of a CompactView (32 bytes, same 
     uint32_t nb, base, blk_begin, blk_end, eb, ee, pad;
 };
 
+// Bins over a PAIR of sorted arrays that share their key segments (see "Count bins" below)
+struct BinsView {
+    const uint4* rec;   // 2 x uint4 per bin; nullptr = absent
+    const KeyDir* kd;   // per key: lo, nb, base (first record), seg_begin / seg_end (shared by the two arrays)
+    uint32_t shift;     // bin width 2^shift (<= 65536: in-bin offsets are u16)
+};
+
 // Device view of an index (pointers into the single HBM slab)
 struct IndexView {
     uint32_t n_keys;
@@ -116,9 +123,9 @@ struct IndexView {
     DirView d_sstart, d_eend, d_pme, d_mfirst, d_mlast;
     CompactView c_sstart, c_eend;  // per-row path of count_overlaps (superseded by the count bins when those are present)
     // Count bins: ONE 32-byte record per coordinate bin answers both rank queries of a count_overlaps row (see CountBin)
-    const uint4* cb_rec;   // 2 x uint4 per bin; nullptr = absent
-    const KeyDir* cb_kd;   // per key: lo, nb, base (first record), seg_begin / seg_end (shared by s_start and e_end)
-    uint32_t cb_shift;     // bin width 2^cb_shift (<= 65536: in-bin offsets are u16)
+    BinsView cb;   // over (s_start, e_end): count_overlaps
+    BinsView cvb;  // over (m_first, m_last): coverage -- the same record answers "first merged interval with last >= qs" and
+                   // "first merged interval with first > qe"
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -358,8 +365,8 @@ __device__ __forceinline__ CompactKey load_compact_key(const CompactView& c, uin
 
 // One count bin record (32 bytes = one sector), loaded once and used for both rank queries of a row.
 struct CountBinRec { uint32_t w[8]; };
-__device__ __forceinline__ CountBinRec load_count_bin(const IndexView& ix, uint32_t rec) {
-    const uint4* r = ix.cb_rec + 2ull * rec;
+__device__ __forceinline__ CountBinRec load_count_bin(const BinsView& bv, uint32_t rec) {
+    const uint4* r = bv.rec + 2ull * rec;
     const uint4 a = __ldg(r), b = __ldg(r + 1);
     CountBinRec x;
     x.w[0] = a.x; x.w[1] = a.y; x.w[2] = a.z; x.w[3] = a.w; x.w[4] = b.x; x.w[5] = b.y; x.w[6] = b.z; x.w[7] = b.w;
@@ -382,6 +389,34 @@ __device__ __forceinline__ uint32_t count_bin_slots(const CountBinRec& x, uint32
 // global index of the first start / end >= the bin's first coordinate
 __device__ __forceinline__ uint32_t count_bin_cs(const CountBinRec& x) { return x.w[0]; }
 __device__ __forceinline__ uint32_t count_bin_ce(const CountBinRec& x) { return x.w[0] - (x.w[1] & 0xFFFFu); }
+
+// Both rank queries of a row through the bins of one array pair:
+//   *ra = seg_begin + #(first array <= qa),  *rb = seg_begin + #(second array < qb)
+// A rank whose record overflowed is left for the caller (returned bit 0: ra missing, bit 1: rb missing).
+__device__ __forceinline__ uint32_t bins_pair_ranks(const BinsView& bv, const KeyDir& k, int32_t qa, int32_t qb, uint32_t* ra,
+                                                    uint32_t* rb) {
+    // bin of qa, bin of qb - 1; outside [lo, lo + nb * width) the segment bounds answer
+    const bool a_in = qa >= k.lo, b_in = qb > k.lo;
+    const uint32_t da = (uint32_t)qa - (uint32_t)k.lo, db = (uint32_t)qb - 1u - (uint32_t)k.lo;
+    const uint32_t ba = da >> bv.shift, bb = db >> bv.shift;
+    const bool need_a = a_in && ba < k.nb, need_b = b_in && bb < k.nb;
+    *ra = a_in ? k.seg_end : k.seg_begin;
+    *rb = b_in ? k.seg_end : k.seg_begin;
+    const uint32_t msk = (1u << bv.shift) - 1u;
+    uint32_t missing = 0;
+    CountBinRec r;
+    if (need_a) {
+        r = load_count_bin(bv, k.base + ba);
+        if (count_bin_overflowed(r)) missing |= 1u;
+        else *ra = count_bin_cs(r) + count_bin_slots<false>(r, da & msk);
+    }
+    if (need_b) {
+        if (!(need_a && bb == ba)) r = load_count_bin(bv, k.base + bb);  // (the usual case: the row lies inside one bin)
+        if (count_bin_overflowed(r)) missing |= 2u;
+        else *rb = count_bin_ce(r) + count_bin_slots<true>(r, db & msk);
+    }
+    return missing;
+}
 
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }

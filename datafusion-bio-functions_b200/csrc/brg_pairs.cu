@@ -179,9 +179,22 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
                                                                      uint64_t* __restrict__ chunk_tot, TodoList todo,
                                                                      uint32_t all_chunks, uint32_t tail_chunk) {
     __shared__ uint64_t wsum[TP_WTILE / 32];
+    // the per-key constants of the three rank directories: every row needs all three, and a table has a few dozen keys
+    constexpr uint32_t SK = 64;
+    __shared__ KeyDir skd[3][SK];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_list = todo.count ? *todo.count : all_chunks;
     const uint32_t n_items = n_list + (tail_chunk != 0xFFFFFFFFu ? 1u : 0u);
+    if (blockIdx.x >= n_items) return;
+    const bool staged = ix.n_keys <= SK;
+    if (staged) {
+        const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
+        const uint32_t* g[3] = {reinterpret_cast<const uint32_t*>(ix.d_sstart.kd), reinterpret_cast<const uint32_t*>(ix.d_pme.kd),
+                                reinterpret_cast<const uint32_t*>(ix.d_eend.kd)};
+        for (int a = 0; a < 3; a++)
+            for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(skd[a])[i] = __ldg(g[a] + i);
+        __syncthreads();
+    }
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t chunk = item < n_list ? (todo.count ? todo.chunks[item] : item) : tail_chunk;
         const uint64_t i = (uint64_t)chunk * TP_WTILE + threadIdx.x;
@@ -193,7 +206,8 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
             if (c < ix.n_keys) {
                 // the three rank queries of the row are independent: directory steps together, bin searches in lock step
                 //   n_le = #(start <= qe),  p0 = first row with prefix_max_end >= qs,  ended = #(end < qs)
-                const KeyDir ks = load_keydir(ix.d_sstart.kd, c), kp = load_keydir(ix.d_pme.kd, c), ke = load_keydir(ix.d_eend.kd, c);
+                const KeyDir ks = staged ? skd[0][c] : load_keydir(ix.d_sstart.kd, c), kp = staged ? skd[1][c] : load_keydir(ix.d_pme.kd, c),
+                             ke = staged ? skd[2][c] : load_keydir(ix.d_eend.kd, c);
                 uint32_t n_le, h0, p0, h1, ended, h2;
                 rank_le_bin(ix.d_sstart, ks, qe, &n_le, &h0);
                 rank_lt_bin(ix.d_pme, kp, qs, &p0, &h1);

@@ -53,29 +53,13 @@ __device__ __forceinline__ uint32_t load_key(const uint32_t* key, uint64_t i) { 
 // skeys = the compact index' per-key constants in shared memory ([0] starts, [n_keys] ends), or nullptr.
 constexpr uint32_t CI_SMEM_KEYS = 256;  // keys whose constants the per-row kernels keep in shared memory (2 x 8 KB)
 __device__ __forceinline__ int64_t count_one_row(const IndexView& ix, const CompactKey* skeys, uint32_t c, int32_t qs, int32_t qe) {
-    if (ix.cb_rec) {  // count bins: one 32-byte record answers both rank queries when the row lies inside one bin (the usual case)
-        const KeyDir k = skeys ? reinterpret_cast<const KeyDir*>(skeys)[c] : load_keydir(ix.cb_kd, c);
+    if (ix.cb.rec) {  // count bins: one 32-byte record answers both rank queries when the row lies inside one bin (the usual case)
+        const KeyDir k = skeys ? reinterpret_cast<const KeyDir*>(skeys)[c] : load_keydir(ix.cb.kd, c);
         if (k.nb == 0) return 0;
-        // #(starts <= qe): bin be;  #(ends < qs) = #(ends <= qs - 1): bin bs   (outside [lo, lo + nb * width): the segment bounds)
-        const bool e_in = qe >= k.lo, s_in = qs > k.lo;  // (qs - 1 >= lo)
-        const uint32_t de = (uint32_t)qe - (uint32_t)k.lo, ds = (uint32_t)qs - 1u - (uint32_t)k.lo;
-        const uint32_t be = de >> ix.cb_shift, bs = ds >> ix.cb_shift;
-        const bool need_e = e_in && be < k.nb, need_s = s_in && bs < k.nb;
-        uint32_t started = e_in ? k.seg_end : k.seg_begin, ended = s_in ? k.seg_end : k.seg_begin;
-        const uint32_t msk = (1u << ix.cb_shift) - 1u;
-        CountBinRec r;
-        bool have = false;
-        if (need_e) {
-            r = load_count_bin(ix, k.base + be);
-            have = true;
-            if (count_bin_overflowed(r)) started = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
-            else started = count_bin_cs(r) + count_bin_slots<false>(r, de & msk);
-        }
-        if (need_s) {
-            if (!(have && bs == be)) r = load_count_bin(ix, k.base + bs);
-            if (count_bin_overflowed(r)) ended = rank_lt_kd(ix.d_eend, load_keydir(ix.d_eend.kd, c), qs);
-            else ended = count_bin_ce(r) + count_bin_slots<true>(r, ds & msk);
-        }
+        uint32_t started, ended;
+        const uint32_t missing = bins_pair_ranks(ix.cb, k, qe, qs, &started, &ended);
+        if (missing & 1u) started = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
+        if (missing & 2u) ended = rank_lt_kd(ix.d_eend, load_keydir(ix.d_eend.kd, c), qs);
         return (int64_t)started - (int64_t)ended;
     }
     if (ix.c_sstart.blocks) {
@@ -90,10 +74,10 @@ __device__ __forceinline__ int64_t count_one_row(const IndexView& ix, const Comp
 }
 // copies the compact index' per-key constants to shared memory (all threads of the CTA; returns nullptr when they do not fit)
 __device__ __forceinline__ const CompactKey* stage_compact_keys(const IndexView& ix, CompactKey* smem) {
-    if (ix.cb_rec) {  // count bins: one 32-byte KeyDir per key
+    if (ix.cb.rec) {  // count bins: one 32-byte KeyDir per key
         if (ix.n_keys > 2 * CI_SMEM_KEYS) return nullptr;
         const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
-        const uint32_t* g = reinterpret_cast<const uint32_t*>(ix.cb_kd);
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(ix.cb.kd);
         uint32_t* s = reinterpret_cast<uint32_t*>(smem);
         for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = __ldg(g + i);
         __syncthreads();
@@ -237,10 +221,38 @@ __device__ __forceinline__ int32_t cov_term(int32_t qs, int32_t qe, int32_t firs
 template <bool EARLY_OUT>
 __device__ __forceinline__ int32_t coverage_from_range(const IndexView& ix, uint32_t lo, uint32_t hi, int32_t qs, int32_t qe);
 
+// [lo, hi) = the merged intervals of key c that overlap [qs, qe]: lo = first j with last_j >= qs, hi = first j with first_j > qe.
+// Through the coverage bins (one 32-byte record for both when the row lies inside a bin) when the build made them, else through
+// the two rank directories.  skeys = the bins' per-key constants in shared memory, or nullptr.
+__device__ __forceinline__ void coverage_row_range(const IndexView& ix, const KeyDir* skeys, uint32_t c, int32_t qs, int32_t qe,
+                                                   uint32_t* lo, uint32_t* hi) {
+    if (ix.cvb.rec) {
+        const KeyDir k = skeys ? skeys[c] : load_keydir(ix.cvb.kd, c);
+        if (k.nb == 0) { *lo = *hi = 0; return; }
+        const uint32_t missing = bins_pair_ranks(ix.cvb, k, qe, qs, hi, lo);
+        if (missing & 1u) *hi = rank_le_kd(ix.d_mfirst, load_keydir(ix.d_mfirst.kd, c), qe);
+        if (missing & 2u) *lo = rank_lt_kd(ix.d_mlast, load_keydir(ix.d_mlast.kd, c), qs);
+        return;
+    }
+    *lo = rank_lt_kd(ix.d_mlast, load_keydir(ix.d_mlast.kd, c), qs);
+    *hi = rank_le_kd(ix.d_mfirst, load_keydir(ix.d_mfirst.kd, c), qe);
+}
+__device__ __forceinline__ const KeyDir* stage_coverage_keys(const IndexView& ix, KeyDir* smem) {
+    if (!ix.cvb.rec || ix.n_keys > CI_SMEM_KEYS) return nullptr;
+    const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(ix.cvb.kd);
+    uint32_t* s = reinterpret_cast<uint32_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = __ldg(g + i);
+    __syncthreads();
+    return smem;
+}
+
 __global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, const uint32_t* __restrict__ key,
                                                               const int32_t* __restrict__ start,
                                                               const int32_t* __restrict__ end, uint64_t n, int strict,
                                                               int64_t* __restrict__ out) {
+    __shared__ KeyDir skeys_buf[CI_SMEM_KEYS];
+    const KeyDir* skeys = stage_coverage_keys(ix, skeys_buf);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
@@ -248,12 +260,10 @@ __global__ void __launch_bounds__(PB_THREADS) coverage_kernel(IndexView ix, cons
         if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
         int32_t acc = 0;
         if (c < ix.n_keys) {
-            KeyDir kl = load_keydir(ix.d_mlast.kd, c);
-            KeyDir kf = load_keydir(ix.d_mfirst.kd, c);
             // merged intervals are disjoint and ascending in both first and last: the ones overlapping [qs,qe]
             // (first <= qe && last >= qs, the coitrees predicate) are exactly the index range [lo, hi)
-            uint32_t lo = rank_lt_kd(ix.d_mlast, kl, qs);   // first j with last_j >= qs
-            uint32_t hi = rank_le_kd(ix.d_mfirst, kf, qe);  // first j with first_j > qe
+            uint32_t lo, hi;
+            coverage_row_range(ix, skeys, c, qs, qe, &lo, &hi);
             acc = coverage_from_range<true>(ix, lo, hi, qs, qe);
         }
         st_stream(out + i, (int64_t)acc);  // interval_tree.rs:207
@@ -392,6 +402,9 @@ __global__ void __launch_bounds__(TP_WTILE) coverage_kernel_todo(IndexView ix, c
                                                                  const int32_t* __restrict__ end, uint64_t n_rows,
                                                                  int strict, int64_t* __restrict__ out, TodoList todo) {
     const uint32_t n_todo = *todo.count;
+    if (blockIdx.x >= n_todo) return;  // (nothing was deferred: skip staging the key constants)
+    __shared__ KeyDir skeys_buf[CI_SMEM_KEYS];
+    const KeyDir* skeys = stage_coverage_keys(ix, skeys_buf);
     for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {
         const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
         if (i >= n_rows) continue;
@@ -400,9 +413,9 @@ __global__ void __launch_bounds__(TP_WTILE) coverage_kernel_todo(IndexView ix, c
         if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
         int32_t acc = 0;
         if (k < ix.n_keys) {
-            const KeyDir kl = load_keydir(ix.d_mlast.kd, k);
-            const KeyDir kf = load_keydir(ix.d_mfirst.kd, k);
-            acc = coverage_from_range<true>(ix, rank_lt_kd(ix.d_mlast, kl, qs), rank_le_kd(ix.d_mfirst, kf, qe), qs, qe);
+            uint32_t lo, hi;
+            coverage_row_range(ix, skeys, k, qs, qe, &lo, &hi);
+            acc = coverage_from_range<true>(ix, lo, hi, qs, qe);
         }
         st_stream(out + i, (int64_t)acc);
     }
