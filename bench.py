@@ -45,7 +45,7 @@ WORKLOADS = {
     "nearest": (50_000_000, 5_000_000, "nearest k=1 50M queries x 5M sparse targets, 24 contigs (configs[3])"),
 }
 KERNELS = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
-           "pairs": "pairs_ranges_todo_kernel+scan+pairs_emit_kernel_flat"}
+           "pairs": "pairs_join_kernel"}
 API = {"count": "brg_count_overlaps", "coverage": "brg_coverage", "nearest": "brg_nearest_k1", "pairs": "brg_overlap_pairs"}
 
 
@@ -353,18 +353,28 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
         alg_bytes = n * 28 + n // 8 + nb * 12
         outs = (left, bits, dd)
     else:
+        fused = os.environ.get("BRG_PAIRS_FUSED", "1") != "0"
         offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
-        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2)
+        ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2 of the chunked form)
         ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
         torch.cuda.synchronize()
         total = int(offsets[-1].item())
         bi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
         pi = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+        tot_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        if fused:
+            del ranges, offsets
+            ranges = offsets = None
 
-        def step():  # count -> scan -> emit
-            ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
-            ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
+            def step():  # ONE launch: ranges -> count -> decoupled look-back -> emit (brg_pairs_join_dev)
+                ix.pairs_join_dev(pk, ps, pe, bi, pi, tot_dev)
+        else:
 
+            def step():  # count -> scan -> emit (three-launch chunked form)
+                ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
+                ix.pairs_fill_dev(ps, offsets, ranges, bi, pi)
+
+        res["pairs_path"] = "brg_pairs_join_dev (one launch)" if fused else "brg_pairs_chunk_offsets_dev + brg_pairs_fill_dev"
         units_per_step = total
         alg_bytes = n * 12 + total * 8 + nb * 12
         outs = (bi, pi)
@@ -407,6 +417,8 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
         pnp = (to_np(pk).astype(np.uint32), to_np(ps), to_np(pe))
         if name == "pairs":
             ok = check_pairs(h, oi, pnp, to_np(bi[:total]), to_np(pi[:total]))
+            if res.get("pairs_path", "").startswith("brg_pairs_join_dev"):
+                ok = ok and int(tot_dev.item()) == total  # the one-launch join's own count
         else:
             ok = check_fixed(h, name, oi, pnp, tuple(to_np(o) for o in outs))
         parity["device_resident"] = bool(h.reduce(1.0 if ok else 0.0, "min") == 1.0)

@@ -9,9 +9,9 @@ The product path fails loudly when libbioranges.so is missing or no sm_100 GPU i
 or calls oracle/.
 """
 from . import _cabi
-from ._cabi import (KEY_ABSENT, PAIRS_ANTI, PAIRS_INNER, PAIRS_SEMI, WANT_ALL, WANT_COUNT, WANT_COVERAGE, WANT_NEAREST,
+from ._cabi import (JOIN_ORDERED, KEY_ABSENT, PAIRS_ANTI, PAIRS_INNER, PAIRS_INNER_ANY_ORDER, PAIRS_SEMI, WANT_ALL, WANT_COUNT, WANT_COVERAGE, WANT_NEAREST,
                     WANT_PAIRS, BioRangesError)
 from .engine import Context, Index, default_context
 
 __all__ = ["Context", "Index", "default_context", "BioRangesError", "KEY_ABSENT", "WANT_ALL", "WANT_COUNT",
-           "WANT_COVERAGE", "WANT_NEAREST", "WANT_PAIRS", "PAIRS_INNER", "PAIRS_SEMI", "PAIRS_ANTI", "_cabi"]
+           "WANT_COVERAGE", "WANT_NEAREST", "WANT_PAIRS", "PAIRS_INNER", "PAIRS_SEMI", "PAIRS_ANTI", "PAIRS_INNER_ANY_ORDER", "JOIN_ORDERED", "_cabi"]

@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("BRG_LIB") or os.path.join(_HERE, "libbioranges.so")  
 KEY_ABSENT = 0xFFFFFFFF
 
 WANT_COUNT, WANT_COVERAGE, WANT_NEAREST, WANT_PAIRS, WANT_ALL = 1, 2, 4, 8, 15
-PAIRS_INNER, PAIRS_SEMI, PAIRS_ANTI = 0, 1, 2
+PAIRS_INNER, PAIRS_SEMI, PAIRS_ANTI, PAIRS_INNER_ANY_ORDER = 0, 1, 2, 3
+JOIN_ORDERED = 1
 
 # every symbol include/bioranges.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
@@ -23,7 +24,7 @@ ABI_SYMBOLS = [
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
     "brg_count_overlaps_arrow", "brg_coverage_arrow", "brg_nearest_k1_arrow",
     "brg_overlap_pairs", "brg_pairs_count_dev", "brg_pairs_emit_dev", "brg_pairs_chunk_rows", "brg_pairs_chunk_offsets_dev",
-    "brg_pairs_fill_dev", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_complement", "brg_gaps_len", "brg_gaps_view", "brg_gaps_start", "brg_gaps_end", "brg_gaps_release", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
+    "brg_pairs_fill_dev", "brg_pairs_join_dev", "brg_pairs_join_chunk_rows", "brg_take_dev", "brg_merge", "brg_cluster", "brg_subtract", "brg_complement", "brg_gaps_len", "brg_gaps_view", "brg_gaps_start", "brg_gaps_end", "brg_gaps_release", "brg_rows_piece_start", "brg_rows_piece_end", "brg_sort_rows",
     "brg_merged_len", "brg_merged_key", "brg_merged_start",
     "brg_merged_end", "brg_merged_count", "brg_merged_release", "brg_rows_len", "brg_rows_build_idx",
     "brg_rows_probe_idx", "brg_rows_valid_bits", "brg_rows_distance", "brg_rows_release", "brg_kernel_launches",
@@ -105,6 +106,8 @@ def lib():
     L.brg_pairs_chunk_rows.restype = u32
     L.brg_pairs_chunk_offsets_dev.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp]
     L.brg_pairs_fill_dev.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.brg_pairs_join_dev.argtypes = [vp, vp, vp, vp, vp, u64, u64, i32, vp, vp, vp, vp, vp]
+    L.brg_pairs_join_chunk_rows.restype = u32
     L.brg_take_dev.argtypes = [vp, vp, u32, vp, vp, u64, vp, vp]
     L.brg_merge.argtypes = [vp, vp, vp, vp, u64, u32, C.c_int64, i32, C.POINTER(vp)]
     L.brg_cluster.argtypes = [vp, vp, vp, vp, u64, u32, C.c_int64, i32, C.POINTER(vp)]

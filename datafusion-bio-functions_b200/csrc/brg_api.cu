@@ -1206,6 +1206,24 @@ extern "C" BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* ix, con
     return launch_pairs_fill(ix->view, s, n, d_chunk_base, d_row_ranges, d_build_idx, d_probe_idx, (cudaStream_t)stream);
 }
 
+extern "C" BRG_API uint32_t brg_pairs_join_chunk_rows(void) { return pairs_join_chunk_rows(); }
+extern "C" BRG_API int brg_pairs_join_dev(brg_ctx* ctx, const brg_index* ix, const uint32_t* k, const int32_t* s, const int32_t* e,
+                                          uint64_t n, uint64_t capacity, int flags, uint32_t* d_build_idx, uint32_t* d_probe_idx,
+                                          uint64_t* d_total, uint64_t* d_chunk_slots, void* stream) {
+    int rc = check_probe(ctx, ix, BRG_WANT_PAIRS, "brg_pairs_join");
+    if (rc) return rc;
+    if (n > 0xFFFFFFFFull) { set_error("probe row index exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
+    if (!d_total || (capacity && (!d_build_idx || !d_probe_idx))) { set_error("brg_pairs_join: NULL output"); return BRG_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    BRG_CUDA(cudaSetDevice(ctx->device));
+    void* state = nullptr;  // the ticket, the cursor, the look-back words: a stream-ordered allocation, nothing to synchronise
+    BRG_CUDA(cudaMallocAsync(&state, pairs_join_state_bytes(n), st));
+    rc = launch_pairs_join(ix->view, k, s, e, n, capacity, (flags & BRG_JOIN_ORDERED) != 0, d_build_idx, d_probe_idx, d_total, d_chunk_slots,
+                           state, st);
+    cudaFreeAsync(state, st);
+    return rc;
+}
+
 extern "C" BRG_API int brg_take_dev(brg_ctx* ctx, const void* d_src, uint32_t elem_bytes, const uint32_t* d_idx,
                             const uint32_t* d_valid_bits, uint64_t n, void* d_out, void* stream) {
     if (!ctx || (n && (!d_src || !d_idx || !d_out))) { set_error("brg_take: NULL argument"); return BRG_ERR_INVALID; }
@@ -1633,7 +1651,9 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     if (rc) return rc;
     if (!out) { set_error("brg_overlap_pairs: NULL out"); return BRG_ERR_INVALID; }
     *out = nullptr;
-    if (mode < BRG_PAIRS_INNER || mode > BRG_PAIRS_ANTI) { set_error("brg_overlap_pairs: bad mode"); return BRG_ERR_INVALID; }
+    if (mode < BRG_PAIRS_INNER || mode > BRG_PAIRS_INNER_ANY_ORDER) { set_error("brg_overlap_pairs: bad mode"); return BRG_ERR_INVALID; }
+    const bool any_order = mode == BRG_PAIRS_INNER_ANY_ORDER && max_rows == 0;
+    if (mode == BRG_PAIRS_INNER_ANY_ORDER) mode = BRG_PAIRS_INNER;  // (with max_rows: the ordered pipeline, whose prefix can be cut)
     if (n > 0xFFFFFFFFull) { set_error("probe row index " + std::to_string(n - 1) + " exceeds UInt32 index capacity"); return BRG_ERR_OVERFLOW; }
     if (n && (!start || !end)) { set_error("brg_overlap_pairs: NULL column"); return BRG_ERR_INVALID; }
     BRG_CUDA(cudaSetDevice(ctx->device));
@@ -1653,6 +1673,40 @@ extern "C" BRG_API int brg_overlap_pairs(brg_ctx* ctx, const brg_index* ix, cons
     const uint32_t* dk = key ? l->in_key[0].as<uint32_t>() : nullptr;
     const int32_t* ds = l->in_s[0].as<int32_t>();
     const int32_t* de = l->in_e[0].as<int32_t>();
+    if (any_order) {
+        // the join in one launch (brg_join.cu) into the lane's output buffers; their size is the capacity.  A first call guesses
+        // 6 pairs per probe row; a call that finds more grows the buffers and runs again (the total is exact either way).
+        if ((rc = l->scratch_b.ensure(pairs_join_state_bytes(n) + 16))) return fail(rc);
+        uint64_t* d_total = l->scratch_b.as<uint64_t>();
+        void* state = l->scratch_b.as<uint64_t>() + 2;
+        uint64_t cap = std::min<uint64_t>(l->out0[0].bytes, l->out1[0].bytes) / 4;
+        if (cap < n * 6) {
+            cap = std::max<uint64_t>(n * 6, 1024);
+            if ((rc = l->out0[0].ensure(cap * 4)) || (rc = l->out1[0].ensure(cap * 4))) return fail(rc);
+        }
+        uint64_t total = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if ((rc = launch_pairs_join(ix->view, dk, ds, de, n, cap, 0, l->out1[0].as<uint32_t>(), l->out0[0].as<uint32_t>(), d_total, nullptr,
+                                        state, st)))
+                return fail(rc);
+            cudaError_t e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error(std::string("pairs total: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+            if (total <= cap) break;
+            cap = total;
+            if ((rc = l->out0[0].ensure(cap * 4)) || (rc = l->out1[0].ensure(cap * 4))) return fail(rc);
+        }
+        r->len = total;
+        if ((rc = pinned_get(ctx, total * 4, &r->blk_probe)) || (rc = pinned_get(ctx, total * 4, &r->blk_build))) return fail(rc);
+        if (total) {
+            cudaError_t e = cudaMemcpyAsync(r->blk_probe.p, l->out0[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(r->blk_build.p, l->out1[0].p, total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error(std::string("pairs D2H: ") + cudaGetErrorString(e)); return fail(BRG_ERR_CUDA); }
+        }
+        *out = r;
+        return BRG_OK;
+    }
     if (mode == BRG_PAIRS_INNER && max_rows == 0) {
         // chunked count -> scan -> emit (brg_pairs.cu): offsets per 256-row chunk, staged coalesced emission
         const uint64_t n_chunks = pairs_chunk_count(n);

@@ -244,6 +244,13 @@ int launch_pairs_chunk_offsets(const IndexView& ix, const uint32_t* key, const i
                                uint64_t* chunk_base /*n_chunks + 1*/, uint64_t* row_rng /*n*/, cudaStream_t st);
 int launch_pairs_fill(const IndexView& ix, const int32_t* s, uint64_t n, const uint64_t* chunk_base, const uint64_t* row_rng,
                       uint32_t* build_idx, uint32_t* probe_idx, cudaStream_t st);
+// the pair join in ONE launch (brg_join.cu): ranges -> count -> output slots -> emit.  Pairs whose output slot is >= capacity are
+// dropped (the total stays exact); d_state = pairs_join_state_bytes(n) bytes of scratch; chunk_slots_out may be NULL
+uint64_t pairs_join_state_bytes(uint64_t n);
+uint32_t pairs_join_chunk_rows();
+int launch_pairs_join(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, uint64_t capacity,
+                      int ordered, uint32_t* build_idx, uint32_t* probe_idx, uint64_t* d_total, uint64_t* chunk_slots_out, void* d_state,
+                      cudaStream_t st);
 int launch_take(const void* src, uint32_t elem_bytes, const uint32_t* idx, const uint32_t* valid_bits, uint64_t n, void* out,
                 cudaStream_t st);
 int launch_semi_anti_flags(const uint32_t* counts, uint64_t n, int anti, uint32_t* flags, cudaStream_t st);

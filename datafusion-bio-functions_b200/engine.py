@@ -350,19 +350,19 @@ class Index:
             owner = _RowsOwner(r)
             L = A.lib()
             m = L.brg_rows_len(r)
-            b = owner.view(L.brg_rows_build_idx(r), m, np.uint32) if mode == A.PAIRS_INNER else None
+            b = owner.view(L.brg_rows_build_idx(r), m, np.uint32) if mode in (A.PAIRS_INNER, A.PAIRS_INNER_ANY_ORDER) else None
             p = owner.view(L.brg_rows_probe_idx(r), m, np.uint32)
-            if mode != A.PAIRS_INNER:
+            if b is None:
                 return (p, consumed.value) if return_consumed else p
             return (b, p, consumed.value) if return_consumed else (b, p)
         try:
             L = A.lib()
             m = L.brg_rows_len(r)
-            b = A.copy_from(L.brg_rows_build_idx(r), m, np.uint32) if mode == A.PAIRS_INNER else None
+            b = A.copy_from(L.brg_rows_build_idx(r), m, np.uint32) if mode in (A.PAIRS_INNER, A.PAIRS_INNER_ANY_ORDER) else None
             p = A.copy_from(L.brg_rows_probe_idx(r), m, np.uint32)
         finally:
             A.lib().brg_rows_release(r)
-        if mode != A.PAIRS_INNER:
+        if b is None:
             return (p, consumed.value) if return_consumed else p
         return (b, p, consumed.value) if return_consumed else (b, p)
 
@@ -420,6 +420,19 @@ class Index:
         st = torch.cuda.current_stream().cuda_stream
         A.check(A.lib().brg_pairs_fill_dev(self.ctx._h, self._h, _tptr(start), start.numel(), _tptr(chunk_base),
                                            _tptr(row_ranges), _tptr(build_idx), _tptr(probe_idx), st))
+
+    def pairs_join_dev(self, key, start, end, build_idx, probe_idx, total, ordered=False, chunk_slots=None):
+        """the join in one launch (brg_join.cu).  build_idx / probe_idx: int32[capacity] output buffers; total: int64[1] (device)
+        receives the exact pair count -- pairs beyond the capacity are dropped.  ordered=False: the pairs of one chunk of
+        brg_pairs_join_chunk_rows() probe rows are contiguous and probe-major, the chunks land in the order they finish;
+        chunk_slots: optional int64[2 * n_chunks] = {first output slot, pairs} per chunk"""
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        cap = min(build_idx.numel(), probe_idx.numel())
+        A.check(A.lib().brg_pairs_join_dev(self.ctx._h, self._h, _tptr(key), _tptr(start), _tptr(end), start.numel(), cap,
+                                           A.JOIN_ORDERED if ordered else 0, _tptr(build_idx), _tptr(probe_idx), _tptr(total),
+                                           _tptr(chunk_slots) if chunk_slots is not None else None, st))
 
 
 class _RowsOwner:

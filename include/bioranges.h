@@ -68,8 +68,14 @@ enum {
 enum {
     BRG_PAIRS_INNER = 0, /* every (build_row, probe_row) pair, probe-major                      */
     BRG_PAIRS_SEMI = 1,  /* probe rows with >= 1 match (RightSemi); build_idx is not produced   */
-    BRG_PAIRS_ANTI = 2   /* probe rows with no match   (RightAnti); build_idx is not produced   */
+    BRG_PAIRS_ANTI = 2,  /* probe rows with no match   (RightAnti); build_idx is not produced   */
+    BRG_PAIRS_INNER_ANY_ORDER = 3 /* INNER through the one-launch join (brg_pairs_join_dev): the same pairs; the pairs of one
+                                   * chunk of brg_pairs_join_chunk_rows() probe rows are contiguous and probe-major, the chunks
+                                   * come in no particular order (the reference's row order is unspecified too: coitrees visit
+                                   * order, batch arrival order across partitions)                        */
 };
+/* flags of brg_pairs_join_dev */
+enum { BRG_JOIN_ORDERED = 1 /* probe-major output throughout (a look-back over the chunks' counts instead of one atomic per chunk) */ };
 
 typedef struct brg_ctx brg_ctx;     /* one per GPU: streams, staging buffers, scratch */
 typedef struct brg_index brg_index; /* immutable build-side index resident in HBM      */
@@ -223,6 +229,19 @@ BRG_API int brg_pairs_chunk_offsets_dev(brg_ctx* ctx, const brg_index* idx, cons
 BRG_API int brg_pairs_fill_dev(brg_ctx* ctx, const brg_index* idx, const int32_t* d_start, uint64_t n,
                        const uint64_t* d_chunk_base, const uint64_t* d_row_ranges, uint32_t* d_build_idx,
                        uint32_t* d_probe_idx, void* stream);
+
+/* the join in ONE launch: per chunk of brg_pairs_join_chunk_rows() probe rows the candidate ranges, the pair count, the chunk's
+ * output slots and the emission, with nothing but the pairs written to HBM (replaces IntervalJoinAlgorithm::get + the RLE
+ * expansion, interval_join.rs:849-863, 1616-1653).  The output size is not known before the launch: the caller passes buffers
+ * of `capacity` pairs; *d_total (device u64) receives the exact pair count, pairs beyond `capacity` are dropped (call again
+ * with larger buffers when *d_total > capacity).  Output order: the pairs of a chunk are contiguous and probe-major (matches
+ * of one probe in (start, end, row id) order); the chunks land in the order they finish unless flags has BRG_JOIN_ORDERED
+ * (then the whole output is probe-major, as in the chunked form, at about twice the kernel time: every chunk has to wait
+ * for the counts of all earlier ones).  d_chunk_slots (may be NULL): 2 u64 per chunk = {first output slot, pairs}. */
+BRG_API uint32_t brg_pairs_join_chunk_rows(void);
+BRG_API int brg_pairs_join_dev(brg_ctx* ctx, const brg_index* idx, const uint32_t* d_key_id, const int32_t* d_start,
+                       const int32_t* d_end, uint64_t n, uint64_t capacity, int flags, uint32_t* d_build_idx,
+                       uint32_t* d_probe_idx, uint64_t* d_total, uint64_t* d_chunk_slots, void* stream);
 
 /* ---- output materialisation on the device (replaces arrow::compute::take of a fixed-width column by the emitted
  *      index column, interval_join.rs:1655-1667, nearest.rs:456-482): d_out[i] = d_src[d_idx[i]], zero where the

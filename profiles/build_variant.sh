@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 pkg="$root/datafusion-bio-functions_b200"
 tmp="$root/variants/obj_$name"
 mkdir -p "$tmp"
-for f in brg_api brg_sort brg_scan brg_probe brg_pairs; do
+for f in brg_api brg_sort brg_scan brg_probe brg_pairs brg_join; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O3,-fvisibility=hidden $extra -c "$pkg/csrc/$f.cu" -o "$tmp/$f.o" 2>&1 | grep -v "deprecated-gpu-targets\|offline compilation" &
 done
 wait
