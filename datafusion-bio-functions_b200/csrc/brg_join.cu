@@ -65,26 +65,30 @@ constexpr int FJ_ROWS = 32 * FJ_PV;  // rows per chunk
 #ifndef BRG_FJ_CTAS
 #define BRG_FJ_CTAS 3
 #endif
+#ifndef BRG_FJ_VEC
+#define BRG_FJ_VEC 0            // 1: 128-bit stores of the staged pairs
+#endif
 constexpr int FJ_WCAP = BRG_FJ_WCAP, FJ_SLOTS = BRG_FJ_SLOTS, FJ_STAGE = BRG_FJ_STAGE, FJ_WARPS = BRG_FJ_WARPS;
 constexpr int FJ_U = 4;         // slot steps in flight per iteration of the test loops
-constexpr int FJ_RSLOTS = FJ_ROWS + FJ_ROWS / FJ_PV + 2;
+constexpr int FJ_RSLOTS = FJ_ROWS + 2;
 #ifndef BRG_FJ_SPIN_NS
 #define BRG_FJ_SPIN_NS 100
 #endif
 constexpr unsigned FJ_SPIN_NS = BRG_FJ_SPIN_NS;
 constexpr int FJ_MAPQ = FJ_SLOTS / 512;  // 16-byte words of the slot -> row map per lane
-constexpr int FJ_PAD = 64;              // sentinel rows behind the window (the unguarded searches overshoot by at most that)
+constexpr int fj_bit_floor(int x) { int b = 1; while (2 * b <= x) b *= 2; return b; }
+constexpr int FJ_PAD = 2 * fj_bit_floor(FJ_WCAP) + 8 - FJ_WCAP;  // sentinel rows behind the window: a search with first step
+                                                                 // S = bit_floor(rows) reads up to row 2 S + 1
 constexpr int FJ_KEYS = 64;       // keys whose directory constants are staged per CTA
 static_assert(FJ_PV == 4 || FJ_PV == 8, "a lane loads its rows as one or two 128-bit words per column");
 static_assert(FJ_SLOTS % 512 == 0 && FJ_SLOTS <= 65536 && FJ_WCAP <= 32768 && FJ_WCAP % 4 == 0 && FJ_STAGE % 4 == 0 && FJ_ROWS <= 256,
               "packing of the row words");
 
-// row r lives at slot r + r / PV: a lane writes the records of its PV consecutive rows, and unpadded the lanes of one such store
-// would share banks
-__device__ __forceinline__ uint32_t fj_row_slot(uint32_t r) { return r + r / FJ_PV; }
-// (the 8-byte records of the fast path: with 4 rows per lane the stores conflict 4-way, four times per chunk -- cheaper than an
-//  add per candidate slot in the test loop)
-__device__ __forceinline__ uint32_t fj_row2_slot(uint32_t r) { return FJ_PV == 4 ? r : r + r / FJ_PV; }
+// Lane l owns the rows l, l + 32, l + 64, ... of its chunk (not PV consecutive ones): in every step of the shared-memory searches
+// the 32 lanes then work on 32 CONSECUTIVE sorted queries, whose positions in the window are about one row apart -- broadcasts
+// and consecutive banks.  With consecutive rows per lane the lanes sat ~PV rows apart in the window: 4-way bank conflicts on every
+// search step, 43 % of all shared-memory wavefronts of a kernel that is bound by the shared-memory pipe (profiles/r2_join_*).
+__device__ __forceinline__ uint32_t fj_row(uint32_t lane, int j) { return lane + 32u * (uint32_t)j; }
 
 struct __align__(16) JoinWarp {
     union {
@@ -204,54 +208,50 @@ __device__ __forceinline__ uint32_t fj_step(const int32_t* w, uint32_t pos, uint
 }
 __device__ __forceinline__ uint32_t bit_floor_u32(uint32_t x) { return x ? 1u << (31 - __clz(x)) : 0u; }
 
-// ranks of the lane's 8 queries in the window rows w[wlo .. nw): out[j] = wlo + #(w <= q[j]) (LE) or wlo + #(w < q[j]).
-// mono (warp-uniform): the 256 queries of the chunk are non-decreasing in row order.  Either way each lane first finds the
-// ranks [lo, hi] that bracket its 8 queries with searches over the whole window (a power-of-two step S covers a range of up
-// to 2 S - 1 rows), then its rows search between them with a trip count that is uniform across the warp.
+// ranks of the lane's PV queries in the window rows w[wlo .. nw): out[j] = #(w[0 .. nw) <= q[j]) (LE) or #(... < q[j]), counting
+// the wlo rows in front as smaller.  PV independent branch-free binary searches in lock step, warp-uniform trip count; no bound
+// check per step: behind the window's last row stand INT32_MAX sentinels as far as a search can reach (a sentinel passes only
+// `<= INT32_MAX`: results are clamped once at the end).  Positions are byte offsets of w[pos - 1].
 template <bool LE>
-__device__ __forceinline__ void fj_ranks8(const int32_t* w, uint32_t wlo, uint32_t nw, const int32_t (&q)[FJ_PV], bool mono,
-                                          uint32_t lane, uint32_t (&out)[FJ_PV]) {
+__device__ __forceinline__ void fj_ranks(const int32_t* w, uint32_t wlo, uint32_t nw, const int32_t (&q)[FJ_PV], uint32_t (&out)[FJ_PV]) {
     const uint32_t Sfull = bit_floor_u32(nw - wlo);
-    uint32_t lo = wlo, hi = wlo;
-    if (mono) {
-        for (uint32_t step = Sfull; step; step >>= 1) lo = fj_step<LE>(w, lo, nw, q[0], step);
-        hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
-        if (lane == 31) hi = nw;
-    } else {
-        int32_t qmin = q[0], qmax = q[0];
+    const char* wb = reinterpret_cast<const char*>(w) - 4;
+    uint32_t ob[FJ_PV];
 #pragma unroll
-        for (int j = 1; j < FJ_PV; j++) { qmin = min(qmin, q[j]); qmax = max(qmax, q[j]); }
-        for (uint32_t step = Sfull; step; step >>= 1) {  // the two bounds of the lane, in lock step
-            lo = fj_step<LE>(w, lo, nw, qmin, step);
-            hi = fj_step<LE>(w, hi, nw, qmax, step);
+    for (int j = 0; j < FJ_PV; j++) ob[j] = wlo * 4u;
+    for (uint32_t step = Sfull * 4u; step >= 4u; step >>= 1) {
+#pragma unroll
+        for (int j = 0; j < FJ_PV; j++) {
+            const uint32_t t = ob[j] + step;
+            const int32_t v = *reinterpret_cast<const int32_t*>(wb + t);
+            ob[j] = (LE ? v <= q[j] : v < q[j]) ? t : ob[j];
         }
     }
-    const uint32_t S = bit_floor_u32(__reduce_max_sync(0xFFFFFFFFu, hi - lo));
-    if (S <= (uint32_t)FJ_PAD / 2) {
-        // Rows at or behind `hi` compare false by themselves (they are > the neighbour lane's first query resp. > the lane's largest
-        // one), and behind the window stand FJ_PAD sentinels: no bound check per step.  Positions are kept as byte offsets of w[pos - 1].
-        const char* wb = reinterpret_cast<const char*>(w) - 4;
-        uint32_t ob[FJ_PV];
 #pragma unroll
-        for (int j = 0; j < FJ_PV; j++) ob[j] = lo * 4u;
-        for (uint32_t step = S * 4u; step >= 4u; step >>= 1) {
+    for (int j = 0; j < FJ_PV; j++) out[j] = min(ob[j] >> 2, nw);
+}
+
+// exclusive prefix of the rows' candidate counts IN ROW ORDER (row = lane + 32 j): one warp scan per group of 32 rows, two groups
+// packed into one 32-bit scan (counts <= FJ_WCAP, sums per group < 65536).  Returns the chunk's total.
+__device__ __forceinline__ uint32_t fj_row_prefix16(const uint32_t (&cand)[FJ_PV], uint32_t lane, uint32_t (&pj)[FJ_PV]) {
+    uint32_t base = 0;
 #pragma unroll
-            for (int j = 0; j < FJ_PV; j++) {
-                const uint32_t t = ob[j] + step;
-                const int32_t v = *reinterpret_cast<const int32_t*>(wb + t);
-                ob[j] = (LE ? v <= q[j] : v < q[j]) ? t : ob[j];
-            }
+    for (int h = 0; h < FJ_PV / 2; h++) {
+        const uint32_t own = cand[2 * h] | (cand[2 * h + 1] << 16);
+        uint32_t incl = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
         }
-#pragma unroll
-        for (int j = 0; j < FJ_PV; j++) out[j] = min(ob[j] >> 2, hi);  // (a sentinel passes `<= INT32_MAX`)
-        return;
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t excl = incl - own;
+        pj[2 * h] = base + (excl & 0xFFFFu);
+        base += tot & 0xFFFFu;
+        pj[2 * h + 1] = base + (excl >> 16);
+        base += tot >> 16;
     }
-#pragma unroll
-    for (int j = 0; j < FJ_PV; j++) out[j] = lo;
-    for (uint32_t step = S; step; step >>= 1) {
-#pragma unroll
-        for (int j = 0; j < FJ_PV; j++) out[j] = fj_step<LE>(w, out[j], hi, q[j], step);
-    }
+    return base;
 }
 
 // the slot -> row map of rows [ra, rb): zero, one byte per non-empty row at its first slot, packed prefix-max
@@ -267,27 +267,24 @@ __device__ __forceinline__ void fj_build_rowof(uint8_t* rowof, uint32_t n_slots,
     uint4* mine = reinterpret_cast<uint4*>(rowof) + lane * FJ_MAPQ;
 #pragma unroll
     for (int q = 0; q < FJ_MAPQ; q++) mine[q] = make_uint4(0u, 0u, 0u, 0u);
-    // the last non-empty row (+ 1) before each of the lane's rows: an inclusive max-scan of the lanes' last ones, shifted by a lane
-    uint32_t last = 0;
+    // the previous non-empty row of each of the lane's rows, in row order: the highest set bit below the lane in the group's ballot,
+    // else the last non-empty row of the groups before (0 before the first one, so that the map starts with that row's id itself)
+    uint32_t prev[FJ_PV];
+    uint32_t before_groups = 0;
+    const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < FJ_PV; j++) {
-        const uint32_t r = lane * FJ_PV + j;
-        if (r >= ra && r < rb && cand[j]) last = r + 1;
+        const uint32_t r = fj_row(lane, j);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, r >= ra && r < rb && cand[j] != 0u);
+        const uint32_t lower = m & below;
+        prev[j] = lower ? 32u * (uint32_t)j + (31u - (uint32_t)__clz(lower)) : before_groups;
+        if (m) before_groups = 32u * (uint32_t)j + (31u - (uint32_t)__clz(m));
     }
-    uint32_t prev = last;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, prev, o);
-        if (lane >= (uint32_t)o) prev = max(prev, y);
-    }
-    prev = __shfl_up_sync(0xFFFFFFFFu, prev, 1);
-    if (lane == 0) prev = 0;
-    prev = prev ? prev - 1 : 0u;  // (before the first non-empty row: id 0, so that the map starts with that row's id itself)
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < FJ_PV; j++) {
-        const uint32_t r = lane * FJ_PV + j;
-        if (r >= ra && r < rb && cand[j]) { rowof[pj[j] - Pa] = (uint8_t)(r - prev); prev = r; }
+        const uint32_t r = fj_row(lane, j);
+        if (r >= ra && r < rb && cand[j]) rowof[pj[j] - Pa] = (uint8_t)(r - prev[j]);
     }
     __syncwarp();
     uint32_t v[4 * FJ_MAPQ];
@@ -326,16 +323,16 @@ __device__ __forceinline__ uint64_t fj_slow_pass(const IndexView& ix, JoinWarp& 
     uint64_t run = 0;  // pairs of this chunk seen so far (warp-uniform)
     uint32_t ra = 0;   // rows [0, ra) are done (warp-uniform)
     while (ra < (uint32_t)FJ_ROWS) {
-        const uint32_t Pa = row4[fj_row_slot(ra)].x;
+        const uint32_t Pa = row4[ra].x;
         uint32_t fit = 0;
         if (!huge) {  // rows [ra, rb) whose candidates fit the slot map together (their prefix is monotone)
 #pragma unroll
-            for (int j = 0; j < FJ_PV; j++) fit += (lane * FJ_PV + j >= ra && pj[j] + cand[j] - Pa <= (uint32_t)FJ_SLOTS) ? 1u : 0u;
+            for (int j = 0; j < FJ_PV; j++) fit += (fj_row(lane, j) >= ra && pj[j] + cand[j] - Pa <= (uint32_t)FJ_SLOTS) ? 1u : 0u;
             fit = __reduce_add_sync(0xFFFFFFFFu, fit);
         }
         if (fit == 0) {
             // one row alone exceeds the map (or the chunk's prefix does not fit 32 bits): the warp sweeps its range
-            const uint4 rw = row4[fj_row_slot(ra)];
+            const uint4 rw = row4[ra];
             const uint32_t rI0 = rw.y, rN = rw.w;
             const int32_t rQ = (int32_t)rw.z;
             for (uint32_t sb = 0; sb < rN; sb += 32) {
@@ -356,7 +353,7 @@ __device__ __forceinline__ uint64_t fj_slow_pass(const IndexView& ix, JoinWarp& 
             continue;
         }
         const uint32_t rb = ra + fit;
-        const uint32_t n_slots = row4[fj_row_slot(rb)].x - Pa;  // (row 256 holds the chunk's total)
+        const uint32_t n_slots = row4[rb].x - Pa;  // (row 256 holds the chunk's total)
         if (n_slots) {
             fj_build_rowof(sm.rowof, n_slots, ra, rb, Pa, pj, cand, lane);
             for (uint32_t sb = 0; sb < n_slots; sb += 32 * FJ_U) {
@@ -367,7 +364,7 @@ __device__ __forceinline__ uint64_t fj_slow_pass(const IndexView& ix, JoinWarp& 
                     const uint32_t s = sb + u * 32 + lane;
                     const bool v = s < n_slots;
                     rr[u] = v ? sm.rowof[s] : ra;
-                    const uint4 rw = row4[fj_row_slot(rr[u])];
+                    const uint4 rw = row4[rr[u]];
                     const uint32_t i = rw.y + (s + Pa - rw.x);
                     mt[u] = v && __ldg(ix.s_end + i) >= (int32_t)rw.z;
                     pos[u] = (EMIT && v) ? __ldg(ix.s_pos + i) : 0u;
@@ -432,16 +429,6 @@ __device__ __forceinline__ uint32_t fj_window_begin(const DirView& d, const KeyD
     return __ldg(d.D + k.base + b);
 }
 
-template <typename T4, typename T>
-__device__ __forceinline__ void fj_load_rows(const T* __restrict__ col, uint64_t row, T (&out)[FJ_PV]) {
-    const T4* p = reinterpret_cast<const T4*>(col + row);
-#pragma unroll
-    for (int h = 0; h < FJ_PV / 4; h++) {
-        const T4 v = __ldcs(p + h);
-        out[4 * h] = v.x; out[4 * h + 1] = v.y; out[4 * h + 2] = v.z; out[4 * h + 3] = v.w;
-    }
-}
-
 __global__ void __launch_bounds__(FJ_WARPS * 32, BRG_FJ_CTAS)
 pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t* __restrict__ start,
                   const int32_t* __restrict__ end, uint64_t n_rows, uint32_t* ticket, ScanState sc, uint64_t capacity,
@@ -474,22 +461,23 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
     int32_t nqs[FJ_PV], nqe[FJ_PV];
     uint32_t nkk[FJ_PV];
     auto load_chunk = [&](uint32_t c, int32_t (&oqs)[FJ_PV], int32_t (&oqe)[FJ_PV], uint32_t (&okk)[FJ_PV]) {
-        const uint64_t r = (uint64_t)c * FJ_ROWS + lane * FJ_PV;
-        if (vec_in && (uint64_t)(c + 1) * FJ_ROWS <= n_rows) {
-            fj_load_rows<int4>(start, r, oqs);
-            fj_load_rows<int4>(end, r, oqe);
-            if (key) fj_load_rows<uint4>(key, r, okk);
-            else {
+        const uint64_t r0 = (uint64_t)c * FJ_ROWS;
+        if (r0 + FJ_ROWS <= n_rows) {  // (32 consecutive rows per load instruction: 128 contiguous bytes)
 #pragma unroll
-                for (int j = 0; j < FJ_PV; j++) okk[j] = 0u;
+            for (int j = 0; j < FJ_PV; j++) {
+                const uint64_t r = r0 + fj_row(lane, j);
+                oqs[j] = __ldcs(start + r);
+                oqe[j] = __ldcs(end + r);
+                okk[j] = key ? __ldcs(key + r) : 0u;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < FJ_PV; j++) {
-                const bool v = r + j < n_rows;
-                oqs[j] = v ? __ldcs(start + r + j) : 0;
-                oqe[j] = v ? __ldcs(end + r + j) : 0;
-                okk[j] = v ? (key ? __ldcs(key + r + j) : 0u) : 0xFFFFFFFFu;  // rows past the end: no key
+                const uint64_t r = r0 + fj_row(lane, j);
+                const bool v = r < n_rows;
+                oqs[j] = v ? __ldcs(start + r) : 0;
+                oqe[j] = v ? __ldcs(end + r) : 0;
+                okk[j] = v ? (key ? __ldcs(key + r) : 0u) : 0xFFFFFFFFu;  // rows past the end: no key
             }
         }
     };
@@ -504,7 +492,7 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
         const uint64_t row0 = (uint64_t)chunk * FJ_ROWS;
         int32_t qs[FJ_PV], qe[FJ_PV];
         uint32_t kk[FJ_PV];
-        bool fast = vec_in && row0 + FJ_ROWS <= n_rows;
+        bool fast = row0 + FJ_ROWS <= n_rows;
         uint32_t next_chunk = 0;
         if (ahead) {
 #pragma unroll
@@ -521,15 +509,21 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
         if (fast) {
             // ---- one key, sorted starts? ---------------------------------------------------------------------------------
             const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, kk[0], 0);
-            bool ok = true, mono_e = true;
+            bool ok = true;
 #pragma unroll
             for (int j = 0; j < FJ_PV; j++) ok = ok & (kk[j] == k0);
 #pragma unroll
-            for (int j = 0; j + 1 < FJ_PV; j++) { ok = ok & (qs[j] <= qs[j + 1]); mono_e = mono_e & (qe[j] <= qe[j + 1]); }
-            const int32_t ns = __shfl_down_sync(0xFFFFFFFFu, qs[0], 1), ne = __shfl_down_sync(0xFFFFFFFFu, qe[0], 1);
-            if (lane < 31) { ok = ok & (qs[FJ_PV - 1] <= ns); mono_e = mono_e & (qe[FJ_PV - 1] <= ne); }
+            for (int j = 0; j < FJ_PV; j++) {  // row lane + 32 j against the next row: the next lane's, or lane 0's of the next group
+                int32_t nx = __shfl_down_sync(0xFFFFFFFFu, qs[j], 1);
+                if (j + 1 < FJ_PV) {
+                    const int32_t wrap = __shfl_sync(0xFFFFFFFFu, qs[j + 1 < FJ_PV ? j + 1 : j], 0);
+                    if (lane == 31) nx = wrap;
+                } else if (lane == 31) {
+                    nx = INT32_MAX;
+                }
+                ok = ok & (qs[j] <= nx);
+            }
             fast = __all_sync(0xFFFFFFFFu, ok);
-            mono_e = __all_sync(0xFFFFFFFFu, mono_e);
             if (fast && k0 >= ix.n_keys) done = true;  // key absent from the build side (interval_join.rs:857): no pairs
             if (fast && !done) {
                 // ---- the chunk's window of the start-sorted build rows: FJ_WCAP rows from W on, by TMA ---------------------
@@ -563,41 +557,32 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                     bool b_pending = true;  // the second copy has to be waited for on every path out of here
                     mbar_wait(&sm.bar[0], ph_a);
                     ph_a ^= 1u;
-#pragma unroll
-                    for (int x = 0; x < FJ_PAD; x += 32) { w_start[nw + x + lane] = INT32_MAX; w_pme[nw + x + lane] = INT32_MAX; }
+                    {   // sentinels as far as the searches can reach: row wlo + 2 * bit_floor(rows)
+                        const uint32_t fill_end = min((uint32_t)(FJ_WCAP + FJ_PAD), wlo + 2u * bit_floor_u32(nw - wlo) + 2u);
+                        for (uint32_t x = nw + lane; x < fill_end; x += 32) { w_start[x] = INT32_MAX; w_pme[x] = INT32_MAX; }
+                    }
                     __syncwarp();
                     FJ_T(2)
                     // ---- per row: i0 = #(prefix_max_end < qs), n_le = #(start <= qe), both relative to Wa --------------------
                     uint32_t i0[FJ_PV], cand[FJ_PV];
-                    fj_ranks8<false>(w_pme, wlo, nw, qs, true, lane, i0);
-                    fj_ranks8<true>(w_start, wlo, nw, qe, mono_e, lane, cand);
+                    fj_ranks<false>(w_pme, wlo, nw, qs, i0);
+                    fj_ranks<true>(w_start, wlo, nw, qe, cand);
                     FJ_T(3)
                     bool beyond = false;  // a row whose candidates may continue behind a truncated window
-                    uint32_t lane_tot = 0;
 #pragma unroll
                     for (int j = 0; j < FJ_PV; j++) {
                         beyond = beyond | (cand[j] == nw);
                         cand[j] = cand[j] > i0[j] ? cand[j] - i0[j] : 0u;
-                        lane_tot += cand[j];
                     }
-                    uint32_t incl = lane_tot;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                        if (lane >= (uint32_t)o) incl += y;
-                    }
-                    const uint32_t n_slots = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    uint32_t pj[FJ_PV];
+                    const uint32_t n_slots = fj_row_prefix16(cand, lane, pj);
                     if (truncated && __any_sync(0xFFFFFFFFu, beyond)) fast = false;
                     else if (n_slots == 0) done = true;
                     else if (n_slots > (uint32_t)FJ_SLOTS) fast = false;
                     if (fast && !done) {
-                        uint32_t pj[FJ_PV];
-                        pj[0] = incl - lane_tot;
-#pragma unroll
-                        for (int j = 1; j < FJ_PV; j++) pj[j] = pj[j - 1] + cand[j - 1];
                         // row record {qs, i0 - prefix}: slot s of the row is window row s + (i0 - prefix)
 #pragma unroll
-                        for (int j = 0; j < FJ_PV; j++) sm.row2[fj_row2_slot(lane * FJ_PV + j)] = make_uint2((uint32_t)qs[j], i0[j] - pj[j]);
+                        for (int j = 0; j < FJ_PV; j++) sm.row2[fj_row(lane, j)] = make_uint2((uint32_t)qs[j], i0[j] - pj[j]);
                         fj_build_rowof(sm.rowof, n_slots, 0u, (uint32_t)FJ_ROWS, 0u, pj, cand, lane);  // (orders the stores above, too)
                         FJ_T(4)
                         mbar_wait(&sm.bar[1], ph_b);
@@ -613,7 +598,7 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                             for (int u = 0; u < FJ_U; u++) {
                                 const uint32_t s = sb + u * 32 + lane;
                                 const uint32_t r = sm.rowof[s];
-                                const uint2 rw = sm.row2[fj_row2_slot(r)];
+                                const uint2 rw = sm.row2[r];
                                 const uint32_t jrel = min(s + rw.y, (uint32_t)FJ_WCAP - 1u);
                                 mt[u] = (s < n_slots) & (sm.w_end[jrel] >= (int32_t)rw.x);
                                 val[u] = jrel | (r << 16);
@@ -649,6 +634,7 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                 const uint32_t r0 = (uint32_t)row0;
                 const uint64_t room = capacity > base ? capacity - base : 0ull;
                 const uint32_t n_out = (uint32_t)min((uint64_t)n_staged, room);
+#if BRG_FJ_VEC
                 // head up to the first 16-byte boundary of the output, 128-bit body, tail (vec_out: both columns are 16-byte aligned)
                 const uint32_t head = vec_out ? min(n_out, (uint32_t)((4u - (uint32_t)(base & 3u)) & 3u)) : n_out;
                 for (uint32_t k = lane; k < head; k += 32) {
@@ -670,6 +656,17 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                     gb[k] = sm.w_pos[v & 0xFFFFu];
                     gp[k] = r0 + (v >> 16);
                 }
+#else
+                // one 32-bit element per lane: every store instruction of the warp writes 128 contiguous bytes, and the staged words
+                // are read without bank conflicts (four consecutive words per lane, as 128-bit stores need them, conflict 4-way; the
+                // kernel is bound by the shared-memory pipe)
+#pragma unroll 4
+                for (uint32_t k = lane; k < n_out; k += 32) {
+                    const uint32_t v = stage[k];
+                    __stcs(gb + k, sm.w_pos[v & 0xFFFFu]);
+                    __stcs(gp + k, r0 + (v >> 16));
+                }
+#endif
             }
             FJ_T(7)
         } else {
@@ -687,30 +684,33 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                 if (qs[j] == INT32_MIN) { act[j] = false; }
             }
             fj_dir_ranks8(ix.d_pme, kk, qm, act, i0);
-            uint64_t lane_tot = 0;
 #pragma unroll
             for (int j = 0; j < FJ_PV; j++) {
                 const bool valid = kk[j] < ix.n_keys;
                 if (valid && qs[j] == INT32_MIN) i0[j] = load_keydir(ix.d_pme.kd, kk[j]).seg_begin;
                 cand[j] = (valid && n_le[j] > i0[j]) ? n_le[j] - i0[j] : 0u;
-                lane_tot += cand[j];
             }
-            uint64_t incl = lane_tot;
+            // exclusive prefix of the candidate counts in row order (row = lane + 32 j), 64-bit: one warp scan per group of 32 rows
+            uint64_t pj64[FJ_PV], all = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= (uint32_t)o) incl += y;
+            for (int j = 0; j < FJ_PV; j++) {
+                uint64_t incl = cand[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= (uint32_t)o) incl += y;
+                }
+                pj64[j] = all + incl - cand[j];
+                all += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
-            const uint64_t all = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const bool huge = all > 0xFFFFFFFFull;  // the chunk's candidate prefix does not fit 32 bits: rows are swept one by one
             uint32_t pj[FJ_PV];
-            pj[0] = (uint32_t)(incl - lane_tot);
 #pragma unroll
-            for (int j = 1; j < FJ_PV; j++) pj[j] = pj[j - 1] + cand[j - 1];
+            for (int j = 0; j < FJ_PV; j++) pj[j] = (uint32_t)pj64[j];
             __syncwarp();  // the previous users of the shared arrays are done
 #pragma unroll
-            for (int j = 0; j < FJ_PV; j++) sm.u.row4[lane * (FJ_PV + 1) + j] = make_uint4(pj[j], i0[j], (uint32_t)qs[j], cand[j]);
-            if (lane == 31) sm.u.row4[fj_row_slot(FJ_ROWS)] = make_uint4((uint32_t)all, 0u, 0u, 0u);
+            for (int j = 0; j < FJ_PV; j++) sm.u.row4[fj_row(lane, j)] = make_uint4(pj[j], i0[j], (uint32_t)qs[j], cand[j]);
+            if (lane == 31) sm.u.row4[FJ_ROWS] = make_uint4((uint32_t)all, 0u, 0u, 0u);
             __syncwarp();
             if (all) {
                 // The chunk's pair count (in ordered mode every later chunk waits for it).  Count identity (no build row with
