@@ -353,7 +353,9 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
         alg_bytes = n * 28 + n // 8 + nb * 12
         outs = (left, bits, dd)
     else:
-        fused = os.environ.get("BRG_PAIRS_FUSED", "1") != "0"
+        # sorted tables: the join in ONE launch, any-order output slots (brg_pairs_join_dev); shuffled tables: the three-launch
+        # chunked form, whose one-row-per-thread kernels are the faster ones there (profiles/r2_join_experiments.txt)
+        fused = os.environ.get("BRG_PAIRS_FUSED", "1") != "0" and order == "sorted"
         offsets = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)  # per 256-row chunk
         ranges = torch.empty(n, dtype=torch.int64, device=device)  # per-row candidate ranges (pass 1 -> pass 2 of the chunked form)
         ix.pairs_chunk_offsets_dev(pk, ps, pe, offsets, ranges)
@@ -402,8 +404,10 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
     res["gpu_launches"] = int(launches)
     kern_ms = float(np.mean(per_step_ms))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    kernel_name = KERNELS[name] if (name != "pairs" or res.get("pairs_path", "").startswith("brg_pairs_join_dev")) else \
+        "pairs_ranges_todo_kernel+scan+pairs_emit_kernel_flat"
     res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": h.peak, "unit": "GB/s", "frac": achieved / h.peak,
-                       "traffic": ncu_traffic(KERNELS[name], name, order, args.scale), "peak_source": h.peak_src, "kernel": KERNELS[name],
+                       "traffic": ncu_traffic(kernel_name, name, order, args.scale), "peak_source": h.peak_src, "kernel": kernel_name,
                        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
     if name == "pairs":
         res["pairs_per_probe"] = total / n
@@ -467,7 +471,7 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
                 o3 = (alloc(n, torch.int32).view(np.uint32), alloc(((n + 31) // 32) * 4, torch.uint8), alloc(n, torch.int64))
                 return (lambda: ix.nearest_k1_into(k_, s_, e_, o3)), (lambda r: o3), n * 12, n * 12 + n // 8
             # pairs: results stay in the library's pinned buffers (zero-copy views)
-            return (lambda: ix.overlap_pairs(k_, s_, e_, copy=False)), (lambda r: r), n * 12, units_per_step * 8
+            return (lambda: ix.overlap_pairs(k_, s_, e_, mode=brg.PAIRS_INNER_ANY_ORDER, copy=False)), (lambda r: r), n * 12, units_per_step * 8
 
         def time_e2e(estep):
             # warm-up: two results alive at once, as in the timed loop (`r` still holds step k - 1 while step k runs), so that

@@ -66,6 +66,24 @@ def test_config1_pairs_10m_x_10m(env, order):
     # the host-buffer call returns the same set
     hb, hp = ix.overlap_pairs(*pnp, copy=False)
     assert len(hb) == total and O.pair_checksum(hb, hp) == want
+    del hb, hp
+    # the join in one launch (brg_pairs_join_dev): any-order output slots, then ordered; and through the host-buffer call
+    import bio_ranges_b200 as brg
+
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for ordered in (False, True):
+        bi.fill_(-1)
+        pi.fill_(-1)
+        ix.pairs_join_dev(pk, ps, pe, bi, pi, tot, ordered=ordered)
+        torch.cuda.synchronize()
+        assert int(tot.item()) == total
+        gb, gp = _np(bi).view(np.uint32), _np(pi).view(np.uint32)
+        if ordered:
+            assert (np.diff(gp.astype(np.int64)) >= 0).all()
+        assert (np.bincount(gp, minlength=n).astype(np.uint64) == cnt).all()
+        assert O.pair_checksum(gb, gp) == want
+    hb, hp = ix.overlap_pairs(*pnp, mode=brg.PAIRS_INNER_ANY_ORDER, copy=False)
+    assert len(hb) == total and O.pair_checksum(hb, hp) == want
     ix.close()
 
 
