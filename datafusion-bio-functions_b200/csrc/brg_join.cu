@@ -69,7 +69,10 @@ constexpr int FJ_ROWS = 32 * FJ_PV;  // rows per chunk
 #define BRG_FJ_VEC 0            // 1: 128-bit stores of the staged pairs
 #endif
 constexpr int FJ_WCAP = BRG_FJ_WCAP, FJ_SLOTS = BRG_FJ_SLOTS, FJ_STAGE = BRG_FJ_STAGE, FJ_WARPS = BRG_FJ_WARPS;
-constexpr int FJ_U = 4;         // slot steps in flight per iteration of the test loops
+#ifndef BRG_FJ_U
+#define BRG_FJ_U 4
+#endif
+constexpr int FJ_U = BRG_FJ_U;  // slot steps in flight per iteration of the test loops
 constexpr int FJ_RSLOTS = FJ_ROWS + 2;
 #ifndef BRG_FJ_SPIN_NS
 #define BRG_FJ_SPIN_NS 100
@@ -453,13 +456,10 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
     __syncthreads();
     uint32_t ph_a = 0, ph_b = 0;  // mbarrier phases: window (start, prefix_max_end), window (end, position)
     FJ_PROF_DECL
-    // Any-order mode: the next chunk's ticket is claimed and its probe rows are loaded while this chunk is worked on (nothing in
-    // this mode ever waits for another warp).  Ordered mode: a warp claims a chunk when it is ready to start it, never earlier --
-    // a warp that WAITS in the look-back while it holds a chunk it has not counted makes every later chunk wait for it; claiming
-    // two tickets ahead serialised the whole kernel (64 ms).
-    const bool ahead = !sc.ordered;
-    int32_t nqs[FJ_PV], nqe[FJ_PV];
-    uint32_t nkk[FJ_PV];
+    // A warp claims a chunk when it is ready to start it, never earlier.  Ordered mode: a warp that WAITS in the look-back while it
+    // holds a chunk it has not counted makes every later chunk wait for it -- claiming two tickets ahead serialised the whole
+    // kernel (64 ms).  Any-order mode: fetching the next chunk's ticket and probe rows ahead costs 12 registers per thread and
+    // spills at 80 (0.213 ms with, 0.196 ms without).
     auto load_chunk = [&](uint32_t c, int32_t (&oqs)[FJ_PV], int32_t (&oqe)[FJ_PV], uint32_t (&okk)[FJ_PV]) {
         const uint64_t r0 = (uint64_t)c * FJ_ROWS;
         if (r0 + FJ_ROWS <= n_rows) {  // (32 consecutive rows per load instruction: 128 contiguous bytes)
@@ -486,22 +486,12 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
         if (lane == 0) t = atomicAdd(ticket, 1u);
         return __shfl_sync(0xFFFFFFFFu, t, 0);
     };
-    uint32_t chunk = claim();
-    if (ahead && chunk < n_chunks) load_chunk(chunk, nqs, nqe, nkk);
-    while (chunk < n_chunks) {
+    for (uint32_t chunk = claim(); chunk < n_chunks; chunk = claim()) {
         const uint64_t row0 = (uint64_t)chunk * FJ_ROWS;
         int32_t qs[FJ_PV], qe[FJ_PV];
         uint32_t kk[FJ_PV];
         bool fast = row0 + FJ_ROWS <= n_rows;
-        uint32_t next_chunk = 0;
-        if (ahead) {
-#pragma unroll
-            for (int j = 0; j < FJ_PV; j++) { qs[j] = nqs[j]; qe[j] = nqe[j]; kk[j] = nkk[j]; }
-            next_chunk = claim();
-            if (next_chunk < n_chunks) load_chunk(next_chunk, nqs, nqe, nkk);
-        } else {
-            load_chunk(chunk, qs, qe, kk);
-        }
+        load_chunk(chunk, qs, qe, kk);
         uint64_t total = 0, base = 0;
         bool done = false;
         uint32_t n_staged = 0;
@@ -747,7 +737,6 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
             if (chunk_slots_out) { chunk_slots_out[2ull * chunk] = base; chunk_slots_out[2ull * chunk + 1] = total; }
             if (sc.ordered && chunk == n_chunks - 1) *total_out = base + total;
         }
-        chunk = ahead ? next_chunk : claim();
     }
     FJ_PROF_FLUSH
 }
