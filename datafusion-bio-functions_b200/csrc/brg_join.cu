@@ -42,6 +42,7 @@
 
 #include "brg_internal.cuh"
 #include "brg_tile.cuh"
+#include "brg_win.cuh"
 
 namespace brg {
 
@@ -79,8 +80,7 @@ constexpr int FJ_RSLOTS = FJ_ROWS + 2;
 #endif
 constexpr unsigned FJ_SPIN_NS = BRG_FJ_SPIN_NS;
 constexpr int FJ_MAPQ = FJ_SLOTS / 512;  // 16-byte words of the slot -> row map per lane
-constexpr int fj_bit_floor(int x) { int b = 1; while (2 * b <= x) b *= 2; return b; }
-constexpr int FJ_PAD = 2 * fj_bit_floor(FJ_WCAP) + 8 - FJ_WCAP;  // sentinel rows behind the window: a search with first step
+constexpr int FJ_PAD = win_pad(FJ_WCAP);  // sentinel rows behind the window: a search with first step
                                                                  // S = bit_floor(rows) reads up to row 2 S + 1
 constexpr int FJ_KEYS = 64;       // keys whose directory constants are staged per CTA
 static_assert(FJ_PV == 4 || FJ_PV == 8, "a lane loads its rows as one or two 128-bit words per column");
@@ -197,41 +197,6 @@ __device__ __forceinline__ uint64_t chunk_slots(const ScanState& sc, uint32_t ch
         return __shfl_sync(0xFFFFFFFFu, b, 0);
     }
     return chunk_lookback(sc, chunk, own, lane);
-}
-
-// One step of the branch-free binary search: pos + #(...) over w[pos .. hi), `step` a power of two.  w[-1] must be readable.
-// (bitwise & on purpose: with && the compiler emits a divergent branch per step -- 22 % of the first version's instructions
-//  were BRA / BSSY / BSYNC, profiles/r2_join_v1_ncu.txt)
-template <bool LE>
-__device__ __forceinline__ uint32_t fj_step(const int32_t* w, uint32_t pos, uint32_t hi, int32_t q, uint32_t step) {
-    const uint32_t t = pos + step;
-    const int32_t v = w[(int32_t)min(t, hi) - 1];
-    const bool go = (t <= hi) & (LE ? v <= q : v < q);
-    return go ? t : pos;
-}
-__device__ __forceinline__ uint32_t bit_floor_u32(uint32_t x) { return x ? 1u << (31 - __clz(x)) : 0u; }
-
-// ranks of the lane's PV queries in the window rows w[wlo .. nw): out[j] = #(w[0 .. nw) <= q[j]) (LE) or #(... < q[j]), counting
-// the wlo rows in front as smaller.  PV independent branch-free binary searches in lock step, warp-uniform trip count; no bound
-// check per step: behind the window's last row stand INT32_MAX sentinels as far as a search can reach (a sentinel passes only
-// `<= INT32_MAX`: results are clamped once at the end).  Positions are byte offsets of w[pos - 1].
-template <bool LE>
-__device__ __forceinline__ void fj_ranks(const int32_t* w, uint32_t wlo, uint32_t nw, const int32_t (&q)[FJ_PV], uint32_t (&out)[FJ_PV]) {
-    const uint32_t Sfull = bit_floor_u32(nw - wlo);
-    const char* wb = reinterpret_cast<const char*>(w) - 4;
-    uint32_t ob[FJ_PV];
-#pragma unroll
-    for (int j = 0; j < FJ_PV; j++) ob[j] = wlo * 4u;
-    for (uint32_t step = Sfull * 4u; step >= 4u; step >>= 1) {
-#pragma unroll
-        for (int j = 0; j < FJ_PV; j++) {
-            const uint32_t t = ob[j] + step;
-            const int32_t v = *reinterpret_cast<const int32_t*>(wb + t);
-            ob[j] = (LE ? v <= q[j] : v < q[j]) ? t : ob[j];
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < FJ_PV; j++) out[j] = min(ob[j] >> 2, nw);
 }
 
 // exclusive prefix of the rows' candidate counts IN ROW ORDER (row = lane + 32 j): one warp scan per group of 32 rows, two groups
@@ -421,17 +386,6 @@ __device__ __forceinline__ void fj_dir_ranks8(const DirView& d, const uint32_t (
     for (int j = 0; j < FJ_PV; j++) out[j] = lo[j];
 }
 
-// ---- the window of a chunk ---------------------------------------------------------------------------------------------
-// W = first row of key k whose bin in the prefix_max_end directory is bin(qs_first - 1): every earlier row of the key has
-// prefix_max_end < qs_first, so no row of the chunk can match it.  One directory word instead of a full rank query (the rank
-// would need 2-3 more dependent loads and save a handful of window rows).
-__device__ __forceinline__ uint32_t fj_window_begin(const DirView& d, const KeyDir& k, int32_t qs_first) {
-    if (k.nb == 0 || qs_first == INT32_MIN || qs_first - 1 < k.lo) return k.seg_begin;
-    const uint32_t b = ((uint32_t)(qs_first - 1) - (uint32_t)k.lo) >> d.shift;
-    if (b >= k.nb) return k.seg_end;
-    return __ldg(d.D + k.base + b);
-}
-
 __global__ void __launch_bounds__(FJ_WARPS * 32, BRG_FJ_CTAS)
 pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t* __restrict__ start,
                   const int32_t* __restrict__ end, uint64_t n_rows, uint32_t* ticket, ScanState sc, uint64_t capacity,
@@ -521,7 +475,7 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                 uint32_t W = 0, seg_begin = 0, seg_end = 0;
                 if (lane == 0) {
                     const KeyDir k = keys_staged ? skd[k0] : load_keydir(ix.d_pme.kd, k0);
-                    W = fj_window_begin(ix.d_pme, k, qs_first);
+                    W = win_begin(ix.d_pme, k, qs_first);
                     seg_begin = k.seg_begin; seg_end = k.seg_end;
                 }
                 W = __shfl_sync(0xFFFFFFFFu, W, 0);
@@ -547,16 +501,14 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
                     bool b_pending = true;  // the second copy has to be waited for on every path out of here
                     mbar_wait(&sm.bar[0], ph_a);
                     ph_a ^= 1u;
-                    {   // sentinels as far as the searches can reach: row wlo + 2 * bit_floor(rows)
-                        const uint32_t fill_end = min((uint32_t)(FJ_WCAP + FJ_PAD), wlo + 2u * bit_floor_u32(nw - wlo) + 2u);
-                        for (uint32_t x = nw + lane; x < fill_end; x += 32) { w_start[x] = INT32_MAX; w_pme[x] = INT32_MAX; }
-                    }
+                    win_sentinels<FJ_WCAP>(w_start, nw, lane);
+                    win_sentinels<FJ_WCAP>(w_pme, nw, lane);
                     __syncwarp();
                     FJ_T(2)
                     // ---- per row: i0 = #(prefix_max_end < qs), n_le = #(start <= qe), both relative to Wa --------------------
                     uint32_t i0[FJ_PV], cand[FJ_PV];
-                    fj_ranks<false>(w_pme, wlo, nw, qs, i0);
-                    fj_ranks<true>(w_start, wlo, nw, qe, cand);
+                    win_ranks<false, FJ_PV, FJ_WCAP>(w_pme, wlo, nw, qs, i0);
+                    win_ranks<true, FJ_PV, FJ_WCAP>(w_start, wlo, nw, qe, cand);
                     FJ_T(3)
                     bool beyond = false;  // a row whose candidates may continue behind a truncated window
 #pragma unroll

@@ -18,6 +18,7 @@
 
 #include "brg_internal.cuh"
 #include "brg_tile.cuh"
+#include "brg_win.cuh"
 
 namespace brg {
 
@@ -625,6 +626,173 @@ __global__ void __launch_bounds__(THREADS, 2) nearest_k1_kernel_tiled(IndexView 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// nearest, k = 1, WINDOWED (round 2): the window machinery of the one-launch pair join (brg_win.cuh) instead of per-warp cursors
+// and inverse searches.  A warp takes 256-row chunks from a contiguous range; a chunk is two halves of 128 rows, lane l owning
+// rows l, l + 32, l + 64, l + 96 of a half (32 consecutive sorted queries per search step: broadcasts and consecutive banks;
+// every output store of the warp writes 128 / 256 contiguous bytes; a ballot is one word of the validity bitmap).  Per half:
+//   * two windows by TMA, each starting at a directory bin (one dependent load): S-order rows from the bin of qs_first - 1 in the
+//     prefix_max_end directory (start, prefix_max_end and the 16-byte records {start, end, row id, prefix_max_end}), E-order rows
+//     from one row before the bin of qs_first - 1 in the end directory (end and the records {start, end, row id});
+//   * the three ranks of nearest_one (nearest_index.rs:91-101,192-234) -- #(start <= qe), first prefix_max_end >= qs, #(end < qs) --
+//     by branch-free searches over the windows; the two candidate records per row come from shared memory.
+// 64 registers / 32 warps per SM instead of 128 / 16.  A half that does not fit (key change, unsorted starts, end < start, window
+// longer than NW_WCAP rows) sends its chunk to the one-row-per-thread kernel through the to-do list; exact for any input.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NW_PV = 4;
+constexpr int NW_ROWS = 32 * NW_PV;
+#ifndef BRG_NW_WCAP
+#define BRG_NW_WCAP 48
+#endif
+#ifndef BRG_NW_WARPS
+#define BRG_NW_WARPS 8
+#endif
+#ifndef BRG_NW_CTAS
+#define BRG_NW_CTAS 4
+#endif
+constexpr int NW_WCAP = BRG_NW_WCAP, NW_PAD = win_pad(NW_WCAP), NW_WARPS = BRG_NW_WARPS;
+static_assert(TP_WTILE == 2 * NW_ROWS, "a to-do chunk is two halves");
+struct __align__(16) NearWarp {
+    int32_t start_[NW_WCAP + 4 + NW_PAD];  // window rows from [4] on; [3] is the guard word read at index -1; sentinels behind
+    int32_t pme_[NW_WCAP + 4 + NW_PAD];
+    int32_t eend_[NW_WCAP + 4 + NW_PAD];
+    int4 s_rec[NW_WCAP];
+    int4 e_rec[NW_WCAP];
+    uint64_t bar[2];
+};
+
+__global__ void __launch_bounds__(NW_WARPS * 32, BRG_NW_CTAS)
+nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int32_t* __restrict__ start,
+                      const int32_t* __restrict__ end, uint64_t n_rows, int include_overlaps, int strict,
+                      uint32_t* __restrict__ left_idx, uint32_t* __restrict__ valid_bits, int64_t* __restrict__ dist, TodoList todo) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    NearWarp& sm = reinterpret_cast<NearWarp*>(smem_raw)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t* const w_start = sm.start_ + 4;
+    int32_t* const w_pme = sm.pme_ + 4;
+    int32_t* const w_eend = sm.eend_ + 4;
+    if (lane == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t ph_s = 0, ph_e = 0;
+    const uint64_t n_chunks = n_rows / TP_WTILE;  // n_rows is a multiple of 256 here
+    const uint64_t n_warps = (uint64_t)gridDim.x * NW_WARPS, wid = (uint64_t)blockIdx.x * NW_WARPS + (threadIdx.x >> 5);
+    const uint64_t c_begin = n_chunks * wid / n_warps, c_end = n_chunks * (wid + 1) / n_warps;
+    uint32_t fails = 0;
+    for (uint64_t chunk = c_begin; chunk < c_end; chunk++) {
+        bool ok = true;
+        for (int half = 0; half < 2 && ok; half++) {
+            const uint64_t row0 = chunk * TP_WTILE + (uint64_t)half * NW_ROWS;
+            int32_t rs[NW_PV], re[NW_PV], qs[NW_PV], qe[NW_PV];
+            uint32_t kk[NW_PV];
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) {
+                const uint64_t r = row0 + lane + 32u * j;
+                rs[j] = __ldcs(start + r);
+                re[j] = __ldcs(end + r);
+                kk[j] = key ? __ldcs(key + r) : 0u;
+                qs[j] = strict ? wadd(rs[j], 1) : rs[j];  // nearest.rs:341-344
+                qe[j] = strict ? wsub(re[j], 1) : re[j];
+            }
+            const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, kk[0], 0);
+            bool fits = true;
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) {
+                int32_t nx = __shfl_down_sync(0xFFFFFFFFu, qs[j], 1);
+                if (j + 1 < NW_PV) {
+                    const int32_t wrap = __shfl_sync(0xFFFFFFFFu, qs[j + 1 < NW_PV ? j + 1 : j], 0);
+                    if (lane == 31) nx = wrap;
+                } else if (lane == 31) {
+                    nx = INT32_MAX;
+                }
+                fits = fits & (kk[j] == k0) & (qs[j] <= nx) & !(qe[j] < qs[j]);
+            }
+            if (!__all_sync(0xFFFFFFFFu, fits)) { ok = false; break; }
+            uint32_t pos[NW_PV];
+            long long dd[NW_PV];
+            bool found[NW_PV];
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) { pos[j] = 0u; dd[j] = 0ll; found[j] = false; }
+            // the key's segment and the two window starts: lane 0 the S-order window, lane 1 the E-order one
+            uint32_t wbeg = 0, seg_b = 0, seg_e = 0;
+            if (k0 < ix.n_keys && lane < 2) {
+                const DirView dv = lane ? ix.d_eend : ix.d_pme;
+                const KeyDir k = load_keydir(dv.kd, k0);
+                wbeg = win_begin(dv, k, __shfl_sync(3u, qs[0], 0));
+                seg_b = k.seg_begin; seg_e = k.seg_end;
+            }
+            const uint32_t Ws = __shfl_sync(0xFFFFFFFFu, wbeg, 0), We = __shfl_sync(0xFFFFFFFFu, wbeg, 1);
+            const uint32_t sb = __shfl_sync(0xFFFFFFFFu, seg_b, 0), se = __shfl_sync(0xFFFFFFFFu, seg_e, 0);  // (same rows in both orders)
+            if (k0 < ix.n_keys && sb < se) {  // else: key absent or without build rows -- is_empty (nearest_index.rs:92-94): NULL rows
+                // S-order window from Ws (at least the key's last row); E-order window from ONE ROW BEFORE We: the left neighbour of
+                // the chunk's first row may be the last row in front of the bin
+                const uint32_t Was = min(Ws, se - 1) & ~3u, Wae = min(We > sb ? We - 1 : We, se - 1) & ~3u;
+                const uint32_t nws = min((uint32_t)NW_WCAP, se - Was), nwe = min((uint32_t)NW_WCAP, se - Wae);
+                const uint32_t wlos = max(sb, Was) - Was, wloe = max(sb, Wae) - Wae;
+                const bool trunc_s = Was + nws < se, trunc_e = Wae + nwe < se;
+                __syncwarp();  // the previous half's readers are done with the windows
+                if (lane == 0) {
+                    const uint32_t bs = ((nws + 3u) & ~3u) * 4u, be = ((nwe + 3u) & ~3u) * 4u;
+                    mbar_expect_tx(&sm.bar[0], 2u * bs + nws * 16u);
+                    tma_load_1d(w_start, ix.s_start + Was, bs, &sm.bar[0], 0ull);
+                    tma_load_1d(w_pme, ix.pme + Was, bs, &sm.bar[0], 0ull);
+                    tma_load_1d(sm.s_rec, ix.s_rec + Was, nws * 16u, &sm.bar[0], 0ull);
+                    mbar_expect_tx(&sm.bar[1], be + nwe * 16u);
+                    tma_load_1d(w_eend, ix.e_end + Wae, be, &sm.bar[1], 0ull);
+                    tma_load_1d(sm.e_rec, ix.e_rec + Wae, nwe * 16u, &sm.bar[1], 0ull);
+                }
+                mbar_wait(&sm.bar[0], ph_s);
+                ph_s ^= 1u;
+                mbar_wait(&sm.bar[1], ph_e);
+                ph_e ^= 1u;
+                win_sentinels<NW_WCAP>(w_start, nws, lane);
+                win_sentinels<NW_WCAP>(w_pme, nws, lane);
+                win_sentinels<NW_WCAP>(w_eend, nwe, lane);
+                __syncwarp();
+                uint32_t n_le[NW_PV], i_pme[NW_PV], l_idx[NW_PV];
+                win_ranks<true, NW_PV, NW_WCAP>(w_start, wlos, nws, qe, n_le);     // #(start <= qe)              partition_point(first <= end)
+                win_ranks<false, NW_PV, NW_WCAP>(w_pme, wlos, nws, qs, i_pme);     // first prefix_max_end >= qs    first_overlap_by_start (:222-234)
+                win_ranks<false, NW_PV, NW_WCAP>(w_eend, wloe, nwe, qs, l_idx);    // #(end < qs)                 partition_point(last < start)
+                bool beyond = false;
+#pragma unroll
+                for (int j = 0; j < NW_PV; j++) beyond = beyond | (trunc_s & (n_le[j] == nws)) | (trunc_e & (l_idx[j] == nwe));
+                if (__any_sync(0xFFFFFFFFu, beyond)) { ok = false; break; }
+#pragma unroll
+                for (int j = 0; j < NW_PV; j++) {
+                    // nearest_one with the ranks known (see nearest_from_ranks): the overlapping row and the right neighbour are never
+                    // needed together, so two records per row
+                    const bool has_left = Wae + l_idx[j] > sb, has_right = Was + n_le[j] < se;
+                    const bool ov = include_overlaps && i_pme[j] < n_le[j];
+                    const int4 r4 = sm.s_rec[min(ov ? i_pme[j] : n_le[j], nws - 1u)];
+                    const int4 l4 = sm.e_rec[has_left ? l_idx[j] - 1u : 0u];
+                    const Cand l{l4.x, l4.y, (uint32_t)l4.z}, r{r4.x, r4.y, (uint32_t)r4.z};
+                    const bool take_left = !ov && has_left && (!has_right || cand_le(qs[j], qe[j], l, r));
+                    const Cand b = take_left ? l : r;
+                    found[j] = ov || (include_overlaps != 2 && (has_left || has_right));  // 2 = overlaps only
+                    pos[j] = found[j] ? b.pos : 0u;
+                    dd[j] = found[j] ? cand_distance(rs[j], re[j], b.s, b.e) : 0ll;  // from RAW probe coordinates (nearest.rs:367-375)
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) {
+                const uint64_t r = row0 + lane + 32u * j;
+                const uint32_t bits = __ballot_sync(0xFFFFFFFFu, found[j]);
+                __stcs(left_idx + r, pos[j]);
+                if (dist) __stcs(reinterpret_cast<long long*>(dist) + r, dd[j]);
+                if (lane == 0) valid_bits[r >> 5] = bits;  // Arrow validity bitmap, LSB first
+            }
+        }
+        if (ok) {
+            fails = 0;
+        } else {
+            todo_push(todo, chunk);
+            if (++fails >= TP_BAIL) {  // this range does not look like a sorted table over a sparse build side: hand the rest over
+                for (uint64_t c = chunk + 1 + lane; c < c_end; c += 32) todo.chunks[atomicAdd(todo.count, 1u)] = (uint32_t)c;
+                break;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TP_WTILE) nearest_k1_kernel_todo(IndexView ix, const uint32_t* __restrict__ key,
                                                                    const int32_t* __restrict__ start,
                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
@@ -928,7 +1096,14 @@ int launch_nearest_k1(const IndexView& ix, const uint32_t* key, const int32_t* s
         nearest_k1_kernel_tiled<T><<<grid, (T), smem, st>>>(ix, key, s, e, done, include_overlaps, strict, left_idx,               \
                                                             reinterpret_cast<uint8_t*>(valid_bits), dist, todo);                   \
     }
-        if (ct == 320) BRG_NEAR_LAUNCH(320)  // (spills: 0.87 ms against 0.57 ms; kept as the measured alternative)
+        static const bool windowed = [] { const char* v = getenv("BRG_NEAREST_WIN"); return !v || v[0] != '0'; }();
+        if (windowed) {
+            const int smem = (int)sizeof(NearWarp) * NW_WARPS;
+            BRG_CUDA(cudaFuncSetAttribute((const void*)nearest_k1_kernel_win, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const uint64_t chunks = done / TP_WTILE;
+            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + NW_WARPS - 1) / NW_WARPS, (uint64_t)kSMs * BRG_NW_CTAS));
+            nearest_k1_kernel_win<<<grid, NW_WARPS * 32, smem, st>>>(ix, key, s, e, done, include_overlaps, strict, left_idx, valid_bits, dist, todo);
+        } else if (ct == 320) BRG_NEAR_LAUNCH(320)  // (spills: 0.87 ms against 0.57 ms; kept as the measured alternative)
         else BRG_NEAR_LAUNCH(256)
 #undef BRG_NEAR_LAUNCH
         BRG_LAUNCH_CHECK();
