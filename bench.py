@@ -44,7 +44,7 @@ WORKLOADS = {
     "coverage": (100_000_000, 1_000_000, "coverage 100M reads (150 bp) x 1M exon-like targets, 24 contigs (configs[2])"),
     "nearest": (50_000_000, 5_000_000, "nearest k=1 50M queries x 5M sparse targets, 24 contigs (configs[3])"),
 }
-KERNELS = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_tiled",
+KERNELS = {"count": "count_kernel_tiled", "coverage": "coverage_kernel_tiled", "nearest": "nearest_k1_kernel_win",
            "pairs": "pairs_join_kernel"}
 API = {"count": "brg_count_overlaps", "coverage": "brg_coverage", "nearest": "brg_nearest_k1", "pairs": "brg_overlap_pairs"}
 

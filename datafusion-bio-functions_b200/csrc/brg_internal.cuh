@@ -370,13 +370,23 @@ __device__ __forceinline__ CompactKey load_compact_key(const CompactView& c, uin
     return k;
 }
 
+#ifndef BRG_LD256
+#define BRG_LD256 1
+#endif
 // One count bin record (32 bytes = one sector), loaded once and used for both rank queries of a row.
 struct CountBinRec { uint32_t w[8]; };
 __device__ __forceinline__ CountBinRec load_count_bin(const BinsView& bv, uint32_t rec) {
     const uint4* r = bv.rec + 2ull * rec;
-    const uint4 a = __ldg(r), b = __ldg(r + 1);
     CountBinRec x;
+#if BRG_LD256
+    // ONE 256-bit load (sm_100: LDG.E.256) per 32-byte record: a shuffled probe row pays per divergent load INSTRUCTION
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x.w[0]), "=r"(x.w[1]), "=r"(x.w[2]), "=r"(x.w[3]), "=r"(x.w[4]), "=r"(x.w[5]), "=r"(x.w[6]), "=r"(x.w[7])
+                 : "l"(r));
+#else
+    const uint4 a = __ldg(r), b = __ldg(r + 1);
     x.w[0] = a.x; x.w[1] = a.y; x.w[2] = a.z; x.w[3] = a.w; x.w[4] = b.x; x.w[5] = b.y; x.w[6] = b.z; x.w[7] = b.w;
+#endif
     return x;
 }
 __device__ __forceinline__ bool count_bin_overflowed(const CountBinRec& x) { return (x.w[1] >> 24) == CB_OVERFLOW; }

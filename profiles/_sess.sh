@@ -1,5 +1,7 @@
-mkdir -p gpurun_out; rm -f gpurun_out/join_exp2.log
-for v in variants/fj_*.so; do
-  BRG_LIB=$v timeout 300 python profiles/exp_join.py --no-chunked --sorted-only --no-ordered >> gpurun_out/join_exp2.log 2>&1; echo "exit $?" >> gpurun_out/join_exp2.log
-done
-cut -c1-200 gpurun_out/join_exp2.log
+for lib in "" variants/ld128.so; do for nb in 0 1000000; do BRG_LIB=$lib BUILD_ROWS=$nb timeout 300 python profiles/exp_shuffled.py 2>&1 | tail -1 | sed "s#^#lib=$lib #"; done; done
+BRG_LIB=variants/nw_w7.so timeout 300 python bench.py --workload nearest --steps 10 --no-extras --no-cpu --no-e2e 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('nearest w7', 'ms', round(d['ms_per_step'], 4), 'frac', round(d['roofline']['frac'], 4), 'parity', d.get('parity_vs_oracle_sample'))
+"

@@ -116,12 +116,14 @@ def _free_port():
 
 
 @pytest.mark.timeout(180)
-def test_sharded_probe_world2_equals_single_process():
+@pytest.mark.parametrize("world,how", [(2, "broadcast"), (4, "broadcast"), (4, "spread")])  # (spread: scatter + all-gather, sharding._spread)
+def test_sharded_probe_equals_single_process(world, how, monkeypatch):
     import torch.multiprocessing as mp
 
     from oracle import oracle as O
 
-    world, port = 2, _free_port()
+    monkeypatch.setenv("BRG_REPLICATE", how)  # (inherited by the spawned ranks)
+    port = _free_port()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     procs = [ctxm.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
