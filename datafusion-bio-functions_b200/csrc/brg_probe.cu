@@ -678,6 +678,7 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
     const uint64_t n_warps = (uint64_t)gridDim.x * NW_WARPS, wid = (uint64_t)blockIdx.x * NW_WARPS + (threadIdx.x >> 5);
     const uint64_t c_begin = n_chunks * wid / n_warps, c_end = n_chunks * (wid + 1) / n_warps;
     uint32_t fails = 0;
+    const int32_t sdelta = strict ? 1 : 0;
     for (uint64_t chunk = c_begin; chunk < c_end; chunk++) {
         bool ok = true;
         for (int half = 0; half < 2 && ok; half++) {
@@ -690,8 +691,8 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
                 rs[j] = __ldcs(start + r);
                 re[j] = __ldcs(end + r);
                 kk[j] = key ? __ldcs(key + r) : 0u;
-                qs[j] = strict ? wadd(rs[j], 1) : rs[j];  // nearest.rs:341-344
-                qe[j] = strict ? wsub(re[j], 1) : re[j];
+                qs[j] = wadd(rs[j], sdelta);  // nearest.rs:341-344
+                qe[j] = wsub(re[j], sdelta);
             }
             const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, kk[0], 0);
             bool fits = true;
@@ -756,30 +757,43 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
 #pragma unroll
                 for (int j = 0; j < NW_PV; j++) beyond = beyond | (trunc_s & (n_le[j] == nws)) | (trunc_e & (l_idx[j] == nwe));
                 if (__any_sync(0xFFFFFFFFu, beyond)) { ok = false; break; }
+                // nearest_one with the ranks known (see nearest_from_ranks): the overlapping row and the right neighbour are never needed
+                // together, so two records per row.  cmp_candidate (nearest_index.rs:262-266) orders by (distance, start, end, row id):
+                // the tie-break beyond the distance is evaluated only when some row of the warp needs it.
 #pragma unroll
                 for (int j = 0; j < NW_PV; j++) {
-                    // nearest_one with the ranks known (see nearest_from_ranks): the overlapping row and the right neighbour are never
-                    // needed together, so two records per row
                     const bool has_left = Wae + l_idx[j] > sb, has_right = Was + n_le[j] < se;
                     const bool ov = include_overlaps && i_pme[j] < n_le[j];
                     const int4 r4 = sm.s_rec[min(ov ? i_pme[j] : n_le[j], nws - 1u)];
                     const int4 l4 = sm.e_rec[has_left ? l_idx[j] - 1u : 0u];
                     const Cand l{l4.x, l4.y, (uint32_t)l4.z}, r{r4.x, r4.y, (uint32_t)r4.z};
-                    const bool take_left = !ov && has_left && (!has_right || cand_le(qs[j], qe[j], l, r));
+                    const uint32_t dl = cand_distance_u32(qs[j], qe[j], l.s, l.e), dr = cand_distance_u32(qs[j], qe[j], r.s, r.e);
+                    const bool need = !ov && has_left;         // the left neighbour is a candidate
+                    bool left_le = !has_right || dl < dr;      // ... and wins without a tie-break
+                    if (__any_sync(0xFFFFFFFFu, need & has_right & (dl == dr))) {
+                        const bool tail = (l.e != r.e) ? l.e < r.e : l.pos <= r.pos;
+                        const bool mid = (l.s != r.s) ? l.s < r.s : tail;
+                        left_le = left_le | ((dl == dr) & mid);
+                    }
+                    const bool take_left = need & left_le;
                     const Cand b = take_left ? l : r;
                     found[j] = ov || (include_overlaps != 2 && (has_left || has_right));  // 2 = overlaps only
                     pos[j] = found[j] ? b.pos : 0u;
-                    dd[j] = found[j] ? cand_distance(rs[j], re[j], b.s, b.e) : 0ll;  // from RAW probe coordinates (nearest.rs:367-375)
+                    // distance from RAW probe coordinates (nearest.rs:367-375); without `strict` they are the searched ones
+                    const uint32_t d = strict ? cand_distance_u32(rs[j], re[j], b.s, b.e) : (take_left ? dl : dr);
+                    dd[j] = found[j] ? (long long)d : 0ll;
                 }
             }
+            uint32_t word = 0;  // lane j < PV ends up with the validity word of rows 32 j .. 32 j + 31 (Arrow bitmap, LSB first)
 #pragma unroll
             for (int j = 0; j < NW_PV; j++) {
                 const uint64_t r = row0 + lane + 32u * j;
                 const uint32_t bits = __ballot_sync(0xFFFFFFFFu, found[j]);
+                word = lane == (uint32_t)j ? bits : word;
                 __stcs(left_idx + r, pos[j]);
                 if (dist) __stcs(reinterpret_cast<long long*>(dist) + r, dd[j]);
-                if (lane == 0) valid_bits[r >> 5] = bits;  // Arrow validity bitmap, LSB first
             }
+            if (lane < (uint32_t)NW_PV) valid_bits[(row0 >> 5) + lane] = word;
         }
         if (ok) {
             fails = 0;
