@@ -807,6 +807,156 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// count_overlaps and coverage, WINDOWED (round 2; same scheme as nearest_k1_kernel_win): two ranks per row from branch-free
+// searches over TMA windows, lane l owning rows l + 32 j of a 128-row half chunk.
+//   count    (interval_tree.rs:41-49):  #(start <= qe) over an S-order window  -  #(end < qs) over an E-order window
+//   coverage (interval_tree.rs:145-152): [first merged interval with last >= qs, first with first > qe) over ONE window of the
+//            merged intervals (first, last and the records {first, last, pre[j], pre[j+1]}), then the clipped-boundary formula
+// ---------------------------------------------------------------------------------------------------
+#ifndef BRG_COUNT_WIN_DEFAULT
+#define BRG_COUNT_WIN_DEFAULT false
+#endif
+#ifndef BRG_COV_WIN_DEFAULT
+#define BRG_COV_WIN_DEFAULT false
+#endif
+#ifndef BRG_R2_WCAP
+#define BRG_R2_WCAP 28   // bit_floor = 16: five search steps cover up to 31 rows
+#endif
+#ifndef BRG_R2_WARPS
+#define BRG_R2_WARPS 8
+#endif
+#ifndef BRG_R2_CTAS
+#define BRG_R2_CTAS 4
+#endif
+constexpr int R2_WCAP = BRG_R2_WCAP, R2_PAD = win_pad(R2_WCAP), R2_WARPS = BRG_R2_WARPS;
+struct __align__(16) Rank2Warp {
+    int32_t a_[R2_WCAP + 4 + R2_PAD];  // searched with `<= qe`: starts (count) / merged firsts (coverage); rows from [4] on
+    int32_t b_[R2_WCAP + 4 + R2_PAD];  // searched with `< qs`:  ends (count) / merged lasts (coverage)
+    int4 rec[R2_WCAP];                 // coverage: m_rec of the window
+    uint64_t bar[2];
+};
+
+template <int OP>  // 0 = count_overlaps, 1 = coverage
+__global__ void __launch_bounds__(R2_WARPS * 32, BRG_R2_CTAS)
+rank2_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                 uint64_t n_rows, int strict, int64_t* __restrict__ out, TodoList todo) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Rank2Warp& sm = reinterpret_cast<Rank2Warp*>(smem_raw)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t* const w_a = sm.a_ + 4;
+    int32_t* const w_b = sm.b_ + 4;
+    if (lane == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t ph_a = 0, ph_b = 0;
+    const DirView& da = OP == 0 ? ix.d_sstart : ix.d_mlast;  // the directory that places window A (coverage: one window, placed by
+    const DirView& db = OP == 0 ? ix.d_eend : ix.d_mlast;    // the lasts: an interval that ends before the chunk also starts before it)
+    const int32_t* ga = OP == 0 ? ix.s_start : ix.m_first;
+    const int32_t* gb = OP == 0 ? ix.e_end : ix.m_last;
+    const uint64_t n_chunks = n_rows / TP_WTILE;  // n_rows is a multiple of 256 here
+    const uint64_t n_warps = (uint64_t)gridDim.x * R2_WARPS, wid = (uint64_t)blockIdx.x * R2_WARPS + (threadIdx.x >> 5);
+    const uint64_t c_begin = n_chunks * wid / n_warps, c_end = n_chunks * (wid + 1) / n_warps;
+    const int32_t sdelta = strict ? 1 : 0;
+    uint32_t fails = 0;
+    for (uint64_t chunk = c_begin; chunk < c_end; chunk++) {
+        bool ok = true;
+        for (int half = 0; half < 2 && ok; half++) {
+            const uint64_t row0 = chunk * TP_WTILE + (uint64_t)half * NW_ROWS;
+            int32_t qs[NW_PV], qe[NW_PV];
+            uint32_t kk[NW_PV];
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) {
+                const uint64_t r = row0 + lane + 32u * j;
+                qs[j] = wadd(__ldcs(start + r), sdelta);
+                qe[j] = wsub(__ldcs(end + r), sdelta);
+                kk[j] = key ? __ldcs(key + r) : 0u;
+            }
+            const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, kk[0], 0);
+            bool fits = true;
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) {
+                int32_t nx = __shfl_down_sync(0xFFFFFFFFu, qs[j], 1);
+                if (j + 1 < NW_PV) {
+                    const int32_t wrap = __shfl_sync(0xFFFFFFFFu, qs[j + 1 < NW_PV ? j + 1 : j], 0);
+                    if (lane == 31) nx = wrap;
+                } else if (lane == 31) {
+                    nx = INT32_MAX;
+                }
+                fits = fits & (kk[j] == k0) & (qs[j] <= nx) & !(qe[j] < qs[j]);
+                if (OP == 1) fits = fits & (qs[j] != INT32_MIN) & (qe[j] != INT32_MAX);  // (wrapping `start - 1` / `end + 1`: per-row path)
+            }
+            if (!__all_sync(0xFFFFFFFFu, fits)) { ok = false; break; }
+            long long res[NW_PV];
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) res[j] = 0ll;
+            const int32_t qs_first = __shfl_sync(0xFFFFFFFFu, qs[0], 0);
+            uint32_t wbeg = 0, seg_b = 0, seg_e = 0;
+            if (k0 < ix.n_keys && lane < 2) {
+                const DirView dv = lane ? db : da;
+                const KeyDir k = load_keydir(dv.kd, k0);
+                wbeg = win_begin(dv, k, qs_first);
+                seg_b = k.seg_begin; seg_e = k.seg_end;
+            }
+            const uint32_t Wa0 = __shfl_sync(0xFFFFFFFFu, wbeg, 0), Wb0 = __shfl_sync(0xFFFFFFFFu, wbeg, 1);
+            const uint32_t sb = __shfl_sync(0xFFFFFFFFu, seg_b, 0), se = __shfl_sync(0xFFFFFFFFu, seg_e, 0);
+            if (k0 < ix.n_keys && sb < se) {  // else: key absent or without build rows -> 0 (interval_tree.rs:265)
+                const uint32_t Wa = min(Wa0, se - 1) & ~3u, Wb = min(Wb0, se - 1) & ~3u;
+                const uint32_t nwa = min((uint32_t)R2_WCAP, se - Wa), nwb = min((uint32_t)R2_WCAP, se - Wb);
+                const uint32_t wloa = max(sb, Wa) - Wa, wlob = max(sb, Wb) - Wb;
+                const bool trunc_a = Wa + nwa < se, trunc_b = Wb + nwb < se;
+                __syncwarp();  // the previous half's readers are done with the windows
+                if (lane == 0) {
+                    const uint32_t ba = ((nwa + 3u) & ~3u) * 4u, bb = ((nwb + 3u) & ~3u) * 4u;
+                    mbar_expect_tx(&sm.bar[0], ba + (OP == 1 ? nwa * 16u : 0u));
+                    tma_load_1d(w_a, ga + Wa, ba, &sm.bar[0], 0ull);
+                    if (OP == 1) tma_load_1d(sm.rec, ix.m_rec + Wa, nwa * 16u, &sm.bar[0], 0ull);
+                    mbar_expect_tx(&sm.bar[1], bb);
+                    tma_load_1d(w_b, gb + Wb, bb, &sm.bar[1], 0ull);
+                }
+                mbar_wait(&sm.bar[0], ph_a);
+                ph_a ^= 1u;
+                mbar_wait(&sm.bar[1], ph_b);
+                ph_b ^= 1u;
+                win_sentinels<R2_WCAP>(w_a, nwa, lane);
+                win_sentinels<R2_WCAP>(w_b, nwb, lane);
+                __syncwarp();
+                uint32_t ra[NW_PV], rb[NW_PV];
+                win_ranks<true, NW_PV, R2_WCAP>(w_a, wloa, nwa, qe, ra);   // #(start <= qe)   / first merged interval with first > qe
+                win_ranks<false, NW_PV, R2_WCAP>(w_b, wlob, nwb, qs, rb);  // #(end < qs)      / first merged interval with last >= qs
+                bool beyond = false;
+#pragma unroll
+                for (int j = 0; j < NW_PV; j++) beyond = beyond | (trunc_a & (ra[j] == nwa)) | (OP == 0 ? (trunc_b & (rb[j] == nwb)) : false);
+                if (__any_sync(0xFFFFFFFFu, beyond)) { ok = false; break; }
+#pragma unroll
+                for (int j = 0; j < NW_PV; j++) {
+                    if (OP == 0) {
+                        res[j] = (long long)(Wa + ra[j]) - (long long)(Wb + rb[j]);  // (segments of the two orders coincide: global indices subtract)
+                    } else {
+                        // merged intervals [lo, hi) overlap the row; both indices relative to window A (= window B's rows: Wa == Wb)
+                        const uint32_t lo = rb[j], hi = ra[j];
+                        const int4 a = sm.rec[min(lo, nwa - 1u)], b = sm.rec[min(hi - 1u, nwa - 1u)];
+                        int32_t acc = cov_term(qs[j], qe[j], a.x, a.y);
+                        const int32_t rest = wadd(cov_term(qs[j], qe[j], b.x, b.y), wsub(b.z, a.w));
+                        acc = (hi > lo + 1) ? wadd(acc, rest) : acc;
+                        res[j] = (lo < hi) ? (long long)acc : 0ll;  // i32 accumulator, widened (interval_tree.rs:207)
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NW_PV; j++) __stcs(reinterpret_cast<long long*>(out) + row0 + lane + 32u * j, res[j]);
+        }
+        if (ok) {
+            fails = 0;
+        } else {
+            todo_push(todo, chunk);
+            if (++fails >= TP_BAIL) {
+                for (uint64_t c = chunk + 1 + lane; c < c_end; c += 32) todo.chunks[atomicAdd(todo.count, 1u)] = (uint32_t)c;
+                break;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TP_WTILE) nearest_k1_kernel_todo(IndexView ix, const uint32_t* __restrict__ key,
                                                                    const int32_t* __restrict__ start,
                                                                    const int32_t* __restrict__ end, uint64_t n_rows,
@@ -1023,11 +1173,38 @@ static inline unsigned probe_grid(uint64_t n, int per_sm) {
     return (unsigned)(want < cap ? want : cap);
 }
 
+// the windowed kernel for whole 256-row chunks (BRG_COUNT_WIN / BRG_COV_WIN select it), its to-do list served by `todo_kernel`
+template <int OP>
+static int launch_rank2_win(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t rows, int strict,
+                            int64_t* out, const TodoList& todo, cudaStream_t st) {
+    const int smem = (int)sizeof(Rank2Warp) * R2_WARPS;
+    BRG_CUDA(cudaFuncSetAttribute((const void*)rank2_kernel_win<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const uint64_t chunks = rows / TP_WTILE;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + R2_WARPS - 1) / R2_WARPS, (uint64_t)kSMs * BRG_R2_CTAS));
+    rank2_kernel_win<OP><<<grid, R2_WARPS * 32, smem, st>>>(ix, key, s, e, rows, strict, out, todo);
+    BRG_LAUNCH_CHECK();
+    return 0;
+}
+static bool win_enabled(const char* env_name, bool dflt) {
+    const char* v = getenv(env_name);
+    return v ? v[0] != '0' : dflt;
+}
+
 int launch_count(const IndexView& ix, const uint32_t* key, const int32_t* s, const int32_t* e, uint64_t n, int strict,
                  int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t done = 0;
-    if (tiled_enabled("count", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+    static const bool count_win = win_enabled("BRG_COUNT_WIN", BRG_COUNT_WIN_DEFAULT);
+    if (count_win && tiled_enabled("count", true) && n >= TP_WTILE && ix.n_keys) {
+        done = (n / TP_WTILE) * TP_WTILE;
+        int rc = 0;
+        TodoList todo;
+        if ((rc = todo_alloc(done, &todo, st))) return rc;
+        if ((rc = launch_rank2_win<0>(ix, key, s, e, done, strict, out, todo, st))) return rc;
+        count_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
+        BRG_LAUNCH_CHECK();
+        if ((rc = todo_free(todo, st))) return rc;
+    } else if (tiled_enabled("count", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
         static const int ct = [] { const char* v = getenv("BRG_COUNT_THREADS"); return v ? atoi(v) : BRG_COUNT_THREADS; }();
         int rc = 0;
@@ -1060,7 +1237,17 @@ int launch_coverage(const IndexView& ix, const uint32_t* key, const int32_t* s, 
                     int strict, int64_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     uint64_t done = 0;
-    if (tiled_enabled("coverage", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
+    static const bool cov_win = win_enabled("BRG_COV_WIN", BRG_COV_WIN_DEFAULT);
+    if (cov_win && tiled_enabled("coverage", true) && n >= TP_WTILE && ix.n_keys) {
+        done = (n / TP_WTILE) * TP_WTILE;
+        int rc = 0;
+        TodoList todo;
+        if ((rc = todo_alloc(done, &todo, st))) return rc;
+        if ((rc = launch_rank2_win<1>(ix, key, s, e, done, strict, out, todo, st))) return rc;
+        coverage_kernel_todo<<<todo_grid(done), TP_WTILE, 0, st>>>(ix, key, s, e, done, strict, out, todo);
+        BRG_LAUNCH_CHECK();
+        if ((rc = todo_free(todo, st))) return rc;
+    } else if (tiled_enabled("coverage", true) && aligned16(key) && aligned16(s) && aligned16(e) && aligned16(out) && n >= PV) {
         done = (n / PV) * PV;
         static const int ct = [] { const char* v = getenv("BRG_COVERAGE_THREADS"); return v ? atoi(v) : BRG_COVERAGE_THREADS; }();
         int rc = 0;
