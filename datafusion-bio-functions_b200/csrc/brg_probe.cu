@@ -636,7 +636,8 @@ __global__ void __launch_bounds__(THREADS, 2) nearest_k1_kernel_tiled(IndexView 
 //     from one row before the bin of qs_first - 1 in the end directory (end and the records {start, end, row id});
 //   * the three ranks of nearest_one (nearest_index.rs:91-101,192-234) -- #(start <= qe), first prefix_max_end >= qs, #(end < qs) --
 //     by branch-free searches over the windows; the two candidate records per row come from shared memory.
-// 64 registers / 32 warps per SM instead of 128 / 16.  A half that does not fit (key change, unsorted starts, end < start, window
+// 64 registers / 32 warps per SM instead of 128 / 16.  (An L2 prefetch of the warp's next chunk of the probe stream costs more issue
+// slots than it saves latency: 0.458 vs 0.441 ms.)  A half that does not fit (key change, unsorted starts, end < start, window
 // longer than NW_WCAP rows) sends its chunk to the one-row-per-thread kernel through the to-do list; exact for any input.
 // ---------------------------------------------------------------------------------------------------
 constexpr int NW_PV = 4;
