@@ -1,27 +1,27 @@
-// brg_join.cu -- K4 in ONE launch: the overlap-pair join as  ranges -> count -> two-level decoupled look-back -> emit  (sm_100a).
+// brg_join.cu -- K4 in ONE launch: the overlap-pair join as  window -> ranges -> count -> output slots -> emit  (sm_100a).
 //
 // Replaces IntervalJoinAlgorithm::get (Coitrees arm, interval_join.rs:849-863: every build row with
 // b.start <= q.end && b.end >= q.start, closed, no guard for degenerate probes) and the RLE expansion of the probe-side
 // indices (interval_join.rs:1616-1653), like the three-launch pipeline of brg_pairs.cu -- but the candidate ranges of the
-// probe rows never leave the SM: nothing is written to HBM except the pairs themselves.
+// probe rows never leave the SM: nothing is written to HBM except the pairs themselves (ncu: 632 MB of DRAM traffic against
+// 642 MB algorithmic on the 10M x 10M join; the three-launch form moves 860 MB).
 //
-// Unit of work: a chunk of 32 x PV probe rows (PV = 4: 128 rows), owned by ONE warp (a lane owns PV consecutive rows).  Chunks
-// are handed out in order by an atomic ticket, so every chunk's predecessors are already running or done; warps never
-// synchronise with each other (no __syncthreads in the loop).
+// Unit of work: a chunk of 32 x PV probe rows (PV = 4: 128 rows), owned by ONE warp; lane l owns rows l, l + 32, l + 64, l + 96.
+// Chunks are handed out in order by an atomic ticket; warps never synchronise with each other (no __syncthreads in the loop).
 //
 // Fast path (rows of one key, coordinate-sorted -- the shape of real interval tables):
 //   1. the chunk's WINDOW of the start-sorted build rows starts at W = the first row in the prefix_max_end directory bin of
 //      (smallest start of the chunk) - 1: every earlier row of the key ends before any row of the chunk starts.  ONE dependent
-//      load; the window is the next FJ_WCAP rows, copied by TMA (start, prefix_max_end | end, position on two mbarriers);
+//      load; the window is the next FJ_WCAP rows, copied by TMA (start, prefix_max_end | end, row id on two mbarriers);
 //   2. per row  i0 = first window row with prefix_max_end >= qs  and  n_le = #(window start <= qe): branch-free binary
-//      searches in shared memory with warp-uniform trip counts.  Sorted queries are searched once per LANE over the whole
-//      window and once per row between the lane's and its neighbour's result (monotone), unsorted ones between the ranks
-//      of the lane's smallest and largest query; a row that reaches the end of a truncated window sends the chunk to the
-//      slow path;
-//   3. the candidate slots [i0, n_le) of all rows are flattened row-major across the warp (a byte map slot -> row built with
-//      one scattered store per row and a packed prefix-max), 32 slots are tested per step (`end >= qs`, from shared
-//      memory), compacted with a ballot and STAGED in shared memory as (window row | row << 16) words;
-//   4. the chunk gets its output slots and the staged pairs leave as 128-bit stores.
+//      searches over the window in shared memory, a fixed number of unrolled steps, no bound checks (sentinels behind the
+//      window), brg_win.cuh; a row that reaches the end of a truncated window sends the chunk to the slow path;
+//   3. the candidate slots [i0, n_le) of all rows are flattened in row order across the warp (a byte map slot -> row built with
+//      one scattered store per non-empty row and a byte-wise prefix sum in registers), 32 slots are tested per step
+//      (`end >= qs`, from shared memory), compacted with a ballot and STAGED in shared memory as (window row | row << 16)
+//      words over the searched arrays, which are dead by then;
+//   4. the chunk gets its output slots and the staged pairs leave, row ids resolved from the window, one 32-bit element per
+//      lane and store (every store instruction writes 128 contiguous bytes).
 // Output slots, two ways (flag BRG_JOIN_ORDERED of brg_pairs_join_dev):
 //   any order (default): one atomicAdd of the chunk's pair count on a global cursor.  The pairs of a chunk are contiguous and
 //     probe-major, the chunks land in the order they finish; the optional chunk-slot table says where.  The reference's row
@@ -30,12 +30,12 @@
 //   ordered: a two-level decoupled look-back over the chunks' counts, so that the output is probe-major throughout (the order
 //     of brg_pairs.cu).  A chunk can only be written once EVERY earlier chunk is counted: with ~3500 chunks in flight each
 //     chunk waits for the slowest of its predecessors, about as long as it works (measured 17k of 38k cycles per chunk; a
-//     second staging buffer that defers the wait by one chunk made it worse, 0.71 vs 0.45 ms -- profiles/r2_join_experiments.txt).
+//     second staging buffer that defers the wait by one chunk made it worse, 0.79 vs 0.45 ms -- profiles/r2_join_experiments.txt).
 // Slow path (key boundary inside the chunk, unsorted rows, window or candidate count above the staging capacity, partial
 // last chunk): per-row rank-directory searches, the count from the count_overlaps identity (or a counting pass over the
-// flattened slots), the look-back, and a pass that writes the pairs straight to global memory.  Exact for any input.
+// flattened slots), the output slots, and a pass that writes the pairs straight to global memory.  Exact for any input.
 //
-// Output order: probe-major; the matches of one probe in (start, end, position) order -- the same as brg_pairs.cu.
+// Order inside a chunk: probe-major; the matches of one probe in (start, end, row id) order -- the same as brg_pairs.cu.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -47,8 +47,8 @@
 namespace brg {
 
 #ifndef BRG_FJ_PV
-#define BRG_FJ_PV 4             // rows per lane.  4 (128-row chunks) instead of the 8 of the tiled probe kernels: the kernel is bound by
-#endif                          // dependent shared-memory chains, and half the shared memory and registers per warp = twice the warps
+#define BRG_FJ_PV 4             // rows per lane.  4 (128-row chunks) instead of the 8 of the tiled probe kernels: half the shared memory
+#endif                          // and registers per warp = twice the warps (8 rows per lane: 0.254 ms against 0.190 ms)
 constexpr int FJ_PV = BRG_FJ_PV;
 constexpr int FJ_ROWS = 32 * FJ_PV;  // rows per chunk
 #ifndef BRG_FJ_WCAP
@@ -80,10 +80,9 @@ constexpr int FJ_RSLOTS = FJ_ROWS + 2;
 #endif
 constexpr unsigned FJ_SPIN_NS = BRG_FJ_SPIN_NS;
 constexpr int FJ_MAPQ = FJ_SLOTS / 512;  // 16-byte words of the slot -> row map per lane
-constexpr int FJ_PAD = win_pad(FJ_WCAP);  // sentinel rows behind the window: a search with first step
-                                                                 // S = bit_floor(rows) reads up to row 2 S + 1
+constexpr int FJ_PAD = win_pad(FJ_WCAP);  // sentinel rows behind the window
 constexpr int FJ_KEYS = 64;       // keys whose directory constants are staged per CTA
-static_assert(FJ_PV == 4 || FJ_PV == 8, "a lane loads its rows as one or two 128-bit words per column");
+static_assert(FJ_PV == 4 || FJ_PV == 8, "two 16-bit candidate counts per packed warp scan");
 static_assert(FJ_SLOTS % 512 == 0 && FJ_SLOTS <= 65536 && FJ_WCAP <= 32768 && FJ_WCAP % 4 == 0 && FJ_STAGE % 4 == 0 && FJ_ROWS <= 256,
               "packing of the row words");
 
@@ -222,7 +221,7 @@ __device__ __forceinline__ uint32_t fj_row_prefix16(const uint32_t (&cand)[FJ_PV
     return base;
 }
 
-// the slot -> row map of rows [ra, rb): zero, one byte per non-empty row at its first slot, packed prefix-max
+// the slot -> row map of rows [ra, rb) whose candidates start at slot Pa
 __device__ __forceinline__ void fj_build_rowof(uint8_t* rowof, uint32_t n_slots, uint32_t ra, uint32_t rb, uint32_t Pa,
                                                const uint32_t (&pj)[FJ_PV], const uint32_t (&cand)[FJ_PV], uint32_t lane) {
     // Row ids rise along the slots, so the map is a byte-wise PREFIX SUM of "row id minus the previous non-empty row's id" dropped at
