@@ -70,6 +70,10 @@ constexpr int FJ_ROWS = 32 * FJ_PV;  // rows per chunk
 #define BRG_FJ_VEC 0            // 1: 128-bit stores of the staged pairs
 #endif
 constexpr int FJ_WCAP = BRG_FJ_WCAP, FJ_SLOTS = BRG_FJ_SLOTS, FJ_STAGE = BRG_FJ_STAGE, FJ_WARPS = BRG_FJ_WARPS;
+#ifndef BRG_FJ_BATCH
+#define BRG_FJ_BATCH 2
+#endif
+constexpr int FJ_BATCH = BRG_FJ_BATCH;  // chunks per ticket in any-order mode
 #ifndef BRG_FJ_U
 #define BRG_FJ_U 4
 #endif
@@ -434,12 +438,28 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
             }
         }
     };
-    auto claim = [&]() {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1u);
-        return __shfl_sync(0xFFFFFFFFu, t, 0);
-    };
-    for (uint32_t chunk = claim(); chunk < n_chunks; chunk = claim()) {
+    // Any-order mode claims FJ_BATCH consecutive chunks per ticket (a sparse join is bound by the chain of dependent round trips
+    // per chunk -- ticket, probe rows, directory word, window, cursor: the batch saves the first for three chunks of four and lets
+    // the probe rows of the whole batch be prefetched into L2 at once).  Ordered mode keeps one chunk per ticket: chunks of a batch
+    // are counted one after the other, and everything behind them would wait that much longer.
+    const uint32_t batch = sc.ordered ? 1u : (uint32_t)FJ_BATCH;
+    uint32_t chunk = 0, batch_end = 0;
+    for (;;) {
+        if (chunk >= batch_end) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(ticket, batch);
+            chunk = __shfl_sync(0xFFFFFFFFu, t, 0);
+            if (chunk >= n_chunks) break;
+            batch_end = min(chunk + batch, n_chunks);
+            if (batch > 1u) {  // the batch's probe rows: (batch_end - chunk) * FJ_ROWS * 4 bytes per column, one 128-byte line per lane and step
+                const uint64_t b0 = (uint64_t)chunk * FJ_ROWS, b1 = min((uint64_t)batch_end * FJ_ROWS, n_rows);
+                for (uint64_t r = b0 + 32u * lane; r < b1; r += 32u * 32u) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(start + r));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(end + r));
+                    if (key) asm volatile("prefetch.global.L2 [%0];" ::"l"(key + r));
+                }
+            }
+        }
         const uint64_t row0 = (uint64_t)chunk * FJ_ROWS;
         int32_t qs[FJ_PV], qe[FJ_PV];
         uint32_t kk[FJ_PV];
@@ -688,6 +708,7 @@ pairs_join_kernel(IndexView ix, const uint32_t* __restrict__ key, const int32_t*
             if (chunk_slots_out) { chunk_slots_out[2ull * chunk] = base; chunk_slots_out[2ull * chunk + 1] = total; }
             if (sc.ordered && chunk == n_chunks - 1) *total_out = base + total;
         }
+        chunk++;
     }
     FJ_PROF_FLUSH
 }
