@@ -29,6 +29,9 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #ifndef BRG_RS_MINB
 #define BRG_RS_MINB 3  // resident CTAs per SM of the scatter kernel: 80 registers; it is latency-bound (ncu: issue slots 9 % busy at 2 CTAs)
 #endif
+#ifndef BRG_RS_PREFETCH
+#define BRG_RS_PREFETCH 1
+#endif
 constexpr int RS_ITEMS = BRG_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 rows per CTA
 constexpr int RS_MAX_ARR = 4;
@@ -113,6 +116,18 @@ __global__ void __launch_bounds__(RS_THREADS, BRG_RS_MINB) radix_scatter_kernel(
     const uint32_t lanemask_lt = (1u << lane) - 1u;
 
     for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&wc[0][0])[i] = 0;
+#if BRG_RS_PREFETCH
+    if (N_ARR != 2) {
+        // The generic version loads each payload array only when it drains it, between two barriers: start those lines towards L2
+        // now (16 KB per array and tile = 128 lines; no registers to hold them in).
+        if (t < 128) {
+            for (int a = 0; a < arr.n_arr; a++) {
+                const uint64_t i = tile_base + (uint64_t)t * 32;
+                if (a != pass.src && i < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(arr.in[a] + i));
+            }
+        }
+    }
+#endif
     __syncthreads();
 
     // tile order = index order: warp w owns rows [w*512, (w+1)*512), round j covers 32 consecutive rows
