@@ -673,6 +673,9 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
     int32_t* const w_pme = sm.pme_ + 4;
     int32_t* const w_eend = sm.eend_ + 4;
     if (lane == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+    win_sentinels_init<NW_WCAP>(w_start, lane);  // the rows behind a full window: once per kernel
+    win_sentinels_init<NW_WCAP>(w_pme, lane);
+    win_sentinels_init<NW_WCAP>(w_eend, lane);
     __syncwarp();
     uint32_t ph_s = 0, ph_e = 0;
     const uint64_t n_chunks = n_rows / TP_WTILE;  // n_rows is a multiple of 256 here
@@ -746,10 +749,12 @@ nearest_k1_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int3
                 ph_s ^= 1u;
                 mbar_wait(&sm.bar[1], ph_e);
                 ph_e ^= 1u;
-                win_sentinels<NW_WCAP>(w_start, nws, lane);
-                win_sentinels<NW_WCAP>(w_pme, nws, lane);
-                win_sentinels<NW_WCAP>(w_eend, nwe, lane);
-                __syncwarp();
+                if (nws < (uint32_t)NW_WCAP || nwe < (uint32_t)NW_WCAP) {  // (a window cut short by the end of the key; warp-uniform)
+                    win_sentinels_short<NW_WCAP>(w_start, nws, lane);
+                    win_sentinels_short<NW_WCAP>(w_pme, nws, lane);
+                    win_sentinels_short<NW_WCAP>(w_eend, nwe, lane);
+                    __syncwarp();
+                }
                 uint32_t n_le[NW_PV], i_pme[NW_PV], l_idx[NW_PV];
                 win_ranks<true, NW_PV, NW_WCAP>(w_start, wlos, nws, qe, n_le);     // #(start <= qe)              partition_point(first <= end)
                 win_ranks<false, NW_PV, NW_WCAP>(w_pme, wlos, nws, qs, i_pme);     // first prefix_max_end >= qs    first_overlap_by_start (:222-234)
@@ -848,6 +853,8 @@ rank2_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int32_t* 
     int32_t* const w_a = sm.a_ + 4;
     int32_t* const w_b = sm.b_ + 4;
     if (lane == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+    win_sentinels_init<R2_WCAP>(w_a, lane);
+    win_sentinels_init<R2_WCAP>(w_b, lane);
     __syncwarp();
     uint32_t ph_a = 0, ph_b = 0;
     const DirView& da = OP == 0 ? ix.d_sstart : ix.d_mlast;  // the directory that places window A (coverage: one window, placed by
@@ -918,9 +925,11 @@ rank2_kernel_win(IndexView ix, const uint32_t* __restrict__ key, const int32_t* 
                 ph_a ^= 1u;
                 mbar_wait(&sm.bar[1], ph_b);
                 ph_b ^= 1u;
-                win_sentinels<R2_WCAP>(w_a, nwa, lane);
-                win_sentinels<R2_WCAP>(w_b, nwb, lane);
-                __syncwarp();
+                if (nwa < (uint32_t)R2_WCAP || nwb < (uint32_t)R2_WCAP) {
+                    win_sentinels_short<R2_WCAP>(w_a, nwa, lane);
+                    win_sentinels_short<R2_WCAP>(w_b, nwb, lane);
+                    __syncwarp();
+                }
                 uint32_t ra[NW_PV], rb[NW_PV];
                 win_ranks<true, NW_PV, R2_WCAP>(w_a, wloa, nwa, qe, ra);   // #(start <= qe)   / first merged interval with first > qe
                 win_ranks<false, NW_PV, R2_WCAP>(w_b, wlob, nwb, qs, rb);  // #(end < qs)      / first merged interval with last >= qs

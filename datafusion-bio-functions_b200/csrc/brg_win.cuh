@@ -32,6 +32,16 @@ __device__ __forceinline__ void win_sentinels(int32_t* w, uint32_t nw, uint32_t 
     constexpr uint32_t END = 2u * (uint32_t)win_bit_floor(CAP) + 4u;
     for (uint32_t x = nw + lane; x < END; x += 32) w[x] = INT32_MAX;  // (a full window: one to three stores)
 }
+// The same in two parts for kernels whose window arrays are not reused for anything else: the rows behind a FULL window are
+// written once per kernel (a TMA copy of at most CAP rows never touches them), and a chunk whose window is cut short by the end
+// of its key -- the rare case -- fills the rest.
+template <int CAP>
+__device__ __forceinline__ void win_sentinels_init(int32_t* w, uint32_t lane) { win_sentinels<CAP>(w, (uint32_t)CAP, lane); }
+template <int CAP>
+__device__ __forceinline__ void win_sentinels_short(int32_t* w, uint32_t nw, uint32_t lane) {
+    if (nw < (uint32_t)CAP)
+        for (uint32_t x = nw + lane; x < (uint32_t)CAP; x += 32) w[x] = INT32_MAX;
+}
 
 // ranks of NQ queries in the window rows w[wlo .. nw), nw <= CAP: out[j] = #(w[0 .. nw) <= q[j]) (LE) or #(... < q[j]), counting the
 // wlo rows in front as smaller.  NQ independent searches in lock step, ALWAYS log2(bit_floor(CAP)) + 1 steps, fully unrolled: a step

@@ -7,3 +7,9 @@ for l in sys.stdin:
     if l.startswith('{'):
         d = json.loads(l); print('nearest', 'ms', round(d['ms_per_step'], 4), 'frac', round(d['roofline']['frac'], 4), 'parity', d.get('parity_vs_oracle_sample'))
 "
+BRG_COUNT_WIN=1 timeout 300 python bench.py --workload count --steps 10 --no-extras --no-cpu --no-e2e 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('count WIN', 'ms', round(d['ms_per_step'], 4), 'frac', round(d['roofline']['frac'], 4), 'parity', d.get('parity_vs_oracle_sample'))
+"
