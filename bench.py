@@ -411,6 +411,29 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
                        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}
     if name == "pairs":
         res["pairs_per_probe"] = total / n
+        if res["pairs_path"].startswith("brg_pairs_join_dev") and rank == 0:
+            # the same join with probe-major output throughout, for the record: the one-launch kernel with its look-back
+            # (BRG_JOIN_ORDERED) and the three-launch chunked form that brg_overlap_pairs(BRG_PAIRS_INNER) takes
+            def timed(fn, reps=max(3, steps)):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            off2 = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=device)
+            rng2 = torch.empty(n, dtype=torch.int64, device=device)
+            t_ord = timed(lambda: ix.pairs_join_dev(pk, ps, pe, bi, pi, tot_dev, ordered=True))
+            t_chk = timed(lambda: (ix.pairs_chunk_offsets_dev(pk, ps, pe, off2, rng2), ix.pairs_fill_dev(ps, off2, rng2, bi, pi)))
+            res["pairs_ordered_output"] = {"one_launch_look_back_ms": t_ord, "three_launch_chunked_ms": t_chk,
+                                           "what": "same join, output probe-major throughout (the default lets the 128-row chunks land in the order they finish)"}
+            del off2, rng2
+            ix.pairs_join_dev(pk, ps, pe, bi, pi, tot_dev)  # (the parity check below reads the any-order result that was timed)
+            torch.cuda.synchronize()
 
     # ---- parity of the DEVICE-RESIDENT result that produced `value`: all rows, this rank ----------------------------------
     parity = {}

@@ -18,7 +18,7 @@ JOIN_ORDERED = 1
 ABI_SYMBOLS = [
     "brg_last_error", "brg_version", "brg_ctx_create", "brg_ctx_destroy", "brg_ctx_device", "brg_ctx_sm_count",
     "brg_pinned_alloc", "brg_pinned_free", "brg_build", "brg_build_dev", "brg_index_destroy", "brg_index_rows",
-    "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_export", "brg_index_import", "brg_index_slab_alloc",
+    "brg_index_merged_rows", "brg_index_device_bytes", "brg_index_bins_info", "brg_index_export", "brg_index_import", "brg_index_slab_alloc",
     "brg_index_slab_free", "brg_index_attach", "brg_index_replicate", "brg_count_overlaps",
     "brg_count_overlaps_dev", "brg_coverage", "brg_coverage_dev", "brg_nearest_k1", "brg_nearest_k1_dev", "brg_nearest",
     "brg_count_overlaps_runs", "brg_coverage_runs", "brg_nearest_k1_runs",
@@ -80,6 +80,8 @@ def lib():
     for f in (L.brg_index_rows, L.brg_index_merged_rows, L.brg_index_device_bytes):
         f.argtypes = [vp]
         f.restype = u64
+    L.brg_index_bins_info.argtypes = [vp, i32, C.POINTER(u32), C.POINTER(u32)]
+    L.brg_index_bins_info.restype = u64
     L.brg_index_export.argtypes = [vp, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
     L.brg_index_import.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.brg_index_slab_alloc.argtypes = [vp, u64, C.POINTER(vp)]

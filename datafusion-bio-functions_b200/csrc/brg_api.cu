@@ -221,9 +221,11 @@ struct IndexHeader {
     // count bins (32-byte records; cbdir.off_kd = per-key constants, cbdir.off_D = the records, cbdir.entries = record count)
     DirDesc cbdir;
     DirDesc cvdir;  // coverage bins over (m_first, m_last), same layout
+    DirDesc nbdir;  // nearest / pair bins over (s_start, pme), same layout
+    // (bins tables: DirDesc.shift = bin width (log2) | record format << 8, see brg_bins.cuh)
 };
 static const uint32_t kMagic = 0x31475242u;  // "BRG1"
-static const uint32_t kVersion = 6;
+static const uint32_t kVersion = 7;
 static const uint64_t kNone = ~0ull;
 static const uint64_t kSlabHeaderBytes = 4096;  // reserved at the front of every slab for the IndexHeader
 static_assert(sizeof(IndexHeader) <= kSlabHeaderBytes, "IndexHeader must fit the reserved slab prefix");
@@ -265,12 +267,14 @@ static IndexView make_view(const IndexHeader& h, void* slab) {
         cv[a]->d.A = (const int32_t*)P(h.off_cS[a]);
         cv[a]->d.shift = h.cdir[a].shift;
     }
-    v.cb.rec = (const uint4*)P(h.cbdir.off_D);
-    v.cb.kd = (const KeyDir*)P(h.cbdir.off_kd);
-    v.cb.shift = h.cbdir.shift;
-    v.cvb.rec = (const uint4*)P(h.cvdir.off_D);
-    v.cvb.kd = (const KeyDir*)P(h.cvdir.off_kd);
-    v.cvb.shift = h.cvdir.shift;
+    const DirDesc* bd[3] = {&h.cbdir, &h.cvdir, &h.nbdir};
+    BinsView* bv[3] = {&v.cb, &v.cvb, &v.nb};
+    for (int i = 0; i < 3; i++) {
+        bv[i]->rec = (const uint4*)P(bd[i]->off_D);
+        bv[i]->kd = (const KeyDir*)P(bd[i]->off_kd);
+        bv[i]->shift = bd[i]->shift & 0xFFu;
+        bv[i]->fmt = bd[i]->shift >> 8;
+    }
     return v;
 }
 
@@ -773,6 +777,12 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     // At most kCbTarget elements of each array per bin on average.  Offsets inside a bin are u16, so bins are at most 65536
     // wide: a build side too sparse for that (more than 2 records per row) keeps the compact rank index below instead.
     static const uint32_t kCbTarget = [] { const char* v = getenv("BRG_CB_TARGET"); const int t = v ? atoi(v) : 2; return (uint32_t)(t > 0 ? t : 0); }();
+    // Record format (brg_bins.cuh): the packed one (18 slots of 10 bits, bins twice as wide for the same overflow odds) halves
+    // a table; it pays when the wide-slot table would not stay in L2 under a shuffled probe table (10M build rows: 194 MB of
+    // records -> 97 MB).  BRG_CB_PACK: 1 = whenever the bins are narrow enough, 0 = never, unset = tables above kPackAbove bytes.
+    // (read at every build: the tests flip it inside one process)
+    const int kCbPack = [] { const char* v = getenv("BRG_CB_PACK"); return v && v[0] ? atoi(v) : -1; }();
+    static const uint64_t kPackAbove = 48ull << 20;
     // plan of one bins table over the array pair (A, B) that shares the key segments `seg`: per-key ranges, bin width, record count
     auto plan_bins = [&](const int32_t* A, const int32_t* B, const uint32_t* seg, uint64_t n_elems, ScratchBuf* kd, uint32_t* shift_out,
                          uint32_t* entries_out, bool* ok) -> int {
@@ -786,23 +796,36 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         // widest bins that still hold at most kCbTarget elements of each array on average (so between target / 2 and target)
         const uint64_t at_least = std::max<uint64_t>(n_elems / kCbTarget, 1);
         uint32_t shift = 0;
-        for (uint32_t sft = 16; sft > 0; sft--)
+        for (uint32_t sft = CB_SHIFT_WIDE; sft > 0; sft--)
             if (bins[sft] >= at_least) { shift = sft; break; }
         if (bins[shift] > 2ull * n_elems + 2ull * n_keys + (1ull << 16)) return 0;  // (too sparse for 65536-wide bins)
-        *shift_out = shift;
+        uint32_t fmt = 0;
+        if (kCbPack != 0 && shift + 1 <= CB_SHIFT_PACKED && (kCbPack > 0 || bins[shift] * 32ull > kPackAbove)) { fmt = 1; shift += 1; }
+        *shift_out = shift | (fmt << 8);
         if ((rc = dir_assign_bases(kd->as<KeyDir>(), n_keys, shift, d_scalar, st))) return rc;
         BRG_CUDA(cudaMemcpyAsync(entries_out, d_scalar, 4, cudaMemcpyDeviceToHost, st));
         BRG_CUDA(cudaStreamSynchronize(st));
         *ok = true;
         return 0;
     };
-    ScratchBuf cb_kd, cv_kd;
-    uint32_t cb_shift = 0, cb_entries = 0, cv_shift = 0, cv_entries = 0;
+    ScratchBuf cb_kd, cv_kd, nb_kd;
+    uint32_t cb_shift = 0, cb_entries = 0, cv_shift = 0, cv_entries = 0, nb_shift = 0, nb_entries = 0;  // (shift | format << 8)
     bool need_cb = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && kCbTarget > 0;
     if (need_cb && (rc = plan_bins(s_start.as<int32_t>(), (const int32_t*)E[2], off.as<uint32_t>(), n_valid, &cb_kd, &cb_shift, &cb_entries, &need_cb))) return rc;
     // coverage: the same bins over the merged intervals' (first, last) -- the per-row coverage kernels (unsorted probe tables)
     bool need_cvb = need_cov && n_merged > 0 && kCbTarget > 0;
     if (need_cvb && (rc = plan_bins(m_first.as<int32_t>(), m_last.as<int32_t>(), m_off.as<uint32_t>(), n_merged, &cv_kd, &cv_shift, &cv_entries, &need_cvb))) return rc;
+    // nearest / pairs: bins over (s_start, prefix_max_end) -- the per-row kernels of those two (unsorted probe tables) read
+    // #(start <= qe) and the first row whose prefix_max_end >= qs from one record.  Not with inverted build rows (start > end):
+    // the kernels' shortcut "no overlap => every row that starts by qe has ended before qs" needs start <= end.
+    // Built with BRG_WANT_NEAREST (50M x 5M shuffled nearest 3.39 -> 2.10 ms for +0.14 ms of build); a pairs-only index gets them
+    // on request (BRG_NB_BINS=2): the shuffled 10M x 10M range pass goes 0.70 -> 0.38 ms, but the 97 MB larger slab made the warm
+    // 10M-row pairs build 4.0 -> 6.4 ms (profiles/r2_bins_experiments.txt), which a join of sorted tables (0.2 ms) would pay for
+    // nothing.  BRG_NB_BINS=0: never.  (read at every build: the tests flip it inside one process)
+    const int kNbBins = [] { const char* v = getenv("BRG_NB_BINS"); return v && v[0] ? atoi(v) : 1; }();
+    const uint32_t nb_wants = kNbBins >= 2 ? (BRG_WANT_NEAREST | BRG_WANT_PAIRS) : kNbBins == 1 ? BRG_WANT_NEAREST : 0u;
+    bool need_nb = (want & nb_wants) != 0 && n_valid > 0 && kCbTarget > 0 && !(idx_props & BRG_IDX_INVERTED);
+    if (need_nb && (rc = plan_bins(s_start.as<int32_t>(), pme.as<int32_t>(), off.as<uint32_t>(), n_valid, &nb_kd, &nb_shift, &nb_entries, &need_nb))) return rc;
     mark("count bins plan");
     const bool need_ci = (want & BRG_WANT_COUNT) != 0 && n_valid > 0 && !need_cb;
     ScratchBuf boff_d, cS[2], cB[2];
@@ -876,6 +899,10 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
     h.cvdir.off_D = place(need_cvb, (uint64_t)cv_entries * 32);
     h.cvdir.shift = cv_shift;
     h.cvdir.entries = cv_entries;
+    h.nbdir.off_kd = place(need_nb, (uint64_t)std::max(1u, n_keys) * sizeof(KeyDir));
+    h.nbdir.off_D = place(need_nb, (uint64_t)nb_entries * 32);
+    h.nbdir.shift = nb_shift;
+    h.nbdir.entries = nb_entries;
     h.slab_bytes = std::max<uint64_t>(cur, 256);
 
     // The slab comes from the stream-ordered pool like the temporaries: cudaMalloc of a few hundred MB costs 1-3 ms (a third of
@@ -913,6 +940,7 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         }
     if (need_cb) chk(copy_in(h.cbdir.off_kd, cb_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
     if (need_cvb) chk(copy_in(h.cvdir.off_kd, cv_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
+    if (need_nb) chk(copy_in(h.nbdir.off_kd, nb_kd.p, (uint64_t)n_keys * sizeof(KeyDir)));
     if (ce == cudaSuccess) ce = cudaMemsetAsync(base, 0, kSlabHeaderBytes, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st);  // (synchronised below, before h dies)
     if (ce != cudaSuccess) { slab_free(); set_error(std::string("slab copy: ") + cudaGetErrorString(ce)); return BRG_ERR_CUDA; }
@@ -927,8 +955,18 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         DirView ds, de;
         ds.kd = db[0].kd.as<KeyDir>(); ds.D = (const uint32_t*)(base + h.dir[0].off_D); ds.A = s_start.as<int32_t>(); ds.shift = db[0].shift;
         de.kd = db[1].kd.as<KeyDir>(); de.D = (const uint32_t*)(base + h.dir[1].off_D); de.A = (const int32_t*)E[2]; de.shift = db[1].shift;
-        rc = cb_fill(ds, de, cb_kd.as<KeyDir>(), n_keys, cb_shift, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(), (uint4*)(base + h.cbdir.off_D),
-                     cb_entries, st);
+        rc = cb_fill(ds, de, cb_kd.as<KeyDir>(), n_keys, cb_shift & 0xFFu, cb_shift >> 8, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(),
+                     (uint4*)(base + h.cbdir.off_D), cb_entries, st);
+        if (rc) { slab_free(); return rc; }
+    }
+    if (need_nb) {  // (after the rank directories of s_start and pme)
+        ScratchBuf cs_tmp, ce_tmp;
+        if ((rc = cs_tmp.ensure(((uint64_t)nb_entries + 1) * 4)) || (rc = ce_tmp.ensure(((uint64_t)nb_entries + 1) * 4))) { slab_free(); return rc; }
+        DirView ds, dp;
+        ds.kd = db[0].kd.as<KeyDir>(); ds.D = (const uint32_t*)(base + h.dir[0].off_D); ds.A = s_start.as<int32_t>(); ds.shift = db[0].shift;
+        dp.kd = db[2].kd.as<KeyDir>(); dp.D = (const uint32_t*)(base + h.dir[2].off_D); dp.A = pme.as<int32_t>(); dp.shift = db[2].shift;
+        rc = cb_fill(ds, dp, nb_kd.as<KeyDir>(), n_keys, nb_shift & 0xFFu, nb_shift >> 8, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(),
+                     (uint4*)(base + h.nbdir.off_D), nb_entries, st);
         if (rc) { slab_free(); return rc; }
     }
     if (need_cvb) {
@@ -937,8 +975,8 @@ extern "C" BRG_API int brg_build_dev(brg_ctx* ctx, const uint32_t* d_key, const 
         DirView df, dl;
         df.kd = db[3].kd.as<KeyDir>(); df.D = (const uint32_t*)(base + h.dir[3].off_D); df.A = m_first.as<int32_t>(); df.shift = db[3].shift;
         dl.kd = db[4].kd.as<KeyDir>(); dl.D = (const uint32_t*)(base + h.dir[4].off_D); dl.A = m_last.as<int32_t>(); dl.shift = db[4].shift;
-        rc = cb_fill(df, dl, cv_kd.as<KeyDir>(), n_keys, cv_shift, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(), (uint4*)(base + h.cvdir.off_D),
-                     cv_entries, st);
+        rc = cb_fill(df, dl, cv_kd.as<KeyDir>(), n_keys, cv_shift & 0xFFu, cv_shift >> 8, cs_tmp.as<uint32_t>(), ce_tmp.as<uint32_t>(),
+                     (uint4*)(base + h.cvdir.off_D), cv_entries, st);
         if (rc) { slab_free(); return rc; }
     }
     if (need_ci)
@@ -1000,6 +1038,16 @@ extern "C" BRG_API void brg_index_destroy(brg_index* ix) {
 extern "C" BRG_API uint64_t brg_index_rows(const brg_index* ix) { return ix ? ix->h.n : 0; }
 extern "C" BRG_API uint64_t brg_index_merged_rows(const brg_index* ix) { return ix ? ix->h.n_merged : 0; }
 extern "C" BRG_API uint64_t brg_index_device_bytes(const brg_index* ix) { return ix ? ix->h.slab_bytes : 0; }
+extern "C" BRG_API uint64_t brg_index_bins_info(const brg_index* ix, int table, uint32_t* bin_shift, uint32_t* format) {
+    if (bin_shift) *bin_shift = 0;
+    if (format) *format = 0;
+    if (!ix || table < 0 || table > 2) return 0;
+    const DirDesc& d = table == 0 ? ix->h.cbdir : table == 1 ? ix->h.cvdir : ix->h.nbdir;
+    if (d.off_D == kNone) return 0;
+    if (bin_shift) *bin_shift = d.shift & 0xFFu;
+    if (format) *format = d.shift >> 8;
+    return d.entries;
+}
 
 extern "C" BRG_API int brg_index_export(const brg_index* ix, void* header_buf, uint64_t cap, uint64_t* header_len, void** d_slab,
                                 uint64_t* slab_bytes) {

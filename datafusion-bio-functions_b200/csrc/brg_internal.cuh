@@ -6,6 +6,8 @@
 #include <atomic>
 #include <string>
 
+#include "brg_bins.cuh"
+
 namespace brg {
 
 constexpr int kSMs = 148;  // B200: 148 SMs (2 dies x 74); grids are sized in multiples of this
@@ -93,7 +95,8 @@ struct CompactKey {       // per-key constants of a CompactView (32 bytes, same 
 struct BinsView {
     const uint4* rec;   // 2 x uint4 per bin; nullptr = absent
     const KeyDir* kd;   // per key: lo, nb, base (first record), seg_begin / seg_end (shared by the two arrays)
-    uint32_t shift;     // bin width 2^shift (<= 65536: in-bin offsets are u16)
+    uint32_t shift;     // bin width 2^shift (format 0: <= 65536, in-bin offsets are u16; format 1: <= 1024, 10-bit offsets)
+    uint32_t fmt;       // record format (brg_bins.cuh): 0 = 12 x u16 slots, 1 = 18 x 10-bit slots
 };
 
 // Device view of an index (pointers into the single HBM slab)
@@ -126,6 +129,8 @@ struct IndexView {
     BinsView cb;   // over (s_start, e_end): count_overlaps
     BinsView cvb;  // over (m_first, m_last): coverage -- the same record answers "first merged interval with last >= qs" and
                    // "first merged interval with first > qe"
+    BinsView nb;   // over (s_start, pme): nearest and the pair range pass on unsorted probe tables -- one record answers
+                   // #(start <= qe) and "first row whose prefix_max_end >= qs" (absent when a build row has start > end)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -145,8 +150,7 @@ struct IndexView {
 //   #(starts <= qe) = cs(bin(qe)) + #(start offsets <= qe's offset);   #(ends < qs) likewise from bin(qs - 1).
 // A 150 bp read has both coordinates in one bin most of the time: 2 divergent loads per row instead of 5-6.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t CB_SLOTS = 12;
-constexpr uint32_t CB_OVERFLOW = 0xFFu;
+// (the record layout and its two formats: brg_bins.cuh)
 
 // ------------------------------------------------------------------------------------------------
 // launchers (each returns a brg_status; all work is enqueued on `st`)
@@ -207,7 +211,7 @@ int ci_pack_table(const uint32_t* D, uint32_t total_entries, uint32_t* P, cudaSt
 // count bins: per-key value range over BOTH arrays (kd.nb = provisional range), then one thread per record
 int cb_key_ranges(const int32_t* s_start, const int32_t* e_end, const uint32_t* off, uint32_t n_keys, KeyDir* kd,
                   unsigned long long* d_bins_by_shift, cudaStream_t st);
-int cb_fill(const DirView& d_sstart, const DirView& d_eend, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* cs_tmp,
+int cb_fill(const DirView& d_sstart, const DirView& d_eend, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t fmt, uint32_t* cs_tmp,
             uint32_t* ce_tmp /* total_entries + 1 words each */, uint4* rec, uint32_t total_entries, cudaStream_t st);
 // rank directory
 int dir_key_ranges(const int32_t* A, const uint32_t* off, uint32_t n_keys, KeyDir* kd, unsigned long long* d_bins_by_shift,
@@ -389,23 +393,15 @@ __device__ __forceinline__ CountBinRec load_count_bin(const BinsView& bv, uint32
 #endif
     return x;
 }
-__device__ __forceinline__ bool count_bin_overflowed(const CountBinRec& x) { return (x.w[1] >> 24) == CB_OVERFLOW; }
+__device__ __forceinline__ bool count_bin_overflowed(const CountBinRec& x) { return cb_overflowed(x.w); }
 // #(elements of the bin <= off) among the starts (ENDS = false) or the ends (true) of a record that did not overflow
 template <bool ENDS>
-__device__ __forceinline__ uint32_t count_bin_slots(const CountBinRec& x, uint32_t off) {
-    const uint32_t ns = (x.w[1] >> 16) & 0xFFu, ne = x.w[1] >> 24;
-    const uint32_t first = ENDS ? ns : 0u, last = ENDS ? ns + ne : ns;
-    uint32_t c = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < CB_SLOTS; i++) {
-        const uint32_t v = (x.w[2 + (i >> 1)] >> ((i & 1u) * 16u)) & 0xFFFFu;
-        c += ((!ENDS || i >= first) && i < last && v <= off) ? 1u : 0u;
-    }
-    return c;
+__device__ __forceinline__ uint32_t count_bin_slots(const CountBinRec& x, uint32_t fmt, uint32_t off) {
+    return cb_count_le<ENDS>(x.w, fmt, off);
 }
 // global index of the first start / end >= the bin's first coordinate
-__device__ __forceinline__ uint32_t count_bin_cs(const CountBinRec& x) { return x.w[0]; }
-__device__ __forceinline__ uint32_t count_bin_ce(const CountBinRec& x) { return x.w[0] - (x.w[1] & 0xFFFFu); }
+__device__ __forceinline__ uint32_t count_bin_cs(const CountBinRec& x) { return cb_first_a(x.w); }
+__device__ __forceinline__ uint32_t count_bin_ce(const CountBinRec& x) { return cb_first_b(x.w); }
 
 // Both rank queries of a row through the bins of one array pair:
 //   *ra = seg_begin + #(first array <= qa),  *rb = seg_begin + #(second array < qb)
@@ -425,12 +421,12 @@ __device__ __forceinline__ uint32_t bins_pair_ranks(const BinsView& bv, const Ke
     if (need_a) {
         r = load_count_bin(bv, k.base + ba);
         if (count_bin_overflowed(r)) missing |= 1u;
-        else *ra = count_bin_cs(r) + count_bin_slots<false>(r, da & msk);
+        else *ra = count_bin_cs(r) + count_bin_slots<false>(r, bv.fmt, da & msk);
     }
     if (need_b) {
         if (!(need_a && bb == ba)) r = load_count_bin(bv, k.base + bb);  // (the usual case: the row lies inside one bin)
         if (count_bin_overflowed(r)) missing |= 2u;
-        else *rb = count_bin_ce(r) + count_bin_slots<true>(r, db & msk);
+        else *rb = count_bin_ce(r) + count_bin_slots<true>(r, bv.fmt, db & msk);
     }
     return missing;
 }

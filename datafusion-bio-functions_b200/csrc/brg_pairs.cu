@@ -24,6 +24,15 @@ __device__ __forceinline__ void pair_range(const IndexView& ix, uint32_t c, int3
                                            uint32_t* i1) {
     *i0 = *i1 = 0;
     if (c >= ix.n_keys) return;  // key absent from the build side (interval_join.rs:857)
+    if (ix.nb.rec) {  // nearest / pair bins: both ranks from one 32-byte record (see IndexView::nb)
+        const KeyDir k = load_keydir(ix.nb.kd, c);
+        uint32_t n_le, p0;
+        const uint32_t missing = bins_pair_ranks(ix.nb, k, qe, qs, &n_le, &p0);
+        if (missing & 1u) n_le = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
+        if (missing & 2u) p0 = rank_lt_kd(ix.d_pme, load_keydir(ix.d_pme.kd, c), qs);
+        if (p0 < n_le) { *i0 = p0; *i1 = n_le; }
+        return;
+    }
     KeyDir ks = load_keydir(ix.d_sstart.kd, c);
     if (ks.seg_begin == ks.seg_end) return;
     uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);
@@ -189,8 +198,10 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
     const bool staged = ix.n_keys <= SK;
     if (staged) {
         const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
-        const uint32_t* g[3] = {reinterpret_cast<const uint32_t*>(ix.d_sstart.kd), reinterpret_cast<const uint32_t*>(ix.d_pme.kd),
-                                reinterpret_cast<const uint32_t*>(ix.d_eend.kd)};
+        // (with the nearest / pair bins their constants take the first slot: the directories of s_start and pme are then read
+        //  only behind a record that overflowed)
+        const uint32_t* g[3] = {reinterpret_cast<const uint32_t*>(ix.nb.rec ? ix.nb.kd : ix.d_sstart.kd),
+                                reinterpret_cast<const uint32_t*>(ix.d_pme.kd), reinterpret_cast<const uint32_t*>(ix.d_eend.kd)};
         for (int a = 0; a < 3; a++)
             for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(skd[a])[i] = __ldg(g[a] + i);
         __syncthreads();
@@ -203,7 +214,20 @@ __global__ void __launch_bounds__(TP_WTILE) pairs_ranges_todo_kernel(IndexView i
             const int32_t qs = ld_stream(start + i), qe = ld_stream(end + i);
             const uint32_t c = key ? ld_stream(key + i) : 0u;
             uint32_t i0 = 0, i1 = 0;
-            if (c < ix.n_keys) {
+            if (c < ix.n_keys && ix.nb.rec) {
+                // nearest / pair bins: n_le and p0 from one 32-byte record; the count identity needs #(end < qs) on top
+                const KeyDir kb = staged ? skd[0][c] : load_keydir(ix.nb.kd, c);
+                uint32_t n_le, p0;
+                const uint32_t missing = bins_pair_ranks(ix.nb, kb, qe, qs, &n_le, &p0);
+                if (missing & 1u) n_le = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
+                if (missing & 2u) p0 = rank_lt_kd(ix.d_pme, staged ? skd[1][c] : load_keydir(ix.d_pme.kd, c), qs);
+                if (p0 < n_le) {
+                    i0 = p0; i1 = n_le;
+                    // (the bins exist only without inverted build rows: the identity holds for every proper probe)
+                    if (!(qe < qs)) cnt = n_le - rank_lt_kd(ix.d_eend, staged ? skd[2][c] : load_keydir(ix.d_eend.kd, c), qs);
+                    else cnt = walk_count(ix, i0, i1, qs);
+                }
+            } else if (c < ix.n_keys) {
                 // the three rank queries of the row are independent: directory steps together, bin searches in lock step
                 //   n_le = #(start <= qe),  p0 = first row with prefix_max_end >= qs,  ended = #(end < qs)
                 const KeyDir ks = staged ? skd[0][c] : load_keydir(ix.d_sstart.kd, c), kp = staged ? skd[1][c] : load_keydir(ix.d_pme.kd, c),

@@ -456,8 +456,50 @@ __device__ __forceinline__ Cand load_e(const IndexView& ix, uint32_t i) {
 }
 
 // one probe: returns true and fills `best` when an interval is found
+// nearest_one through the nearest bins (unsorted probe tables): ONE 32-byte record gives n_le = #(start <= qe) and
+// i_pme = first row whose prefix_max_end >= qs, then one or two 16-byte candidate records -- 3 divergent loads per row where
+// the rank directories below take about a dozen.  The index holds no row with start > end (the bins are not built otherwise),
+// so without an overlap every row that starts by qe has ended before qs and every later row ends after qe: #(end < qs) = n_le.
+__device__ __forceinline__ bool nearest_one_bins(const IndexView& ix, const KeyDir& k, uint32_t c, int32_t qs, int32_t qe,
+                                                 int include_overlaps, Cand* best) {
+    if (k.seg_begin == k.seg_end) return false;                         // is_empty (nearest_index.rs:92-94)
+    uint32_t n_le, i_pme;
+    const uint32_t missing = bins_pair_ranks(ix.nb, k, qe, qs, &n_le, &i_pme);
+    if (missing & 1u) n_le = rank_le_kd(ix.d_sstart, load_keydir(ix.d_sstart.kd, c), qe);
+    if (missing & 2u) i_pme = rank_lt_kd(ix.d_pme, load_keydir(ix.d_pme.kd, c), qs);
+    const bool proper = !(qe < qs);
+    if (include_overlaps && proper && i_pme < n_le) {                   // first_overlap_by_start (:222-234)
+        *best = load_s(ix, i_pme);
+        return true;
+    }
+    if (include_overlaps == 2) return false;                            // overlaps only (BRG_NEAREST_OVERLAP_ONLY)
+    // nearest_non_overlap_one (:192-220): left = last row in (end, start, position) order with end < qs
+    uint32_t left_idx = n_le;
+    if (!(include_overlaps && proper))                                  // (overlaps skipped or a degenerate probe: rank the ends)
+        left_idx = rank_lt_kd(ix.d_eend, load_keydir(ix.d_eend.kd, c), qs);
+    const bool has_left = left_idx > k.seg_begin, has_right = n_le < k.seg_end;
+    if (!has_left && !has_right) return false;
+    Cand l, r;
+    if (has_left) l = load_e(ix, left_idx - 1);
+    if (has_right) r = load_s(ix, n_le);
+    if (has_left && has_right) *best = cand_le(qs, qe, l, r) ? l : r;
+    else *best = has_left ? l : r;
+    return true;
+}
+// the nearest bins' per-key constants in shared memory (all threads of the CTA; nullptr when absent or too many keys)
+constexpr uint32_t NB_SMEM_KEYS = 64;
+__device__ __forceinline__ const KeyDir* stage_nearest_keys(const IndexView& ix, KeyDir* smem) {
+    if (!ix.nb.rec || ix.n_keys > NB_SMEM_KEYS) return nullptr;
+    const uint32_t words = ix.n_keys * (uint32_t)(sizeof(KeyDir) / 4);
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(ix.nb.kd);
+    uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sm[i] = __ldg(g + i);
+    __syncthreads();
+    return smem;
+}
 __device__ __forceinline__ bool nearest_one(const IndexView& ix, uint32_t c, int32_t qs, int32_t qe,
-                                            int include_overlaps, Cand* best) {
+                                            int include_overlaps, Cand* best, const KeyDir* skeys = nullptr) {
+    if (ix.nb.rec) return nearest_one_bins(ix, skeys ? skeys[c] : load_keydir(ix.nb.kd, c), c, qs, qe, include_overlaps, best);
     KeyDir ks = load_keydir(ix.d_sstart.kd, c);
     if (ks.seg_begin == ks.seg_end) return false;                       // is_empty (nearest_index.rs:92-94)
     const uint32_t n_le = rank_le_kd(ix.d_sstart, ks, qe);              // partition_point(first <= end)
@@ -487,6 +529,8 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k1_kernel(IndexView ix, co
                                                                 uint32_t* __restrict__ left_idx,
                                                                 uint32_t* __restrict__ valid_bits,
                                                                 int64_t* __restrict__ dist) {
+    __shared__ KeyDir skeys_buf[NB_SMEM_KEYS];
+    const KeyDir* skeys = stage_nearest_keys(ix, skeys_buf);
     // whole warps stay converged so that the ballot below packs 32 validity bits per store
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_round = (n + 31) & ~31ull;
@@ -499,7 +543,7 @@ __global__ void __launch_bounds__(PB_THREADS) nearest_k1_kernel(IndexView ix, co
             uint32_t c = load_key(key, i);
             int32_t qs = rs, qe = re;
             if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }  // nearest.rs:341-344
-            if (c < ix.n_keys) found = nearest_one(ix, c, qs, qe, include_overlaps, &b);
+            if (c < ix.n_keys) found = nearest_one(ix, c, qs, qe, include_overlaps, &b, skeys);
         }
         uint32_t bits = __ballot_sync(0xFFFFFFFFu, found);
         if ((threadIdx.x & 31) == 0) valid_bits[i >> 5] = bits;  // Arrow validity bitmap, LSB first
@@ -975,6 +1019,9 @@ __global__ void __launch_bounds__(TP_WTILE) nearest_k1_kernel_todo(IndexView ix,
                                                                    uint32_t* __restrict__ valid_bits,
                                                                    int64_t* __restrict__ dist, TodoList todo) {
     const uint32_t n_todo = *todo.count;
+    if (blockIdx.x >= n_todo) return;  // (nothing was deferred to this CTA: skip staging the key constants)
+    __shared__ KeyDir skeys_buf[NB_SMEM_KEYS];
+    const KeyDir* skeys = stage_nearest_keys(ix, skeys_buf);
     for (uint32_t c = blockIdx.x; c < n_todo; c += gridDim.x) {  // whole 256-row chunks: warps stay converged
         const uint64_t i = (uint64_t)todo.chunks[c] * TP_WTILE + threadIdx.x;
         const int32_t rs = ld_stream(start + i), re = ld_stream(end + i);
@@ -982,7 +1029,7 @@ __global__ void __launch_bounds__(TP_WTILE) nearest_k1_kernel_todo(IndexView ix,
         int32_t qs = rs, qe = re;
         if (strict) { qs = wadd(qs, 1); qe = wsub(qe, 1); }
         Cand b{0, 0, 0};
-        const bool found = k < ix.n_keys && nearest_one(ix, k, qs, qe, include_overlaps, &b);
+        const bool found = k < ix.n_keys && nearest_one(ix, k, qs, qe, include_overlaps, &b, skeys);
         const uint32_t bits = __ballot_sync(0xFFFFFFFFu, found);
         if ((threadIdx.x & 31) == 0) valid_bits[i >> 5] = bits;
         st_stream(left_idx + i, found ? b.pos : 0u);

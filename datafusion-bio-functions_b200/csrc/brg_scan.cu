@@ -575,10 +575,10 @@ __global__ void cb_bounds_kernel(DirView ds, DirView de, const KeyDir* __restric
     cs[g] = rank_lt_kd(ds, load_keydir(ds.kd, c), (int32_t)thr);
     ce[g] = rank_lt_kd(de, load_keydir(de.kd, c), (int32_t)thr);
 }
-// pass 2: the records (the bin's elements are S[cs[g] .. cs[g + 1]) and E[ce[g] .. ce[g + 1]))
+// pass 2: the records (the bin's elements are S[cs[g] .. cs[g + 1]) and E[ce[g] .. ce[g + 1])); layout and formats: brg_bins.cuh
 __global__ void cb_fill_kernel(const int32_t* __restrict__ S, const int32_t* __restrict__ E, const KeyDir* __restrict__ kd,
-                               uint32_t n_keys, uint32_t shift, const uint32_t* __restrict__ csv, const uint32_t* __restrict__ cev,
-                               uint4* __restrict__ rec, uint32_t total) {
+                               uint32_t n_keys, uint32_t shift, uint32_t fmt, const uint32_t* __restrict__ csv,
+                               const uint32_t* __restrict__ cev, uint4* __restrict__ rec, uint32_t total) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
     uint32_t c;
@@ -591,27 +591,23 @@ __global__ void cb_fill_kernel(const int32_t* __restrict__ S, const int32_t* __r
         const uint32_t cs = csv[g], ce = cev[g];
         const uint32_t cs1 = csv[g + 1], ce1 = cev[g + 1];  // (record g + 1 is the next bin of this key or its sentinel)
         const uint32_t ns = cs1 - cs, ne = ce1 - ce;
-        w[0] = cs;
         // depth = cs - ce: intervals that start before the bin and have not ended (negative only with inverted rows: overflow)
-        if (ns + ne > CB_SLOTS || ce > cs || cs - ce >= 0xFFFFu) {
-            w[1] = CB_OVERFLOW << 24;
-        } else {
-            w[1] = (cs - ce) | (ns << 16) | (ne << 24);
+        if (cb_encode_header(w, fmt, cs, ce, ns, ne)) {
             for (uint32_t i = 0; i < ns + ne; i++) {
                 const int64_t v = (int64_t)(i < ns ? S[cs + i] : E[ce + (i - ns)]) - thr;  // 0 .. 2^shift - 1
-                w[2 + (i >> 1)] |= ((uint32_t)v & 0xFFFFu) << ((i & 1u) * 16u);
+                cb_encode_slot(w, fmt, i, (uint32_t)v);
             }
         }
     }
     rec[2ull * g] = make_uint4(w[0], w[1], w[2], w[3]);
     rec[2ull * g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-int cb_fill(const DirView& ds, const DirView& de, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t* cs_tmp,
+int cb_fill(const DirView& ds, const DirView& de, const KeyDir* kd, uint32_t n_keys, uint32_t shift, uint32_t fmt, uint32_t* cs_tmp,
             uint32_t* ce_tmp, uint4* rec, uint32_t total, cudaStream_t st) {
     if (total == 0 || n_keys == 0) return 0;
     cb_bounds_kernel<<<(total + 255) / 256, 256, 0, st>>>(ds, de, kd, n_keys, shift, cs_tmp, ce_tmp, total);
     BRG_LAUNCH_CHECK();
-    cb_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ds.A, de.A, kd, n_keys, shift, cs_tmp, ce_tmp, rec, total);
+    cb_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(ds.A, de.A, kd, n_keys, shift, fmt, cs_tmp, ce_tmp, rec, total);
     BRG_LAUNCH_CHECK();
     return 0;
 }

@@ -195,6 +195,13 @@ class Index:
     def device_bytes(self):
         return A.lib().brg_index_device_bytes(self._h)
 
+    def bins_info(self, table):
+        """the bins table read for unsorted probe tables: table 0 = count, 1 = coverage, 2 = nearest / pairs.
+        -> {"records", "bin_shift", "format"} (records == 0: the index holds no such table)"""
+        sh, fmt = C.c_uint32(), C.c_uint32()
+        n = A.lib().brg_index_bins_info(self._h, int(table), C.byref(sh), C.byref(fmt))
+        return {"records": int(n), "bin_shift": int(sh.value), "format": int(fmt.value)}
+
     def export(self):
         """(header bytes, slab tensor) for replication to other GPUs."""
         n = C.c_uint64()

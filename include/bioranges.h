@@ -106,6 +106,12 @@ BRG_API void brg_index_destroy(brg_index* idx);
 BRG_API uint64_t brg_index_rows(const brg_index* idx);        /* build rows with a valid key */
 BRG_API uint64_t brg_index_merged_rows(const brg_index* idx); /* merged (coverage) intervals  */
 BRG_API uint64_t brg_index_device_bytes(const brg_index* idx);
+/* Diagnostics: the bins tables the index holds for UNSORTED probe tables (one 32-byte record per coordinate bin, read by the
+ * one-row-per-thread kernels).  table: 0 = count bins over (start, end) order, 1 = coverage bins over the merged intervals,
+ * 2 = nearest / pair bins over (start, prefix-max end).  Returns the record count (0 = table absent); *bin_shift = log2 of the
+ * bin width, *format = 0 (12 slots of 16 bits) or 1 (18 slots of 10 bits).  Either pointer may be NULL.  No reference
+ * counterpart: the reference's index is the coitrees / sorted-array structure of interval_tree.rs:75-143. */
+BRG_API uint64_t brg_index_bins_info(const brg_index* idx, int table, uint32_t* bin_shift, uint32_t* format);
 
 /* Replication across GPUs (one process per GPU): the index is one device slab plus a small POD header.
  * Rank 0 exports, every other rank imports the header, receives the slab with ncclBroadcast
