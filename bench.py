@@ -406,6 +406,8 @@ def run_workload(h, name, order, steps, warmup, want_e2e, want_pageable=False, w
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     kernel_name = KERNELS[name] if (name != "pairs" or res.get("pairs_path", "").startswith("brg_pairs_join_dev")) else \
         "pairs_ranges_todo_kernel+scan+pairs_emit_kernel_flat"
+    if order == "shuffled" and name != "pairs":  # unsorted rows: the tiled kernel hands every chunk to the one-row-per-thread kernel
+        kernel_name = {"count": "count_kernel_todo", "coverage": "coverage_kernel_todo", "nearest": "nearest_k1_kernel_todo"}[name]
     res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": h.peak, "unit": "GB/s", "frac": achieved / h.peak,
                        "traffic": ncu_traffic(kernel_name, name, order, args.scale), "peak_source": h.peak_src, "kernel": kernel_name,
                        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms}

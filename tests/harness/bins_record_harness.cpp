@@ -62,11 +62,13 @@ static int run_case(uint32_t seed, uint32_t fmt, uint32_t shift, uint32_t n, uin
             const uint32_t (&w)[8] = rec[ba].w;
             if (cb_overflowed(w)) miss_a = true;
             else ra = cb_first_a(w) + cb_count_le<false>(w, fmt, da & msk);
+            if (!miss_a && fmt && cb_count_le<false>(w, fmt, da & msk) != cb_count_le_fmt<1, false>(w, da & msk)) { std::printf("packed count differs from the slot loop (A)\n"); return 1; }
         }
         if (b_in && bb < nb) {
             const uint32_t (&w)[8] = rec[bb].w;
             if (cb_overflowed(w)) miss_b = true;
             else rb = cb_first_b(w) + cb_count_le<true>(w, fmt, db & msk);
+            if (!miss_b && fmt && cb_count_le<true>(w, fmt, db & msk) != cb_count_le_fmt<1, true>(w, db & msk)) { std::printf("packed count differs from the slot loop (B)\n"); return 1; }
         }
         *answered += (a_in && ba < nb && !miss_a) + (b_in && bb < nb && !miss_b);
         const uint32_t want_a = seg_begin + (uint32_t)(std::upper_bound(A.begin(), A.end(), qa) - A.begin());
@@ -105,6 +107,26 @@ int main() {
             if (cb_slot_get<1>(w, j) != (j == i ? 1023u : 0u)) { std::printf("packed slot %u leaks into %u\n", i, j); return 1; }
     }
     if (answered < 1000000 || overflowed < 100) { std::printf("vacuous: %llu ranks answered from records, %llu overflowed records\n", (unsigned long long)answered, (unsigned long long)overflowed); return 1; }
+    {   // the packed decoder against the slot loop on arbitrary slot contents (not only ascending ones), every split, many offsets
+        std::mt19937 rng(7);
+        for (int it = 0; it < 20000; it++) {
+            const uint32_t na = rng() % 19, nb = rng() % (19 - na);
+            cb_encode_header(w, 1, 100, 50, na, nb);
+            for (uint32_t i = 0; i < na + nb; i++) cb_encode_slot(w, 1, i, (it % 3 == 0) ? (rng() % 4) * 341u : rng() % 1024);
+            for (int q = 0; q < 24; q++) {
+                const uint32_t off = q < 4 ? (uint32_t[]){0u, 1u, 1022u, 1023u}[q] : rng() % 1024;
+                if (cb_count_le<false>(w, 1, off) != cb_count_le_fmt<1, false>(w, off) || cb_count_le<true>(w, 1, off) != cb_count_le_fmt<1, true>(w, off)) {
+                    std::printf("packed decoder: na %u nb %u off %u\n", na, nb, off);
+                    return 1;
+                }
+            }
+        }
+        for (uint32_t n = 0; n <= 18; n++) {  // the range masks: exactly the bits of the slots below n
+            uint32_t want = 0;
+            for (uint32_t i = 0; i < n; i++) want |= 1u << (10u * (i / 6) + i % 6);
+            if ((cb_packed_below(n) & 0x03F0FC3Fu) != want) { std::printf("cb_packed_below(%u)\n", n); return 1; }
+        }
+    }
     std::printf("OK %llu cases, %llu ranks answered from records, %llu overflowed records\n", (unsigned long long)cases, (unsigned long long)answered, (unsigned long long)overflowed);
     return 0;
 }
