@@ -473,6 +473,40 @@ void brgo_overlap_checksum(const brgo_index *ix, const uint32_t *key, const int3
     sums[0] = S1; sums[1] = S2; sums[2] = X; sums[3] = N;
 }
 
+/* The pair join as the reference runs it on `threads` partitions (IJ:1616-1653 per probe batch of a partition): every thread
+ * takes one contiguous range of the probe rows and MATERIALISES its own build-index vector and the run-length-expanded
+ * probe-index vector, exactly like brgo_overlap_pairs above; nothing is concatenated (the reference hands each partition's
+ * batches downstream as they are).  This is the CPU baseline of bench.py's pairs workload -- the work the reference does,
+ * output vectors included -- and returns the pair count; sums (may be NULL) receives the order-independent checksum of the
+ * materialised vectors in the layout of brgo_overlap_checksum, which is how tests/ know the vectors were right. */
+uint64_t brgo_overlap_pairs_partitions(const brgo_index *ix, const uint32_t *key, const int32_t *start, const int32_t *end,
+                                       uint64_t n, uint64_t row_base, int threads, uint64_t *sums) {
+    const int T = threads > 0 ? threads : 1;
+    uint64_t S1 = 0, S2 = 0, X = 0, N = 0;
+#pragma omp parallel for schedule(static, 1) num_threads(T) reduction(+ : S1, S2, N) reduction(^ : X)
+    for (int t = 0; t < T; t++) {
+        const uint64_t lo = n * (uint64_t)t / (uint64_t)T, hi = n * (uint64_t)(t + 1) / (uint64_t)T;
+        u32vec b = {0}, p = {0};
+        for (uint64_t i = lo; i < hi; i++) {
+            const key_index_t *k = lookup(ix, key, i);
+            if (!k) continue;
+            const uint64_t before = b.n;
+            tree_query(k->by_start, k->tree_max, 0, (int64_t)k->n, start[i], end[i], pos_visit, &b);
+            for (uint64_t j = before; j < b.n; j++) u32vec_push(&p, (uint32_t)i);
+        }
+        if (sums)
+            for (uint64_t j = 0; j < b.n; j++) {
+                const uint64_t h = brgo_pair_hash(b.v[j], row_base + p.v[j]);
+                S1 += h; S2 += h * h; X ^= h;
+            }
+        N += b.n;
+        free(b.v); free(p.v);
+    }
+    if (sums) { sums[0] = S1; sums[1] = S2; sums[2] = X; sums[3] = N; }
+    return N;
+}
+
+
 /* IT:52-73 exposed for the unit-test literals (IT:291-353): input need not be sorted */
 uint64_t brgo_merge_intervals(const int32_t *first, const int32_t *last, uint64_t n,
                               int32_t *out_first, int32_t *out_last) {

@@ -51,6 +51,8 @@ def lib():
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.brgo_overlap_counts.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, _u64p, C.c_int]
         L.brgo_overlap_checksum.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint64, C.c_void_p, _u64p, C.c_int]
+        L.brgo_overlap_pairs_partitions.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        L.brgo_overlap_pairs_partitions.restype = C.c_uint64
         L.brgo_merge_intervals.restype = C.c_uint64
         L.brgo_merge_intervals.argtypes = [_i32p, _i32p, C.c_uint64, _i32p, _i32p]
         L.brgo_free.argtypes = [C.c_void_p]
@@ -148,6 +150,16 @@ class OracleIndex:
         lib().brgo_overlap_counts(self._h, kp, start, end, len(start), out, threads)
         return out
 
+
+    def overlap_pairs_partitions(self, key, start, end, threads=1, row_base=0, checksum=False):
+        """the pair join on `threads` partitions of the probe rows, every partition materialising its own (build_idx, probe_idx)
+        vectors as the reference does; -> pair count, or (sum h, sum h^2, xor h, n_pairs) of the materialised vectors"""
+        start, end = _i32(start), _i32(end)
+        k, kp = _keyptr(key)
+        sums = np.zeros(4, np.uint64) if checksum else None
+        m = lib().brgo_overlap_pairs_partitions(self._h, kp, start, end, len(start), int(row_base), int(threads),
+                                                sums.ctypes.data if checksum else None)
+        return tuple(int(x) for x in sums) if checksum else int(m)
 
     def overlap_checksum(self, key, start, end, row_base=0, threads=1, counts=False):
         """order-independent checksum of the pair set: (sum h, sum h^2, xor h, n_pairs) as python ints, h = pair_hash(build_row,

@@ -172,3 +172,19 @@ def test_reference_superintervals_on_golden_fixture():
     rb, rp = O.canonical_pairs(*si.pairs(pk, g["exons_start"], g["exons_end"]))
     b, p = O.canonical_pairs(*ix.overlap_pairs(pk, g["exons_start"], g["exons_end"]))
     assert len(rb) == 54343 and (rb == b).all() and (rp == p).all()
+
+
+def test_oracle_partitioned_pair_join_materialises_the_same_pairs():
+    """bench.py's CPU baseline of the pairs workload (brgo_overlap_pairs_partitions: every thread materialises the index vectors
+    of its probe-row range, IJ:1616-1653) produces the pair set of the single-threaded join, whatever the partition count"""
+    rng = np.random.default_rng(17)
+    bk, bs, be = _rand(rng, 20_000, 3, 300_000, 400)
+    pk, ps, pe = _rand(rng, 30_001, 3, 301_000, 300)
+    oi = O.OracleIndex(bk, bs, be, 3)
+    bi, pi = oi.overlap_pairs(pk, ps, pe)
+    want = O.pair_checksum(bi, pi)
+    assert want[3] == len(bi) > 0
+    for threads in (1, 2, 7, 16):
+        assert oi.overlap_pairs_partitions(pk, ps, pe, threads=threads, checksum=True) == want
+        assert oi.overlap_pairs_partitions(pk, ps, pe, threads=threads) == len(bi)
+    assert oi.overlap_checksum(pk, ps, pe, threads=4) == want
